@@ -1,0 +1,77 @@
+"""Generate tests/golden/*.npz from the REAL reference (container-only).
+
+TEST INFRASTRUCTURE ONLY.  Run as ``python -m oracle.make_golden`` in the build
+container where /root/reference exists.  The reference's own modules
+(networks.EfficientSATRN.EfficientSATRN, postprocessing.decode, .beam_search)
+are imported through oracle/ref_shim.py, loaded with the seeded synthetic
+checkpoint (oracle/synth.py, ``load_state_dict(strict=True)``), and run on CPU
+fp32.  Inputs are NOT stored: they are regenerated from the seed
+(oracle.synth.synth_images / synth_state_dict are bit-reproducible); a sha256
+of the checkpoint bytes is stored so a host that generates different weights
+is detected.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_shim, satrn, synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def state_dict_digest(sd) -> str:
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(sd[k].detach().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def main():
+    torch.set_grad_enabled(False)
+    torch.manual_seed(0)
+    ref = ref_shim.load_reference()
+    spec = satrn.ModelSpec()
+    for seed, batch in ((0, 4), (1, 2)):
+        sd = synth.synth_state_dict(spec, seed)
+        model = ref.networks.EfficientSATRN(ref_shim.reference_flags(), ref_shim.reference_vocab()).eval()
+        model.load_state_dict(sd, strict=True)
+        images = synth.synth_images(spec, batch, seed)
+        expected = satrn.expected_tokens(batch)
+        # greedy through the reference's own entry point (decoding.py:34-40)
+        logits = model(images, expected, False, 0.0)
+        tokens = ref.postprocessing.decode(model, images, expected=expected, method="greedy")
+        memory = model.encoder(images).contiguous()
+        out = dict(
+            digest=np.array(state_dict_digest(sd)),
+            memory=memory.numpy(),
+            logits=logits.numpy().astype(np.float32),
+            tokens=tokens.numpy(),
+        )
+        if seed == 0:
+            loader = ref_shim.reference_loader()
+            for bw in (4, 8):
+                with ref_shim.cpu_get_device():
+                    out["beam%d" % bw] = ref.postprocessing.decode(
+                        model, images, data_loader=loader, expected=expected, method="beam",
+                        beam_width=bw).numpy()
+            # teacher-forced branch (:488-495), eval mode so dropout is identity
+            g = torch.Generator().manual_seed(7)
+            text = torch.randint(3, 244, (batch, 24), generator=g)
+            text[:, 0] = satrn.SOS_ID
+            text[0, 15:] = satrn.PAD_ID
+            text[2, 9:] = satrn.PAD_ID
+            exp_tf = torch.cat([text, torch.full((batch, 1), satrn.EOS_ID)], 1)
+            out["tf_text"] = text.numpy()
+            out["tf_logits"] = model(images, exp_tf, True, 1.0).numpy()
+        path = os.path.join(GOLDEN_DIR, "efficientsatrn_seed%d.npz" % seed)
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB", "digest", out["digest"])
+
+
+if __name__ == "__main__":
+    main()
