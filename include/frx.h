@@ -1,0 +1,152 @@
+/*
+ * frx.h -- C ABI of the B200-native formula-recognition hot path.
+ *
+ * The reference (bcaitech1/p4-fr-sorry-math-but-love-you) is pure Python/PyTorch
+ * and has no FFI of its own, so these entry points are the ones its operator
+ * API for this path would bind.  Each one names the reference
+ * interface it replaces (file:line under /root/reference).  Plain pointers and
+ * sizes only -- no torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from frx_last_error(h) (the Python host raises RuntimeError);
+ *   - device pointers are caller-owned (torch storage), valid for the call,
+ *     and all work is enqueued on the passed stream (a cudaStream_t passed as
+ *     void*) -- no hidden synchronisation unless stated;
+ *   - the handle owns packed weights, KV caches and workspaces;
+ *   - one handle per (process, device); not thread-safe (the reference is
+ *     single-threaded).
+ */
+#ifndef FRX_H_
+#define FRX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct frx_handle frx_handle;
+
+enum { FRX_NET_EFFICIENT_SATRN = 0, FRX_NET_LITE_SATRN = 1 };
+enum { FRX_PREC_FP32 = 0, FRX_PREC_BF16 = 1 };
+enum { FRX_DTYPE_F32 = 0, FRX_DTYPE_I64 = 1 };
+
+/* Mirrors what the constructors read from FLAGS and the vocab:
+ * networks/EfficientSATRN.py:664-692 (EfficientSATRN.__init__),
+ * networks/LiteSATRN.py:548-576. */
+typedef struct frx_config {
+  int32_t network;      /* FRX_NET_* */
+  int32_t height;       /* FLAGS.input_size.height */
+  int32_t width;        /* FLAGS.input_size.width  */
+  int32_t in_ch;        /* FLAGS.data.rgb */
+  int32_t enc_hidden, enc_filter, enc_layers, enc_heads;          /* FLAGS.SATRN.encoder.* */
+  int32_t dec_src, dec_hidden, dec_filter, dec_layers, dec_heads; /* FLAGS.SATRN.decoder.* */
+  int32_t num_classes;  /* len(train_dataset.id_to_token) */
+  int32_t sos_id, eos_id, pad_id;
+  int32_t max_batch;    /* per-GPU image batch the workspaces are sized for */
+  int32_t max_steps;    /* decode steps the KV cache is sized for (expected.size(1)-1) */
+  int32_t precision;    /* FRX_PREC_* : arithmetic of the dense contractions / KV cache */
+  int32_t device;       /* CUDA device ordinal */
+} frx_config;
+
+/* Library / build identification ("frx <ver> sm_100a"). */
+const char* frx_version(void);
+
+/* Replaces the nn.Module constructors (EfficientSATRN.py:664-695). */
+int frx_create(const frx_config* cfg, frx_handle** out);
+void frx_destroy(frx_handle* h);
+const char* frx_last_error(const frx_handle* h);
+
+/* Replaces nn.Module.load_state_dict (EfficientSATRN.py:694-695): call once per
+ * state_dict entry with the reference's own key.  `data` may
+ * be a host or a device pointer (cudaMemcpyDefault); the library keeps its own
+ * copy.  Also used for the three host-built positional tables that are NOT in
+ * the state_dict (EfficientSATRN.py:95-99,404-405) under the reserved names
+ * "pe2d.h" [h,C], "pe2d.w" [w,C], "pe1d" [500,D]. */
+int frx_load_tensor(frx_handle* h, const char* name, const void* data,
+                    const int64_t* shape, int32_t ndim, int32_t dtype);
+
+/* Packs everything loaded so far into the kernels' layouts (eval-mode BN folded
+ * to per-channel scale/shift, conv weights to [O][kh][kw][I], decoder linears
+ * concatenated/transposed).  Fails if a tensor the network needs is missing or
+ * has the wrong shape.  Must be called after the last frx_load_tensor and again
+ * after any re-load. */
+int frx_finalize_weights(frx_handle* h);
+
+/* SATRNEncoder.forward (EfficientSATRN.py:311-323).
+ * images  : device fp32 [B, in_ch, H, W] (NCHW, contiguous)
+ * memory  : device fp32 [B, h*w, enc_hidden] (the reference's `src`, contiguous) */
+int frx_encode(frx_handle* h, const float* images, int32_t batch, float* memory, void* stream);
+
+/* SATRNDecoder.forward, inference branch (EfficientSATRN.py:528-566) followed by
+ * decode()'s topk(1) (postprocessing/decoding.py:38-40).
+ * memory  : device fp32 [B, h*w, dec_src]
+ * logits  : device fp32 [B, steps, num_classes] or NULL
+ * tokens  : device int64 [B, steps] or NULL
+ * forced  : device int64 [B, steps] or NULL; when given, token t+1 fed to the
+ *           decoder is forced[:, t] instead of the argmax (forced decoding,
+ *           used by the parity tests; the reference's teacher_forcing_ratio=0
+ *           loop is forced == NULL). */
+int frx_decode_greedy(frx_handle* h, const float* memory, int32_t batch, int32_t steps,
+                      float* logits, int64_t* tokens, const int64_t* forced, void* stream);
+
+/* EfficientSATRN.forward(input, expected, is_train=False, ...) (EfficientSATRN.py:697-706):
+ * encode + greedy decode with DEVICE buffers. */
+int frx_forward_greedy(frx_handle* h, const float* images, int32_t batch, int32_t steps,
+                       float* logits, int64_t* tokens, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D of the images, encode,
+ * decode, D2H of tokens (and of logits when logits_host != NULL); synchronises
+ * the stream before returning.  This is the end-to-end entry bench.py times. */
+int frx_forward_greedy_host(frx_handle* h, const float* images_host, int32_t batch, int32_t steps,
+                            float* logits_host, int64_t* tokens_host, void* stream);
+
+/* EfficientSATRN_decoder.reset_status / step_forward (EfficientSATRN.py:932-952),
+ * the stateful API the ensemble driver uses (utils/ensemble_utils.py:83-118).
+ * frx_decode_begin projects the cross-attention K/V of `memory` once and
+ * resets step_idx; frx_decode_step consumes target [B] int64 and writes
+ * logits [B, num_classes] for position step_idx, then increments it. */
+int frx_decode_begin(frx_handle* h, const float* memory, int32_t batch, void* stream);
+int frx_decode_step(frx_handle* h, const int64_t* target, float* logits, void* stream);
+
+/* EfficientSATRN.beam_search (EfficientSATRN.py:708-867) with topk=1 via
+ * decode(method="beam") (postprocessing/decoding.py:42-48): per-sample
+ * best-first search, score -logp/len in fp64 (decoding.py:80), node order on
+ * len (decoding.py:83-87), budget (max_sequence-1) expansions, stop at the
+ * first popped EOS, rows start with SOS and are PAD-padded.
+ * tokens  : device int64 [B, max_sequence] */
+int frx_beam_search(frx_handle* h, const float* memory, int32_t batch, int32_t beam_width,
+                    int32_t max_sequence, int64_t* tokens, void* stream);
+
+/* SATRNDecoder.forward, teacher-forced branch (EfficientSATRN.py:488-495) in
+ * eval mode (dropout = identity).
+ * text    : device int64 [B, L] (= expected[:, :-1])
+ * logits  : device fp32 [B, L, num_classes] */
+int frx_decode_teacher_forced(frx_handle* h, const float* memory, const int64_t* text,
+                              int32_t batch, int32_t length, float* logits, void* stream);
+
+/* Introspection for bench.py / tests: number of kernel launches the library
+ * has enqueued since creation (nodes of replayed CUDA graphs included), and the
+ * bytes currently allocated by the handle. */
+int64_t frx_launch_count(const frx_handle* h);
+int64_t frx_device_bytes(const frx_handle* h);
+
+/* Debug taps used by the parity tests: copy an internal activation (NHWC fp32)
+ * produced by the last frx_encode into `out` (device).  Names: "stem",
+ * "eff_block.<s>.<i>", "trunk", "pe2d", "enc_layer<i>".  Returns the number of
+ * floats written through *count.  Only available when the handle was created
+ * with taps enabled via frx_set_option(h, "taps", 1). */
+int frx_set_option(frx_handle* h, const char* key, int64_t value);
+int frx_read_tap(frx_handle* h, const char* name, float* out, int64_t capacity, int64_t* count,
+                 int32_t* shape4, void* stream);
+
+/* Times (milliseconds, CUDA events on the launching stream) of the phases of the
+ * last frx_forward_greedy* call when option "timing" is 1: [0]=encode,
+ * [1]=cross-KV + decode loop, [2]=total. */
+int frx_last_timing(const frx_handle* h, float* ms3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRX_H_ */

@@ -1,0 +1,110 @@
+// common.cuh -- shared declarations for the frx CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "frx is written for sm_100a (B200) only"
+#endif
+
+namespace frx {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_SIGMOID = 3 };
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_SILU: return v / (1.f + expf(-v));
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// Parameter blocks (plain structs passed by value to the kernels)
+// ---------------------------------------------------------------------------
+// Implicit-GEMM convolution / dense GEMM:  C[M,N] = epi( A[M,K] * W[N,K]^T )
+struct GemmP {
+  const float* A;      // dense: [M, lda]; conv: NHWC activation
+  const float* W;      // [N, K]  (K contiguous; conv K index = (kh*KW+kw)*Cin + ci)
+  float* C;            // [M, ldc]
+  int M, N, K;
+  int lda, ldc;
+  int conv;            // 0 = dense, 1 = NHWC gather
+  int H, Wd, Cin, OH, OW, KH, KW, stride, pad_t, pad_l;
+  const float* gate;   // dense only: per-image per-k multiplier [M/rows_per_img, K] (SE excite)
+  int rows_per_img;
+  const float* scale;  // per-N: v = v*scale[n] + shift[n]   (folded eval BatchNorm)
+  const float* shift;  // per-N: bias when scale == nullptr
+  int act;
+  const float* res;    // residual added after the activation, [M, ldr]
+  int ldr;
+};
+
+struct DwP {
+  const float* in;     // NHWC [B,H,W,C]
+  const float* w;      // [9][C]
+  const float* scale;  // [C]
+  const float* shift;  // [C]  (conv bias already folded in)
+  float* out;          // NHWC [B,OH,OW,C]
+  int B, H, Wd, C, OH, OW, stride, pad_t, pad_l, act;
+};
+
+struct Seg {           // output column segment of a decoder GEMM
+  int n_begin, n_end;
+  float* dst;          // element (m, n) -> dst[m*row_stride + slot*slot_stride + (n - n_begin)]
+  long long row_stride;
+  long long slot_stride;   // multiplied by row_slot[m] when row_slot != nullptr
+};
+
+struct DecGemmP {
+  const float* A;      // [M, K] row-major (pre-LayerNorm values when ln_g != nullptr)
+  const float* Wt;     // [K, N] (N contiguous)
+  const float* bias;   // [N]
+  int M, N, K, lda;
+  int act;
+  const float* res;    // [M, ldr] added after the activation
+  int ldr;
+  const float* ln_g;   // LayerNorm applied to A rows on load (requires K == row width)
+  const float* ln_b;
+  float* a_norm_out;   // normalised A written back by the n-tile-0 blocks (or nullptr)
+  const int* row_slot; // optional per-row slot index for Seg::slot_stride
+  int nseg;
+  Seg seg[4];
+};
+
+struct AttnP {
+  const float* q;      // [M, ldq]  query rows (head h at columns h*HD)
+  int ldq;
+  const float* kcache; // [Bimg, rows_per_img, D]
+  const float* vcache;
+  int rows_per_img;    // row capacity per image in the cache
+  int D;               // model width of the cache rows
+  int n_hist;          // number of cached rows attended (when hist_len == nullptr)
+  const int* hist_len; // optional per-row history length
+  const int* chain;    // optional [M, chain_stride] row indices (tree-structured history)
+  int chain_stride;
+  const float* cur_k;  // optional current key/value row per query [M, ld_cur] (extra last key)
+  const float* cur_v;
+  int ld_cur;
+  int q_per_img;       // query rows per image (1 for incremental decode, L for teacher forcing)
+  float temperature;   // scores are DIVIDED by this
+  float* out;          // [M, ldo]
+  int ldo;
+  int M;
+  int heads;
+};
+
+}  // namespace frx

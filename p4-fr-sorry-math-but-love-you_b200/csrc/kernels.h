@@ -1,0 +1,31 @@
+// kernels.h -- host-callable launchers of the frx kernels.
+#pragma once
+#include "common.cuh"
+
+namespace frx {
+
+// fp32 kernel set (kernels_f32.cu)
+void launch_stem_conv(const float* in, const float* w, const float* scale, const float* shift, float* out,
+                      int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st);
+void launch_igemm_f32(const GemmP& p, cudaStream_t st);
+void launch_dwconv_f32(const DwP& p, cudaStream_t st);
+void launch_se_gate_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                        float* gate, int B, int HW, int C, int R, cudaStream_t st);
+void launch_maxpool2_f32(const float* in, float* out, int B, int H, int W, int C, cudaStream_t st);
+void launch_pe2d_f32(const float* x, const float* w0, const float* b0, const float* w1, const float* b1,
+                     const float* peh, const float* pew, float* out, int B, int h, int w, int C,
+                     cudaStream_t st);
+void launch_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta, float* out,
+                          int M, int C, int scramble_S, cudaStream_t st);
+void launch_enc_attn_f32(const float* qkv, float* out, int B, int S, int D, int heads, cudaStream_t st);
+void launch_dec_gemm_f32(const DecGemmP& p, cudaStream_t st);
+void launch_dec_attn_f32(const AttnP& p, int head_dim, cudaStream_t st);
+void launch_dec_embed_f32(const int* tok, const long long* tok64, int fixed_token, const float* emb,
+                          const float* pe, int pos, const int* pos_arr, int pos_mod, float scale, float* x,
+                          int M, int D, cudaStream_t st);
+void launch_dec_argmax_embed(const float* logits, long long ld_logits, int V, long long* tokens_out,
+                             long long ld_tok, const long long* forced, long long ld_forced, int* cur_tok,
+                             const float* emb, const float* pe_next, float scale, float* x, int M, int D,
+                             cudaStream_t st);
+
+}  // namespace frx

@@ -1,0 +1,951 @@
+// runtime.cu -- host runtime behind the C ABI in include/frx.h.
+//
+// Owns: the packed weights (one device arena), the activation workspaces, the
+// decoder's KV caches, and the CUDA graphs of the decode loop.  Everything is
+// enqueued on the caller's stream.  No CPU fallback: every entry point fails
+// loudly if the device or a kernel launch fails.
+//
+// Reference lines cited are in /root/reference/networks/EfficientSATRN.py.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/frx.h"
+#include "kernels.h"
+#include "runtime.h"
+
+using namespace frx;
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+static int fail(frx_handle* h, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return 1;
+}
+
+#define CK(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fail(h, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define CKL()                                                                             \
+  do {                                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess)                                                               \
+      return fail(h, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    h->launches++;                                                                        \
+  } while (0)
+
+static int dev_alloc(frx_handle* h, void** p, size_t bytes) {
+  if (bytes == 0) bytes = 256;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) return fail(h, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  h->allocs.push_back(*p);
+  h->device_bytes += (int64_t)bytes;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// weight arena: packed on the host, uploaded once
+// ---------------------------------------------------------------------------
+struct ArenaBuilder {
+  std::vector<float> host;
+  size_t add(const float* src, size_t n) {
+    size_t off = (host.size() + 63) / 64 * 64;
+    host.resize(off + n);
+    if (src) memcpy(host.data() + off, src, n * sizeof(float));
+    return off;
+  }
+  float* at(size_t off) { return host.data() + off; }
+};
+
+static const HostTensor* find(frx_handle* h, const std::string& name) {
+  auto it = h->raw.find(name);
+  return it == h->raw.end() ? nullptr : &it->second;
+}
+
+static int need(frx_handle* h, const std::string& name, std::initializer_list<int64_t> shape,
+                const HostTensor** out) {
+  const HostTensor* t = find(h, name);
+  if (!t) return fail(h, "missing tensor '%s'", name.c_str());
+  std::vector<int64_t> s(shape);
+  if (t->shape != s) {
+    std::string got, want;
+    for (auto v : t->shape) got += std::to_string(v) + ",";
+    for (auto v : s) want += std::to_string(v) + ",";
+    return fail(h, "tensor '%s' has shape [%s] expected [%s]", name.c_str(), got.c_str(), want.c_str());
+  }
+  *out = t;
+  return 0;
+}
+
+// eval-mode BatchNorm folded to y = x*alpha + beta, computed like ATen's CPU path
+// (invstd = 1/sqrt(var+eps); alpha = w*invstd; beta = b - mean*alpha).
+static int fold_bn(frx_handle* h, ArenaBuilder& ab, const std::string& p, int C, float eps,
+                   const float* conv_bias, size_t* off_scale, size_t* off_shift) {
+  const HostTensor *w, *b, *mu, *var;
+  if (need(h, p + ".weight", {C}, &w) || need(h, p + ".bias", {C}, &b) ||
+      need(h, p + ".running_mean", {C}, &mu) || need(h, p + ".running_var", {C}, &var))
+    return 1;
+  *off_scale = ab.add(nullptr, C);
+  *off_shift = ab.add(nullptr, C);
+  for (int c = 0; c < C; ++c) {
+    float invstd = 1.0f / sqrtf(var->f[c] + eps);
+    float alpha = w->f[c] * invstd;
+    float beta = b->f[c] - mu->f[c] * alpha;
+    if (conv_bias) beta += conv_bias[c] * alpha;
+    ab.at(*off_scale)[c] = alpha;
+    ab.at(*off_shift)[c] = beta;
+  }
+  return 0;
+}
+
+// conv weight [O][I][kh][kw] -> [O][kh][kw][I]  (K index = (kh*KW+kw)*I + i)
+static int pack_conv(frx_handle* h, ArenaBuilder& ab, const std::string& name, int O, int I, int k,
+                     size_t* off) {
+  const HostTensor* w;
+  if (need(h, name, {O, I, k, k}, &w)) return 1;
+  *off = ab.add(nullptr, (size_t)O * I * k * k);
+  float* d = ab.at(*off);
+  for (int o = 0; o < O; ++o)
+    for (int i = 0; i < I; ++i)
+      for (int t = 0; t < k * k; ++t) d[((size_t)o * k * k + t) * I + i] = w->f[((size_t)o * I + i) * k * k + t];
+  return 0;
+}
+
+// depthwise weight [C][1][3][3] -> [9][C]
+static int pack_dw(frx_handle* h, ArenaBuilder& ab, const std::string& name, int C, size_t* off) {
+  const HostTensor* w;
+  if (need(h, name, {C, 1, 3, 3}, &w)) return 1;
+  *off = ab.add(nullptr, (size_t)9 * C);
+  float* d = ab.at(*off);
+  for (int c = 0; c < C; ++c)
+    for (int t = 0; t < 9; ++t) d[(size_t)t * C + c] = w->f[(size_t)c * 9 + t];
+  return 0;
+}
+
+// linear weight [N][K] placed transposed into a [K][Ntot] matrix at column col0
+static void put_transposed(float* dst, int Ntot, int col0, const float* w, int N, int K) {
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) dst[(size_t)k * Ntot + col0 + n] = w[(size_t)n * K + k];
+}
+
+static void same_pad(int in, int k, int stride, int* out, int* pad_lo) {
+  // timm 0.4.9 layers/padding.py: static symmetric for stride 1, TF dynamic for stride 2
+  *out = (in + stride - 1) / stride;
+  if (stride == 1) { *pad_lo = (k - 1) / 2; return; }
+  int pad = (*out - 1) * stride + k - in;
+  if (pad < 0) pad = 0;
+  *pad_lo = pad / 2;
+}
+
+// (kind, repeats, kernel, stride, expand, out_ch, se_ratio_x100)  -- SURVEY App. A.1
+static const int kArch[6][7] = {
+    {0, 2, 3, 1, 1, 24, 0},  {1, 4, 3, 2, 4, 48, 0},    {1, 4, 3, 2, 4, 64, 0},
+    {2, 6, 3, 2, 4, 128, 25}, {2, 9, 3, 1, 6, 160, 25}, {2, 15, 3, 2, 6, 256, 25}};
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" const char* frx_version(void) { return "frx 0.1 sm_100a"; }
+
+extern "C" const char* frx_last_error(const frx_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int frx_create(const frx_config* cfg, frx_handle** out) {
+  if (!cfg || !out) return 1;
+  frx_handle* h = new frx_handle();
+  h->cfg = *cfg;
+  *out = h;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, "no CUDA device available (%s): frx has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(h, "device %d out of range", cfg->device);
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(h, "device is sm_%d%d; frx is built for sm_100a (B200) only", prop.major, prop.minor);
+  h->num_sms = prop.multiProcessorCount;
+  if (cfg->network != FRX_NET_EFFICIENT_SATRN && cfg->network != FRX_NET_LITE_SATRN)
+    return fail(h, "unknown network %d", cfg->network);
+  if (cfg->dec_hidden % cfg->dec_heads || (cfg->dec_hidden / cfg->dec_heads != 32 && cfg->dec_hidden / cfg->dec_heads != 64))
+    return fail(h, "decoder head_dim must be 32 or 64");
+  if (cfg->dec_hidden > 256) return fail(h, "decoder hidden_dim > 256 not supported yet");
+  if (cfg->max_batch <= 0 || cfg->max_steps <= 0) return fail(h, "max_batch/max_steps must be positive");
+  return 0;
+}
+
+extern "C" void frx_destroy(frx_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& kv : h->taps) cudaFree(kv.second.data);
+  if (h->ev[0]) for (int i = 0; i < 3; ++i) cudaEventDestroy(h->ev[i]);
+  delete h;
+}
+
+extern "C" int frx_load_tensor(frx_handle* h, const char* name, const void* data, const int64_t* shape,
+                               int32_t ndim, int32_t dtype) {
+  if (!h || !name || !data) return fail(h, "frx_load_tensor: null argument");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  if (dtype == FRX_DTYPE_F32) {
+    t.f.resize(n);
+    CK(cudaMemcpy(t.f.data(), data, n * sizeof(float), cudaMemcpyDefault));
+  } else if (dtype == FRX_DTYPE_I64) {
+    std::vector<int64_t> tmp(n);
+    CK(cudaMemcpy(tmp.data(), data, n * sizeof(int64_t), cudaMemcpyDefault));
+    t.f.resize(n);
+    for (size_t i = 0; i < n; ++i) t.f[i] = (float)tmp[i];
+  } else {
+    return fail(h, "frx_load_tensor('%s'): unsupported dtype %d", name, dtype);
+  }
+  h->raw[name] = std::move(t);
+  h->finalized = false;
+  return 0;
+}
+
+extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
+  if (!h || !key) return 1;
+  std::string k(key);
+  if (k == "taps") h->opt_taps = value != 0;
+  else if (k == "graphs") h->opt_graphs = value != 0;
+  else if (k == "timing") h->opt_timing = value != 0;
+  else if (k == "parts") { h->opt_parts = (int)value & 3; h->finalized = false; }
+  else return fail(h, "unknown option '%s'", key);
+  return 0;
+}
+
+extern "C" int64_t frx_launch_count(const frx_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t frx_device_bytes(const frx_handle* h) { return h ? h->device_bytes : 0; }
+
+extern "C" int frx_last_timing(const frx_handle* h, float* ms3) {
+  if (!h || !ms3) return 1;
+  for (int i = 0; i < 3; ++i) ms3[i] = h->last_ms[i];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// finalize: pack weights, allocate workspaces
+// ---------------------------------------------------------------------------
+static int pack_trunk_efficientnet(frx_handle* h, ArenaBuilder& ab) {
+  const frx_config& c = h->cfg;
+  const std::string e = "encoder.shallow_cnn.";
+  const HostTensor* w;
+  if (need(h, e + "conv_stem.weight", {24, c.in_ch, 3, 3}, &w)) return 1;
+  h->stem_w = ab.add(w->f.data(), w->f.size());
+  if (fold_bn(h, ab, e + "bn1", 24, 1e-3f, nullptr, &h->stem_sc, &h->stem_sh)) return 1;
+  int cin = 24;
+  h->blocks.clear();
+  for (int s = 0; s < 6; ++s) {
+    for (int r = 0; r < kArch[s][1]; ++r) {
+      BlockW b{};
+      b.kind = kArch[s][0];
+      b.k = kArch[s][2];
+      b.stride = r == 0 ? kArch[s][3] : 1;
+      b.cin = cin;
+      b.cout = kArch[s][5];
+      b.mid = cin * kArch[s][4];
+      b.se_r = cin * kArch[s][6] / 100;
+      b.residual = (b.cin == b.cout && b.stride == 1);
+      std::string p = e + "eff_block." + std::to_string(s) + "." + std::to_string(r);
+      b.name = "eff_block." + std::to_string(s) + "." + std::to_string(r);
+      if (b.kind == 0) {
+        if (pack_conv(h, ab, p + ".conv.weight", b.cout, b.cin, b.k, &b.w_a)) return 1;
+        if (fold_bn(h, ab, p + ".bn1", b.cout, 1e-3f, nullptr, &b.sc_a, &b.sh_a)) return 1;
+      } else if (b.kind == 1) {
+        if (pack_conv(h, ab, p + ".conv_exp.weight", b.mid, b.cin, b.k, &b.w_a)) return 1;
+        if (fold_bn(h, ab, p + ".bn1", b.mid, 1e-3f, nullptr, &b.sc_a, &b.sh_a)) return 1;
+        if (pack_conv(h, ab, p + ".conv_pwl.weight", b.cout, b.mid, 1, &b.w_b)) return 1;
+        if (fold_bn(h, ab, p + ".bn2", b.cout, 1e-3f, nullptr, &b.sc_b, &b.sh_b)) return 1;
+      } else {
+        if (pack_conv(h, ab, p + ".conv_pw.weight", b.mid, b.cin, 1, &b.w_a)) return 1;
+        if (fold_bn(h, ab, p + ".bn1", b.mid, 1e-3f, nullptr, &b.sc_a, &b.sh_a)) return 1;
+        if (pack_dw(h, ab, p + ".conv_dw.weight", b.mid, &b.w_dw)) return 1;
+        if (fold_bn(h, ab, p + ".bn2", b.mid, 1e-3f, nullptr, &b.sc_dw, &b.sh_dw)) return 1;
+        const HostTensor *w1, *b1, *w2, *b2;
+        if (need(h, p + ".se.conv_reduce.weight", {b.se_r, b.mid, 1, 1}, &w1) ||
+            need(h, p + ".se.conv_reduce.bias", {b.se_r}, &b1) ||
+            need(h, p + ".se.conv_expand.weight", {b.mid, b.se_r, 1, 1}, &w2) ||
+            need(h, p + ".se.conv_expand.bias", {b.mid}, &b2))
+          return 1;
+        b.se_w1 = ab.add(w1->f.data(), w1->f.size());
+        b.se_b1 = ab.add(b1->f.data(), b1->f.size());
+        b.se_w2 = ab.add(w2->f.data(), w2->f.size());
+        b.se_b2 = ab.add(b2->f.data(), b2->f.size());
+        if (pack_conv(h, ab, p + ".conv_pwl.weight", b.cout, b.mid, 1, &b.w_b)) return 1;
+        if (fold_bn(h, ab, p + ".bn3", b.cout, 1e-3f, nullptr, &b.sc_b, &b.sh_b)) return 1;
+      }
+      h->blocks.push_back(b);
+      cin = b.cout;
+    }
+  }
+  if (pack_conv(h, ab, e + "conv_last.weight", c.enc_hidden, 256, 1, &h->last_w)) return 1;
+  if (fold_bn(h, ab, e + "bn2", c.enc_hidden, 1e-5f, nullptr, &h->last_sc, &h->last_sh)) return 1;
+  return 0;
+}
+
+static int pack_trunk_lite(frx_handle* h, ArenaBuilder& ab) {
+  // LiteSATRN.py:21-70: 4 x (conv3x3 p1 no-bias, BN, ReLU, maxpool2)
+  const frx_config& c = h->cfg;
+  const std::string e = "encoder.shallow_cnn.";
+  int H = c.enc_hidden;
+  int chans[4][2] = {{c.in_ch, H / 2}, {H / 2, H}, {H, H}, {H, H}};
+  for (int i = 0; i < 4; ++i) {
+    LiteConvW& L = h->lite[i];
+    L.cin = chans[i][0];
+    L.cout = chans[i][1];
+    if (i == 0) {
+      const HostTensor* w;
+      if (need(h, e + "conv0.weight", {L.cout, L.cin, 3, 3}, &w)) return 1;
+      L.w = ab.add(w->f.data(), w->f.size());  // direct kernel uses [O][I][3][3]
+    } else if (pack_conv(h, ab, e + "conv" + std::to_string(i) + ".weight", L.cout, L.cin, 3, &L.w)) {
+      return 1;
+    }
+    if (fold_bn(h, ab, e + "batch_norm" + std::to_string(i), L.cout, 1e-5f, nullptr, &L.sc, &L.sh)) return 1;
+  }
+  return 0;
+}
+
+static int pack_encoder(frx_handle* h, ArenaBuilder& ab) {
+  const frx_config& c = h->cfg;
+  const int C = c.enc_hidden, F = c.enc_filter;
+  const std::string pe = "encoder.positional_encoding.";
+  const HostTensor *w0, *b0, *w1, *b1, *th, *tw;
+  if (need(h, pe + "dense0.weight", {C / 2, C}, &w0) || need(h, pe + "dense0.bias", {C / 2}, &b0) ||
+      need(h, pe + "dense1.weight", {2 * C, C / 2}, &w1) || need(h, pe + "dense1.bias", {2 * C}, &b1) ||
+      need(h, "pe2d.h", {h->feat_h, C}, &th) || need(h, "pe2d.w", {h->feat_w, C}, &tw))
+    return 1;
+  h->pe_w0 = ab.add(w0->f.data(), w0->f.size());
+  h->pe_b0 = ab.add(b0->f.data(), b0->f.size());
+  h->pe_w1 = ab.add(w1->f.data(), w1->f.size());
+  h->pe_b1 = ab.add(b1->f.data(), b1->f.size());
+  h->pe_h = ab.add(th->f.data(), th->f.size());
+  h->pe_w = ab.add(tw->f.data(), tw->f.size());
+  h->enc.clear();
+  for (int i = 0; i < c.enc_layers; ++i) {
+    EncLayerW L{};
+    std::string p = "encoder.attention_layers." + std::to_string(i) + ".";
+    const HostTensor *g, *b, *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo, *dwb;
+    if (need(h, p + "norm.weight", {C}, &g) || need(h, p + "norm.bias", {C}, &b)) return 1;
+    L.ln_g = ab.add(g->f.data(), C);
+    L.ln_b = ab.add(b->f.data(), C);
+    std::string a = p + "attention_layer.";
+    if (need(h, a + "q_linear.weight", {C, C}, &wq) || need(h, a + "q_linear.bias", {C}, &bq) ||
+        need(h, a + "k_linear.weight", {C, C}, &wk) || need(h, a + "k_linear.bias", {C}, &bk) ||
+        need(h, a + "v_linear.weight", {C, C}, &wv) || need(h, a + "v_linear.bias", {C}, &bv) ||
+        need(h, a + "out_linear.weight", {C, C}, &wo) || need(h, a + "out_linear.bias", {C}, &bo))
+      return 1;
+    L.w_qkv = ab.add(nullptr, (size_t)3 * C * C);  // [3C][C] : q rows, k rows, v rows
+    memcpy(ab.at(L.w_qkv), wq->f.data(), (size_t)C * C * 4);
+    memcpy(ab.at(L.w_qkv) + (size_t)C * C, wk->f.data(), (size_t)C * C * 4);
+    memcpy(ab.at(L.w_qkv) + (size_t)2 * C * C, wv->f.data(), (size_t)C * C * 4);
+    L.b_qkv = ab.add(nullptr, 3 * C);
+    memcpy(ab.at(L.b_qkv), bq->f.data(), C * 4);
+    memcpy(ab.at(L.b_qkv) + C, bk->f.data(), C * 4);
+    memcpy(ab.at(L.b_qkv) + 2 * C, bv->f.data(), C * 4);
+    L.w_o = ab.add(wo->f.data(), (size_t)C * C);
+    L.b_o = ab.add(bo->f.data(), C);
+    if (pack_conv(h, ab, p + "conv0.weight", F, C, 1, &L.w_c0)) return 1;
+    if (fold_bn(h, ab, p + "norm0", F, 1e-5f, nullptr, &L.sc_c0, &L.sh_c0)) return 1;
+    if (pack_dw(h, ab, p + "depthwise.weight", F, &L.w_dw)) return 1;
+    if (need(h, p + "depthwise.bias", {F}, &dwb)) return 1;
+    if (fold_bn(h, ab, p + "depthwise_norm", F, 1e-5f, dwb->f.data(), &L.sc_dw, &L.sh_dw)) return 1;
+    if (pack_conv(h, ab, p + "conv1.weight", C, F, 1, &L.w_c1)) return 1;
+    if (fold_bn(h, ab, p + "norm1", C, 1e-5f, nullptr, &L.sc_c1, &L.sh_c1)) return 1;
+    h->enc.push_back(L);
+  }
+  return 0;
+}
+
+static int pack_decoder(frx_handle* h, ArenaBuilder& ab) {
+  const frx_config& c = h->cfg;
+  const int D = c.dec_hidden, F = c.dec_filter, S = c.dec_src, V = c.num_classes, L = c.dec_layers;
+  const HostTensor *emb, *pe, *gw, *gb;
+  if (need(h, "decoder.embedding.weight", {V + 1, D}, &emb) || need(h, "pe1d", {500, D}, &pe) ||
+      need(h, "decoder.generator.weight", {V, D}, &gw) || need(h, "decoder.generator.bias", {V}, &gb))
+    return 1;
+  h->emb = ab.add(emb->f.data(), emb->f.size());
+  h->pe1d = ab.add(pe->f.data(), pe->f.size());
+  h->gen_w = ab.add(gw->f.data(), gw->f.size());  // [V][D] for the teacher-forced GEMM
+  h->gen_b = ab.add(gb->f.data(), gb->f.size());
+  struct Lin { const HostTensor *w, *b; };
+  std::vector<std::map<std::string, Lin>> lw(L);
+  h->dec.assign(L, DecLayerW{});
+  for (int l = 0; l < L; ++l) {
+    std::string p = "decoder.attention_layers." + std::to_string(l) + ".";
+    auto lin = [&](const std::string& key, const std::string& name, int N, int K) -> int {
+      Lin x;
+      if (need(h, p + name + ".weight", {N, K}, &x.w) || need(h, p + name + ".bias", {N}, &x.b)) return 1;
+      lw[l][key] = x;
+      return 0;
+    };
+    if (lin("sq", "self_attention_layer.q_linear", D, D) || lin("sk", "self_attention_layer.k_linear", D, D) ||
+        lin("sv", "self_attention_layer.v_linear", D, D) || lin("so", "self_attention_layer.out_linear", D, D) ||
+        lin("cq", "attention_layer.q_linear", D, D) || lin("ck", "attention_layer.k_linear", D, S) ||
+        lin("cv", "attention_layer.v_linear", D, S) || lin("co", "attention_layer.out_linear", D, D) ||
+        lin("f0", "feedforward_layer.linear0", F, D) || lin("f1", "feedforward_layer.linear1", D, F))
+      return 1;
+    DecLayerW& W = h->dec[l];
+    auto ln = [&](const std::string& name, size_t* g, size_t* b) -> int {
+      const HostTensor *tg, *tb;
+      if (need(h, p + name + ".weight", {D}, &tg) || need(h, p + name + ".bias", {D}, &tb)) return 1;
+      *g = ab.add(tg->f.data(), D);
+      *b = ab.add(tb->f.data(), D);
+      return 0;
+    };
+    if (ln("self_attention_norm", &W.ln1_g, &W.ln1_b) || ln("attention_norm", &W.ln2_g, &W.ln2_b) ||
+        ln("feedforward_norm", &W.ln3_g, &W.ln3_b))
+      return 1;
+    auto tr = [&](const std::string& key, int N, int K, size_t* wo, size_t* bo) {
+      *wo = ab.add(nullptr, (size_t)N * K);
+      put_transposed(ab.at(*wo), N, 0, lw[l][key].w->f.data(), N, K);
+      *bo = ab.add(lw[l][key].b->f.data(), N);
+    };
+    tr("so", D, D, &W.wt_o, &W.b_o);
+    tr("cq", D, D, &W.wt_q2, &W.b_q2);
+    tr("co", D, D, &W.wt_o2, &W.b_o2);
+    tr("f0", F, D, &W.wt_f0, &W.b_f0);
+    tr("f1", D, F, &W.wt_f1, &W.b_f1);
+    // row-major copies for the teacher-forced path (igemm wants [N][K])
+    W.w_o = ab.add(lw[l]["so"].w->f.data(), (size_t)D * D);
+    W.w_q2 = ab.add(lw[l]["cq"].w->f.data(), (size_t)D * D);
+    W.w_o2 = ab.add(lw[l]["co"].w->f.data(), (size_t)D * D);
+    W.w_f0 = ab.add(lw[l]["f0"].w->f.data(), (size_t)F * D);
+    W.w_f1 = ab.add(lw[l]["f1"].w->f.data(), (size_t)D * F);
+    W.w_sqkv = ab.add(nullptr, (size_t)3 * D * D);
+    memcpy(ab.at(W.w_sqkv), lw[l]["sq"].w->f.data(), (size_t)D * D * 4);
+    memcpy(ab.at(W.w_sqkv) + (size_t)D * D, lw[l]["sk"].w->f.data(), (size_t)D * D * 4);
+    memcpy(ab.at(W.w_sqkv) + (size_t)2 * D * D, lw[l]["sv"].w->f.data(), (size_t)D * D * 4);
+    W.b_sqkv = ab.add(nullptr, 3 * D);
+    memcpy(ab.at(W.b_sqkv), lw[l]["sq"].b->f.data(), D * 4);
+    memcpy(ab.at(W.b_sqkv) + D, lw[l]["sk"].b->f.data(), D * 4);
+    memcpy(ab.at(W.b_sqkv) + 2 * D, lw[l]["sv"].b->f.data(), D * 4);
+  }
+  // fused step GEMMs: F_0 = [q0 k0 v0]; F_l = [k_{l-1} v_{l-1} q_l k_l v_l]; F_L = [k_{L-1} v_{L-1} gen]
+  h->fused.assign(L + 1, FusedW{});
+  for (int l = 0; l <= L; ++l) {
+    FusedW& Fw = h->fused[l];
+    int N = (l == 0 ? 0 : 2 * D) + (l < L ? 3 * D : V);
+    Fw.N = N;
+    Fw.wt = ab.add(nullptr, (size_t)D * N);
+    Fw.b = ab.add(nullptr, N);
+    float* wt = ab.at(Fw.wt);
+    float* bb = ab.at(Fw.b);
+    int col = 0;
+    auto put = [&](const HostTensor* w, const HostTensor* b, int n) {
+      put_transposed(wt, N, col, w->f.data(), n, D);
+      memcpy(bb + col, b->f.data(), n * 4);
+      col += n;
+    };
+    if (l > 0) { put(lw[l - 1]["sk"].w, lw[l - 1]["sk"].b, D); put(lw[l - 1]["sv"].w, lw[l - 1]["sv"].b, D); }
+    if (l < L) { put(lw[l]["sq"].w, lw[l]["sq"].b, D); put(lw[l]["sk"].w, lw[l]["sk"].b, D); put(lw[l]["sv"].w, lw[l]["sv"].b, D); }
+    else put(gw, gb, V);
+  }
+  // cross-attention K/V of the encoder memory: one [L*2*D][S] matrix (k_l rows then v_l rows)
+  h->w_cross = ab.add(nullptr, (size_t)L * 2 * D * S);
+  h->b_cross = ab.add(nullptr, (size_t)L * 2 * D);
+  for (int l = 0; l < L; ++l) {
+    memcpy(ab.at(h->w_cross) + (size_t)(l * 2) * D * S, lw[l]["ck"].w->f.data(), (size_t)D * S * 4);
+    memcpy(ab.at(h->w_cross) + (size_t)(l * 2 + 1) * D * S, lw[l]["cv"].w->f.data(), (size_t)D * S * 4);
+    memcpy(ab.at(h->b_cross) + (size_t)(l * 2) * D, lw[l]["ck"].b->f.data(), D * 4);
+    memcpy(ab.at(h->b_cross) + (size_t)(l * 2 + 1) * D, lw[l]["cv"].b->f.data(), D * 4);
+  }
+  return 0;
+}
+
+extern "C" int frx_finalize_weights(frx_handle* h) {
+  if (!h) return 1;
+  const frx_config& c = h->cfg;
+  CK(cudaSetDevice(c.device));
+  int down = c.network == FRX_NET_LITE_SATRN ? 16 : 32;
+  h->feat_h = c.height / down;
+  h->feat_w = c.width / down;
+  ArenaBuilder ab;
+  const bool want_enc = h->opt_parts & 1, want_dec = h->opt_parts & 2;
+  if (want_enc) {
+    if (c.network == FRX_NET_EFFICIENT_SATRN) {
+      if (pack_trunk_efficientnet(h, ab)) return 1;
+    } else if (pack_trunk_lite(h, ab)) {
+      return 1;
+    }
+    if (pack_encoder(h, ab)) return 1;
+  }
+  if (want_dec && pack_decoder(h, ab)) return 1;
+  // upload (re-finalize re-uses the arena when the size is unchanged)
+  size_t bytes = ab.host.size() * sizeof(float);
+  if (!h->arena || h->arena_bytes != bytes) {
+    void* p;
+    if (dev_alloc(h, &p, bytes)) return 1;
+    h->arena = (float*)p;
+    h->arena_bytes = bytes;
+  }
+  CK(cudaMemcpy(h->arena, ab.host.data(), bytes, cudaMemcpyHostToDevice));
+
+  if (!h->ws_ready) {
+    // ---- activation workspaces sized for max_batch ------------------------
+    const size_t B = c.max_batch;
+    size_t act_max = 0, mid_max = 0;
+    if (c.network == FRX_NET_EFFICIENT_SATRN) {
+      int H = (c.height - 3) / 2 + 1, W = (c.width - 3) / 2 + 1;
+      act_max = (size_t)H * W * 24;
+      for (const BlockW& b : h->blocks) {
+        int OH, OW, pl;
+        same_pad(H, b.k, b.stride, &OH, &pl);
+        same_pad(W, b.k, b.stride, &OW, &pl);
+        size_t mid = b.kind == 1 ? (size_t)OH * OW * b.mid : (b.kind == 2 ? (size_t)H * W * b.mid : 0);
+        if (mid > mid_max) mid_max = mid;
+        H = OH; W = OW;
+        if ((size_t)H * W * b.cout > act_max) act_max = (size_t)H * W * b.cout;
+      }
+    } else {
+      act_max = (size_t)c.height * c.width * (c.enc_hidden / 2);
+      mid_max = act_max;
+    }
+    size_t S = (size_t)h->feat_h * h->feat_w, C = c.enc_hidden;
+    size_t enc_act = S * 3 * C;
+    if (enc_act > mid_max) mid_max = enc_act;
+    if (S * C > act_max) act_max = S * C;
+    void* p;
+    if (want_enc) {
+      for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * act_max * 4)) return 1; h->act[i] = (float*)p; }
+      for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * mid_max * 4)) return 1; h->mid[i] = (float*)p; }
+      if (dev_alloc(h, &p, B * 2048 * 4)) return 1;
+      h->gate = (float*)p;
+    }
+    // ---- decoder state ----------------------------------------------------
+    const size_t D = c.dec_hidden, F = c.dec_filter, L = c.dec_layers, T = c.max_steps, V = c.num_classes;
+    if (want_dec) {
+    if (dev_alloc(h, &p, L * B * T * D * 4)) return 1; h->kself = (float*)p;
+    if (dev_alloc(h, &p, L * B * T * D * 4)) return 1; h->vself = (float*)p;
+    if (dev_alloc(h, &p, B * S * L * 2 * D * 4)) return 1; h->cross = (float*)p;
+    float** small[] = {&h->dx, &h->datt, &h->dpre1, &h->dpre2, &h->du, &h->dw, &h->dq2};
+    for (float** q : small) { if (dev_alloc(h, &p, B * D * 4)) return 1; *q = (float*)p; }
+    if (dev_alloc(h, &p, B * 3 * D * 4)) return 1; h->dqkv = (float*)p;
+    if (dev_alloc(h, &p, B * F * 4)) return 1; h->dff = (float*)p;
+    if (dev_alloc(h, &p, B * T * V * 4)) return 1; h->logits_int = (float*)p;
+    if (dev_alloc(h, &p, B * T * 8)) return 1; h->tokens_int = (long long*)p;
+    if (dev_alloc(h, &p, B * T * 8)) return 1; h->forced_int = (long long*)p;
+    if (dev_alloc(h, &p, B * 4)) return 1; h->cur_tok = (int*)p;
+    }
+    if (dev_alloc(h, &p, B * S * C * 4)) return 1; h->memory_int = (float*)p;
+    if (dev_alloc(h, &p, (size_t)c.in_ch * c.height * c.width * B * 4)) return 1; h->images_int = (float*)p;
+    for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&h->ev[i]));
+    h->ws_ready = true;
+  }
+  // graphs bake arena pointers: drop them when weights are re-packed
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+  h->finalized = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// encoder
+// ---------------------------------------------------------------------------
+static int tap(frx_handle* h, const std::string& name, const float* src, int B, int H, int W, int C,
+               cudaStream_t st) {
+  if (!h->opt_taps) return 0;
+  Tap& t = h->taps[name];
+  size_t n = (size_t)B * H * W * C;
+  if (t.capacity < n) {
+    if (t.data) cudaFree(t.data);
+    CK(cudaMalloc((void**)&t.data, n * 4));
+    t.capacity = n;
+  }
+  t.shape[0] = B; t.shape[1] = H; t.shape[2] = W; t.shape[3] = C;
+  CK(cudaMemcpyAsync(t.data, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int frx_read_tap(frx_handle* h, const char* name, float* out, int64_t capacity, int64_t* count,
+                            int32_t* shape4, void* stream) {
+  if (!h || !name) return 1;
+  auto it = h->taps.find(name);
+  if (it == h->taps.end()) return fail(h, "no tap named '%s' (enable with frx_set_option(h,\"taps\",1))", name);
+  const Tap& t = it->second;
+  int64_t n = (int64_t)t.shape[0] * t.shape[1] * t.shape[2] * t.shape[3];
+  if (count) *count = n;
+  if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = t.shape[i];
+  if (out) {
+    if (capacity < n) return fail(h, "tap '%s' needs %lld floats", name, (long long)n);
+    CK(cudaMemcpyAsync(out, t.data, n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return 0;
+}
+
+static GemmP dense_gemm(const float* A, int M, int K, const float* W, int N, float* C, int ldc) {
+  GemmP g{};
+  g.A = A; g.W = W; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldc = ldc; g.conv = 0; g.rows_per_img = 1;
+  return g;
+}
+
+static GemmP conv_gemm(const float* A, int B, int H, int W, int Cin, const float* Wt, int Cout, int k,
+                       int stride, float* C, int* OH, int* OW) {
+  GemmP g{};
+  int pt, pl;
+  same_pad(H, k, stride, OH, &pt);
+  same_pad(W, k, stride, OW, &pl);
+  g.A = A; g.W = Wt; g.C = C;
+  g.M = B * (*OH) * (*OW); g.N = Cout; g.K = k * k * Cin; g.lda = 0; g.ldc = Cout;
+  g.conv = 1; g.H = H; g.Wd = W; g.Cin = Cin; g.OH = *OH; g.OW = *OW; g.KH = k; g.KW = k;
+  g.stride = stride; g.pad_t = pt; g.pad_l = pl; g.rows_per_img = 1;
+  return g;
+}
+
+static int run_trunk_efficientnet(frx_handle* h, const float* images, int B, float** out, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  const float* A = h->arena;
+  int H = (c.height - 3) / 2 + 1, W = (c.width - 3) / 2 + 1;
+  float* x = h->act[0];
+  float* y = h->act[1];
+  launch_stem_conv(images, A + h->stem_w, A + h->stem_sc, A + h->stem_sh, x, B, c.in_ch, c.height, c.width, H, W, 24, st);
+  CKL();
+  if (tap(h, "stem", x, B, H, W, 24, st)) return 1;
+  for (const BlockW& b : h->blocks) {
+    int OH, OW;
+    if (b.kind == 0) {
+      GemmP g = conv_gemm(x, B, H, W, b.cin, A + b.w_a, b.cout, b.k, b.stride, y, &OH, &OW);
+      g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
+      if (b.residual) { g.res = x; g.ldr = b.cout; }
+      launch_igemm_f32(g, st); CKL();
+    } else if (b.kind == 1) {
+      GemmP g = conv_gemm(x, B, H, W, b.cin, A + b.w_a, b.mid, b.k, b.stride, h->mid[0], &OH, &OW);
+      g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
+      launch_igemm_f32(g, st); CKL();
+      GemmP g2 = dense_gemm(h->mid[0], B * OH * OW, b.mid, A + b.w_b, b.cout, y, b.cout);
+      g2.scale = A + b.sc_b; g2.shift = A + b.sh_b; g2.act = ACT_NONE;
+      if (b.residual) { g2.res = x; g2.ldr = b.cout; }
+      launch_igemm_f32(g2, st); CKL();
+    } else {
+      GemmP g = dense_gemm(x, B * H * W, b.cin, A + b.w_a, b.mid, h->mid[0], b.mid);
+      g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
+      launch_igemm_f32(g, st); CKL();
+      int pt, pl;
+      same_pad(H, b.k, b.stride, &OH, &pt);
+      same_pad(W, b.k, b.stride, &OW, &pl);
+      DwP d{h->mid[0], A + b.w_dw, A + b.sc_dw, A + b.sh_dw, h->mid[1], B, H, W, b.mid, OH, OW, b.stride, pt, pl, ACT_SILU};
+      launch_dwconv_f32(d, st); CKL();
+      launch_se_gate_f32(h->mid[1], A + b.se_w1, A + b.se_b1, A + b.se_w2, A + b.se_b2, h->gate, B, OH * OW, b.mid, b.se_r, st);
+      CKL();
+      GemmP g2 = dense_gemm(h->mid[1], B * OH * OW, b.mid, A + b.w_b, b.cout, y, b.cout);
+      g2.gate = h->gate; g2.rows_per_img = OH * OW;
+      g2.scale = A + b.sc_b; g2.shift = A + b.sh_b; g2.act = ACT_NONE;
+      if (b.residual) { g2.res = x; g2.ldr = b.cout; }
+      launch_igemm_f32(g2, st); CKL();
+    }
+    H = OH; W = OW;
+    float* t = x; x = y; y = t;
+    if (tap(h, b.name, x, B, H, W, b.cout, st)) return 1;
+  }
+  GemmP g = dense_gemm(x, B * H * W, 256, A + h->last_w, c.enc_hidden, y, c.enc_hidden);
+  g.scale = A + h->last_sc; g.shift = A + h->last_sh; g.act = ACT_SILU;
+  launch_igemm_f32(g, st); CKL();
+  if (H != h->feat_h || W != h->feat_w) return fail(h, "trunk output %dx%d != expected %dx%d", H, W, h->feat_h, h->feat_w);
+  *out = y;
+  return 0;
+}
+
+extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* memory, void* stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "frx_encode: weights not finalized");
+  if (!(h->opt_parts & 1)) return fail(h, "frx_encode: handle was created without the encoder part");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, "frx_encode: batch %d outside (0, %d]", B, h->cfg.max_batch);
+  if (h->cfg.network != FRX_NET_EFFICIENT_SATRN) return fail(h, "frx_encode: LiteSATRN trunk not implemented yet");
+  const frx_config& c = h->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(c.device));
+  const float* A = h->arena;
+  float* t = nullptr;
+  if (run_trunk_efficientnet(h, images, B, &t, st)) return 1;
+  const int fh = h->feat_h, fw = h->feat_w, S = fh * fw, C = c.enc_hidden, F = c.enc_filter;
+  if (tap(h, "trunk", t, B, fh, fw, C, st)) return 1;
+  float* x = (t == h->act[0]) ? h->act[1] : h->act[0];
+  launch_pe2d_f32(t, A + h->pe_w0, A + h->pe_b0, A + h->pe_w1, A + h->pe_b1, A + h->pe_h, A + h->pe_w, x, B, fh, fw, C, st);
+  CKL();
+  if (tap(h, "pe2d", x, B, fh, fw, C, st)) return 1;
+  float* other = t;
+  const int M = B * S;
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const EncLayerW& L = h->enc[i];
+    float* ln = h->mid[0];          // [M,C]
+    float* qkv = h->mid[1];         // [M,3C]
+    launch_layernorm_f32(x, nullptr, A + L.ln_g, A + L.ln_b, ln, M, C, 0, st); CKL();
+    GemmP g = dense_gemm(ln, M, C, A + L.w_qkv, 3 * C, qkv, 3 * C);
+    g.shift = A + L.b_qkv;
+    launch_igemm_f32(g, st); CKL();
+    float* att = h->mid[0];         // ln no longer needed
+    launch_enc_attn_f32(qkv, att, B, S, C, c.enc_heads, st); CKL();
+    float* proj = h->mid[1];        // qkv no longer needed
+    GemmP go = dense_gemm(att, M, C, A + L.w_o, C, proj, C);
+    go.shift = A + L.b_o;
+    launch_igemm_f32(go, st); CKL();
+    float* scr = h->mid[0];         // LN(x + proj) stored in the reinterpreted (:269) layout
+    launch_layernorm_f32(proj, x, A + L.ln_g, A + L.ln_b, scr, M, C, S, st); CKL();
+    float* c0 = h->mid[1];
+    GemmP g0 = dense_gemm(scr, M, C, A + L.w_c0, F, c0, F);
+    g0.scale = A + L.sc_c0; g0.shift = A + L.sh_c0; g0.act = ACT_RELU;
+    launch_igemm_f32(g0, st); CKL();
+    float* dwo = h->mid[0];
+    DwP d{c0, A + L.w_dw, A + L.sc_dw, A + L.sh_dw, dwo, B, fh, fw, F, fh, fw, 1, 1, 1, ACT_RELU};
+    launch_dwconv_f32(d, st); CKL();
+    float* dst = (i == c.enc_layers - 1) ? memory : other;
+    GemmP g1 = dense_gemm(dwo, M, F, A + L.w_c1, C, dst, C);
+    g1.scale = A + L.sc_c1; g1.shift = A + L.sh_c1; g1.act = ACT_RELU; g1.res = x; g1.ldr = C;
+    launch_igemm_f32(g1, st); CKL();
+    if (tap(h, "enc_layer" + std::to_string(i), dst, B, fh, fw, C, st)) return 1;
+    other = x;
+    x = dst;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// decoder
+// ---------------------------------------------------------------------------
+static int run_cross_kv(frx_handle* h, const float* memory, int B, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  const int S = h->feat_h * h->feat_w;
+  GemmP g = dense_gemm(memory, B * S, c.dec_src, h->arena + h->w_cross, c.dec_layers * 2 * c.dec_hidden, h->cross,
+                       c.dec_layers * 2 * c.dec_hidden);
+  g.shift = h->arena + h->b_cross;
+  launch_igemm_f32(g, st); CKL();
+  return 0;
+}
+
+// One decoder step at position t for all B rows.  The input
+// row x must already be in h->dx.  Logits go to logits_dst[m*ld_logits + v].
+static int run_decode_step(frx_handle* h, int B, int t, float* logits_dst, long long ld_logits, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  const float* A = h->arena;
+  const int D = c.dec_hidden, F = c.dec_filter, L = c.dec_layers, V = c.num_classes, T = c.max_steps;
+  const int S = h->feat_h * h->feat_w, HD = D / c.dec_heads;
+  const float temp = sqrtf((float)D);
+  auto base_gemm = [&](const float* Ain, int K, const float* Wt, const float* bias, int N) {
+    DecGemmP p{};
+    p.A = Ain; p.Wt = Wt; p.bias = bias; p.M = B; p.N = N; p.K = K; p.lda = K; p.act = ACT_NONE;
+    return p;
+  };
+  auto one_seg = [&](DecGemmP& p, float* dst, int ld) {
+    p.nseg = 1;
+    p.seg[0] = Seg{0, p.N, dst, ld, 0};
+  };
+  {  // layer 0 q|k|v of the embedded input
+    DecGemmP p = base_gemm(h->dx, D, A + h->fused[0].wt, A + h->fused[0].b, 3 * D);
+    one_seg(p, h->dqkv, 3 * D);
+    launch_dec_gemm_f32(p, st); CKL();
+  }
+  for (int l = 0; l < L; ++l) {
+    const DecLayerW& W = h->dec[l];
+    float* kc = h->kself + (size_t)l * B * T * D;
+    float* vc = h->vself + (size_t)l * B * T * D;
+    {  // self attention over the t cached output rows + the current input row (:387-388)
+      AttnP a{};
+      a.q = h->dqkv; a.ldq = 3 * D; a.kcache = kc; a.vcache = vc; a.rows_per_img = T; a.D = D; a.n_hist = t;
+      a.cur_k = h->dqkv + D; a.cur_v = h->dqkv + 2 * D; a.ld_cur = 3 * D; a.q_per_img = 1; a.temperature = temp;
+      a.out = h->datt; a.ldo = D; a.M = B; a.heads = c.dec_heads;
+      launch_dec_attn_f32(a, HD, st); CKL();
+    }
+    {  // pre1 = out_linear(a) + x
+      DecGemmP p = base_gemm(h->datt, D, A + W.wt_o, A + W.b_o, D);
+      p.res = h->dx; p.ldr = D;
+      one_seg(p, h->dpre1, D);
+      launch_dec_gemm_f32(p, st); CKL();
+    }
+    {  // u = LN(pre1); q2 = q_linear(u)
+      DecGemmP p = base_gemm(h->dpre1, D, A + W.wt_q2, A + W.b_q2, D);
+      p.ln_g = A + W.ln1_g; p.ln_b = A + W.ln1_b; p.a_norm_out = h->du;
+      one_seg(p, h->dq2, D);
+      launch_dec_gemm_f32(p, st); CKL();
+    }
+    {  // cross attention over the S memory tokens
+      AttnP a{};
+      a.q = h->dq2; a.ldq = D; a.kcache = h->cross + (size_t)l * 2 * D; a.vcache = h->cross + (size_t)l * 2 * D + D;
+      a.rows_per_img = S; a.D = L * 2 * D; a.n_hist = S; a.q_per_img = 1; a.temperature = temp;
+      a.out = h->datt; a.ldo = D; a.M = B; a.heads = c.dec_heads;
+      launch_dec_attn_f32(a, HD, st); CKL();
+    }
+    {  // pre2 = out_linear(c) + u
+      DecGemmP p = base_gemm(h->datt, D, A + W.wt_o2, A + W.b_o2, D);
+      p.res = h->du; p.ldr = D;
+      one_seg(p, h->dpre2, D);
+      launch_dec_gemm_f32(p, st); CKL();
+    }
+    {  // w = LN(pre2); ff = relu(linear0(w))
+      DecGemmP p = base_gemm(h->dpre2, D, A + W.wt_f0, A + W.b_f0, F);
+      p.ln_g = A + W.ln2_g; p.ln_b = A + W.ln2_b; p.a_norm_out = h->dw; p.act = ACT_RELU;
+      one_seg(p, h->dff, F);
+      launch_dec_gemm_f32(p, st); CKL();
+    }
+    {  // pre1 = relu(linear1(ff)) + w      (:339-346 ReLU after both linears)
+      DecGemmP p = base_gemm(h->dff, F, A + W.wt_f1, A + W.b_f1, D);
+      p.act = ACT_RELU; p.res = h->dw; p.ldr = D;
+      one_seg(p, h->dpre1, D);
+      launch_dec_gemm_f32(p, st); CKL();
+    }
+    {  // y = LN(pre1) -> x ; K/V rows of y into the cache ; next layer's q|k|v or the logits
+      const FusedW& Fw = h->fused[l + 1];
+      DecGemmP p = base_gemm(h->dpre1, D, A + Fw.wt, A + Fw.b, Fw.N);
+      p.ln_g = A + W.ln3_g; p.ln_b = A + W.ln3_b; p.a_norm_out = h->dx;
+      p.nseg = 3;
+      p.seg[0] = Seg{0, D, kc + (size_t)t * D, (long long)T * D, 0};
+      p.seg[1] = Seg{D, 2 * D, vc + (size_t)t * D, (long long)T * D, 0};
+      if (l + 1 < L) p.seg[2] = Seg{2 * D, 5 * D, h->dqkv, 3 * D, 0};
+      else p.seg[2] = Seg{2 * D, 2 * D + V, logits_dst, ld_logits, 0};
+      launch_dec_gemm_f32(p, st); CKL();
+    }
+  }
+  return 0;
+}
+
+static int run_greedy_loop(frx_handle* h, int B, int steps, bool forced, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  const float* A = h->arena;
+  const int D = c.dec_hidden, V = c.num_classes;
+  const float scale = sqrtf((float)D);
+  launch_dec_embed_f32(nullptr, nullptr, c.sos_id, A + h->emb, A + h->pe1d, 0, nullptr, 0, scale, h->dx, B, D, st);
+  CKL();
+  for (int t = 0; t < steps; ++t) {
+    float* lg = h->logits_int + (size_t)t * V;
+    if (run_decode_step(h, B, t, lg, (long long)steps * V, st)) return 1;
+    const float* pe_next = (t + 1 < steps) ? A + h->pe1d + (size_t)(t + 1) * D : nullptr;
+    launch_dec_argmax_embed(lg, (long long)steps * V, V, h->tokens_int + t, steps,
+                            forced ? h->forced_int + t : nullptr, steps, h->cur_tok, A + h->emb, pe_next, scale,
+                            h->dx, B, D, st);
+    CKL();
+  }
+  return 0;
+}
+
+static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int steps, float* logits,
+                              int64_t* tokens, const int64_t* forced, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  if (!h->finalized) return fail(h, "decode: weights not finalized");
+  if (!(h->opt_parts & 2)) return fail(h, "decode: handle was created without the decoder part");
+  if (B <= 0 || B > c.max_batch) return fail(h, "decode: batch %d outside (0, %d]", B, c.max_batch);
+  if (steps <= 0 || steps > c.max_steps) return fail(h, "decode: steps %d outside (0, %d]", steps, c.max_steps);
+  if (steps > 500) return fail(h, "decode: steps exceed the 1-D positional table (500)");
+  CK(cudaSetDevice(c.device));
+  if (run_cross_kv(h, memory, B, st)) return 1;
+  if (forced) CK(cudaMemcpyAsync(h->forced_int, forced, (size_t)B * steps * 8, cudaMemcpyDeviceToDevice, st));
+  if (h->opt_graphs) {
+    GraphKey key{B, steps, forced != nullptr};
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+      cudaStream_t cs;
+      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      int64_t before = h->launches;
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      int rc = run_greedy_loop(h, B, steps, forced != nullptr, cs);
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(cs, &graph);
+      cudaStreamDestroy(cs);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+      if (e != cudaSuccess) return fail(h, "graph capture failed: %s", cudaGetErrorString(e));
+      GraphEntry ge{};
+      ge.nodes = h->launches - before;
+      h->launches = before;
+      e = cudaGraphInstantiate(&ge.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return fail(h, "graph instantiate failed: %s", cudaGetErrorString(e));
+      it = h->graphs.emplace(key, ge).first;
+    }
+    CK(cudaGraphLaunch(it->second.exec, st));
+    h->launches += it->second.nodes;
+  } else if (run_greedy_loop(h, B, steps, forced != nullptr, st)) {
+    return 1;
+  }
+  if (logits) CK(cudaMemcpyAsync(logits, h->logits_int, (size_t)B * steps * c.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+  if (tokens) CK(cudaMemcpyAsync(tokens, h->tokens_int, (size_t)B * steps * 8, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int frx_decode_greedy(frx_handle* h, const float* memory, int32_t B, int32_t steps, float* logits,
+                                 int64_t* tokens, const int64_t* forced, void* stream) {
+  if (!h) return 1;
+  return decode_greedy_impl(h, memory, B, steps, logits, tokens, forced, (cudaStream_t)stream);
+}
+
+extern "C" int frx_forward_greedy(frx_handle* h, const float* images, int32_t B, int32_t steps, float* logits,
+                                  int64_t* tokens, void* stream) {
+  if (!h) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->opt_timing) CK(cudaEventRecord(h->ev[0], st));
+  if (frx_encode(h, images, B, h->memory_int, stream)) return 1;
+  if (h->opt_timing) CK(cudaEventRecord(h->ev[1], st));
+  if (decode_greedy_impl(h, h->memory_int, B, steps, logits, tokens, nullptr, st)) return 1;
+  if (h->opt_timing) {
+    CK(cudaEventRecord(h->ev[2], st));
+    CK(cudaEventSynchronize(h->ev[2]));
+    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]));
+    CK(cudaEventElapsedTime(&h->last_ms[2], h->ev[0], h->ev[2]));
+  }
+  return 0;
+}
+
+extern "C" int frx_forward_greedy_host(frx_handle* h, const float* images_host, int32_t B, int32_t steps,
+                                       float* logits_host, int64_t* tokens_host, void* stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "forward: weights not finalized");
+  const frx_config& c = h->cfg;
+  if (B <= 0 || B > c.max_batch) return fail(h, "forward: batch %d outside (0, %d]", B, c.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(c.device));
+  size_t img_bytes = (size_t)B * c.in_ch * c.height * c.width * 4;
+  CK(cudaMemcpyAsync(h->images_int, images_host, img_bytes, cudaMemcpyHostToDevice, st));
+  if (frx_forward_greedy(h, h->images_int, B, steps, nullptr, nullptr, stream)) return 1;
+  if (tokens_host) CK(cudaMemcpyAsync(tokens_host, h->tokens_int, (size_t)B * steps * 8, cudaMemcpyDeviceToHost, st));
+  if (logits_host) CK(cudaMemcpyAsync(logits_host, h->logits_int, (size_t)B * steps * c.num_classes * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int frx_decode_begin(frx_handle* h, const float* memory, int32_t B, void* stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "decode_begin: weights not finalized");
+  if (!(h->opt_parts & 2)) return fail(h, "decode_begin: handle was created without the decoder part");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, "decode_begin: batch %d outside (0, %d]", B, h->cfg.max_batch);
+  CK(cudaSetDevice(h->cfg.device));
+  if (run_cross_kv(h, memory, B, (cudaStream_t)stream)) return 1;
+  h->step_idx = 0;
+  h->step_batch = B;
+  return 0;
+}
+
+extern "C" int frx_decode_step(frx_handle* h, const int64_t* target, float* logits, void* stream) {
+  if (!h) return 1;
+  if (h->step_batch <= 0) return fail(h, "decode_step: call frx_decode_begin first");
+  if (h->step_idx >= h->cfg.max_steps) return fail(h, "decode_step: step %d exceeds max_steps %d", h->step_idx, h->cfg.max_steps);
+  const frx_config& c = h->cfg;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(c.device));
+  launch_dec_embed_f32(nullptr, (const long long*)target, 0, h->arena + h->emb, h->arena + h->pe1d, h->step_idx, nullptr, 0,
+                       sqrtf((float)c.dec_hidden), h->dx, h->step_batch, c.dec_hidden, st);
+  CKL();
+  if (run_decode_step(h, h->step_batch, h->step_idx, logits, c.num_classes, st)) return 1;
+  h->step_idx++;
+  return 0;
+}
+
+extern "C" int frx_beam_search(frx_handle* h, const float*, int32_t, int32_t, int32_t, int64_t*, void*) {
+  return fail(h, "frx_beam_search: not implemented yet");
+}
+
+extern "C" int frx_decode_teacher_forced(frx_handle* h, const float*, const int64_t*, int32_t, int32_t, float*, void*) {
+  return fail(h, "frx_decode_teacher_forced: not implemented yet");
+}

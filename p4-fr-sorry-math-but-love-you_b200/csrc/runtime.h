@@ -1,0 +1,84 @@
+// runtime.h -- the handle behind include/frx.h (host-side state only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/frx.h"
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> f;
+};
+
+// Offsets (in floats) into the weight arena.
+struct BlockW {
+  int kind;  // 0 ConvBnAct, 1 EdgeResidual (fused-MBConv), 2 InvertedResidual (MBConv + SE)
+  int cin, cout, k, stride, mid, se_r;
+  bool residual;
+  std::string name;
+  size_t w_a, sc_a, sh_a;      // first conv (3x3 for kinds 0/1, 1x1 expand for kind 2) + folded BN
+  size_t w_dw, sc_dw, sh_dw;   // depthwise 3x3 + folded BN (kind 2)
+  size_t se_w1, se_b1, se_w2, se_b2;
+  size_t w_b, sc_b, sh_b;      // 1x1 projection + folded BN (kinds 1/2)
+};
+struct LiteConvW { int cin, cout; size_t w, sc, sh; };
+struct EncLayerW {
+  size_t ln_g, ln_b, w_qkv, b_qkv, w_o, b_o;
+  size_t w_c0, sc_c0, sh_c0, w_dw, sc_dw, sh_dw, w_c1, sc_c1, sh_c1;
+};
+struct DecLayerW {
+  size_t wt_o, b_o, wt_q2, b_q2, wt_o2, b_o2, wt_f0, b_f0, wt_f1, b_f1;   // [K][N] for the step kernels
+  size_t w_o, w_q2, w_o2, w_f0, w_f1, w_sqkv, b_sqkv;                     // [N][K] for the teacher-forced path
+  size_t ln1_g, ln1_b, ln2_g, ln2_b, ln3_g, ln3_b;
+};
+struct FusedW { size_t wt, b; int N; };
+struct Tap { float* data = nullptr; size_t capacity = 0; int shape[4] = {0, 0, 0, 0}; };
+typedef std::tuple<int, int, bool> GraphKey;
+struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; };
+
+struct frx_handle {
+  frx_config cfg{};
+  std::string err;
+  int num_sms = 0;
+  std::map<std::string, HostTensor> raw;
+  bool finalized = false, ws_ready = false;
+  bool opt_taps = false, opt_graphs = true, opt_timing = false;
+  int opt_parts = 3;  // bit0: encoder weights/workspaces, bit1: decoder
+  int feat_h = 0, feat_w = 0;
+  std::vector<void*> allocs;
+  int64_t device_bytes = 0, launches = 0;
+
+  float* arena = nullptr;
+  size_t arena_bytes = 0;
+  // trunk
+  size_t stem_w = 0, stem_sc = 0, stem_sh = 0, last_w = 0, last_sc = 0, last_sh = 0;
+  std::vector<BlockW> blocks;
+  LiteConvW lite[4]{};
+  // encoder
+  size_t pe_w0 = 0, pe_b0 = 0, pe_w1 = 0, pe_b1 = 0, pe_h = 0, pe_w = 0;
+  std::vector<EncLayerW> enc;
+  // decoder
+  size_t emb = 0, pe1d = 0, gen_w = 0, gen_b = 0, w_cross = 0, b_cross = 0;
+  std::vector<DecLayerW> dec;
+  std::vector<FusedW> fused;
+
+  // workspaces
+  float *act[2] = {nullptr, nullptr}, *mid[2] = {nullptr, nullptr}, *gate = nullptr;
+  float *kself = nullptr, *vself = nullptr, *cross = nullptr;
+  float *dx = nullptr, *dqkv = nullptr, *datt = nullptr, *dpre1 = nullptr, *dpre2 = nullptr, *du = nullptr,
+        *dw = nullptr, *dq2 = nullptr, *dff = nullptr;
+  float *logits_int = nullptr, *memory_int = nullptr, *images_int = nullptr;
+  long long *tokens_int = nullptr, *forced_int = nullptr;
+  int* cur_tok = nullptr;
+
+  std::map<GraphKey, GraphEntry> graphs;
+  std::map<std::string, Tap> taps;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  float last_ms[3] = {0, 0, 0};
+  int step_idx = 0, step_batch = 0;
+};

@@ -1,0 +1,179 @@
+"""state_dict layout of the networks this package serves -- the checkpoint
+contract.  ``build_param_tree`` creates an
+``nn.Module`` tree whose ``state_dict()`` has exactly the reference's keys,
+shapes and dtypes, so reference checkpoints load with ``strict=True`` and
+checkpoints saved from this package load into the reference.
+
+Module definitions mirrored (names only, no arithmetic):
+networks/EfficientSATRN.py:63-79 (EfficientNet), :90-109 (PositionalEncoding),
+:231-257 (EncoderLayer), :175-196 (MultiHeadAttention), :326-337 (Feedforward),
+:349-372 (TransformerDecoderLayer), :429-461 (SATRNDecoder); timm 0.4.9
+``tf_efficientnetv2_s`` ``.blocks`` (requirements.txt:15).
+"""
+import collections
+
+import torch
+import torch.nn as nn
+
+# (block kind, repeats, kernel, stride, expand, out channels, SE ratio)
+EFFNETV2_S = (
+    ("cn", 2, 3, 1, 1, 24, 0.0),
+    ("er", 4, 3, 2, 4, 48, 0.0),
+    ("er", 4, 3, 2, 4, 64, 0.0),
+    ("ir", 6, 3, 2, 4, 128, 0.25),
+    ("ir", 9, 3, 1, 6, 160, 0.25),
+    ("ir", 15, 3, 2, 6, 256, 0.25),
+)
+
+BUFFER_LEAVES = ("running_mean", "running_var", "num_batches_tracked")
+
+
+def _bn(s, p, c):
+    s[p + ".weight"] = (c,)
+    s[p + ".bias"] = (c,)
+    s[p + ".running_mean"] = (c,)
+    s[p + ".running_var"] = (c,)
+    s[p + ".num_batches_tracked"] = ()
+
+
+def _mha(s, p, q_ch, k_ch, d):
+    for name, cin in (("q_linear", q_ch), ("k_linear", k_ch), ("v_linear", k_ch)):
+        s["%s.%s.weight" % (p, name)] = (d, cin)
+        s["%s.%s.bias" % (p, name)] = (d,)
+    s[p + ".out_linear.weight"] = (q_ch, d)
+    s[p + ".out_linear.bias"] = (q_ch,)
+
+
+def encoder_shapes(dims, prefix="encoder."):
+    s = collections.OrderedDict()
+    cnn = prefix + "shallow_cnn."
+    hidden, filt = dims["enc_hidden"], dims["enc_filter"]
+    s[cnn + "conv_stem.weight"] = (24, dims["in_ch"], 3, 3)
+    _bn(s, cnn + "bn1", 24)
+    cin = 24
+    for si, (kind, reps, k, stride, expand, cout, se) in enumerate(EFFNETV2_S):
+        for r in range(reps):
+            p = "%seff_block.%d.%d" % (cnn, si, r)
+            mid = cin * expand
+            if kind == "cn":
+                s[p + ".conv.weight"] = (cout, cin, k, k)
+                _bn(s, p + ".bn1", cout)
+            elif kind == "er":
+                s[p + ".conv_exp.weight"] = (mid, cin, k, k)
+                _bn(s, p + ".bn1", mid)
+                s[p + ".conv_pwl.weight"] = (cout, mid, 1, 1)
+                _bn(s, p + ".bn2", cout)
+            else:
+                red = int(cin * se)
+                s[p + ".conv_pw.weight"] = (mid, cin, 1, 1)
+                _bn(s, p + ".bn1", mid)
+                s[p + ".conv_dw.weight"] = (mid, 1, k, k)
+                _bn(s, p + ".bn2", mid)
+                s[p + ".se.conv_reduce.weight"] = (red, mid, 1, 1)
+                s[p + ".se.conv_reduce.bias"] = (red,)
+                s[p + ".se.conv_expand.weight"] = (mid, red, 1, 1)
+                s[p + ".se.conv_expand.bias"] = (mid,)
+                s[p + ".conv_pwl.weight"] = (cout, mid, 1, 1)
+                _bn(s, p + ".bn3", cout)
+            cin = cout
+    s[cnn + "conv_last.weight"] = (hidden, 256, 1, 1)
+    _bn(s, cnn + "bn2", hidden)
+    pe = prefix + "positional_encoding."
+    s[pe + "dense0.weight"] = (hidden // 2, hidden)
+    s[pe + "dense0.bias"] = (hidden // 2,)
+    s[pe + "dense1.weight"] = (hidden * 2, hidden // 2)
+    s[pe + "dense1.bias"] = (hidden * 2,)
+    for i in range(dims["enc_layers"]):
+        p = "%sattention_layers.%d." % (prefix, i)
+        s[p + "norm.weight"] = (hidden,)
+        s[p + "norm.bias"] = (hidden,)
+        _mha(s, p + "attention_layer", hidden, hidden, hidden)
+        s[p + "conv0.weight"] = (filt, hidden, 1, 1)
+        _bn(s, p + "norm0", filt)
+        s[p + "depthwise.weight"] = (filt, 1, 3, 3)
+        s[p + "depthwise.bias"] = (filt,)
+        _bn(s, p + "depthwise_norm", filt)
+        s[p + "conv1.weight"] = (hidden, filt, 1, 1)
+        _bn(s, p + "norm1", hidden)
+    return s
+
+
+def decoder_shapes(dims, prefix="decoder."):
+    s = collections.OrderedDict()
+    d, f, src, v = dims["dec_hidden"], dims["dec_filter"], dims["dec_src"], dims["num_classes"]
+    s[prefix + "embedding.weight"] = (v + 1, d)
+    for i in range(dims["dec_layers"]):
+        p = "%sattention_layers.%d." % (prefix, i)
+        _mha(s, p + "self_attention_layer", d, d, d)
+        s[p + "self_attention_norm.weight"] = (d,)
+        s[p + "self_attention_norm.bias"] = (d,)
+        _mha(s, p + "attention_layer", d, src, d)
+        s[p + "attention_norm.weight"] = (d,)
+        s[p + "attention_norm.bias"] = (d,)
+        s[p + "feedforward_layer.linear0.weight"] = (f, d)
+        s[p + "feedforward_layer.linear0.bias"] = (f,)
+        s[p + "feedforward_layer.linear1.weight"] = (d, f)
+        s[p + "feedforward_layer.linear1.bias"] = (d,)
+        s[p + "feedforward_norm.weight"] = (d,)
+        s[p + "feedforward_norm.bias"] = (d,)
+    s[prefix + "generator.weight"] = (v, d)
+    s[prefix + "generator.bias"] = (v,)
+    return s
+
+
+def dims_from_flags(FLAGS, num_classes):
+    """The fields the constructors read (networks/EfficientSATRN.py:667-688)."""
+    enc, dec = FLAGS.SATRN.encoder, FLAGS.SATRN.decoder
+    return dict(
+        height=FLAGS.input_size.height, width=FLAGS.input_size.width, in_ch=FLAGS.data.rgb,
+        enc_hidden=enc.hidden_dim, enc_filter=enc.filter_dim, enc_layers=enc.layer_num, enc_heads=enc.head_num,
+        dec_src=dec.src_dim, dec_hidden=dec.hidden_dim, dec_filter=dec.filter_dim,
+        dec_layers=dec.layer_num, dec_heads=dec.head_num, num_classes=num_classes)
+
+
+class ParamTree(nn.Module):
+    """A module that only holds parameters/buffers under reference names."""
+
+    def add(self, dotted, tensor, is_buffer):
+        head, _, rest = dotted.partition(".")
+        if rest:
+            if head not in self._modules:
+                self.add_module(head, ParamTree())
+            self._modules[head].add(rest, tensor, is_buffer)
+        elif is_buffer:
+            self.register_buffer(head, tensor)
+        else:
+            self.register_parameter(head, nn.Parameter(tensor))
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("ParamTree holds weights only; compute runs in libfrx.so")
+
+
+def _init_tensor(name, shape):
+    leaf = name.rsplit(".", 1)[-1]
+    if leaf == "num_batches_tracked":
+        return torch.zeros((), dtype=torch.long)
+    if leaf == "running_mean":
+        return torch.zeros(shape)
+    if leaf == "running_var":
+        return torch.ones(shape)
+    is_norm = any(t in name for t in (".bn", "norm"))
+    if is_norm:
+        return torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+    if leaf == "bias":
+        return torch.zeros(shape)
+    t = torch.empty(shape)
+    if name.endswith("embedding.weight"):
+        return nn.init.normal_(t)
+    if t.dim() >= 2:
+        return nn.init.xavier_normal_(t)  # :193-196,:255-257,:336-337
+    return t.zero_()
+
+
+def build_param_tree(shapes, strip_prefix):
+    tree = ParamTree()
+    for name, shape in shapes.items():
+        assert name.startswith(strip_prefix)
+        leaf = name.rsplit(".", 1)[-1]
+        tree.add(name[len(strip_prefix):], _init_tensor(name, shape), leaf in BUFFER_LEAVES)
+    return tree

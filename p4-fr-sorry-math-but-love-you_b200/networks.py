@@ -1,0 +1,324 @@
+"""Drop-in ``nn.Module`` front-ends for the reference's ``networks/`` constructors.
+
+Same constructor signatures, attribute tree, ``state_dict`` layout and method
+contracts as /root/reference/networks/EfficientSATRN.py:664-952; the arithmetic
+runs in ``lib/libfrx.so`` through the C ABI of include/frx.h.  PyTorch is only
+the plumbing here (parameter storage, device memory, the CUDA stream).
+"""
+import ctypes
+import math
+import random
+
+import torch
+import torch.nn as nn
+
+from . import _lib, layout
+
+START, END, PAD = "<SOS>", "<EOS>", "<PAD>"  # data/dataset.py:12-14
+
+_PRECISIONS = {"fp32": 0, "bf16": 1}
+
+
+def pe2d_table(length, hidden):
+    """Host-built 2-D positional table, computed exactly like
+    PositionalEncoding.get_position_encoding (EfficientSATRN.py:111-127):
+    fp32 torch ops on the CPU, sin||cos concatenated."""
+    position = torch.arange(length).float()
+    n_ts = hidden // 2
+    log_inc = math.log(1.0e4 / 1.0) / (torch.FloatTensor([n_ts]) - 1)
+    inv = 1.0 * torch.exp(torch.arange(n_ts) * -log_inc)
+    scaled = position.unsqueeze(1) * inv.unsqueeze(0)
+    return torch.cat((torch.sin(scaled), torch.cos(scaled)), dim=1).contiguous()
+
+
+def pe1d_table(channels, max_len=500):
+    """PositionEncoder1D.generate_encoder (EfficientSATRN.py:408-418)."""
+    pos = torch.arange(max_len).float().unsqueeze(1)
+    i = torch.arange(channels).float().unsqueeze(0)
+    table = pos * (1 / torch.pow(10000, (2 * (i // 2)) / channels))
+    table[:, 0::2] = torch.sin(table[:, 0::2])
+    table[:, 1::2] = torch.cos(table[:, 1::2])
+    return table.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p()
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _Engine:
+    """One frx handle bound to (device, max_batch, max_steps, precision)."""
+
+    def __init__(self, dims, ids, device, max_batch, max_steps, precision, parts):
+        cfg = _lib.FrxConfig()
+        cfg.network = 0
+        for k in ("height", "width", "in_ch", "enc_hidden", "enc_filter", "enc_layers", "enc_heads",
+                  "dec_src", "dec_hidden", "dec_filter", "dec_layers", "dec_heads", "num_classes"):
+            setattr(cfg, k, int(dims[k]))
+        cfg.sos_id, cfg.eos_id, cfg.pad_id = ids
+        cfg.max_batch, cfg.max_steps = int(max_batch), int(max_steps)
+        cfg.precision = _PRECISIONS[precision]
+        cfg.device = device.index if device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", cfg.device)
+        self.max_batch, self.max_steps, self.precision = int(max_batch), int(max_steps), precision
+        self.dims = dims
+        self.h = _lib.Handle(cfg)
+        self.h.call("frx_set_option", b"parts", parts)
+
+    def load(self, state_dict):
+        def put(name, t):
+            if t.dtype == torch.int64:
+                t, dt = t.detach().contiguous(), 1
+            else:
+                t, dt = t.detach().float().contiguous(), 0
+            shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
+            self.h.call("frx_load_tensor", name.encode(), _ptr(t), shape, t.dim(), dt)
+
+        for name, t in state_dict.items():
+            if not name.endswith("num_batches_tracked"):
+                put(name, t)
+        d = self.dims
+        put("pe2d.h", pe2d_table(d["height"] // 32, d["enc_hidden"]))
+        put("pe2d.w", pe2d_table(d["width"] // 32, d["enc_hidden"]))
+        put("pe1d", pe1d_table(d["dec_hidden"]))
+        self.h.call("frx_finalize_weights")
+
+    def option(self, key, value):
+        self.h.call("frx_set_option", key.encode(), int(value))
+
+    @property
+    def launches(self):
+        return int(self.h.lib.frx_launch_count(self.h.ptr))
+
+    @property
+    def device_bytes(self):
+        return int(self.h.lib.frx_device_bytes(self.h.ptr))
+
+
+class _FrxModule(nn.Module):
+    """Shared engine management (lazy creation, weight re-sync when dirty)."""
+
+    _parts = 3  # bit0 encoder, bit1 decoder
+
+    def _setup(self, FLAGS, train_dataset, precision, max_batch, max_steps):
+        self._dims = layout.dims_from_flags(FLAGS, len(train_dataset.id_to_token))
+        t2i = train_dataset.token_to_id
+        self._ids = (int(t2i[START]), int(t2i.get(END, 1)), int(t2i[PAD]))
+        self._precision = precision
+        self._max_batch = max_batch
+        self._max_steps = max_steps
+        self._engine = None
+        self._dirty = True
+        self._options = {}
+
+    # --- keep the device copy of the weights coherent with the nn.Parameters ---
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._dirty = True
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._dirty = True
+        return out
+
+    def refresh(self):
+        """Call after mutating parameters in place (e.g. an optimizer step)."""
+        self._dirty = True
+
+    def set_option(self, key, value):
+        self._options[key] = int(value)
+        if self._engine is not None:
+            self._engine.option(key, value)
+
+    def engine(self, device, batch, steps):
+        if device.type != "cuda":
+            raise RuntimeError("frx runs on a CUDA device (B200) only; there is no CPU fallback "
+                               "(input is on %s)" % device)
+        e = self._engine
+        need_b = max(batch, self._max_batch or 0)
+        need_t = max(steps, self._max_steps or 0)
+        if e is None or e.device != torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()) \
+                or e.max_batch < batch or e.max_steps < steps:
+            if e is not None:
+                need_b, need_t = max(need_b, e.max_batch), max(need_t, e.max_steps)
+                e.h.close()
+            e = _Engine(self._dims, self._ids, device, need_b, need_t, self._precision, self._parts)
+            for k, v in self._options.items():
+                e.option(k, v)
+            self._engine = e
+            self._dirty = True
+        if self._dirty:
+            e.load(self.state_dict())
+            self._dirty = False
+        return e
+
+
+class EfficientSATRN(_FrxModule):
+    """networks/EfficientSATRN.py:664-867.
+
+    Extra keyword-only arguments (not in the reference): ``precision``
+    ("fp32" | "bf16"), ``max_batch`` / ``max_steps`` to pre-size the workspaces
+    (they grow on demand otherwise)."""
+
+    def __init__(self, FLAGS, train_dataset, checkpoint=None, decoding_manager=None, *,
+                 precision="fp32", max_batch=None, max_steps=None):
+        super().__init__()
+        self._setup(FLAGS, train_dataset, precision, max_batch, max_steps)
+        self.encoder = layout.build_param_tree(layout.encoder_shapes(self._dims), "encoder.")
+        self.decoder = layout.build_param_tree(layout.decoder_shapes(self._dims), "decoder.")
+        d = self.decoder
+        d.hidden_dim, d.filter_dim = self._dims["dec_hidden"], self._dims["dec_filter"]
+        d.num_classes, d.layer_num = self._dims["num_classes"], self._dims["dec_layers"]
+        d.pad_id, d.st_id = self._ids[2], self._ids[0]
+        d.manager = decoding_manager
+        self.criterion = nn.CrossEntropyLoss(ignore_index=self._ids[2])
+        if checkpoint:
+            self.load_state_dict(checkpoint)
+
+    def _check_manager(self):
+        if self.decoder.manager is not None:
+            raise NotImplementedError(
+                "DecodingManager rule masks (postprocessing/postprocessing.py:182-404) are not part of "
+                "the accelerated path yet (SURVEY 8f-1); construct with decoding_manager=None")
+
+    def forward(self, input, expected, is_train, teacher_forcing_ratio):
+        """:697-706 -> logits [B, expected.size(1)-1, num_classes] fp32 on input's device."""
+        if self.training:
+            raise NotImplementedError("train-mode step (BN batch statistics, dropout, backward) is not "
+                                      "built yet; call .eval() for the accelerated forward")
+        b, steps = input.size(0), expected.size(1) - 1
+        eng = self.engine(input.device, b, steps)
+        x = input.detach().float().contiguous()
+        v = self._dims["num_classes"]
+        if is_train and random.random() < teacher_forcing_ratio:  # :488-495 (consumes the RNG like the reference)
+            text = expected[:, :-1].to(device=x.device, dtype=torch.int64).contiguous()
+            memory = torch.empty(b, self.memory_tokens, self._dims["enc_hidden"], device=x.device)
+            logits = torch.empty(b, steps, v, device=x.device)
+            st = _stream(x.device)
+            eng.h.call("frx_encode", _ptr(x), b, _ptr(memory), st)
+            eng.h.call("frx_decode_teacher_forced", _ptr(memory), _ptr(text), b, steps, _ptr(logits), st)
+            return logits
+        self._check_manager()
+        logits = torch.empty(b, steps, v, device=x.device)
+        eng.h.call("frx_forward_greedy", _ptr(x), b, steps, _ptr(logits), None, _stream(x.device))
+        return logits
+
+    @property
+    def memory_tokens(self):
+        return (self._dims["height"] // 32) * (self._dims["width"] // 32)
+
+    def encode(self, input):
+        """SATRNEncoder.forward :311-323 -> src [B, h*w, C]."""
+        b = input.size(0)
+        eng = self.engine(input.device, b, 1)
+        x = input.detach().float().contiguous()
+        memory = torch.empty(b, self.memory_tokens, self._dims["enc_hidden"], device=x.device)
+        eng.h.call("frx_encode", _ptr(x), b, _ptr(memory), _stream(x.device))
+        return memory
+
+    def greedy(self, input, steps, forced=None, want_logits=True):
+        """Encode + greedy loop returning (logits | None, tokens [B, steps] int64)
+        on the input's device; ``forced`` feeds given tokens (forced decoding)."""
+        b = input.size(0)
+        eng = self.engine(input.device, b, steps)
+        x = input.detach().float().contiguous()
+        dev = x.device
+        memory = self.encode(x)
+        logits = torch.empty(b, steps, self._dims["num_classes"], device=dev) if want_logits else None
+        tokens = torch.empty(b, steps, dtype=torch.int64, device=dev)
+        f = forced.to(device=dev, dtype=torch.int64).contiguous() if forced is not None else None
+        eng.h.call("frx_decode_greedy", _ptr(memory), b, steps, _ptr(logits), _ptr(tokens), _ptr(f), _stream(dev))
+        return logits, tokens
+
+    def greedy_host(self, images_host, steps, tokens_host=None, logits_host=None):
+        """End-to-end call with HOST buffers (frx_forward_greedy_host): H2D of the
+        images, encode, decode, D2H of the tokens; returns the host token tensor."""
+        b = images_host.size(0)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        eng = self.engine(dev, b, steps)
+        if tokens_host is None:
+            tokens_host = torch.empty(b, steps, dtype=torch.int64).pin_memory()
+        eng.h.call("frx_forward_greedy_host", _ptr(images_host), b, steps, _ptr(logits_host), _ptr(tokens_host),
+                   _stream(dev))
+        return tokens_host
+
+    def beam_search(self, input, data_loader=None, topk=1, beam_width=5, max_sequence=230):
+        """:708-867 (topk=1) -> LongTensor [B, max_sequence] on the CPU."""
+        if topk != 1:
+            raise NotImplementedError("only topk=1 (what decode() uses, postprocessing/decoding.py:43-48)")
+        b = input.size(0)
+        eng = self.engine(input.device, b, max_sequence)
+        memory = self.encode(input)
+        out = torch.empty(b, max_sequence, dtype=torch.int64, device=input.device)
+        eng.h.call("frx_beam_search", _ptr(memory), b, beam_width, max_sequence, _ptr(out), _stream(input.device))
+        return out.cpu()
+
+    def read_tap(self, name):
+        eng = self._engine
+        n, shape = ctypes.c_int64(), (ctypes.c_int32 * 4)()
+        eng.h.call("frx_read_tap", name.encode(), None, 0, ctypes.byref(n), shape, None)
+        out = torch.empty(tuple(shape), device=eng.device)
+        eng.h.call("frx_read_tap", name.encode(), _ptr(out), n.value, ctypes.byref(n), shape, _stream(eng.device))
+        return out  # NHWC
+
+
+class EfficientSATRN_encoder(_FrxModule):
+    """:870-894 -- the ensemble driver's encoder half (utils/ensemble_utils.py:168-176)."""
+
+    _parts = 1
+
+    def __init__(self, FLAGS, train_dataset, checkpoint=None, *, precision="fp32", max_batch=None):
+        super().__init__()
+        self._setup(FLAGS, train_dataset, precision, max_batch, 1)
+        self.encoder = layout.build_param_tree(layout.encoder_shapes(self._dims), "encoder.")
+        if checkpoint:
+            self.load_state_dict(checkpoint)
+
+    def forward(self, input):
+        b = input.size(0)
+        eng = self.engine(input.device, b, 1)
+        x = input.detach().float().contiguous()
+        s = (self._dims["height"] // 32) * (self._dims["width"] // 32)
+        memory = torch.empty(b, s, self._dims["enc_hidden"], device=x.device)
+        eng.h.call("frx_encode", _ptr(x), b, _ptr(memory), _stream(x.device))
+        return memory
+
+
+class EfficientSATRN_decoder(_FrxModule):
+    """:897-952 -- stateful ``step_forward`` / ``reset_status`` used by the
+    ensemble driver (utils/ensemble_utils.py:83-118)."""
+
+    _parts = 2
+
+    def __init__(self, FLAGS, train_dataset, checkpoint=None, *, precision="fp32", max_batch=None, max_steps=231):
+        super().__init__()
+        self._setup(FLAGS, train_dataset, precision, max_batch, max_steps)
+        self.decoder = layout.build_param_tree(layout.decoder_shapes(self._dims), "decoder.")
+        self.decoder.layer_num = self._dims["dec_layers"]
+        self.decoder.st_id, self.decoder.pad_id = self._ids[0], self._ids[2]
+        self.step_idx = 0
+        self.features = [None] * self._dims["dec_layers"]  # kept for API compatibility; state lives in the handle
+        if checkpoint:
+            self.load_state_dict(checkpoint)
+
+    def step_forward(self, src, target):
+        """:932-948  src [b, S, C], target [b] int64 -> logits [b, 1, V]."""
+        b = src.size(0)
+        eng = self.engine(src.device, b, self._max_steps or 231)
+        st = _stream(src.device)
+        if self.step_idx == 0:
+            eng.h.call("frx_decode_begin", _ptr(src.detach().float().contiguous()), b, st)
+        tgt = target.to(device=src.device, dtype=torch.int64).contiguous()
+        out = torch.empty(b, 1, self._dims["num_classes"], device=src.device)
+        eng.h.call("frx_decode_step", _ptr(tgt), _ptr(out), st)
+        self.step_idx += 1
+        return out
+
+    def reset_status(self):
+        """:950-952"""
+        self.step_idx = 0
+        self.features = [None] * self._dims["dec_layers"]
