@@ -107,4 +107,35 @@ struct AttnP {
   int heads;
 };
 
+
+// ---------------------------------------------------------------------------
+// bf16 persistent decode kernel (kernels_decode_bf16.cu)
+// ---------------------------------------------------------------------------
+constexpr int DEC_CLUSTER = 8;   // CTAs per cluster
+constexpr int DEC_IMG = 16;      // images per cluster (= M of mma.m16n8k16)
+constexpr int DEC_FMAX = 1024;   // decoder filter_dim the kernel is specialised for
+constexpr int DEC_TMAX = 232;    // max decode steps (score buffer)
+
+struct DecClusterLayer {
+  const uint4 *w_o, *w_q2, *w_o2, *w_f0, *w_f1, *w_next;   // fragment-packed bf16, per-CTA blocks
+  const float *b_o, *b_q2, *b_o2, *b_f0, *b_f1, *b_next;   // fp32 biases, natural column order
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+};
+
+struct DecClusterP {
+  int B, steps, T, L, V, S, sos;
+  const uint4* w_first;          // layer-0 q|k|v
+  const float* b_first;
+  DecClusterLayer layer[4];
+  const float* emb;              // [V+1][D] fp32
+  const float* pe;               // [500][D] fp32
+  __nv_bfloat16* kself;          // [L][B][H][T][32]
+  __nv_bfloat16* vself;
+  const __nv_bfloat16* kcross;   // [L][B][H][S][32]
+  const __nv_bfloat16* vcross;
+  float* logits;                 // [B][steps][V] or nullptr
+  long long* tokens;             // [B][steps] or nullptr
+  const long long* forced;       // [B][steps] or nullptr
+};
+
 }  // namespace frx

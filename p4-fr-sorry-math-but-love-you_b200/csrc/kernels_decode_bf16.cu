@@ -1,0 +1,595 @@
+// kernels_decode_bf16.cu -- the whole greedy decode loop as ONE persistent kernel.
+//
+// Design (DESIGN.md "decode"): every operation of the decoder step is local to
+// an image, so there is no reason for grid-wide synchronisation.  A thread-block
+// CLUSTER of 8 CTAs owns 16 images (the M of one mma.m16n8k16) for all steps:
+//   * each CTA computes 1/8 of the output columns of every linear layer, with
+//     the bf16 weights streamed from L2 straight into tensor-core B fragments
+//     (pre-packed on the host in fragment order -> coalesced 16-byte loads);
+//   * the partial rows are all-gathered through distributed shared memory
+//     (each CTA stores its slice into all 8 CTAs' buffers) and a cluster
+//     barrier separates the stages -- no global-memory round trips, no grid sync;
+//   * attention over the bf16 KV cache (head-major [L][B][H][T][32], 64 B rows)
+//     is done by one warp per (image, head) with 16-byte coalesced loads and
+//     warp-shuffle reductions; the step's K/V rows are written by the CTA that
+//     owns that head's columns.
+// Tensor cores are used through mma.sync (M=16 images per cluster); tcgen05's
+// minimum tile (M=64..128 rows) does not fit a 16-row per-step problem, and the
+// step is bandwidth/latency-bound, not MMA-bound.
+//
+// Implements the recurrence of SURVEY App. A.4 (networks/EfficientSATRN.py:374-397,
+// :539-558): cached layer OUTPUTS, current layer INPUT as the last key, scores
+// divided by sqrt(d_model), post-LN, ReLU after both FFN linears.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace frx {
+
+namespace {
+
+constexpr int CL = DEC_CLUSTER;   // CTAs per cluster
+constexpr int IMG = DEC_IMG;      // images per cluster
+constexpr int D = 256;            // decoder width this kernel is specialised for
+constexpr int HD = 32;
+constexpr int H = D / HD;         // 8 heads
+constexpr int NTHR = 256;
+constexpr int APAD = 8;           // bf16 padding of the A-operand rows (bank-conflict-free fragments)
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint64_t make_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ uint4 ldg_weights(const uint4* p, uint64_t pol) {
+  uint4 v;  // weights are re-read every step by every cluster: ask L2 to keep them
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+struct Smem {
+  float xres[IMG][D];              // residual stream (fp32)
+  float pre[IMG][D];               // gathered pre-LayerNorm rows
+  float qkv[IMG][3 * D];           // q | k | v of the current layer input (also q2, logits)
+  __nv_bfloat16 abf[IMG][D + APAD];        // A operand (bf16) of the next GEMM, K = D
+  __nv_bfloat16 abf2[IMG][DEC_FMAX + APAD];  // A operand of FFN linear1, K = F
+  float sc[NTHR / 32][DEC_TMAX + 8];        // per-warp attention scores
+  float red[4][32][4];             // K-split partial accumulators
+  int tok[IMG];
+};
+
+// ---------------------------------------------------------------------------
+// One GEMM stage: out[16, NT*8 columns of this CTA] = A[16, K] * W^T, A in smem
+// (bf16), W pre-packed for this CTA: [NT tiles][K/32][32 lanes] uint4.
+// NT >= 8: warp w owns tiles w, w+8, ...; NT == 4: two warps split K per tile.
+// Epi(tile, acc, lane) is called by the warp that holds the final accumulator.
+// ---------------------------------------------------------------------------
+template <int K, int NT, typename Epi>
+__device__ __forceinline__ void gemm_stage(Smem& s, uint64_t pol, const __nv_bfloat16* A, int lda,
+                                           const uint4* __restrict__ Wp, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  constexpr int KP = K / 32;
+  if constexpr (NT >= 8) {
+    constexpr int TPW = (NT + 7) / 8;
+    float acc[TPW][2][4];
+#pragma unroll
+    for (int i = 0; i < TPW; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+#pragma unroll 4
+    for (int kp = 0; kp < KP; ++kp) {
+      uint4 w[TPW];
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        int tile = warp + 8 * i;
+        if (tile < NT) w[i] = ldg_weights(Wp + ((size_t)tile * KP + kp) * 32 + lane, pol);
+      }
+      uint32_t a0[4], a1[4];
+      const __nv_bfloat16* ap = A + gid * lda + kp * 32 + tig * 2;
+      a0[0] = *reinterpret_cast<const uint32_t*>(ap);
+      a0[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda);
+      a0[2] = *reinterpret_cast<const uint32_t*>(ap + 8);
+      a0[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 8);
+      a1[0] = *reinterpret_cast<const uint32_t*>(ap + 16);
+      a1[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 16);
+      a1[2] = *reinterpret_cast<const uint32_t*>(ap + 24);
+      a1[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 24);
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        if (warp + 8 * i < NT) {
+          mma_bf16(acc[i][0], a0, w[i].x, w[i].y);
+          mma_bf16(acc[i][1], a1, w[i].z, w[i].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+      int tile = warp + 8 * i;
+      if (tile < NT) {
+        float c[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[e] = acc[i][0][e] + acc[i][1][e];
+        epi(tile, c, lane);
+      }
+    }
+  } else {
+    static_assert(NT == 4, "NT must be 4 or >= 8");
+    const int tile = warp & 3, half = warp >> 2;
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    constexpr int KH = KP / 2;
+#pragma unroll 4
+    for (int kk = 0; kk < KH; ++kk) {
+      const int kp = half * KH + kk;
+      uint4 w = ldg_weights(Wp + ((size_t)tile * KP + kp) * 32 + lane, pol);
+      uint32_t a0[4], a1[4];
+      const __nv_bfloat16* ap = A + gid * lda + kp * 32 + tig * 2;
+      a0[0] = *reinterpret_cast<const uint32_t*>(ap);
+      a0[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda);
+      a0[2] = *reinterpret_cast<const uint32_t*>(ap + 8);
+      a0[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 8);
+      a1[0] = *reinterpret_cast<const uint32_t*>(ap + 16);
+      a1[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 16);
+      a1[2] = *reinterpret_cast<const uint32_t*>(ap + 24);
+      a1[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 24);
+      mma_bf16(acc[0], a0, w.x, w.y);
+      mma_bf16(acc[1], a1, w.z, w.w);
+    }
+    float c[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e] = acc[0][e] + acc[1][e];
+    if (half == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s.red[tile][lane][e] = c[e];
+    }
+    __syncthreads();
+    if (half == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[e] += s.red[tile][lane][e];
+      epi(tile, c, lane);
+    }
+  }
+}
+
+// All-gather stores: the same smem offset in every CTA of the cluster.
+__device__ __forceinline__ void ag_store_f2(cg::cluster_group& cl, float* local, float a, float b) {
+#pragma unroll
+  for (int r = 0; r < CL; ++r) *reinterpret_cast<float2*>(cl.map_shared_rank(local, r)) = make_float2(a, b);
+}
+__device__ __forceinline__ void ag_store_u32(cg::cluster_group& cl, void* local, uint32_t v) {
+#pragma unroll
+  for (int r = 0; r < CL; ++r) *reinterpret_cast<uint32_t*>(cl.map_shared_rank(local, r)) = v;
+}
+__device__ __forceinline__ void ag_store_u4(cg::cluster_group& cl, void* local, uint4 v) {
+#pragma unroll
+  for (int r = 0; r < CL; ++r) *reinterpret_cast<uint4*>(cl.map_shared_rank(local, r)) = v;
+}
+
+// LayerNorm of the 16 gathered rows (every CTA does all rows: the result is
+// needed everywhere and recomputing is cheaper than another exchange).
+__device__ __forceinline__ void layernorm_rows(Smem& s, const float* __restrict__ g, const float* __restrict__ b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int rr = 0; rr < IMG / 8; ++rr) {
+    const int row = warp * (IMG / 8) + rr;
+    float v[D / 32];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) { v[i] = s.pre[row][i * 32 + lane]; sum += v[i]; }
+    const float mean = warp_sum(sum) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) {
+      const int c = i * 32 + lane;
+      float o = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+      s.xres[row][c] = o;
+      s.abf[row][c] = __float2bfloat16_rn(o);
+    }
+  }
+}
+
+// Attention of one (image, head) pair by one warp.  Lane (g = lane>>2, c = lane&3)
+// handles keys j = g (mod 8) and head dims [8c, 8c+8).  K/V rows are 32 bf16
+// (64 B), contiguous over keys -> each warp load covers 512 contiguous bytes.
+// Result: lanes with g == 0 return the 8 output dims [8c, 8c+8) in o[].
+__device__ __forceinline__ void attend_pair(const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
+                                            const __nv_bfloat16* __restrict__ Vc, int n_hist,
+                                            const float* __restrict__ kx, const float* __restrict__ vx,
+                                            float* __restrict__ sc, float temperature, float (&o)[8]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  float qv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qv[i] = q[c * 8 + i];
+  const int nk = n_hist + (kx ? 1 : 0);
+  float mx = -INFINITY;
+  // ---- scores --------------------------------------------------------------
+#pragma unroll 4
+  for (int j0 = 0; j0 < n_hist; j0 += 8) {
+    const int j = j0 + g;
+    float part = 0.f;
+    if (j < n_hist) {
+      float kf[8];
+      unpack8(ldg_stream(Kc + (size_t)j * HD + c * 8), kf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part = fmaf(qv[i], kf[i], part);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    const float sv = part / temperature;
+    if (j < n_hist) {
+      if (c == 0) sc[j] = sv;
+      mx = fmaxf(mx, sv);
+    }
+  }
+  if (kx) {
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part = fmaf(qv[i], kx[c * 8 + i], part);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    const float sv = part / temperature;
+    if (lane == 0) sc[n_hist] = sv;
+    mx = fmaxf(mx, sv);
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < nk; j += 32) {
+    float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  // ---- P.V -------------------------------------------------------------------
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int j0 = 0; j0 < n_hist; j0 += 8) {
+    const int j = j0 + g;
+    if (j < n_hist) {
+      float vf[8];
+      unpack8(ldg_stream(Vc + (size_t)j * HD + c * 8), vf);
+      const float pj = sc[j] / sum;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, vf[i], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (vx) {
+    const float pj = sc[n_hist] / sum;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, vx[c * 8 + i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = acc[i];
+  __syncwarp();
+}
+
+}  // namespace
+
+// ===========================================================================
+// The persistent decode kernel
+// ===========================================================================
+__global__ void __cluster_dims__(DEC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
+dec_cluster_bf16_kernel(const DecClusterP p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  cg::cluster_group cl = cg::this_cluster();
+  const int r = (int)cl.block_rank();
+  const int img0 = (blockIdx.x / CL) * IMG;  // first image of this cluster
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint64_t pol = make_evict_last_policy();
+  const float temperature = sqrtf((float)D);
+  const float emb_scale = sqrtf((float)D);
+  const int L = p.L, T = p.T, V = p.V, B = p.B;
+
+  // ---- step 0 input: <SOS> embedding + position 0 --------------------------------
+  for (int i = tid; i < IMG * D; i += NTHR) {
+    const int row = i / D, c = i % D;
+    float v = __ldg(p.emb + (size_t)p.sos * D + c) * emb_scale + __ldg(p.pe + c);
+    s.xres[row][c] = v;
+    s.abf[row][c] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  cl.sync();  // every CTA of the cluster is resident before the first remote store
+
+  for (int t = 0; t < p.steps; ++t) {
+    for (int l = 0; l < L; ++l) {
+      const DecClusterLayer& W = p.layer[l];
+      // ---- S1 (layer 0 only): q | k | v of the embedded input -------------------------
+      if (l == 0) {
+        const uint4* wp = p.w_first + (size_t)r * 12 * (D / 32) * 32;
+        gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, wp, [&](int tile, float (&c)[4], int ln) {
+          const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2;
+          const float b0 = __ldg(p.b_first + col), b1 = __ldg(p.b_first + col + 1);
+          ag_store_f2(cl, &s.qkv[ln >> 2][col], c[0] + b0, c[1] + b1);
+          ag_store_f2(cl, &s.qkv[(ln >> 2) + 8][col], c[2] + b0, c[3] + b1);
+        });
+        cl.sync();
+      }
+      // ---- S2: self attention over t cached rows + the current input row ------------------
+      {
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          const int pair = warp * 2 + pp;
+          const int li = r * 2 + (pair >> 3), hh = pair & 7;  // cluster-local image, head
+          const int b = img0 + li;
+          float o[8];
+          if (b < B) {
+            const size_t base = ((((size_t)l * B + b) * H + hh) * T) * HD;
+            attend_pair(&s.qkv[li][hh * HD], p.kself + base, p.vself + base, t, &s.qkv[li][D + hh * HD],
+                        &s.qkv[li][2 * D + hh * HD], s.sc[warp], temperature, o);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = 0.f;
+          }
+          if ((lane >> 2) == 0) {
+            uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            ag_store_u4(cl, &s.abf[li][hh * HD + (lane & 3) * 8], v);
+          }
+        }
+        cl.sync();
+      }
+      // ---- S3: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
+      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o + (size_t)r * 4 * (D / 32) * 32,
+                       [&](int tile, float (&c)[4], int ln) {
+                         const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
+                         const float b0 = __ldg(W.b_o + col), b1 = __ldg(W.b_o + col + 1);
+                         ag_store_f2(cl, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
+                         ag_store_f2(cl, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
+                                     c[3] + b1 + s.xres[row + 8][col + 1]);
+                       });
+      cl.sync();
+      layernorm_rows(s, W.ln1_g, W.ln1_b);
+      __syncthreads();
+      // ---- S4: q2 = q_linear(u) ---------------------------------------------------------------
+      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_q2 + (size_t)r * 4 * (D / 32) * 32,
+                       [&](int tile, float (&c)[4], int ln) {
+                         const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
+                         const float b0 = __ldg(W.b_q2 + col), b1 = __ldg(W.b_q2 + col + 1);
+                         ag_store_f2(cl, &s.qkv[row][col], c[0] + b0, c[1] + b1);
+                         ag_store_f2(cl, &s.qkv[row + 8][col], c[2] + b0, c[3] + b1);
+                       });
+      cl.sync();
+      // ---- S5: cross attention over the S memory tokens --------------------------------------------
+      {
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          const int pair = warp * 2 + pp;
+          const int li = r * 2 + (pair >> 3), hh = pair & 7;
+          const int b = img0 + li;
+          float o[8];
+          if (b < B) {
+            const size_t base = ((((size_t)l * B + b) * H + hh) * p.S) * HD;
+            attend_pair(&s.qkv[li][hh * HD], p.kcross + base, p.vcross + base, p.S, nullptr, nullptr, s.sc[warp],
+                        temperature, o);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = 0.f;
+          }
+          if ((lane >> 2) == 0) {
+            uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            ag_store_u4(cl, &s.abf[li][hh * HD + (lane & 3) * 8], v);
+          }
+        }
+        cl.sync();
+      }
+      // ---- S6: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
+      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o2 + (size_t)r * 4 * (D / 32) * 32,
+                       [&](int tile, float (&c)[4], int ln) {
+                         const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
+                         const float b0 = __ldg(W.b_o2 + col), b1 = __ldg(W.b_o2 + col + 1);
+                         ag_store_f2(cl, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
+                         ag_store_f2(cl, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
+                                     c[3] + b1 + s.xres[row + 8][col + 1]);
+                       });
+      cl.sync();
+      layernorm_rows(s, W.ln2_g, W.ln2_b);
+      __syncthreads();
+      // ---- S7: ff = relu(linear0(w))  (F = 4 segments of D columns) --------------------------------
+      gemm_stage<D, 16>(s, pol, &s.abf[0][0], D + APAD, W.w_f0 + (size_t)r * 16 * (D / 32) * 32,
+                        [&](int tile, float (&c)[4], int ln) {
+                          const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
+                          const float b0 = __ldg(W.b_f0 + col), b1 = __ldg(W.b_f0 + col + 1);
+                          ag_store_u32(cl, &s.abf2[row][col], pack_bf16(fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f)));
+                          ag_store_u32(cl, &s.abf2[row + 8][col], pack_bf16(fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f)));
+                        });
+      cl.sync();
+      // ---- S8: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
+      gemm_stage<DEC_FMAX, 4>(s, pol, &s.abf2[0][0], DEC_FMAX + APAD, W.w_f1 + (size_t)r * 4 * (DEC_FMAX / 32) * 32,
+                              [&](int tile, float (&c)[4], int ln) {
+                                const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
+                                const float b0 = __ldg(W.b_f1 + col), b1 = __ldg(W.b_f1 + col + 1);
+                                ag_store_f2(cl, &s.pre[row][col], fmaxf(c[0] + b0, 0.f) + s.xres[row][col],
+                                            fmaxf(c[1] + b1, 0.f) + s.xres[row][col + 1]);
+                                ag_store_f2(cl, &s.pre[row + 8][col], fmaxf(c[2] + b0, 0.f) + s.xres[row + 8][col],
+                                            fmaxf(c[3] + b1, 0.f) + s.xres[row + 8][col + 1]);
+                              });
+      cl.sync();
+      layernorm_rows(s, W.ln3_g, W.ln3_b);
+      __syncthreads();
+      // ---- S9: K/V rows of y -> cache; next layer's q|k|v, or the vocabulary logits -------------------
+      auto kv_store = [&](int tile, float (&c)[4], int ln) {
+        // tiles 0..3: K columns of head r; tiles 4..7: V columns of head r
+        const int seg = tile >> 2, dcol = (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
+        const float* bias = W.b_next + seg * D + r * 32 + dcol;
+        const float b0 = __ldg(bias), b1 = __ldg(bias + 1);
+        __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const int b = img0 + row + hrow * 8;
+          if (b < B) {
+            const size_t off = (((((size_t)l * B + b) * H + r) * T) + t) * HD + dcol;
+            *reinterpret_cast<uint32_t*>(dst + off) = pack_bf16(c[hrow * 2] + b0, c[hrow * 2 + 1] + b1);
+          }
+        }
+      };
+      if (l + 1 < L) {
+        gemm_stage<D, 20>(s, pol, &s.abf[0][0], D + APAD, W.w_next + (size_t)r * 20 * (D / 32) * 32,
+                          [&](int tile, float (&c)[4], int ln) {
+                            if (tile < 8) { kv_store(tile, c, ln); return; }
+                            const int seg = tile >> 2;  // 2,3,4 -> q,k,v of layer l+1
+                            const int col = (seg - 2) * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
+                            const float b0 = __ldg(W.b_next + 2 * D + col), b1 = __ldg(W.b_next + 2 * D + col + 1);
+                            ag_store_f2(cl, &s.qkv[row][col], c[0] + b0, c[1] + b1);
+                            ag_store_f2(cl, &s.qkv[row + 8][col], c[2] + b0, c[3] + b1);
+                          });
+      } else {
+        // generator: V columns padded to 256; CTA r owns columns [32r, 32r+32) (tiles 8..11)
+        gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, W.w_next + (size_t)r * 12 * (D / 32) * 32,
+                          [&](int tile, float (&c)[4], int ln) {
+                            if (tile < 8) { kv_store(tile, c, ln); return; }
+                            const int col = r * 32 + (tile - 8) * 8 + (ln & 3) * 2, row = ln >> 2;
+                            const float b0 = col < V ? __ldg(W.b_next + 2 * D + col) : 0.f;
+                            const float b1 = col + 1 < V ? __ldg(W.b_next + 2 * D + col + 1) : 0.f;
+                            const float v00 = c[0] + b0, v01 = c[1] + b1, v10 = c[2] + b0, v11 = c[3] + b1;
+                            ag_store_f2(cl, &s.qkv[row][col], v00, v01);
+                            ag_store_f2(cl, &s.qkv[row + 8][col], v10, v11);
+                            if (p.logits) {
+                              const int bA = img0 + row, bB = img0 + row + 8;
+                              if (bA < B) {
+                                float* lp = p.logits + ((size_t)bA * p.steps + t) * V;
+                                if (col < V) lp[col] = v00;
+                                if (col + 1 < V) lp[col + 1] = v01;
+                              }
+                              if (bB < B) {
+                                float* lp = p.logits + ((size_t)bB * p.steps + t) * V;
+                                if (col < V) lp[col] = v10;
+                                if (col + 1 < V) lp[col + 1] = v11;
+                              }
+                            }
+                          });
+      }
+      cl.sync();
+    }  // layers
+    // ---- greedy pick (first max index) + next input: every CTA does all 16 rows -------------------------
+#pragma unroll
+    for (int rr = 0; rr < IMG / 8; ++rr) {
+      const int row = warp * (IMG / 8) + rr;
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int i = lane; i < V; i += 32) {
+        float v = s.qkv[row][i];
+        if (v > best) { best = v; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (bi < 0 || bi >= V) bi = 0;
+      const int b = img0 + row;
+      int nxt = bi;
+      if (b < B) {
+        if (p.forced) nxt = (int)p.forced[(size_t)b * p.steps + t];
+        if (r == 0 && lane == 0 && p.tokens) p.tokens[(size_t)b * p.steps + t] = bi;
+      }
+      if (t + 1 < p.steps) {
+        const float* pe = p.pe + (size_t)(t + 1) * D;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) {
+          const int c = i * 32 + lane;
+          float v = __ldg(p.emb + (size_t)nxt * D + c) * emb_scale + __ldg(pe + c);
+          s.xres[row][c] = v;
+          s.abf[row][c] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+    __syncthreads();
+    // the next step's first remote stores (S1 -> qkv) must not overtake a peer that is still
+    // reading the logits out of its qkv buffer
+    cl.sync();
+  }
+}
+
+size_t dec_cluster_smem_bytes() { return sizeof(Smem); }
+
+int launch_dec_cluster_bf16(const DecClusterP& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dec_cluster_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int clusters = (p.B + IMG - 1) / IMG;
+  dec_cluster_bf16_kernel<<<clusters * CL, NTHR, sizeof(Smem), st>>>(p);
+  return 0;
+}
+
+// ===========================================================================
+// cross K/V: fp32 [B*S][L*2*D] (k_l | v_l per layer) -> bf16 head-major
+// [L][B][H][S][32] caches
+// ===========================================================================
+__global__ void __launch_bounds__(256) cross_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ kc,
+                                                            __nv_bfloat16* __restrict__ vc, int B, int S, int L, int Dm) {
+  const int Hh = Dm / 32;
+  long long total = (long long)B * S * L * 2 * Dm;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int col = (int)(idx % (L * 2 * Dm));
+  long long row = idx / (L * 2 * Dm);
+  int sidx = (int)(row % S), b = (int)(row / S);
+  int l = col / (2 * Dm), which = (col / Dm) & 1, d = col % Dm;
+  int hh = d / 32, dd = d % 32;
+  size_t off = (((((size_t)l * B + b) * Hh + hh) * S) + sidx) * 32 + dd;
+  (which ? vc : kc)[off] = __float2bfloat16_rn(src[idx]);
+}
+
+void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc, int B, int S, int L, int Dm,
+                          cudaStream_t st) {
+  long long total = (long long)B * S * L * 2 * Dm;
+  cross_to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, kc, vc, B, S, L, Dm);
+}
+
+}  // namespace frx

@@ -468,6 +468,86 @@ static int pack_decoder(frx_handle* h, ArenaBuilder& ab) {
   return 0;
 }
 
+static inline uint32_t bf16_bits(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0u;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return u >> 16;
+}
+
+// B-fragment order of mma.m16n8k16 for the persistent decode kernel:
+// [cta r][tile][k-pair kp][lane] -> uint4 {b0b1(k-step 2kp), b2b3(2kp), b0b1(2kp+1), b2b3(2kp+1)}.
+// rowptr(r, tile, gid) returns the K-float weight row of output column (tile, gid) of CTA r, or nullptr.
+template <class F>
+static size_t pack_frag_stage(ArenaBuilder& ab, int NT, int K, F rowptr) {
+  const int KP = K / 32;
+  size_t off = ab.add(nullptr, (size_t)DEC_CLUSTER * NT * KP * 32 * 4);
+  uint32_t* d = reinterpret_cast<uint32_t*>(ab.at(off));
+  for (int r = 0; r < DEC_CLUSTER; ++r)
+    for (int tile = 0; tile < NT; ++tile)
+      for (int kp = 0; kp < KP; ++kp)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int gid = lane >> 2, tig = lane & 3;
+          const float* w = rowptr(r, tile, gid);
+          uint32_t* o = d + ((((size_t)r * NT + tile) * KP + kp) * 32 + lane) * 4;
+          for (int q = 0; q < 4; ++q) {
+            const int k = (2 * kp + (q >> 1)) * 16 + tig * 2 + (q & 1) * 8;
+            o[q] = w ? (bf16_bits(w[k]) | (bf16_bits(w[k + 1]) << 16)) : 0u;
+          }
+        }
+  return off;
+}
+
+static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
+  const frx_config& c = h->cfg;
+  const int D = c.dec_hidden, F = c.dec_filter, V = c.num_classes, L = c.dec_layers;
+  if (D != 256 || F != DEC_FMAX || c.dec_heads != 8 || L > 4 || V > 256)
+    return fail(h, "bf16 decode kernel is specialised for hidden 256 / filter 1024 / 8 heads / <=4 layers / <=256 classes");
+  auto W = [&](int l, const char* name) -> const float* {
+    return find(h, "decoder.attention_layers." + std::to_string(l) + "." + name + ".weight")->f.data();
+  };
+  const float* gen = find(h, "decoder.generator.weight")->f.data();
+  h->dpack.assign(L, DecPackW{});
+  h->dpack_first = pack_frag_stage(ab, 12, D, [&](int r, int tile, int gid) {
+    const char* names[3] = {"self_attention_layer.q_linear", "self_attention_layer.k_linear", "self_attention_layer.v_linear"};
+    return W(0, names[tile >> 2]) + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
+  });
+  for (int l = 0; l < L; ++l) {
+    DecPackW& P = h->dpack[l];
+    auto square = [&](const char* name, int K) {
+      const float* w = W(l, name);
+      return pack_frag_stage(ab, 4, K, [=](int r, int tile, int gid) { return w + (size_t)(r * 32 + tile * 8 + gid) * K; });
+    };
+    P.w_o = square("self_attention_layer.out_linear", D);
+    P.w_q2 = square("attention_layer.q_linear", D);
+    P.w_o2 = square("attention_layer.out_linear", D);
+    P.w_f1 = square("feedforward_layer.linear1", F);
+    const float* f0 = W(l, "feedforward_layer.linear0");
+    P.w_f0 = pack_frag_stage(ab, 16, D, [=](int r, int tile, int gid) {
+      return f0 + (size_t)((tile >> 2) * 256 + r * 32 + (tile & 3) * 8 + gid) * D;
+    });
+    const float* wk = W(l, "self_attention_layer.k_linear");
+    const float* wv = W(l, "self_attention_layer.v_linear");
+    if (l + 1 < L) {
+      const float* nq = W(l + 1, "self_attention_layer.q_linear");
+      const float* nk = W(l + 1, "self_attention_layer.k_linear");
+      const float* nv = W(l + 1, "self_attention_layer.v_linear");
+      P.w_next = pack_frag_stage(ab, 20, D, [=](int r, int tile, int gid) {
+        const float* segs[5] = {wk, wv, nq, nk, nv};
+        return segs[tile >> 2] + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
+      });
+    } else {
+      P.w_next = pack_frag_stage(ab, 12, D, [=](int r, int tile, int gid) -> const float* {
+        if (tile < 8) return (tile < 4 ? wk : wv) + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
+        int n = r * 32 + (tile - 8) * 8 + gid;
+        return n < V ? gen + (size_t)n * D : nullptr;
+      });
+    }
+  }
+  return 0;
+}
+
 extern "C" int frx_finalize_weights(frx_handle* h) {
   if (!h) return 1;
   const frx_config& c = h->cfg;
@@ -486,6 +566,7 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
     if (pack_encoder(h, ab)) return 1;
   }
   if (want_dec && pack_decoder(h, ab)) return 1;
+  if (want_dec && c.precision == FRX_PREC_BF16 && pack_decoder_bf16(h, ab)) return 1;
   // upload (re-finalize re-uses the arena when the size is unchanged)
   size_t bytes = ab.host.size() * sizeof(float);
   if (!h->arena || h->arena_bytes != bytes) {
@@ -541,6 +622,12 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
     if (dev_alloc(h, &p, B * T * 8)) return 1; h->tokens_int = (long long*)p;
     if (dev_alloc(h, &p, B * T * 8)) return 1; h->forced_int = (long long*)p;
     if (dev_alloc(h, &p, B * 4)) return 1; h->cur_tok = (int*)p;
+    if (c.precision == FRX_PREC_BF16) {
+      if (dev_alloc(h, &p, L * B * T * D * 2)) return 1; h->kself_bf = p;
+      if (dev_alloc(h, &p, L * B * T * D * 2)) return 1; h->vself_bf = p;
+      if (dev_alloc(h, &p, L * B * S * D * 2)) return 1; h->kcross_bf = p;
+      if (dev_alloc(h, &p, L * B * S * D * 2)) return 1; h->vcross_bf = p;
+    }
     }
     if (dev_alloc(h, &p, B * S * C * 4)) return 1; h->memory_int = (float*)p;
     if (dev_alloc(h, &p, (size_t)c.in_ch * c.height * c.width * B * 4)) return 1; h->images_int = (float*)p;
@@ -831,6 +918,40 @@ static int run_greedy_loop(frx_handle* h, int B, int steps, bool forced, cudaStr
   return 0;
 }
 
+static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, long long* tokens,
+                              const long long* forced, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  const float* A = h->arena;
+  const int S = h->feat_h * h->feat_w, L = c.dec_layers, D = c.dec_hidden;
+  if (steps > DEC_TMAX) return fail(h, "bf16 decode kernel supports at most %d steps", DEC_TMAX);
+  launch_cross_to_bf16(h->cross, (__nv_bfloat16*)h->kcross_bf, (__nv_bfloat16*)h->vcross_bf, B, S, L, D, st);
+  CKL();
+  DecClusterP p{};
+  p.B = B; p.steps = steps; p.T = c.max_steps; p.L = L; p.V = c.num_classes; p.S = S; p.sos = c.sos_id;
+  p.w_first = reinterpret_cast<const uint4*>(A + h->dpack_first);
+  p.b_first = A + h->fused[0].b;
+  for (int l = 0; l < L; ++l) {
+    const DecPackW& P = h->dpack[l];
+    const DecLayerW& W = h->dec[l];
+    DecClusterLayer& Q = p.layer[l];
+    Q.w_o = reinterpret_cast<const uint4*>(A + P.w_o);   Q.w_q2 = reinterpret_cast<const uint4*>(A + P.w_q2);
+    Q.w_o2 = reinterpret_cast<const uint4*>(A + P.w_o2); Q.w_f0 = reinterpret_cast<const uint4*>(A + P.w_f0);
+    Q.w_f1 = reinterpret_cast<const uint4*>(A + P.w_f1); Q.w_next = reinterpret_cast<const uint4*>(A + P.w_next);
+    Q.b_o = A + W.b_o; Q.b_q2 = A + W.b_q2; Q.b_o2 = A + W.b_o2; Q.b_f0 = A + W.b_f0; Q.b_f1 = A + W.b_f1;
+    Q.b_next = A + h->fused[l + 1].b;
+    Q.ln1_g = A + W.ln1_g; Q.ln1_b = A + W.ln1_b; Q.ln2_g = A + W.ln2_g; Q.ln2_b = A + W.ln2_b;
+    Q.ln3_g = A + W.ln3_g; Q.ln3_b = A + W.ln3_b;
+  }
+  p.emb = A + h->emb; p.pe = A + h->pe1d;
+  p.kself = (__nv_bfloat16*)h->kself_bf; p.vself = (__nv_bfloat16*)h->vself_bf;
+  p.kcross = (const __nv_bfloat16*)h->kcross_bf; p.vcross = (const __nv_bfloat16*)h->vcross_bf;
+  p.logits = logits; p.tokens = tokens; p.forced = forced;
+  int rc = launch_dec_cluster_bf16(p, st);
+  if (rc) return fail(h, "decode cluster kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
+  CKL();
+  return 0;
+}
+
 static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int steps, float* logits,
                               int64_t* tokens, const int64_t* forced, cudaStream_t st) {
   const frx_config& c = h->cfg;
@@ -841,6 +962,9 @@ static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int ste
   if (steps > 500) return fail(h, "decode: steps exceed the 1-D positional table (500)");
   CK(cudaSetDevice(c.device));
   if (run_cross_kv(h, memory, B, st)) return 1;
+  if (c.precision == FRX_PREC_BF16)  // one persistent kernel; writes the caller's buffers directly
+    return decode_greedy_bf16(h, B, steps, logits, (long long*)(tokens ? tokens : (int64_t*)h->tokens_int),
+                              (const long long*)forced, st);
   if (forced) CK(cudaMemcpyAsync(h->forced_int, forced, (size_t)B * steps * 8, cudaMemcpyDeviceToDevice, st));
   if (h->opt_graphs) {
     GraphKey key{B, steps, forced != nullptr};
@@ -908,7 +1032,10 @@ extern "C" int frx_forward_greedy_host(frx_handle* h, const float* images_host, 
   CK(cudaSetDevice(c.device));
   size_t img_bytes = (size_t)B * c.in_ch * c.height * c.width * 4;
   CK(cudaMemcpyAsync(h->images_int, images_host, img_bytes, cudaMemcpyHostToDevice, st));
-  if (frx_forward_greedy(h, h->images_int, B, steps, nullptr, nullptr, stream)) return 1;
+  if (frx_forward_greedy(h, h->images_int, B, steps,
+                         (c.precision == FRX_PREC_BF16 && logits_host) ? h->logits_int : nullptr,
+                         (c.precision == FRX_PREC_BF16) ? (int64_t*)h->tokens_int : nullptr, stream))
+    return 1;
   if (tokens_host) CK(cudaMemcpyAsync(tokens_host, h->tokens_int, (size_t)B * steps * 8, cudaMemcpyDeviceToHost, st));
   if (logits_host) CK(cudaMemcpyAsync(logits_host, h->logits_int, (size_t)B * steps * c.num_classes * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -37,6 +37,8 @@ struct DecLayerW {
   size_t ln1_g, ln1_b, ln2_g, ln2_b, ln3_g, ln3_b;
 };
 struct FusedW { size_t wt, b; int N; };
+// fragment-packed bf16 weights of the persistent decode kernel (offsets in floats = u32 words)
+struct DecPackW { size_t w_o, w_q2, w_o2, w_f0, w_f1, w_next; };
 struct Tap { float* data = nullptr; size_t capacity = 0; int shape[4] = {0, 0, 0, 0}; };
 typedef std::tuple<int, int, bool> GraphKey;
 struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; };
@@ -66,6 +68,8 @@ struct frx_handle {
   size_t emb = 0, pe1d = 0, gen_w = 0, gen_b = 0, w_cross = 0, b_cross = 0;
   std::vector<DecLayerW> dec;
   std::vector<FusedW> fused;
+  std::vector<DecPackW> dpack;
+  size_t dpack_first = 0;
 
   // workspaces
   float *act[2] = {nullptr, nullptr}, *mid[2] = {nullptr, nullptr}, *gate = nullptr;
@@ -75,6 +79,7 @@ struct frx_handle {
   float *logits_int = nullptr, *memory_int = nullptr, *images_int = nullptr;
   long long *tokens_int = nullptr, *forced_int = nullptr;
   int* cur_tok = nullptr;
+  void *kself_bf = nullptr, *vself_bf = nullptr, *kcross_bf = nullptr, *vcross_bf = nullptr;  // bf16 caches
 
   std::map<GraphKey, GraphEntry> graphs;
   std::map<std::string, Tap> taps;

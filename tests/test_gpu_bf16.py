@@ -1,0 +1,77 @@
+"""bf16 mode (tensor-core contractions, bf16 KV cache): logits within a stated
+relative tolerance of the reference under forced decoding, free-running
+token-sequence agreement reported (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import make_model
+from oracle import satrn, synth
+
+pytestmark = pytest.mark.gpu
+
+BF16_REL_TOL = 4e-2   # max |logit - ref| / max |ref| under forced decoding (bf16 weights + bf16 KV cache)
+MIN_AGREEMENT = 0.80  # free-running token agreement with the fp32 reference (reported, loose floor)
+
+
+@pytest.fixture(scope="module")
+def model_bf16(ckpt0):
+    return make_model(ckpt0, precision="bf16").cuda().eval()
+
+
+def _decode(model, mem, steps, forced=None):
+    b = mem.size(0)
+    eng = model.engine(mem.device, b, steps)
+    logits = torch.empty(b, steps, 245, device="cuda")
+    tokens = torch.empty(b, steps, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    f = forced.cuda().contiguous() if forced is not None else None
+    eng.h.call("frx_decode_greedy", mem.data_ptr(), b, steps, logits.data_ptr(), tokens.data_ptr(),
+               f.data_ptr() if f is not None else None, st)
+    torch.cuda.synchronize()
+    return logits.cpu(), tokens.cpu()
+
+
+def test_bf16_decode_forced_within_tolerance(model_bf16):
+    g = load_golden(0)
+    mem = torch.from_numpy(g["memory"]).cuda()
+    ref = torch.from_numpy(g["logits"])
+    logits, _ = _decode(model_bf16, mem, 231, forced=torch.from_numpy(g["tokens"]))
+    rel = ((logits - ref).abs().max() / ref.abs().max()).item()
+    print("bf16 forced-decoding max rel logit error: %.4f" % rel)
+    assert rel <= BF16_REL_TOL
+    # argmax agreement under forced decoding (per step, independent of error compounding)
+    agree = (logits.argmax(-1) == ref.argmax(-1)).float().mean().item()
+    print("bf16 forced-decoding per-step argmax agreement: %.4f" % agree)
+    assert agree >= 0.95
+
+
+def test_bf16_free_running_agreement_reported(model_bf16):
+    g = load_golden(0)
+    mem = torch.from_numpy(g["memory"]).cuda()
+    _, tokens = _decode(model_bf16, mem, 231)
+    agree = (tokens == torch.from_numpy(g["tokens"])).float().mean().item()
+    print("bf16 free-running token agreement with the fp32 reference: %.4f" % agree)
+    assert agree >= MIN_AGREEMENT
+
+
+def test_bf16_matches_fp32_path_on_step_zero(ckpt0, model_bf16, spec):
+    """Step 0 has no history: bf16 and fp32 modes must agree to bf16 rounding."""
+    x = synth.synth_images(spec, 5, 7).cuda()
+    m32 = make_model(ckpt0).cuda().eval()
+    with torch.no_grad():
+        l32, _ = m32.greedy(x, 3)
+        l16, _ = model_bf16.greedy(x, 3)
+    rel = ((l16 - l32).abs().max() / l32.abs().max()).item()
+    assert rel <= BF16_REL_TOL, rel
+
+
+def test_bf16_deterministic_and_batch_invariant(model_bf16, spec):
+    x = synth.synth_images(spec, 40, 9).cuda()   # 3 clusters, the last one ragged (8 of 16 rows)
+    with torch.no_grad():
+        l1, t1 = model_bf16.greedy(x, 60)
+        l2, t2 = model_bf16.greedy(x, 60)
+        ls, ts = model_bf16.greedy(x[16:23].contiguous(), 60)
+    assert torch.equal(l1, l2) and torch.equal(t1, t2)
+    assert torch.equal(l1[16:23], ls) and torch.equal(t1[16:23], ts)
