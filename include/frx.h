@@ -146,6 +146,10 @@ int frx_read_tap(frx_handle* h, const char* name, float* out, int64_t capacity, 
  * [1]=cross-KV + decode loop, [2]=total. */
 int frx_last_timing(const frx_handle* h, float* ms3);
 
+/* Per-stage SM-cycle totals of the last bf16 decode kernel (option "prof" = 1;
+ * recorded by one thread of cluster 0): 16 counters, see DESIGN.md. */
+int frx_read_prof(frx_handle* h, int64_t* out16);
+
 #ifdef __cplusplus
 }
 #endif

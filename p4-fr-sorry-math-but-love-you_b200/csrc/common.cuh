@@ -114,7 +114,8 @@ struct AttnP {
 constexpr int DEC_CLUSTER = 8;   // CTAs per cluster
 constexpr int DEC_IMG = 16;      // images per cluster (= M of mma.m16n8k16)
 constexpr int DEC_FMAX = 1024;   // decoder filter_dim the kernel is specialised for
-constexpr int DEC_TMAX = 232;    // max decode steps (score buffer)
+constexpr int DEC_TMAX = 232;    // max decode steps
+constexpr int DEC_MAX_CLUSTERS_8 = 32;  // co-resident 8-CTA clusters at 2 CTAs/SM (measured: 33 on B200)
 
 struct DecClusterLayer {
   const uint4 *w_o, *w_q2, *w_o2, *w_f0, *w_f1, *w_next;   // fragment-packed bf16, per-CTA blocks
@@ -136,6 +137,7 @@ struct DecClusterP {
   float* logits;                 // [B][steps][V] or nullptr
   long long* tokens;             // [B][steps] or nullptr
   const long long* forced;       // [B][steps] or nullptr
+  long long* prof;               // optional [16] per-stage cycle totals (cluster 0, CTA 0, thread 0)
 };
 
 }  // namespace frx

@@ -21,6 +21,8 @@
 // :539-558): cached layer OUTPUTS, current layer INPUT as the last key, scores
 // divided by sqrt(d_model), post-LN, ReLU after both FFN linears.
 #include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -32,7 +34,7 @@ namespace frx {
 namespace {
 
 constexpr int CL = DEC_CLUSTER;   // CTAs per cluster
-constexpr int IMG = DEC_IMG;      // images per cluster
+constexpr int IMG = DEC_IMG;      // smem rows per cluster (= M of the MMA); NIMG <= IMG of them hold images
 constexpr int D = 256;            // decoder width this kernel is specialised for
 constexpr int HD = 32;
 constexpr int H = D / HD;         // 8 heads
@@ -40,7 +42,7 @@ constexpr int NTHR = 256;
 constexpr int APAD = 8;           // bf16 padding of the A-operand rows (bank-conflict-free fragments)
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -54,14 +56,15 @@ __device__ __forceinline__ uint64_t make_evict_last_policy() {
 
 __device__ __forceinline__ uint4 ldg_weights(const uint4* p, uint64_t pol) {
   uint4 v;  // weights are re-read every step by every cluster: ask L2 to keep them
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;\n"
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;\n"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
   return v;
 }
 
+// KV-cache rows are written by other SMs earlier in this kernel: coherent (L2) load, L1 bypassed.
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
@@ -83,12 +86,13 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 struct Smem {
   float xres[IMG][D];              // residual stream (fp32)
   float pre[IMG][D];               // gathered pre-LayerNorm rows
-  float qkv[IMG][3 * D];           // q | k | v of the current layer input (also q2, logits)
+  float q[IMG][D];                 // q of the current layer input (also q2, logits)
+  __nv_bfloat16 kv[IMG][2 * D];    // k | v of the current layer input (the extra "current" key/value)
   __nv_bfloat16 abf[IMG][D + APAD];        // A operand (bf16) of the next GEMM, K = D
   __nv_bfloat16 abf2[IMG][DEC_FMAX + APAD];  // A operand of FFN linear1, K = F
-  float sc[NTHR / 32][DEC_TMAX + 8];        // per-warp attention scores
   float red[4][32][4];             // K-split partial accumulators
-  int tok[IMG];
+  long long prof[16];
+  DecClusterLayer lw[4];           // per-layer pointers (dynamic indexing of kernel params would spill them)
 };
 
 // ---------------------------------------------------------------------------
@@ -206,11 +210,21 @@ __device__ __forceinline__ void ag_store_u4(cg::cluster_group& cl, void* local, 
 
 // LayerNorm of the 16 gathered rows (every CTA does all rows: the result is
 // needed everywhere and recomputing is cheaper than another exchange).
-__device__ __forceinline__ void layernorm_rows(Smem& s, const float* __restrict__ g, const float* __restrict__ b) {
+struct LnParams { float g[D / 32], b[D / 32]; };
+__device__ __forceinline__ LnParams load_ln(const float* __restrict__ g, const float* __restrict__ b) {
+  LnParams o;  // issued BEFORE the cluster barrier so the L2 latency overlaps the wait
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < D / 32; ++i) { o.g[i] = __ldg(g + i * 32 + lane); o.b[i] = __ldg(b + i * 32 + lane); }
+  return o;
+}
+
+template <int NIMG>
+__device__ __forceinline__ void layernorm_rows(Smem& s, const LnParams& P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int rr = 0; rr < IMG / 8; ++rr) {
-    const int row = warp * (IMG / 8) + rr;
+  for (int rr = 0; rr < NIMG / 8; ++rr) {
+    const int row = warp * (NIMG / 8) + rr;
     float v[D / 32];
     float sum = 0.f;
 #pragma unroll
@@ -223,95 +237,114 @@ __device__ __forceinline__ void layernorm_rows(Smem& s, const float* __restrict_
 #pragma unroll
     for (int i = 0; i < D / 32; ++i) {
       const int c = i * 32 + lane;
-      float o = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+      float o = (v[i] - mean) * rstd * P.g[i] + P.b[i];
       s.xres[row][c] = o;
       s.abf[row][c] = __float2bfloat16_rn(o);
     }
   }
 }
 
-// Attention of one (image, head) pair by one warp.  Lane (g = lane>>2, c = lane&3)
-// handles keys j = g (mod 8) and head dims [8c, 8c+8).  K/V rows are 32 bf16
-// (64 B), contiguous over keys -> each warp load covers 512 contiguous bytes.
-// Result: lanes with g == 0 return the 8 output dims [8c, 8c+8) in o[].
+// Attention of one (image, head) pair by one warp, single pass (online softmax).
+// Lane (g = lane>>2, c = lane&3) handles keys j = g (mod 8) and head dims [8c, 8c+8).
+// K/V rows are 32 bf16 (64 B), contiguous over keys -> each warp load covers 512
+// contiguous bytes; 4 K rows + 4 V rows are in flight per lane before any math.
+// Every lane group keeps its own running (max, sum, acc) and the 8 groups are
+// merged with shuffles at the end.  All lanes return the 8 output dims [8c, 8c+8).
 __device__ __forceinline__ void attend_pair(const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
                                             const __nv_bfloat16* __restrict__ Vc, int n_hist,
-                                            const float* __restrict__ kx, const float* __restrict__ vx,
-                                            float* __restrict__ sc, float temperature, float (&o)[8]) {
+                                            const __nv_bfloat16* __restrict__ kx,
+                                            const __nv_bfloat16* __restrict__ vx, float inv_temp,
+                                            float (&o)[8]) {
   const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   float qv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) qv[i] = q[c * 8 + i];
-  const int nk = n_hist + (kx ? 1 : 0);
-  float mx = -INFINITY;
-  // ---- scores --------------------------------------------------------------
-#pragma unroll 4
-  for (int j0 = 0; j0 < n_hist; j0 += 8) {
-    const int j = j0 + g;
-    float part = 0.f;
-    if (j < n_hist) {
-      float kf[8];
-      unpack8(ldg_stream(Kc + (size_t)j * HD + c * 8), kf);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) part = fmaf(qv[i], kf[i], part);
-    }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    const float sv = part / temperature;
-    if (j < n_hist) {
-      if (c == 0) sc[j] = sv;
-      mx = fmaxf(mx, sv);
-    }
-  }
-  if (kx) {
-    float part = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) part = fmaf(qv[i], kx[c * 8 + i], part);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    const float sv = part / temperature;
-    if (lane == 0) sc[n_hist] = sv;
-    mx = fmaxf(mx, sv);
-  }
-  mx = warp_max(mx);
-  __syncwarp();
-  float sum = 0.f;
-  for (int j = lane; j < nk; j += 32) {
-    float e = expf(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-  // ---- P.V -------------------------------------------------------------------
-  float acc[8];
+  float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 4
-  for (int j0 = 0; j0 < n_hist; j0 += 8) {
-    const int j = j0 + g;
-    if (j < n_hist) {
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int j0 = 0; j0 < n_hist; j0 += 32) {
+    uint4 kk[4], vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 8 + g;
+      kk[u] = j < n_hist ? ldg_stream(Kc + (size_t)j * HD + c * 8) : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 8 + g;
+      vv[u] = j < n_hist ? ldg_stream(Vc + (size_t)j * HD + c * 8) : zero;
+    }
+    float sv[4];
+    float cm = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float kf[8];
+      unpack8(kk[u], kf);
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part = fmaf(qv[i], kf[i], part);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      sv[u] = (j0 + u * 8 + g < n_hist) ? part * inv_temp : -INFINITY;
+      cm = fmaxf(cm, sv[u]);
+    }
+    const float scale = (m == -INFINITY) ? 0.f : __expf(m - cm);
+    l *= scale;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= scale;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float pj = (sv[u] == -INFINITY) ? 0.f : __expf(sv[u] - cm);
       float vf[8];
-      unpack8(ldg_stream(Vc + (size_t)j * HD + c * 8), vf);
-      const float pj = sc[j] / sum;
+      unpack8(vv[u], vf);
+      l += pj;
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, vf[i], acc[i]);
     }
+    m = cm;
   }
+  // ---- merge the 8 lane groups (+ the current key) --------------------------------
+  float M = m;
+  M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 4));
+  M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 8));
+  M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
+  float s_cur = -INFINITY;
+  float vcur[8];
+  if (kx) {
+    float kf[8];
+    unpack8(*reinterpret_cast<const uint4*>(kx + c * 8), kf);
+    unpack8(*reinterpret_cast<const uint4*>(vx + c * 8), vcur);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part = fmaf(qv[i], kf[i], part);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    s_cur = part * inv_temp;
+    M = fmaxf(M, s_cur);
+  }
+  const float gs = (m == -INFINITY) ? 0.f : __expf(m - M);
+  l *= gs;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= gs;
+  l += __shfl_xor_sync(0xffffffffu, l, 4);
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
   }
-  if (vx) {
-    const float pj = sc[n_hist] / sum;
+  if (kx) {
+    const float pc = __expf(s_cur - M);
+    l += pc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, vx[c * 8 + i], acc[i]);
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pc, vcur[i], acc[i]);
   }
+  const float inv = __fdividef(1.f, l);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = acc[i];
-  __syncwarp();
+  for (int i = 0; i < 8; ++i) o[i] = acc[i] * inv;
 }
 
 }  // namespace
@@ -319,19 +352,24 @@ __device__ __forceinline__ void attend_pair(const float* __restrict__ q, const _
 // ===========================================================================
 // The persistent decode kernel
 // ===========================================================================
-__global__ void __cluster_dims__(DEC_CLUSTER, 1, 1) __launch_bounds__(256, 1)
+template <int NIMG>
+__global__ void __cluster_dims__(DEC_CLUSTER, 1, 1) __launch_bounds__(256, 2)
 dec_cluster_bf16_kernel(const DecClusterP p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   cg::cluster_group cl = cg::this_cluster();
   const int r = (int)cl.block_rank();
-  const int img0 = (blockIdx.x / CL) * IMG;  // first image of this cluster
+  const int img0 = (blockIdx.x / CL) * NIMG;  // first image of this cluster
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint64_t pol = make_evict_last_policy();
-  const float temperature = sqrtf((float)D);
+  const float inv_temp = 1.f / sqrtf((float)D);  // D = 256: exact reciprocal of 16
   const float emb_scale = sqrtf((float)D);
   const int L = p.L, T = p.T, V = p.V, B = p.B;
 
+  if (tid == 0) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) s.lw[l] = p.layer[l];
+  }
   // ---- step 0 input: <SOS> embedding + position 0 --------------------------------
   for (int i = tid; i < IMG * D; i += NTHR) {
     const int row = i / D, c = i % D;
@@ -342,32 +380,53 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
   __syncthreads();
   cl.sync();  // every CTA of the cluster is resident before the first remote store
 
+  const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+  if (profiling) for (int i = 0; i < 16; ++i) s.prof[i] = 0;
+  long long tprev = clock64();
+  auto mark = [&](int id) {
+    if (profiling) {
+      long long now = clock64();
+      s.prof[id] += now - tprev;
+      tprev = now;
+    }
+  };
   for (int t = 0; t < p.steps; ++t) {
     for (int l = 0; l < L; ++l) {
-      const DecClusterLayer& W = p.layer[l];
+      const DecClusterLayer& W = s.lw[l];
       // ---- S1 (layer 0 only): q | k | v of the embedded input -------------------------
       if (l == 0) {
         const uint4* wp = p.w_first + (size_t)r * 12 * (D / 32) * 32;
         gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, wp, [&](int tile, float (&c)[4], int ln) {
-          const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2;
+          const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
           const float b0 = __ldg(p.b_first + col), b1 = __ldg(p.b_first + col + 1);
-          ag_store_f2(cl, &s.qkv[ln >> 2][col], c[0] + b0, c[1] + b1);
-          ag_store_f2(cl, &s.qkv[(ln >> 2) + 8][col], c[2] + b0, c[3] + b1);
+          if (seg == 0) {
+            ag_store_f2(cl, &s.q[row][col], c[0] + b0, c[1] + b1);
+            if (NIMG == 16) {
+            ag_store_f2(cl, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
+            }
+          } else {
+            ag_store_u32(cl, &s.kv[row][col - D], pack_bf16(c[0] + b0, c[1] + b1));
+            if (NIMG == 16) {
+            ag_store_u32(cl, &s.kv[row + 8][col - D], pack_bf16(c[2] + b0, c[3] + b1));
+            }
+          }
         });
+        mark(0);
         cl.sync();
+        mark(1);
       }
       // ---- S2: self attention over t cached rows + the current input row ------------------
       {
 #pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-          const int pair = warp * 2 + pp;
-          const int li = r * 2 + (pair >> 3), hh = pair & 7;  // cluster-local image, head
+        for (int pp = 0; pp < NIMG / 8; ++pp) {
+          const int pair = warp * (NIMG / 8) + pp;
+          const int li = r * (NIMG / 8) + (pair >> 3), hh = pair & 7;  // cluster-local image, head
           const int b = img0 + li;
           float o[8];
           if (b < B) {
             const size_t base = ((((size_t)l * B + b) * H + hh) * T) * HD;
-            attend_pair(&s.qkv[li][hh * HD], p.kself + base, p.vself + base, t, &s.qkv[li][D + hh * HD],
-                        &s.qkv[li][2 * D + hh * HD], s.sc[warp], temperature, o);
+            attend_pair(&s.q[li][hh * HD], p.kself + base, p.vself + base, t, &s.kv[li][hh * HD],
+                        &s.kv[li][D + hh * HD], inv_temp, o);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -377,7 +436,9 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
             ag_store_u4(cl, &s.abf[li][hh * HD + (lane & 3) * 8], v);
           }
         }
+        mark(2);
         cl.sync();
+        mark(3);
       }
       // ---- S3: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
       gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o + (size_t)r * 4 * (D / 32) * 32,
@@ -385,33 +446,42 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_o + col), b1 = __ldg(W.b_o + col + 1);
                          ag_store_f2(cl, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
+                         if (NIMG == 16) {
                          ag_store_f2(cl, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
                                      c[3] + b1 + s.xres[row + 8][col + 1]);
+                         }
                        });
+      mark(4);
+      const LnParams lnp1 = load_ln(W.ln1_g, W.ln1_b);
       cl.sync();
-      layernorm_rows(s, W.ln1_g, W.ln1_b);
+      mark(5);
+      layernorm_rows<NIMG>(s, lnp1);
       __syncthreads();
+      mark(6);
       // ---- S4: q2 = q_linear(u) ---------------------------------------------------------------
       gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_q2 + (size_t)r * 4 * (D / 32) * 32,
                        [&](int tile, float (&c)[4], int ln) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_q2 + col), b1 = __ldg(W.b_q2 + col + 1);
-                         ag_store_f2(cl, &s.qkv[row][col], c[0] + b0, c[1] + b1);
-                         ag_store_f2(cl, &s.qkv[row + 8][col], c[2] + b0, c[3] + b1);
+                         ag_store_f2(cl, &s.q[row][col], c[0] + b0, c[1] + b1);
+                         if (NIMG == 16) {
+                         ag_store_f2(cl, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
+                         }
                        });
+      mark(4);
       cl.sync();
+      mark(5);
       // ---- S5: cross attention over the S memory tokens --------------------------------------------
       {
 #pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-          const int pair = warp * 2 + pp;
-          const int li = r * 2 + (pair >> 3), hh = pair & 7;
+        for (int pp = 0; pp < NIMG / 8; ++pp) {
+          const int pair = warp * (NIMG / 8) + pp;
+          const int li = r * (NIMG / 8) + (pair >> 3), hh = pair & 7;
           const int b = img0 + li;
           float o[8];
           if (b < B) {
             const size_t base = ((((size_t)l * B + b) * H + hh) * p.S) * HD;
-            attend_pair(&s.qkv[li][hh * HD], p.kcross + base, p.vcross + base, p.S, nullptr, nullptr, s.sc[warp],
-                        temperature, o);
+            attend_pair(&s.q[li][hh * HD], p.kcross + base, p.vcross + base, p.S, nullptr, nullptr, inv_temp, o);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -421,7 +491,9 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
             ag_store_u4(cl, &s.abf[li][hh * HD + (lane & 3) * 8], v);
           }
         }
+        mark(7);
         cl.sync();
+        mark(3);
       }
       // ---- S6: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
       gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o2 + (size_t)r * 4 * (D / 32) * 32,
@@ -429,21 +501,31 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_o2 + col), b1 = __ldg(W.b_o2 + col + 1);
                          ag_store_f2(cl, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
+                         if (NIMG == 16) {
                          ag_store_f2(cl, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
                                      c[3] + b1 + s.xres[row + 8][col + 1]);
+                         }
                        });
+      mark(4);
+      const LnParams lnp2 = load_ln(W.ln2_g, W.ln2_b);
       cl.sync();
-      layernorm_rows(s, W.ln2_g, W.ln2_b);
+      mark(5);
+      layernorm_rows<NIMG>(s, lnp2);
       __syncthreads();
+      mark(6);
       // ---- S7: ff = relu(linear0(w))  (F = 4 segments of D columns) --------------------------------
       gemm_stage<D, 16>(s, pol, &s.abf[0][0], D + APAD, W.w_f0 + (size_t)r * 16 * (D / 32) * 32,
                         [&](int tile, float (&c)[4], int ln) {
                           const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
                           const float b0 = __ldg(W.b_f0 + col), b1 = __ldg(W.b_f0 + col + 1);
                           ag_store_u32(cl, &s.abf2[row][col], pack_bf16(fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f)));
+                          if (NIMG == 16) {
                           ag_store_u32(cl, &s.abf2[row + 8][col], pack_bf16(fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f)));
+                          }
                         });
+      mark(8);
       cl.sync();
+      mark(5);
       // ---- S8: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
       gemm_stage<DEC_FMAX, 4>(s, pol, &s.abf2[0][0], DEC_FMAX + APAD, W.w_f1 + (size_t)r * 4 * (DEC_FMAX / 32) * 32,
                               [&](int tile, float (&c)[4], int ln) {
@@ -451,12 +533,18 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                                 const float b0 = __ldg(W.b_f1 + col), b1 = __ldg(W.b_f1 + col + 1);
                                 ag_store_f2(cl, &s.pre[row][col], fmaxf(c[0] + b0, 0.f) + s.xres[row][col],
                                             fmaxf(c[1] + b1, 0.f) + s.xres[row][col + 1]);
+                                if (NIMG == 16) {
                                 ag_store_f2(cl, &s.pre[row + 8][col], fmaxf(c[2] + b0, 0.f) + s.xres[row + 8][col],
                                             fmaxf(c[3] + b1, 0.f) + s.xres[row + 8][col + 1]);
+                                }
                               });
+      mark(9);
+      const LnParams lnp3 = load_ln(W.ln3_g, W.ln3_b);
       cl.sync();
-      layernorm_rows(s, W.ln3_g, W.ln3_b);
+      mark(5);
+      layernorm_rows<NIMG>(s, lnp3);
       __syncthreads();
+      mark(6);
       // ---- S9: K/V rows of y -> cache; next layer's q|k|v, or the vocabulary logits -------------------
       auto kv_store = [&](int tile, float (&c)[4], int ln) {
         // tiles 0..3: K columns of head r; tiles 4..7: V columns of head r
@@ -465,7 +553,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
         const float b0 = __ldg(bias), b1 = __ldg(bias + 1);
         __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
 #pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
+        for (int hrow = 0; hrow < NIMG / 8; ++hrow) {
           const int b = img0 + row + hrow * 8;
           if (b < B) {
             const size_t off = (((((size_t)l * B + b) * H + r) * T) + t) * HD + dcol;
@@ -480,8 +568,17 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                             const int seg = tile >> 2;  // 2,3,4 -> q,k,v of layer l+1
                             const int col = (seg - 2) * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
                             const float b0 = __ldg(W.b_next + 2 * D + col), b1 = __ldg(W.b_next + 2 * D + col + 1);
-                            ag_store_f2(cl, &s.qkv[row][col], c[0] + b0, c[1] + b1);
-                            ag_store_f2(cl, &s.qkv[row + 8][col], c[2] + b0, c[3] + b1);
+                            if (seg == 2) {
+                              ag_store_f2(cl, &s.q[row][col], c[0] + b0, c[1] + b1);
+                              if (NIMG == 16) {
+                              ag_store_f2(cl, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
+                              }
+                            } else {
+                              ag_store_u32(cl, &s.kv[row][col - D], pack_bf16(c[0] + b0, c[1] + b1));
+                              if (NIMG == 16) {
+                              ag_store_u32(cl, &s.kv[row + 8][col - D], pack_bf16(c[2] + b0, c[3] + b1));
+                              }
+                            }
                           });
       } else {
         // generator: V columns padded to 256; CTA r owns columns [32r, 32r+32) (tiles 8..11)
@@ -492,8 +589,10 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                             const float b0 = col < V ? __ldg(W.b_next + 2 * D + col) : 0.f;
                             const float b1 = col + 1 < V ? __ldg(W.b_next + 2 * D + col + 1) : 0.f;
                             const float v00 = c[0] + b0, v01 = c[1] + b1, v10 = c[2] + b0, v11 = c[3] + b1;
-                            ag_store_f2(cl, &s.qkv[row][col], v00, v01);
-                            ag_store_f2(cl, &s.qkv[row + 8][col], v10, v11);
+                            ag_store_f2(cl, &s.q[row][col], v00, v01);
+                            if (NIMG == 16) {
+                            ag_store_f2(cl, &s.q[row + 8][col], v10, v11);
+                            }
                             if (p.logits) {
                               const int bA = img0 + row, bB = img0 + row + 8;
                               if (bA < B) {
@@ -501,7 +600,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                                 if (col < V) lp[col] = v00;
                                 if (col + 1 < V) lp[col + 1] = v01;
                               }
-                              if (bB < B) {
+                              if (NIMG == 16 && bB < B) {
                                 float* lp = p.logits + ((size_t)bB * p.steps + t) * V;
                                 if (col < V) lp[col] = v10;
                                 if (col + 1 < V) lp[col + 1] = v11;
@@ -509,16 +608,18 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                             }
                           });
       }
+      mark(10);
       cl.sync();
+      mark(5);
     }  // layers
     // ---- greedy pick (first max index) + next input: every CTA does all 16 rows -------------------------
 #pragma unroll
-    for (int rr = 0; rr < IMG / 8; ++rr) {
-      const int row = warp * (IMG / 8) + rr;
+    for (int rr = 0; rr < NIMG / 8; ++rr) {
+      const int row = warp * (NIMG / 8) + rr;
       float best = -INFINITY;
       int bi = 0x7fffffff;
       for (int i = lane; i < V; i += 32) {
-        float v = s.qkv[row][i];
+        float v = s.q[row][i];
         if (v > best) { best = v; bi = i; }
       }
 #pragma unroll
@@ -546,25 +647,49 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       }
     }
     __syncthreads();
+    mark(11);
     // the next step's first remote stores (S1 -> qkv) must not overtake a peer that is still
     // reading the logits out of its qkv buffer
     cl.sync();
+    mark(5);
   }
+  if (profiling) for (int i = 0; i < 16; ++i) p.prof[i] = s.prof[i];
 }
 
 size_t dec_cluster_smem_bytes() { return sizeof(Smem); }
 
-int launch_dec_cluster_bf16(const DecClusterP& p, cudaStream_t st) {
+template <int NIMG>
+static int launch_variant(const DecClusterP& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dec_cluster_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(dec_cluster_bf16_kernel<NIMG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int clusters = (p.B + IMG - 1) / IMG;
-  dec_cluster_bf16_kernel<<<clusters * CL, NTHR, sizeof(Smem), st>>>(p);
+  const int clusters = (p.B + NIMG - 1) / NIMG;
+  if (getenv("FRX_DEBUG")) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = sizeof(Smem);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, dec_cluster_bf16_kernel<NIMG>, &cfg);
+    fprintf(stderr, "[frx] decode kernel: %d clusters of %d CTAs requested, max co-resident clusters = %d (%s), smem %zu B\n",
+            clusters, CL, n, cudaGetErrorString(e), sizeof(Smem));
+  }
+  dec_cluster_bf16_kernel<NIMG><<<clusters * CL, NTHR, sizeof(Smem), st>>>(p);
   return 0;
+}
+
+// 8 images per cluster while all clusters can be co-resident (two CTAs per SM: the
+// second CTA's latency chains fill the first one's stalls); 16 per cluster beyond.
+int launch_dec_cluster_bf16(const DecClusterP& p, int images_per_cluster, cudaStream_t st) {
+  int n = images_per_cluster;
+  if (n == 0) n = (p.B + 7) / 8 <= DEC_MAX_CLUSTERS_8 ? 8 : 16;
+  return n == 8 ? launch_variant<8>(p, st) : launch_variant<16>(p, st);
 }
 
 // ===========================================================================

@@ -225,6 +225,11 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   if (k == "taps") h->opt_taps = value != 0;
   else if (k == "graphs") h->opt_graphs = value != 0;
   else if (k == "timing") h->opt_timing = value != 0;
+  else if (k == "cluster_images") h->opt_cluster_images = (value == 8 || value == 16) ? (int)value : 0;
+  else if (k == "prof") {
+    h->opt_prof = value != 0;
+    if (h->opt_prof && !h->prof) { void* p; if (dev_alloc(h, &p, 16 * 8)) return 1; h->prof = (long long*)p; }
+  }
   else if (k == "parts") { h->opt_parts = (int)value & 3; h->finalized = false; }
   else return fail(h, "unknown option '%s'", key);
   return 0;
@@ -232,6 +237,12 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
 
 extern "C" int64_t frx_launch_count(const frx_handle* h) { return h ? h->launches : 0; }
 extern "C" int64_t frx_device_bytes(const frx_handle* h) { return h ? h->device_bytes : 0; }
+
+extern "C" int frx_read_prof(frx_handle* h, int64_t* out16) {
+  if (!h || !out16 || !h->prof) return fail(h, "profiling not enabled (frx_set_option(h, \"prof\", 1))");
+  CK(cudaMemcpy(out16, h->prof, 16 * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 extern "C" int frx_last_timing(const frx_handle* h, float* ms3) {
   if (!h || !ms3) return 1;
@@ -946,7 +957,9 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
   p.kself = (__nv_bfloat16*)h->kself_bf; p.vself = (__nv_bfloat16*)h->vself_bf;
   p.kcross = (const __nv_bfloat16*)h->kcross_bf; p.vcross = (const __nv_bfloat16*)h->vcross_bf;
   p.logits = logits; p.tokens = tokens; p.forced = forced;
-  int rc = launch_dec_cluster_bf16(p, st);
+  p.prof = h->opt_prof ? h->prof : nullptr;
+  if (p.prof) CK(cudaMemsetAsync(h->prof, 0, 16 * 8, st));
+  int rc = launch_dec_cluster_bf16(p, h->opt_cluster_images, st);
   if (rc) return fail(h, "decode cluster kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
   CKL();
   return 0;

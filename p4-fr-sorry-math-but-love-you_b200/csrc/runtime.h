@@ -50,6 +50,9 @@ struct frx_handle {
   std::map<std::string, HostTensor> raw;
   bool finalized = false, ws_ready = false;
   bool opt_taps = false, opt_graphs = true, opt_timing = false;
+  bool opt_prof = false;
+  int opt_cluster_images = 0;  // 0 = auto
+  long long* prof = nullptr;
   int opt_parts = 3;  // bit0: encoder weights/workspaces, bit1: decoder
   int feat_h = 0, feat_w = 0;
   std::vector<void*> allocs;
