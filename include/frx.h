@@ -146,6 +146,14 @@ int frx_read_tap(frx_handle* h, const char* name, float* out, int64_t capacity, 
  * [1]=cross-KV + decode loop, [2]=total. */
 int frx_last_timing(const frx_handle* h, float* ms3);
 
+/* Test / micro-benchmark hook: the tcgen05 implicit-GEMM kernel on its own.
+ * C[M,N] = act((A * W^T) * scale + shift); A bf16 [M,K] (dense) or, when conv7 !=
+ * NULL, an NHWC bf16 activation gathered as a k x k convolution with conv7 =
+ * {B, H, W, Cin, k, stride, tf_same_padding}; W bf16 [N,K]; C bf16 or fp32. */
+int frx_tc_gemm(frx_handle* h, const void* A, const void* W, void* C, int32_t M, int32_t N, int32_t K,
+                const int32_t* conv7, const float* scale, const float* shift, int32_t act, int32_t out_f32,
+                void* stream);
+
 /* Per-stage SM-cycle totals of the last bf16 decode kernel (option "prof" = 1;
  * recorded by one thread of cluster 0): 16 counters, see DESIGN.md. */
 int frx_read_prof(frx_handle* h, int64_t* out16);

@@ -12,7 +12,7 @@ SYMBOLS = [
     "frx_finalize_weights", "frx_encode", "frx_decode_greedy", "frx_forward_greedy",
     "frx_forward_greedy_host", "frx_decode_begin", "frx_decode_step", "frx_beam_search",
     "frx_decode_teacher_forced", "frx_launch_count", "frx_device_bytes", "frx_set_option",
-    "frx_read_tap", "frx_last_timing", "frx_read_prof",
+    "frx_read_tap", "frx_last_timing", "frx_read_prof", "frx_tc_gemm",
 ]
 
 
@@ -65,6 +65,7 @@ def load_library():
     lib.frx_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.frx_read_tap.argtypes = [vp, ctypes.c_char_p, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i32), vp]
     lib.frx_read_prof.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.frx_tc_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, ctypes.POINTER(i32), vp, vp, i32, i32, vp]
     lib.frx_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     _LIB = lib
     return lib

@@ -108,6 +108,21 @@ struct AttnP {
 };
 
 
+// tcgen05 implicit GEMM (kernels_tc.cu):  C[M,N] = epi( A[M,K] * W[N,K]^T ), bf16 operands
+struct TcGemmP {
+  const __nv_bfloat16* A;   // dense [M, lda] or NHWC activation (conv = 1)
+  const __nv_bfloat16* W;   // [N, ldw], K contiguous (conv K index = (kh*KW+kw)*Cin + ci)
+  void* C;                  // bf16 or fp32 [M, ldc]
+  int M, N, K, lda, ldw, ldc;
+  int BN;                   // N tile (multiple of 16, <= 256); 0 = choose
+  int conv, H, Wd, Cin, OH, OW, KW, stride, pad_t, pad_l;
+  const float* scale;       // per-N folded BatchNorm (v*scale + shift) or nullptr
+  const float* shift;       // per-N bias when scale == nullptr
+  int act;
+  const void* res;          // residual added after the activation ([M, ldr], bf16 or fp32)
+  int res_f32, ldr, out_f32;
+};
+
 // ---------------------------------------------------------------------------
 // bf16 persistent decode kernel (kernels_decode_bf16.cu)
 // ---------------------------------------------------------------------------

@@ -29,6 +29,20 @@ void launch_dec_argmax_embed(const float* logits, long long ld_logits, int V, lo
                              cudaStream_t st);
 
 
+// tcgen05 implicit GEMM + bf16 trunk kernels (kernels_tc.cu, kernels_bf16.cu)
+int launch_tc_igemm(TcGemmP p, cudaStream_t st);
+void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
+void launch_stem_conv_bf16(const float* in, const float* w, const float* scale, const float* shift,
+                           __nv_bfloat16* out, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st);
+void launch_dwconv_bf16(const __nv_bfloat16* in, const float* w, const float* scale, const float* shift,
+                        __nv_bfloat16* out, int B, int H, int W, int C, int OH, int OW, int stride, int pad_t,
+                        int pad_l, int act, cudaStream_t st);
+void launch_se_scale_bf16(__nv_bfloat16* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                          int B, int HW, int C, int R, cudaStream_t st);
+void launch_layernorm_bf16out(const float* x, const float* res, const float* gamma, const float* beta,
+                              __nv_bfloat16* out, int M, int C, int scramble_S, cudaStream_t st);
+void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st);
+
 // bf16 persistent decode (kernels_decode_bf16.cu)
 size_t dec_cluster_smem_bytes();
 int launch_dec_cluster_bf16(const DecClusterP& p, int images_per_cluster, cudaStream_t st);

@@ -1,0 +1,181 @@
+// kernels_bf16.cu -- bandwidth-bound kernels of the bf16 trunk (NHWC bf16
+// activations, fp32 arithmetic): stem conv, depthwise 3x3, squeeze-excite.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace frx {
+
+namespace {
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+}  // namespace
+
+// Stem: conv3x3 s2 p0 + BN + SiLU (EfficientSATRN.py:67-73,:82-83); NCHW fp32 in, NHWC bf16 out.
+// One thread per output pixel x 8 channels (16-byte store).
+__global__ void __launch_bounds__(256) stem_conv_bf16_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             __nv_bfloat16* __restrict__ out, int B, int Cin, int H, int W,
+                                                             int OH, int OW, int Cout) {
+  extern __shared__ float ws[];
+  for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) ws[i] = w[i];
+  float* ssc = ws + Cout * Cin * 9;
+  float* ssh = ssc + Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+  __syncthreads();
+  const int C8 = Cout / 8;
+  long long total = (long long)B * OH * OW * C8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co0 = (int)(idx % C8) * 8;
+  long long pix = idx / C8;
+  const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* ip = in + (((long long)n * Cin + ci) * H + oh * 2) * W + ow * 2;
+    float x[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) x[kh * 3 + kw] = __ldg(ip + kh * W + kw);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wp = ws + ((co0 + j) * Cin + ci) * 9;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[j] = fmaf(x[t], wp[t], acc[j]);
+    }
+  }
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = act_apply(acc[j] * ssc[co0 + j] + ssh[co0 + j], ACT_SILU);
+  *reinterpret_cast<uint4*>(out + pix * Cout + co0) = pack8(o);
+}
+
+void launch_stem_conv_bf16(const float* in, const float* w, const float* scale, const float* shift,
+                           __nv_bfloat16* out, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st) {
+  long long total = (long long)B * OH * OW * (Cout / 8);
+  int smem = (Cout * Cin * 9 + 2 * Cout) * sizeof(float);
+  stem_conv_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(in, w, scale, shift, out, B, Cin, H, W, OH, OW, Cout);
+}
+
+// Depthwise 3x3 + folded BN (+bias) + activation; 8 channels (16 bytes) per thread.
+__global__ void __launch_bounds__(256) dwconv3x3_bf16_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, int OH,
+                                                             int OW, int stride, int pad_t, int pad_l, int act) {
+  const int C8 = C >> 3;
+  long long total = (long long)B * OH * OW * C8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C8) * 8;
+  long long pix = idx / C8;
+  const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = oh * stride - pad_t + kh;
+    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = ow * stride - pad_l + kw;
+      if (iw < 0 || iw >= W) continue;
+      float x[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((long long)n * H + ih) * W + iw) * C + c)), x);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C + c + 4));
+      acc[0] = fmaf(x[0], w0.x, acc[0]); acc[1] = fmaf(x[1], w0.y, acc[1]);
+      acc[2] = fmaf(x[2], w0.z, acc[2]); acc[3] = fmaf(x[3], w0.w, acc[3]);
+      acc[4] = fmaf(x[4], w1.x, acc[4]); acc[5] = fmaf(x[5], w1.y, acc[5]);
+      acc[6] = fmaf(x[6], w1.z, acc[6]); acc[7] = fmaf(x[7], w1.w, acc[7]);
+    }
+  }
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = act_apply(acc[j] * __ldg(scale + c + j) + __ldg(shift + c + j), act);
+  *reinterpret_cast<uint4*>(out + pix * C + c) = pack8(o);
+}
+
+void launch_dwconv_bf16(const __nv_bfloat16* in, const float* w, const float* scale, const float* shift,
+                        __nv_bfloat16* out, int B, int H, int W, int C, int OH, int OW, int stride, int pad_t,
+                        int pad_l, int act, cudaStream_t st) {
+  long long total = (long long)B * OH * OW * (C / 8);
+  dwconv3x3_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, w, scale, shift, out, B, H, W, C, OH, OW,
+                                                                        stride, pad_t, pad_l, act);
+}
+
+// Squeeze-excite, one CTA per image: gate = sigmoid(W2 silu(W1 mean_hw(x) + b1) + b2), then x *= gate
+// in place (so the following 1x1 projection is a plain tcgen05 GEMM).  Deterministic (no atomics).
+__global__ void __launch_bounds__(256) se_scale_bf16_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ w1,
+                                                            const float* __restrict__ b1, const float* __restrict__ w2,
+                                                            const float* __restrict__ b2, int HW, int C, int R) {
+  extern __shared__ float sm[];
+  float* mean = sm;       // C
+  float* red = sm + C;    // R
+  float* gate = red + R;  // C
+  const int n = blockIdx.x;
+  __nv_bfloat16* xp = x + (long long)n * HW * C;
+  const float inv = 1.f / (float)HW;
+  for (int c8 = threadIdx.x; c8 < C / 8; c8 += blockDim.x) {
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (int q = 0; q < HW; ++q) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(xp + (long long)q * C + c8 * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mean[c8 * 8 + j] = s[j] * inv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += 8) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w1 + (long long)r * C + c), mean[c], s);
+    s = warp_sum(s);
+    if (lane == 0) red[r] = act_apply(s + __ldg(b1 + r), ACT_SILU);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = __ldg(b2 + c);
+    const float* wr = w2 + (long long)c * R;
+    for (int r = 0; r < R; ++r) s = fmaf(__ldg(wr + r), red[r], s);
+    gate[c] = 1.f / (1.f + expf(-s));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW * (C / 8); i += blockDim.x) {
+    const int c8 = i % (C / 8);
+    uint4* ptr = reinterpret_cast<uint4*>(xp + (long long)(i / (C / 8)) * C + c8 * 8);
+    float v[8];
+    unpack8(*ptr, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= gate[c8 * 8 + j];
+    *ptr = pack8(v);
+  }
+}
+
+void launch_se_scale_bf16(__nv_bfloat16* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                          int B, int HW, int C, int R, cudaStream_t st) {
+  se_scale_bf16_kernel<<<B, 256, (2 * C + R) * sizeof(float), st>>>(x, w1, b1, w2, b2, HW, C, R);
+}
+
+}  // namespace frx

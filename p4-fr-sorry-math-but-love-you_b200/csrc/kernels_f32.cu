@@ -420,11 +420,15 @@ void launch_pe2d_f32(const float* x, const float* w0, const float* b0, const flo
 //    SURVEY F4) in NHWC terms: flat index f = q*C + ch of image b is written to
 //    pixel p = f % S, channel c' = f / S.
 // ===========================================================================
+__device__ __forceinline__ void store_as(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_as(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename OutT>
 __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restrict__ x,
                                                             const float* __restrict__ res,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
-                                                            float* __restrict__ out, int M, int C,
+                                                            OutT* __restrict__ out, int M, int C,
                                                             int scramble_S) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + warp;
@@ -458,9 +462,9 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
         int b = m / scramble_S, qd = m % scramble_S;
         long long f = (long long)qd * C + ch;
         int pp = (int)(f % scramble_S), cc = (int)(f / scramble_S);
-        out[((long long)b * scramble_S + pp) * C + cc] = o;
+        store_as(out + ((long long)b * scramble_S + pp) * C + cc, o);
       } else {
-        out[(long long)m * C + ch] = o;
+        store_as(out + (long long)m * C + ch, o);
       }
     }
   }
@@ -468,15 +472,21 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
 
 void launch_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta,
                           float* out, int M, int C, int scramble_S, cudaStream_t st) {
-  layernorm_f32_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+  layernorm_f32_kernel<float><<<(M + 7) / 8, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+}
+
+void launch_layernorm_bf16out(const float* x, const float* res, const float* gamma, const float* beta,
+                              __nv_bfloat16* out, int M, int C, int scramble_S, cudaStream_t st) {
+  layernorm_f32_kernel<__nv_bfloat16><<<(M + 7) / 8, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
 }
 
 // ===========================================================================
 // 8. Encoder self-attention (:164-172,:198-228): one CTA per (image, head);
 //    S tokens x HD=64; scores divided by sqrt(heads*HD).
 // ===========================================================================
+template <typename OutT>
 __global__ void __launch_bounds__(128) enc_attn_f32_kernel(const float* __restrict__ qkv,  // [B*S, 3*D]
-                                                           float* __restrict__ out,       // [B*S, D]
+                                                           OutT* __restrict__ out,        // [B*S, D]
                                                            int S, int D, int heads, float temperature) {
   extern __shared__ float sm[];
   const int HD = D / heads;  // 64
@@ -518,21 +528,28 @@ __global__ void __launch_bounds__(128) enc_attn_f32_kernel(const float* __restri
     for (int c = lane; c < HD; c += 32) {
       float acc = 0.f;
       for (int j = 0; j < S; ++j) acc = fmaf(Pw[j] / sum, V[j * LDS_ + c], acc);
-      out[((long long)b * S + i) * D + hh * HD + c] = acc;
+      store_as(out + ((long long)b * S + i) * D + hh * HD + c, acc);
     }
     __syncwarp();
   }
 }
 
-void launch_enc_attn_f32(const float* qkv, float* out, int B, int S, int D, int heads, cudaStream_t st) {
+template <typename OutT>
+static void enc_attn_launch(const float* qkv, OutT* out, int B, int S, int D, int heads, cudaStream_t st) {
   int HD = D / heads;
   size_t smem = (size_t)(3 * S * (HD + 1) + 4 * S) * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(enc_attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(enc_attn_f32_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  enc_attn_f32_kernel<<<B * heads, 128, smem, st>>>(qkv, out, S, D, heads, sqrtf((float)D));
+  enc_attn_f32_kernel<OutT><<<B * heads, 128, smem, st>>>(qkv, out, S, D, heads, sqrtf((float)D));
+}
+void launch_enc_attn_f32(const float* qkv, float* out, int B, int S, int D, int heads, cudaStream_t st) {
+  enc_attn_launch<float>(qkv, out, B, S, D, heads, st);
+}
+void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st) {
+  enc_attn_launch<__nv_bfloat16>(qkv, out, B, S, D, heads, st);
 }
 
 // ===========================================================================

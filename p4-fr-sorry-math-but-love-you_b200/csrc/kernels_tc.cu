@@ -1,0 +1,357 @@
+// kernels_tc.cu -- tcgen05 (5th-gen tensor core) implicit-GEMM for the dense
+// contractions: the EfficientNetV2 trunk convolutions (3x3 as implicit GEMM, 1x1
+// as plain GEMM), the SATRN encoder projections / 1x1 convs, the cross-attention
+// K/V projection.
+//
+//   C[M, N] = epilogue( A[M, K] * W[N, K]^T )        bf16 operands, fp32 accumulate
+//
+// * A is either a dense row-major bf16 matrix or an NHWC bf16 activation that is
+//   gathered on the fly (k index = (kh*KW + kw)*Cin + ci, TF-"same"/explicit
+//   padding zero-filled) -- no im2col buffer ever touches HBM.
+// * Operand tiles (A: 128 x 64, W: BN x 64 bf16) are staged in shared memory in
+//   the canonical K-major SWIZZLE_128B UMMA layout by all 256 threads with 16-byte
+//   cp.async (zero-fill for padding / ragged edges), 3-stage ring.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16 x4 per stage) with
+//   the accumulator in TMEM; tcgen05.commit arrives on an mbarrier per stage so
+//   the ring slot can be refilled while later MMAs run.
+// * Epilogue: tcgen05.ld (32 lanes x 16 columns per warp instruction) -> folded
+//   BatchNorm / bias, activation, residual -> bf16 or fp32 store.
+//
+// Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor /
+// InstrDescriptor) of the CUTLASS tree vendored in this image.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace frx {
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_STAGES = 3;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// Bounded spin: a protocol bug traps (error returned to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  for (int spins = 0; spins < (1 << 24); ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups of 1024 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // layout type SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=BN.
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+}  // namespace
+
+template <int NCOLS>
+__global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
+  extern __shared__ unsigned char dyn_smem[];
+  __shared__ __align__(8) uint64_t mma_done[TC_STAGES];
+  __shared__ __align__(8) uint64_t acc_done;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN;
+  const uint32_t b_bytes = (uint32_t)BN * (TC_BK * 2);
+  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+  const uint32_t smem0 = (smem_u32(dyn_smem) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int KB = (p.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 32) {
+#pragma unroll
+    for (int s = 0; s < TC_STAGES; ++s) mbar_init(&mma_done[s], 1);
+    mbar_init(&acc_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  // ---- loader coordinates: thread -> 16-byte chunk c of rows rbase + 32*i ----------------
+  const int c = tid & 7, rbase = tid >> 3;
+  const __nv_bfloat16* a_ptr[4];
+  int a_ih0[4], a_iw0[4];
+  bool a_ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + rbase + 32 * i;
+    a_ok[i] = m < p.M;
+    a_ih0[i] = a_iw0[i] = 0;
+    a_ptr[i] = p.A;
+    if (a_ok[i]) {
+      if (p.conv) {
+        const int ow = m % p.OW;
+        const int t = m / p.OW;
+        const int oh = t % p.OH;
+        const int n = t / p.OH;
+        a_ptr[i] = p.A + (size_t)n * p.H * p.Wd * p.Cin;
+        a_ih0[i] = oh * p.stride - p.pad_t;
+        a_iw0[i] = ow * p.stride - p.pad_l;
+      } else {
+        a_ptr[i] = p.A + (size_t)m * p.lda;
+      }
+    }
+  }
+  const int nb_rows = (BN + 31) / 32;  // B rows handled per thread (<= 8)
+
+  auto load_stage = [&](int kb, int stage) {
+    const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
+    const uint32_t sb = sa + TC_A_BYTES;
+    const int k = kb * TC_BK + c * 8;
+    // A: 128 rows
+    int tap = 0, ci = k, kh = 0, kw = 0;
+    if (p.conv) {
+      tap = k / p.Cin;
+      ci = k - tap * p.Cin;
+      kh = tap / p.KW;
+      kw = tap - kh * p.KW;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = rbase + 32 * i;
+      const uint32_t dst = sa + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+      const __nv_bfloat16* src = p.A;
+      uint32_t bytes = 0;
+      if (a_ok[i] && k < p.K) {
+        if (p.conv) {
+          const int ih = a_ih0[i] + kh, iw = a_iw0[i] + kw;
+          if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) {
+            src = a_ptr[i] + ((size_t)ih * p.Wd + iw) * p.Cin + ci;
+            bytes = 16;
+          }
+        } else {
+          src = a_ptr[i] + k;
+          bytes = 16;
+        }
+      }
+      cp_async16(dst, src, bytes);
+    }
+    // B: BN rows of the weight matrix [N][ldw]
+    for (int j = 0; j < nb_rows; ++j) {
+      const int row = rbase + 32 * j;
+      if (row < BN) {
+        const uint32_t dst = sb + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+        const int n = n0 + row;
+        const bool ok = n < p.N && k < p.K;
+        cp_async16(dst, ok ? p.W + (size_t)n * p.ldw + k : p.W, ok ? 16u : 0u);
+      }
+    }
+  };
+
+  // ---- main loop --------------------------------------------------------------------------
+#pragma unroll
+  for (int s = 0; s < TC_STAGES - 1; ++s) {
+    if (s < KB) load_stage(s, s);
+    cp_async_commit();
+  }
+  const uint32_t idesc = make_idesc(BN);
+  for (int kb = 0; kb < KB; ++kb) {
+    cp_async_wait<TC_STAGES - 2>();                          // this thread's chunks of k-block kb have landed
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+    __syncthreads();
+    const int stage = kb % TC_STAGES;
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
+      const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + TC_A_BYTES);
+#pragma unroll
+      for (int j = 0; j < TC_BK / 16; ++j)  // +32 bytes (2 x 16-byte units) per K=16 step inside the swizzle atom
+        umma_bf16(tmem, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
+      umma_commit(&mma_done[stage]);
+      if (kb == KB - 1) umma_commit(&acc_done);
+    }
+    const int nk = kb + TC_STAGES - 1;
+    if (nk < KB) {
+      if (kb >= 1) mbar_wait(&mma_done[(kb - 1) % TC_STAGES], (uint32_t)(((kb - 1) / TC_STAGES) & 1));
+      load_stage(nk, nk % TC_STAGES);
+    }
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  mbar_wait(&acc_done, 0);
+  tc_fence_after();
+
+  // ---- epilogue: TMEM -> registers -> global ---------------------------------------------------
+  {
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    const bool m_ok = m < p.M;
+    for (int cc = (warp >> 2); cc * 16 < BN; cc += 2) {
+      uint32_t r[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 16), r);
+      const int nb = n0 + cc * 16;
+      if (m_ok && nb < p.N) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+      const bool full = nb + 16 <= p.N;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = nb + i;
+        if (full || n < p.N) {
+          if (p.scale) v[i] = v[i] * __ldg(p.scale + n) + __ldg(p.shift + n);
+          else if (p.shift) v[i] += __ldg(p.shift + n);
+          v[i] = act_apply(v[i], p.act);
+        }
+      }
+      if (p.res) {
+        if (p.res_f32) {
+          const float* rp = reinterpret_cast<const float*>(p.res) + (size_t)m * p.ldr + nb;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (full || nb + i < p.N) v[i] += __ldg(rp + i);
+        } else {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + (size_t)m * p.ldr + nb;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (full || nb + i < p.N) v[i] += __bfloat162float(rp[i]);
+        }
+      }
+      if (p.out_f32) {
+        float* cp = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + nb;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+          for (int i = 0; i < 16; ++i)
+            if (nb + i < p.N) cp[i] = v[i];
+        }
+      } else {
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + nb;
+        if (full) {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+          for (int i = 0; i < 16; ++i)
+            if (nb + i < p.N) cp[i] = __float2bfloat16_rn(v[i]);
+        }
+      }
+      }  // m_ok
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(NCOLS) : "memory");
+  }
+}
+
+static int tc_pick_bn(int N) {
+  if (N <= 256) return (N + 15) / 16 * 16;
+  // widest tile that divides N evenly into 16-column multiples, else 256 with a ragged last tile
+  for (int bn = 256; bn >= 128; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 256;
+}
+
+template <int NCOLS>
+static int tc_launch(const TcGemmP& p, cudaStream_t st) {
+  const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_igemm_kernel<NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + p.BN - 1) / p.BN);
+  tc_igemm_kernel<NCOLS><<<grid, 256, smem, st>>>(p);
+  return 0;
+}
+
+int launch_tc_igemm(TcGemmP p, cudaStream_t st) {
+  if (p.BN == 0) p.BN = tc_pick_bn(p.N);
+  if (p.BN <= 32) { p.BN = 32; return tc_launch<32>(p, st); }
+  if (p.BN <= 64) return tc_launch<64>(p, st);
+  if (p.BN <= 128) return tc_launch<128>(p, st);
+  return tc_launch<256>(p, st);
+}
+
+// ===========================================================================
+// small helpers of the bf16 path
+// ===========================================================================
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(in + i));
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  } else {
+    for (; i < n; ++i) out[i] = __float2bfloat16_rn(in[i]);
+  }
+}
+
+void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
+  f32_to_bf16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(in, out, n);
+}
+
+}  // namespace frx

@@ -226,6 +226,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   else if (k == "graphs") h->opt_graphs = value != 0;
   else if (k == "timing") h->opt_timing = value != 0;
   else if (k == "cluster_images") h->opt_cluster_images = (value == 8 || value == 16) ? (int)value : 0;
+  else if (k == "enc_fp32") h->opt_enc_fp32 = value != 0;
   else if (k == "prof") {
     h->opt_prof = value != 0;
     if (h->opt_prof && !h->prof) { void* p; if (dev_alloc(h, &p, 16 * 8)) return 1; h->prof = (long long*)p; }
@@ -510,6 +511,37 @@ static size_t pack_frag_stage(ArenaBuilder& ab, int NT, int K, F rowptr) {
   return off;
 }
 
+// bf16 copy of a packed fp32 [N][K] matrix that already lives in the arena (2 values per float slot)
+static size_t pack_bf16_copy(ArenaBuilder& ab, size_t src_off, size_t n) {
+  size_t off = ab.add(nullptr, (n + 1) / 2);
+  const float* s = ab.at(src_off);
+  uint16_t* d = reinterpret_cast<uint16_t*>(ab.at(off));
+  for (size_t i = 0; i < n; ++i) d[i] = (uint16_t)bf16_bits(s[i]);
+  return off;
+}
+
+static void pack_encoder_bf16(frx_handle* h, ArenaBuilder& ab) {
+  const frx_config& c = h->cfg;
+  for (BlockW& b : h->blocks) {
+    if (b.kind == 0) b.wb_a = pack_bf16_copy(ab, b.w_a, (size_t)b.cout * b.k * b.k * b.cin);
+    else if (b.kind == 1) {
+      b.wb_a = pack_bf16_copy(ab, b.w_a, (size_t)b.mid * b.k * b.k * b.cin);
+      b.wb_b = pack_bf16_copy(ab, b.w_b, (size_t)b.cout * b.mid);
+    } else {
+      b.wb_a = pack_bf16_copy(ab, b.w_a, (size_t)b.mid * b.cin);
+      b.wb_b = pack_bf16_copy(ab, b.w_b, (size_t)b.cout * b.mid);
+    }
+  }
+  const size_t C = c.enc_hidden, F = c.enc_filter;
+  h->last_wb = pack_bf16_copy(ab, h->last_w, C * 256);
+  for (EncLayerW& L : h->enc) {
+    L.wb_qkv = pack_bf16_copy(ab, L.w_qkv, 3 * C * C);
+    L.wb_o = pack_bf16_copy(ab, L.w_o, C * C);
+    L.wb_c0 = pack_bf16_copy(ab, L.w_c0, F * C);
+    L.wb_c1 = pack_bf16_copy(ab, L.w_c1, C * F);
+  }
+}
+
 static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
   const frx_config& c = h->cfg;
   const int D = c.dec_hidden, F = c.dec_filter, V = c.num_classes, L = c.dec_layers;
@@ -578,6 +610,10 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
   }
   if (want_dec && pack_decoder(h, ab)) return 1;
   if (want_dec && c.precision == FRX_PREC_BF16 && pack_decoder_bf16(h, ab)) return 1;
+  if (c.precision == FRX_PREC_BF16) {
+    if (want_enc && c.network == FRX_NET_EFFICIENT_SATRN) pack_encoder_bf16(h, ab);
+    if (want_dec) h->cross_wb = pack_bf16_copy(ab, h->w_cross, (size_t)c.dec_layers * 2 * c.dec_hidden * c.dec_src);
+  }
   // upload (re-finalize re-uses the arena when the size is unchanged)
   size_t bytes = ab.host.size() * sizeof(float);
   if (!h->arena || h->arena_bytes != bytes) {
@@ -638,6 +674,7 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
       if (dev_alloc(h, &p, L * B * T * D * 2)) return 1; h->vself_bf = p;
       if (dev_alloc(h, &p, L * B * S * D * 2)) return 1; h->kcross_bf = p;
       if (dev_alloc(h, &p, L * B * S * D * 2)) return 1; h->vcross_bf = p;
+      if (dev_alloc(h, &p, B * S * (size_t)c.dec_src * 2)) return 1; h->mem_bf = p;
     }
     }
     if (dev_alloc(h, &p, B * S * C * 4)) return 1; h->memory_int = (float*)p;
@@ -758,6 +795,118 @@ static int run_trunk_efficientnet(frx_handle* h, const float* images, int B, flo
   return 0;
 }
 
+static TcGemmP tc_dense(const void* A, int M, int K, const float* arena, size_t w_off, int N, void* C, int out_f32) {
+  TcGemmP g{};
+  g.A = (const __nv_bfloat16*)A; g.W = (const __nv_bfloat16*)(arena + w_off); g.C = C;
+  g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.out_f32 = out_f32;
+  return g;
+}
+
+static TcGemmP tc_conv(const void* A, int B, int H, int W, int Cin, const float* arena, size_t w_off, int Cout, int k,
+                       int stride, void* C, int* OH, int* OW) {
+  TcGemmP g{};
+  int pt, pl;
+  same_pad(H, k, stride, OH, &pt);
+  same_pad(W, k, stride, OW, &pl);
+  g.A = (const __nv_bfloat16*)A; g.W = (const __nv_bfloat16*)(arena + w_off); g.C = C;
+  g.M = B * (*OH) * (*OW); g.N = Cout; g.K = k * k * Cin; g.ldw = g.K; g.ldc = Cout;
+  g.conv = 1; g.H = H; g.Wd = W; g.Cin = Cin; g.OH = *OH; g.OW = *OW; g.KW = k; g.stride = stride; g.pad_t = pt; g.pad_l = pl;
+  return g;
+}
+
+#define TCL(g)                                                                                         \
+  do {                                                                                                 \
+    int rc__ = launch_tc_igemm(g, st);                                                                 \
+    if (rc__) return fail(h, "tcgen05 GEMM configuration failed: %s", cudaGetErrorString((cudaError_t)rc__)); \
+    CKL();                                                                                             \
+  } while (0)
+
+// bf16 encoder: tcgen05 implicit GEMMs for every dense contraction, bf16 NHWC activations in the trunk,
+// fp32 residual stream in the SATRN encoder layers.
+static int encode_bf16(frx_handle* h, const float* images, int B, float* memory, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  const float* A = h->arena;
+  typedef __nv_bfloat16 bf;
+  int H = (c.height - 3) / 2 + 1, W = (c.width - 3) / 2 + 1;
+  bf* x = (bf*)h->act[0];
+  bf* y = (bf*)h->act[1];
+  bf* m0 = (bf*)h->mid[0];
+  bf* m1 = (bf*)h->mid[1];
+  launch_stem_conv_bf16(images, A + h->stem_w, A + h->stem_sc, A + h->stem_sh, x, B, c.in_ch, c.height, c.width, H, W, 24, st);
+  CKL();
+  for (const BlockW& b : h->blocks) {
+    int OH, OW;
+    if (b.kind == 0) {
+      TcGemmP g = tc_conv(x, B, H, W, b.cin, A, b.wb_a, b.cout, b.k, b.stride, y, &OH, &OW);
+      g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
+      if (b.residual) { g.res = x; g.ldr = b.cout; }
+      TCL(g);
+    } else if (b.kind == 1) {
+      TcGemmP g = tc_conv(x, B, H, W, b.cin, A, b.wb_a, b.mid, b.k, b.stride, m0, &OH, &OW);
+      g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
+      TCL(g);
+      TcGemmP g2 = tc_dense(m0, B * OH * OW, b.mid, A, b.wb_b, b.cout, y, 0);
+      g2.scale = A + b.sc_b; g2.shift = A + b.sh_b;
+      if (b.residual) { g2.res = x; g2.ldr = b.cout; }
+      TCL(g2);
+    } else {
+      TcGemmP g = tc_dense(x, B * H * W, b.cin, A, b.wb_a, b.mid, m0, 0);
+      g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
+      TCL(g);
+      int pt, pl;
+      same_pad(H, b.k, b.stride, &OH, &pt);
+      same_pad(W, b.k, b.stride, &OW, &pl);
+      launch_dwconv_bf16(m0, A + b.w_dw, A + b.sc_dw, A + b.sh_dw, m1, B, H, W, b.mid, OH, OW, b.stride, pt, pl, ACT_SILU, st);
+      CKL();
+      launch_se_scale_bf16(m1, A + b.se_w1, A + b.se_b1, A + b.se_w2, A + b.se_b2, B, OH * OW, b.mid, b.se_r, st);
+      CKL();
+      TcGemmP g2 = tc_dense(m1, B * OH * OW, b.mid, A, b.wb_b, b.cout, y, 0);
+      g2.scale = A + b.sc_b; g2.shift = A + b.sh_b;
+      if (b.residual) { g2.res = x; g2.ldr = b.cout; }
+      TCL(g2);
+    }
+    H = OH; W = OW;
+    bf* t = x; x = y; y = t;
+  }
+  if (H != h->feat_h || W != h->feat_w) return fail(h, "trunk output %dx%d != expected %dx%d", H, W, h->feat_h, h->feat_w);
+  const int fh = h->feat_h, fw = h->feat_w, S = fh * fw, C = c.enc_hidden, F = c.enc_filter, M = B * S;
+  float* tf = (float*)y;  // conv_last output, fp32 [M, C]
+  {
+    TcGemmP g = tc_dense(x, M, 256, A, h->last_wb, C, tf, 1);
+    g.scale = A + h->last_sc; g.shift = A + h->last_sh; g.act = ACT_SILU;
+    TCL(g);
+  }
+  float* xf = (float*)x;
+  launch_pe2d_f32(tf, A + h->pe_w0, A + h->pe_b0, A + h->pe_w1, A + h->pe_b1, A + h->pe_h, A + h->pe_w, xf, B, fh, fw, C, st);
+  CKL();
+  float* other = tf;
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const EncLayerW& L = h->enc[i];
+    launch_layernorm_bf16out(xf, nullptr, A + L.ln_g, A + L.ln_b, m0, M, C, 0, st); CKL();
+    float* qkv = (float*)m1;
+    TcGemmP g = tc_dense(m0, M, C, A, L.wb_qkv, 3 * C, qkv, 1);
+    g.shift = A + L.b_qkv;
+    TCL(g);
+    launch_enc_attn_bf16out(qkv, m0, B, S, C, c.enc_heads, st); CKL();
+    float* proj = (float*)m1;
+    TcGemmP go = tc_dense(m0, M, C, A, L.wb_o, C, proj, 1);
+    go.shift = A + L.b_o;
+    TCL(go);
+    launch_layernorm_bf16out(proj, xf, A + L.ln_g, A + L.ln_b, m0, M, C, S, st); CKL();  // reinterpreted (:269) layout
+    TcGemmP g0 = tc_dense(m0, M, C, A, L.wb_c0, F, m1, 0);
+    g0.scale = A + L.sc_c0; g0.shift = A + L.sh_c0; g0.act = ACT_RELU;
+    TCL(g0);
+    launch_dwconv_bf16(m1, A + L.w_dw, A + L.sc_dw, A + L.sh_dw, m0, B, fh, fw, F, fh, fw, 1, 1, 1, ACT_RELU, st); CKL();
+    float* dst = (i == c.enc_layers - 1) ? memory : other;
+    TcGemmP g1 = tc_dense(m0, M, F, A, L.wb_c1, C, dst, 1);
+    g1.scale = A + L.sc_c1; g1.shift = A + L.sh_c1; g1.act = ACT_RELU; g1.res = xf; g1.res_f32 = 1; g1.ldr = C;
+    TCL(g1);
+    other = xf;
+    xf = dst;
+  }
+  return 0;
+}
+
 extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* memory, void* stream) {
   if (!h) return 1;
   if (!h->finalized) return fail(h, "frx_encode: weights not finalized");
@@ -767,6 +916,7 @@ extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* 
   const frx_config& c = h->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(c.device));
+  if (c.precision == FRX_PREC_BF16 && !h->opt_enc_fp32) return encode_bf16(h, images, B, memory, st);
   const float* A = h->arena;
   float* t = nullptr;
   if (run_trunk_efficientnet(h, images, B, &t, st)) return 1;
@@ -818,6 +968,13 @@ extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* 
 static int run_cross_kv(frx_handle* h, const float* memory, int B, cudaStream_t st) {
   const frx_config& c = h->cfg;
   const int S = h->feat_h * h->feat_w;
+  if (c.precision == FRX_PREC_BF16) {
+    launch_f32_to_bf16(memory, (__nv_bfloat16*)h->mem_bf, (long long)B * S * c.dec_src, st); CKL();
+    TcGemmP t = tc_dense(h->mem_bf, B * S, c.dec_src, h->arena, h->cross_wb, c.dec_layers * 2 * c.dec_hidden, h->cross, 1);
+    t.shift = h->arena + h->b_cross;
+    TCL(t);
+    return 0;
+  }
   GemmP g = dense_gemm(memory, B * S, c.dec_src, h->arena + h->w_cross, c.dec_layers * 2 * c.dec_hidden, h->cross,
                        c.dec_layers * 2 * c.dec_hidden);
   g.shift = h->arena + h->b_cross;
@@ -1088,4 +1245,27 @@ extern "C" int frx_beam_search(frx_handle* h, const float*, int32_t, int32_t, in
 
 extern "C" int frx_decode_teacher_forced(frx_handle* h, const float*, const int64_t*, int32_t, int32_t, float*, void*) {
   return fail(h, "frx_decode_teacher_forced: not implemented yet");
+}
+
+// Test / micro-benchmark hook for the tcgen05 implicit-GEMM kernel (see include/frx.h).
+extern "C" int frx_tc_gemm(frx_handle* h, const void* A, const void* W, void* C, int32_t M, int32_t N, int32_t K,
+                           const int32_t* conv7, const float* scale, const float* shift, int32_t act,
+                           int32_t out_f32, void* stream) {
+  if (!h) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->cfg.device));
+  TcGemmP g{};
+  g.A = (const __nv_bfloat16*)A; g.W = (const __nv_bfloat16*)W; g.C = C;
+  g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.out_f32 = out_f32;
+  g.scale = scale; g.shift = shift; g.act = act;
+  if (conv7) {  // {B, H, W, Cin, ksize, stride, same_pad(1) or zero pad(0)}
+    int B = conv7[0], H = conv7[1], Wd = conv7[2], Cin = conv7[3], k = conv7[4], s = conv7[5];
+    int OH, OW, pt = 0, pl = 0;
+    if (conv7[6]) { same_pad(H, k, s, &OH, &pt); same_pad(Wd, k, s, &OW, &pl); }
+    else { OH = (H - k) / s + 1; OW = (Wd - k) / s + 1; }
+    if (M != B * OH * OW || K != k * k * Cin) return fail(h, "frx_tc_gemm: conv shape mismatch (M %d vs %d, K %d vs %d)", M, B * OH * OW, K, k * k * Cin);
+    g.conv = 1; g.H = H; g.Wd = Wd; g.Cin = Cin; g.OH = OH; g.OW = OW; g.KW = k; g.stride = s; g.pad_t = pt; g.pad_l = pl;
+  }
+  TCL(g);
+  return 0;
 }

@@ -25,11 +25,13 @@ struct BlockW {
   size_t w_dw, sc_dw, sh_dw;   // depthwise 3x3 + folded BN (kind 2)
   size_t se_w1, se_b1, se_w2, se_b2;
   size_t w_b, sc_b, sh_b;      // 1x1 projection + folded BN (kinds 1/2)
+  size_t wb_a = 0, wb_b = 0;   // bf16 copies of w_a / w_b ([N][K], K contiguous) for the tcgen05 path
 };
 struct LiteConvW { int cin, cout; size_t w, sc, sh; };
 struct EncLayerW {
   size_t ln_g, ln_b, w_qkv, b_qkv, w_o, b_o;
   size_t w_c0, sc_c0, sh_c0, w_dw, sc_dw, sh_dw, w_c1, sc_c1, sh_c1;
+  size_t wb_qkv = 0, wb_o = 0, wb_c0 = 0, wb_c1 = 0;   // bf16 copies
 };
 struct DecLayerW {
   size_t wt_o, b_o, wt_q2, b_q2, wt_o2, b_o2, wt_f0, b_f0, wt_f1, b_f1;   // [K][N] for the step kernels
@@ -52,6 +54,7 @@ struct frx_handle {
   bool opt_taps = false, opt_graphs = true, opt_timing = false;
   bool opt_prof = false;
   int opt_cluster_images = 0;  // 0 = auto
+  bool opt_enc_fp32 = false;   // bf16 handle, but run the encoder on the fp32 SIMT path (debug)
   long long* prof = nullptr;
   int opt_parts = 3;  // bit0: encoder weights/workspaces, bit1: decoder
   int feat_h = 0, feat_w = 0;
@@ -69,6 +72,7 @@ struct frx_handle {
   std::vector<EncLayerW> enc;
   // decoder
   size_t emb = 0, pe1d = 0, gen_w = 0, gen_b = 0, w_cross = 0, b_cross = 0;
+  size_t last_wb = 0, cross_wb = 0;   // bf16 copies of conv_last / cross K|V weights
   std::vector<DecLayerW> dec;
   std::vector<FusedW> fused;
   std::vector<DecPackW> dpack;
@@ -82,6 +86,7 @@ struct frx_handle {
   float *logits_int = nullptr, *memory_int = nullptr, *images_int = nullptr;
   long long *tokens_int = nullptr, *forced_int = nullptr;
   int* cur_tok = nullptr;
+  void* mem_bf = nullptr;  // bf16 copy of the encoder memory (A operand of the cross K/V GEMM)
   void *kself_bf = nullptr, *vself_bf = nullptr, *kcross_bf = nullptr, *vcross_bf = nullptr;  // bf16 caches
 
   std::map<GraphKey, GraphEntry> graphs;
