@@ -31,6 +31,7 @@ void launch_dec_argmax_embed(const float* logits, long long ld_logits, int V, lo
 
 // tcgen05 implicit GEMM + bf16 trunk kernels (kernels_tc.cu, kernels_bf16.cu)
 int launch_tc_igemm(TcGemmP p, cudaStream_t st);
+void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
 void launch_stem_conv_bf16(const float* in, const float* w, const float* scale, const float* shift,
                            __nv_bfloat16* out, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st);

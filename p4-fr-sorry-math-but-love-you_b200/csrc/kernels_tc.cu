@@ -354,4 +354,13 @@ void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaSt
   f32_to_bf16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(in, out, n);
 }
 
+
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st) {
+  bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+}
+
 }  // namespace frx

@@ -723,6 +723,21 @@ extern "C" int frx_read_tap(frx_handle* h, const char* name, float* out, int64_t
   return 0;
 }
 
+static int tap_bf16(frx_handle* h, const std::string& name, const void* src, int B, int H, int W, int C, cudaStream_t st) {
+  if (!h->opt_taps) return 0;
+  Tap& t = h->taps[name];
+  size_t n = (size_t)B * H * W * C;
+  if (t.capacity < n) {
+    if (t.data) cudaFree(t.data);
+    CK(cudaMalloc((void**)&t.data, n * 4));
+    t.capacity = n;
+  }
+  t.shape[0] = B; t.shape[1] = H; t.shape[2] = W; t.shape[3] = C;
+  launch_bf16_to_f32((const __nv_bfloat16*)src, t.data, (long long)n, st);
+  CKL();
+  return 0;
+}
+
 static GemmP dense_gemm(const float* A, int M, int K, const float* W, int N, float* C, int ldc) {
   GemmP g{};
   g.A = A; g.W = W; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldc = ldc; g.conv = 0; g.rows_per_img = 1;
@@ -834,6 +849,7 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
   bf* m1 = (bf*)h->mid[1];
   launch_stem_conv_bf16(images, A + h->stem_w, A + h->stem_sc, A + h->stem_sh, x, B, c.in_ch, c.height, c.width, H, W, 24, st);
   CKL();
+  if (tap_bf16(h, "stem", x, B, H, W, 24, st)) return 1;
   for (const BlockW& b : h->blocks) {
     int OH, OW;
     if (b.kind == 0) {
@@ -867,6 +883,7 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
     }
     H = OH; W = OW;
     bf* t = x; x = y; y = t;
+    if (tap_bf16(h, b.name, x, B, H, W, b.cout, st)) return 1;
   }
   if (H != h->feat_h || W != h->feat_w) return fail(h, "trunk output %dx%d != expected %dx%d", H, W, h->feat_h, h->feat_w);
   const int fh = h->feat_h, fw = h->feat_w, S = fh * fw, C = c.enc_hidden, F = c.enc_filter, M = B * S;
@@ -876,9 +893,11 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
     g.scale = A + h->last_sc; g.shift = A + h->last_sh; g.act = ACT_SILU;
     TCL(g);
   }
+  if (tap(h, "trunk", tf, B, fh, fw, C, st)) return 1;
   float* xf = (float*)x;
   launch_pe2d_f32(tf, A + h->pe_w0, A + h->pe_b0, A + h->pe_w1, A + h->pe_b1, A + h->pe_h, A + h->pe_w, xf, B, fh, fw, C, st);
   CKL();
+  if (tap(h, "pe2d", xf, B, fh, fw, C, st)) return 1;
   float* other = tf;
   for (int i = 0; i < c.enc_layers; ++i) {
     const EncLayerW& L = h->enc[i];
@@ -901,6 +920,7 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
     TcGemmP g1 = tc_dense(m0, M, F, A, L.wb_c1, C, dst, 1);
     g1.scale = A + L.sc_c1; g1.shift = A + L.sh_c1; g1.act = ACT_RELU; g1.res = xf; g1.res_f32 = 1; g1.ldr = C;
     TCL(g1);
+    if (tap(h, "enc_layer" + std::to_string(i), dst, B, fh, fw, C, st)) return 1;
     other = xf;
     xf = dst;
   }
