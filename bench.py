@@ -184,12 +184,12 @@ def run_frx(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     lt = (torch.zeros(3) if False else None)
     import ctypes
-    ms3 = (ctypes.c_float * 3)()
+    ms3 = (ctypes.c_float * 4)()
 
     # ---- timed region 1: device-resident inputs, CUDA events -------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = eng.launches
-    enc_ms, dec_ms = [], []
+    enc_ms, dec_ms, kern_ms = [], [], []
     barrier()
     with ClockSampler(local_rank) as clocks:
         for s, e in ev:
@@ -199,7 +199,7 @@ def run_frx(args, rank, world, local_rank):
             e.record()
             e.synchronize()
             eng.h.lib.frx_last_timing(eng.h.ptr, ms3)
-            enc_ms.append(ms3[0]); dec_ms.append(ms3[1])
+            enc_ms.append(ms3[0]); dec_ms.append(ms3[1]); kern_ms.append(ms3[3])
         barrier()
     gpu_launches = eng.launches - launches0
     total_ms = sum(s.elapsed_time(e) for s, e in ev)
@@ -226,6 +226,9 @@ def run_frx(args, rank, world, local_rank):
     hbm, tflops, how = peaks()
     dec_s = statistics.mean(dec_ms) / 1e3
     enc_s = statistics.mean(enc_ms) / 1e3
+    single_kernel = args.precision == "bf16" and statistics.mean(kern_ms) > 0
+    if single_kernel:
+        dec_s = statistics.mean(kern_ms) / 1e3
     dec_bytes = DECODE_BYTES_PER_IMAGE[args.precision] * B
     achieved = dec_bytes / dec_s / 1e9
     line = {
@@ -243,7 +246,10 @@ def run_frx(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(tokens_host.numel() * 8)},
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": None, "kernel": "greedy decode loop (cross-KV + 231 steps)",
+                     "traffic": None,
+                     "kernel": "dec_cluster_bf16_kernel (one launch = all 231 decode steps of the batch)" if single_kernel
+                     else "greedy decode loop (CUDA graph of the fp32 step kernels)",
+                     "algorithmic_bytes_per_launch": dec_bytes,
                      "ms": dec_s * 1e3, "peak_source": how},
         "roofline_encoder": {"bound": "tensor", "achieved": ENCODE_FLOP_PER_IMAGE * B / enc_s / 1e12, "peak": tflops,
                              "unit": "TFLOP/s", "frac": ENCODE_FLOP_PER_IMAGE * B / enc_s / 1e12 / tflops,
@@ -253,13 +259,21 @@ def run_frx(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         ips, cores, cpu_tok, dt = cpu_reference_throughput(sd, args.cpu_sample, 1)
         with torch.no_grad():
-            _, gpu_tok = model.greedy(synthetic_images(args.cpu_sample, 0).to(dev), T)
+            xs = synthetic_images(args.cpu_sample, 0).to(dev)
+            _, gpu_tok = model.greedy(xs, T)
+            import frx
+            from helpers import Vocab, flags_dict
+            m32 = frx.EfficientSATRN(frx.Flags(flags_dict()).get(), Vocab(), sd, None, precision="fp32",
+                                     max_batch=args.cpu_sample, max_steps=T).to(dev).eval()
+            _, gpu_tok32 = m32.greedy(xs, T)
         agree = (gpu_tok.cpu() == cpu_tok).float().mean().item()
+        agree32 = (gpu_tok32.cpu() == cpu_tok).float().mean().item()
         line["cpu_baseline"] = {
             "value": ips, "unit": "images/s", "cores": cores, "kind": "port",
             "sample": "1 batch of %d images x 231 decode steps (%.1f s), oracle port of the reference's "
                       "as-written CPU algorithm, torch %s fp32" % (args.cpu_sample, dt, torch.__version__),
-            "token_agreement_with_gpu": agree}
+            "gpu_fp32_mode_token_agreement": agree32,
+            "gpu_%s_mode_token_agreement" % args.precision: agree}
     print(json.dumps(line), flush=True)
 
 
@@ -270,7 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="frx", choices=["frx", "reference"])
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--precision", default=os.environ.get("FRX_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("FRX_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

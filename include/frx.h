@@ -143,8 +143,9 @@ int frx_read_tap(frx_handle* h, const char* name, float* out, int64_t capacity, 
 
 /* Times (milliseconds, CUDA events on the launching stream) of the phases of the
  * last frx_forward_greedy* call when option "timing" is 1: [0]=encode,
- * [1]=cross-KV + decode loop, [2]=total. */
-int frx_last_timing(const frx_handle* h, float* ms3);
+ * [1]=cross-KV + decode loop, [2]=total, [3]=the persistent decode kernel alone
+ * (bf16 mode; 0 otherwise). */
+int frx_last_timing(const frx_handle* h, float* ms4);
 
 /* Test / micro-benchmark hook: the tcgen05 implicit-GEMM kernel on its own.
  * C[M,N] = act((A * W^T) * scale + shift); A bf16 [M,K] (dense) or, when conv7 !=

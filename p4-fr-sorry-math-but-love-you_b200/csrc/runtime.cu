@@ -193,7 +193,7 @@ extern "C" void frx_destroy(frx_handle* h) {
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& kv : h->taps) cudaFree(kv.second.data);
-  if (h->ev[0]) for (int i = 0; i < 3; ++i) cudaEventDestroy(h->ev[i]);
+  if (h->ev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(h->ev[i]);
   delete h;
 }
 
@@ -245,9 +245,9 @@ extern "C" int frx_read_prof(frx_handle* h, int64_t* out16) {
   return 0;
 }
 
-extern "C" int frx_last_timing(const frx_handle* h, float* ms3) {
-  if (!h || !ms3) return 1;
-  for (int i = 0; i < 3; ++i) ms3[i] = h->last_ms[i];
+extern "C" int frx_last_timing(const frx_handle* h, float* ms4) {
+  if (!h || !ms4) return 1;
+  for (int i = 0; i < 4; ++i) ms4[i] = h->last_ms[i];
   return 0;
 }
 
@@ -679,7 +679,7 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
     }
     if (dev_alloc(h, &p, B * S * C * 4)) return 1; h->memory_int = (float*)p;
     if (dev_alloc(h, &p, (size_t)c.in_ch * c.height * c.width * B * 4)) return 1; h->images_int = (float*)p;
-    for (int i = 0; i < 3; ++i) CK(cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&h->ev[i]));
     h->ws_ready = true;
   }
   // graphs bake arena pointers: drop them when weights are re-packed
@@ -1136,9 +1136,12 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
   p.logits = logits; p.tokens = tokens; p.forced = forced;
   p.prof = h->opt_prof ? h->prof : nullptr;
   if (p.prof) CK(cudaMemsetAsync(h->prof, 0, 16 * 8, st));
+  if (h->opt_timing) CK(cudaEventRecord(h->ev[3], st));
   int rc = launch_dec_cluster_bf16(p, h->opt_cluster_images, st);
   if (rc) return fail(h, "decode cluster kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
   CKL();
+  if (h->opt_timing) CK(cudaEventRecord(h->ev[4], st));
+  h->timed_kernel = h->opt_timing;
   return 0;
 }
 
@@ -1208,6 +1211,8 @@ extern "C" int frx_forward_greedy(frx_handle* h, const float* images, int32_t B,
     CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]));
     CK(cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]));
     CK(cudaEventElapsedTime(&h->last_ms[2], h->ev[0], h->ev[2]));
+    h->last_ms[3] = 0.f;
+    if (h->timed_kernel) CK(cudaEventElapsedTime(&h->last_ms[3], h->ev[3], h->ev[4]));
   }
   return 0;
 }

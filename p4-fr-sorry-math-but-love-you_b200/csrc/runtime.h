@@ -91,7 +91,8 @@ struct frx_handle {
 
   std::map<GraphKey, GraphEntry> graphs;
   std::map<std::string, Tap> taps;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  float last_ms[3] = {0, 0, 0};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float last_ms[4] = {0, 0, 0, 0};
   int step_idx = 0, step_batch = 0;
+  bool timed_kernel = false;
 };

@@ -24,7 +24,7 @@ model.set_option("timing", 1)
 model.set_option("prof", 1)
 model.set_option("cluster_images", a.cluster_images)
 NAMES = ["S1 gemm", "S1 sync", "self-attn", "attn sync", "gemm N=256 (S3/S4/S6)", "cluster sync (other)", "layernorm", "cross-attn", "S7 ffn0", "S8 ffn1", "S9 kv+next", "argmax+embed"]
-ms3 = (ctypes.c_float * 3)()
+ms3 = (ctypes.c_float * 4)()
 for b in [int(x) for x in a.batches.split(",")]:
     x = bench.synthetic_images(b, 0).to(dev)
     eng = model.engine(dev, b, a.steps)
