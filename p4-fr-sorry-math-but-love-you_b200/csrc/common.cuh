@@ -94,6 +94,8 @@ struct AttnP {
   int D;               // model width of the cache rows
   int n_hist;          // number of cached rows attended (when hist_len == nullptr)
   const int* hist_len; // optional per-row history length
+  int causal_L;        // > 0: history length of row m is (m % causal_L) + 1 (teacher-forced causal mask)
+  const unsigned char* key_mask;  // optional [Bimg, rows_per_img]: 1 = key masked (-inf), e.g. PAD tokens
   const int* chain;    // optional [M, chain_stride] row indices (tree-structured history)
   int chain_stride;
   const float* cur_k;  // optional current key/value row per query [M, ld_cur] (extra last key)
@@ -107,6 +109,19 @@ struct AttnP {
   int heads;
 };
 
+
+// best-first "beam" search state (kernels_beam.cu); arrays are [B][cap] unless noted
+struct BeamP {
+  int B, V, bw, max_seq, T, cap, sos, eos, pad;
+  double* hscore; int* hnode; int* hsize;                          // binary heap (heapq order)
+  int* nprev; int* ntok; int* nlen; double* nlogp; int* nkv; int* ncount;   // search-tree nodes
+  int *num_steps, *done, *endnode, *nexp, *cur_node;               // [B]
+  int *cur_tok, *pos, *slot, *active;                              // [B] inputs of the decoder step
+  int* chain;                                                      // [B][T] K/V cache rows of the ancestors
+  int* n_active;                                                   // [1]
+  const float* logits;                                             // [B][V]
+  long long* out;                                                  // [B][max_seq]
+};
 
 // tcgen05 implicit GEMM (kernels_tc.cu):  C[M,N] = epi( A[M,K] * W[N,K]^T ), bf16 operands
 struct TcGemmP {

@@ -29,6 +29,14 @@ void launch_dec_argmax_embed(const float* logits, long long ld_logits, int V, lo
                              cudaStream_t st);
 
 
+void launch_pad_mask(const long long* text, unsigned char* mask, int B, int L, int pad_id, cudaStream_t st);
+
+// best-first search bookkeeping (kernels_beam.cu)
+void launch_beam_init(const BeamP& p, cudaStream_t st);
+void launch_beam_select(const BeamP& p, cudaStream_t st);
+void launch_beam_push(const BeamP& p, cudaStream_t st);
+void launch_beam_finish(const BeamP& p, cudaStream_t st);
+
 // tcgen05 implicit GEMM + bf16 trunk kernels (kernels_tc.cu, kernels_bf16.cu)
 int launch_tc_igemm(TcGemmP p, cudaStream_t st);
 void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);

@@ -660,7 +660,8 @@ __global__ void __launch_bounds__(256) dec_attn_f32_kernel(const AttnP p) {
   const int m = gw / p.heads, hh = gw % p.heads;
   if (m >= p.M) return;
   const int img = m / p.q_per_img;
-  const int nh = p.hist_len ? __ldg(p.hist_len + m) : p.n_hist;
+  const int nh = p.causal_L > 0 ? (m % p.causal_L) + 1 : (p.hist_len ? __ldg(p.hist_len + m) : p.n_hist);
+  const unsigned char* kmask = p.key_mask ? p.key_mask + (long long)img * p.rows_per_img : nullptr;
   const int nk = nh + (p.cur_k ? 1 : 0);
   float* sc = sm + (size_t)warp * (p.rows_per_img + 1);
   constexpr int PER = HD / 32;
@@ -690,6 +691,7 @@ __global__ void __launch_bounds__(256) dec_attn_f32_kernel(const AttnP p) {
       s = fmaf(qv[c + 2], t.z, s); s = fmaf(qv[c + 3], t.w, s);
     }
     s = s / p.temperature;
+    if (kmask && j < nh && kmask[j]) s = -INFINITY;  // masked_fill(-inf) (:168)
     sc[j] = s;
     mx = fmaxf(mx, s);
   }
@@ -797,6 +799,18 @@ void launch_dec_argmax_embed(const float* logits, long long ld_logits, int V, lo
                              cudaStream_t st) {
   dec_argmax_embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(logits, ld_logits, V, tokens_out, ld_tok, forced,
                                                        ld_forced, cur_tok, emb, pe_next, scale, x, M, D);
+}
+
+
+// pad_mask (:469-473): key j of a text row is masked when text[j] == PAD and j > 0
+__global__ void __launch_bounds__(256) pad_mask_kernel(const long long* __restrict__ text, unsigned char* __restrict__ mask,
+                                                       int B, int L, int pad_id) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L) return;
+  mask[i] = (text[i] == pad_id && (i % L) != 0) ? 1 : 0;
+}
+void launch_pad_mask(const long long* text, unsigned char* mask, int B, int L, int pad_id, cudaStream_t st) {
+  pad_mask_kernel<<<(B * L + 255) / 256, 256, 0, st>>>(text, mask, B, L, pad_id);
 }
 
 }  // namespace frx

@@ -1004,7 +1004,14 @@ static int run_cross_kv(frx_handle* h, const float* memory, int B, cudaStream_t 
 
 // One decoder step at position t for all B rows.  The input
 // row x must already be in h->dx.  Logits go to logits_dst[m*ld_logits + v].
-static int run_decode_step(frx_handle* h, int B, int t, float* logits_dst, long long ld_logits, cudaStream_t st) {
+struct StepRows {            // per-row (tree-structured) history for the best-first search; all nullptr = greedy
+  const int* hist_len = nullptr;   // [B] number of cached rows attended
+  const int* slot = nullptr;       // [B] cache row that receives this step's K/V
+  const int* chain = nullptr;      // [B][T] cache rows of the ancestors
+};
+
+static int run_decode_step(frx_handle* h, int B, int t, float* logits_dst, long long ld_logits, cudaStream_t st,
+                           const StepRows& rows = StepRows()) {
   const frx_config& c = h->cfg;
   const float* A = h->arena;
   const int D = c.dec_hidden, F = c.dec_filter, L = c.dec_layers, V = c.num_classes, T = c.max_steps;
@@ -1031,6 +1038,7 @@ static int run_decode_step(frx_handle* h, int B, int t, float* logits_dst, long 
     {  // self attention over the t cached output rows + the current input row (:387-388)
       AttnP a{};
       a.q = h->dqkv; a.ldq = 3 * D; a.kcache = kc; a.vcache = vc; a.rows_per_img = T; a.D = D; a.n_hist = t;
+      a.hist_len = rows.hist_len; a.chain = rows.chain; a.chain_stride = T;
       a.cur_k = h->dqkv + D; a.cur_v = h->dqkv + 2 * D; a.ld_cur = 3 * D; a.q_per_img = 1; a.temperature = temp;
       a.out = h->datt; a.ldo = D; a.M = B; a.heads = c.dec_heads;
       launch_dec_attn_f32(a, HD, st); CKL();
@@ -1077,8 +1085,14 @@ static int run_decode_step(frx_handle* h, int B, int t, float* logits_dst, long 
       DecGemmP p = base_gemm(h->dpre1, D, A + Fw.wt, A + Fw.b, Fw.N);
       p.ln_g = A + W.ln3_g; p.ln_b = A + W.ln3_b; p.a_norm_out = h->dx;
       p.nseg = 3;
-      p.seg[0] = Seg{0, D, kc + (size_t)t * D, (long long)T * D, 0};
-      p.seg[1] = Seg{D, 2 * D, vc + (size_t)t * D, (long long)T * D, 0};
+      if (rows.slot) {
+        p.row_slot = rows.slot;
+        p.seg[0] = Seg{0, D, kc, (long long)T * D, D};
+        p.seg[1] = Seg{D, 2 * D, vc, (long long)T * D, D};
+      } else {
+        p.seg[0] = Seg{0, D, kc + (size_t)t * D, (long long)T * D, 0};
+        p.seg[1] = Seg{D, 2 * D, vc + (size_t)t * D, (long long)T * D, 0};
+      }
       if (l + 1 < L) p.seg[2] = Seg{2 * D, 5 * D, h->dqkv, 3 * D, 0};
       else p.seg[2] = Seg{2 * D, 2 * D + V, logits_dst, ld_logits, 0};
       launch_dec_gemm_f32(p, st); CKL();
@@ -1264,12 +1278,129 @@ extern "C" int frx_decode_step(frx_handle* h, const int64_t* target, float* logi
   return 0;
 }
 
-extern "C" int frx_beam_search(frx_handle* h, const float*, int32_t, int32_t, int32_t, int64_t*, void*) {
-  return fail(h, "frx_beam_search: not implemented yet");
+static int ws_alloc(frx_handle* h, void** p, size_t bytes) {
+  if (*p) return 0;
+  return dev_alloc(h, p, bytes);
 }
 
-extern "C" int frx_decode_teacher_forced(frx_handle* h, const float*, const int64_t*, int32_t, int32_t, float*, void*) {
-  return fail(h, "frx_decode_teacher_forced: not implemented yet");
+// EfficientSATRN.beam_search (:708-867), topk = 1: all samples advance one expansion per round.
+extern "C" int frx_beam_search(frx_handle* h, const float* memory, int32_t B, int32_t beam_width,
+                               int32_t max_sequence, int64_t* tokens, void* stream) {
+  if (!h) return 1;
+  const frx_config& c = h->cfg;
+  if (!h->finalized) return fail(h, "beam_search: weights not finalized");
+  if (!(h->opt_parts & 2)) return fail(h, "beam_search: handle was created without the decoder part");
+  if (B <= 0 || B > c.max_batch) return fail(h, "beam_search: batch %d outside (0, %d]", B, c.max_batch);
+  if (beam_width < 1 || beam_width > 8) return fail(h, "beam_search: beam_width %d outside [1, 8]", beam_width);
+  if (max_sequence < 2 || max_sequence > c.max_steps) return fail(h, "beam_search: max_sequence %d outside [2, %d]", max_sequence, c.max_steps);
+  if (c.num_classes > 256) return fail(h, "beam_search: more than 256 classes not supported");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(c.device));
+  const int T = c.max_steps, V = c.num_classes, D = c.dec_hidden;
+  const size_t Bm = c.max_batch;
+  const int cap = (T - 1) * 8 + 2;  // root + beam_width children per expansion
+  BeamWs& w = h->beam;
+  if (ws_alloc(h, (void**)&w.hscore, Bm * cap * 8) || ws_alloc(h, (void**)&w.hnode, Bm * cap * 4) ||
+      ws_alloc(h, (void**)&w.nprev, Bm * cap * 4) || ws_alloc(h, (void**)&w.ntok, Bm * cap * 4) ||
+      ws_alloc(h, (void**)&w.nlen, Bm * cap * 4) || ws_alloc(h, (void**)&w.nlogp, Bm * cap * 8) ||
+      ws_alloc(h, (void**)&w.nkv, Bm * cap * 4) || ws_alloc(h, (void**)&w.chain, Bm * T * 4) ||
+      ws_alloc(h, (void**)&w.small, Bm * 12 * 4 + 64) || ws_alloc(h, (void**)&w.logits, Bm * V * 4))
+    return 1;
+  if (!w.host_flag) CK(cudaMallocHost((void**)&w.host_flag, sizeof(int)));
+  BeamP p{};
+  p.B = B; p.V = V; p.bw = beam_width; p.max_seq = max_sequence; p.T = T; p.cap = cap;
+  p.sos = c.sos_id; p.eos = c.eos_id; p.pad = c.pad_id;
+  p.hscore = w.hscore; p.hnode = w.hnode; p.nprev = w.nprev; p.ntok = w.ntok; p.nlen = w.nlen; p.nlogp = w.nlogp;
+  p.nkv = w.nkv; p.chain = w.chain;
+  int* s = w.small;
+  p.hsize = s; p.ncount = s + Bm; p.num_steps = s + 2 * Bm; p.done = s + 3 * Bm; p.endnode = s + 4 * Bm;
+  p.nexp = s + 5 * Bm; p.cur_node = s + 6 * Bm; p.cur_tok = s + 7 * Bm; p.pos = s + 8 * Bm; p.slot = s + 9 * Bm;
+  p.active = s + 10 * Bm; p.n_active = s + 11 * Bm;
+  p.logits = w.logits; p.out = (long long*)tokens;
+  if (run_cross_kv(h, memory, B, st)) return 1;
+  launch_beam_init(p, st); CKL();
+  StepRows rows;
+  rows.hist_len = p.pos; rows.slot = p.slot; rows.chain = p.chain;
+  const float scale = sqrtf((float)D);
+  const int max_rounds = max_sequence + 1;
+  for (int round = 0; round < max_rounds; ++round) {
+    CK(cudaMemsetAsync(p.n_active, 0, sizeof(int), st));
+    launch_beam_select(p, st); CKL();
+    launch_dec_embed_f32(p.cur_tok, nullptr, 0, h->arena + h->emb, h->arena + h->pe1d, 0, p.pos, 0, scale, h->dx, B, D, st);
+    CKL();
+    if (run_decode_step(h, B, 0, w.logits, V, st, rows)) return 1;
+    launch_beam_push(p, st); CKL();
+    if ((round & 7) == 7 || round == max_rounds - 1) {  // every 8 rounds: has every sample finished?
+      CK(cudaMemcpyAsync(w.host_flag, p.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (*w.host_flag == 0) break;
+    }
+  }
+  launch_beam_finish(p, st); CKL();
+  return 0;
+}
+
+// SATRNDecoder.forward, teacher-forced branch (:488-495) with masks (:469-478), eval mode.
+extern "C" int frx_decode_teacher_forced(frx_handle* h, const float* memory, const int64_t* text, int32_t B,
+                                         int32_t L, float* logits, void* stream) {
+  if (!h) return 1;
+  const frx_config& c = h->cfg;
+  if (!h->finalized) return fail(h, "teacher_forced: weights not finalized");
+  if (!(h->opt_parts & 2)) return fail(h, "teacher_forced: handle was created without the decoder part");
+  if (B <= 0 || B > c.max_batch) return fail(h, "teacher_forced: batch %d outside (0, %d]", B, c.max_batch);
+  if (L <= 0 || L > c.max_steps || L > 500) return fail(h, "teacher_forced: length %d outside (0, %d]", L, c.max_steps);
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(c.device));
+  const float* A = h->arena;
+  const int D = c.dec_hidden, F = c.dec_filter, V = c.num_classes, T = c.max_steps, NL = c.dec_layers;
+  const int S = h->feat_h * h->feat_w, HD = D / c.dec_heads, M = B * L;
+  const size_t Mm = (size_t)c.max_batch * T;
+  TfWs& w = h->tf;
+  if (ws_alloc(h, (void**)&w.x, Mm * D * 4) || ws_alloc(h, (void**)&w.y, Mm * D * 4) || ws_alloc(h, (void**)&w.z, Mm * D * 4) ||
+      ws_alloc(h, (void**)&w.qkv, Mm * 3 * D * 4) || ws_alloc(h, (void**)&w.ff, Mm * F * 4) || ws_alloc(h, (void**)&w.mask, Mm))
+    return 1;
+  if (run_cross_kv(h, memory, B, st)) return 1;
+  const float temp = sqrtf((float)D);
+  launch_dec_embed_f32(nullptr, (const long long*)text, 0, A + h->emb, A + h->pe1d, 0, nullptr, L, temp, w.x, M, D, st);
+  CKL();
+  launch_pad_mask((const long long*)text, w.mask, B, L, c.pad_id, st); CKL();
+  auto lin = [&](const float* in, int K, size_t wo, size_t bo, int N, float* out, int act, const float* res) {
+    GemmP g = dense_gemm(in, M, K, A + wo, N, out, N);
+    g.shift = A + bo; g.act = act;
+    if (res) { g.res = res; g.ldr = N; }
+    return g;
+  };
+  float* x = w.x;
+  for (int l = 0; l < NL; ++l) {
+    const DecLayerW& W = h->dec[l];
+    { GemmP g = lin(x, D, W.w_sqkv, W.b_sqkv, 3 * D, w.qkv, ACT_NONE, nullptr); launch_igemm_f32(g, st); CKL(); }
+    {  // masked self attention: key j <= i and not (PAD at j > 0)   (:492, :168)
+      AttnP a{};
+      a.q = w.qkv; a.ldq = 3 * D; a.kcache = w.qkv + D; a.vcache = w.qkv + 2 * D; a.rows_per_img = L; a.D = 3 * D;
+      a.causal_L = L; a.key_mask = w.mask; a.q_per_img = L; a.temperature = temp; a.out = w.y; a.ldo = D; a.M = M;
+      a.heads = c.dec_heads;
+      launch_dec_attn_f32(a, HD, st); CKL();
+    }
+    { GemmP g = lin(w.y, D, W.w_o, W.b_o, D, w.z, ACT_NONE, x); launch_igemm_f32(g, st); CKL(); }
+    launch_layernorm_f32(w.z, nullptr, A + W.ln1_g, A + W.ln1_b, w.y, M, D, 0, st); CKL();          // u -> y
+    { GemmP g = lin(w.y, D, W.w_q2, W.b_q2, D, w.z, ACT_NONE, nullptr); launch_igemm_f32(g, st); CKL(); }  // q2 -> z
+    {
+      AttnP a{};
+      a.q = w.z; a.ldq = D; a.kcache = h->cross + (size_t)l * 2 * D; a.vcache = h->cross + (size_t)l * 2 * D + D;
+      a.rows_per_img = S; a.D = NL * 2 * D; a.n_hist = S; a.q_per_img = L; a.temperature = temp; a.out = x; a.ldo = D;
+      a.M = M; a.heads = c.dec_heads;
+      launch_dec_attn_f32(a, HD, st); CKL();                                                          // c -> x (x is dead)
+    }
+    { GemmP g = lin(x, D, W.w_o2, W.b_o2, D, w.z, ACT_NONE, w.y); launch_igemm_f32(g, st); CKL(); }
+    launch_layernorm_f32(w.z, nullptr, A + W.ln2_g, A + W.ln2_b, w.y, M, D, 0, st); CKL();          // w -> y
+    { GemmP g = lin(w.y, D, W.w_f0, W.b_f0, F, w.ff, ACT_RELU, nullptr); launch_igemm_f32(g, st); CKL(); }
+    { GemmP g = lin(w.ff, F, W.w_f1, W.b_f1, D, w.z, ACT_RELU, w.y); launch_igemm_f32(g, st); CKL(); }
+    launch_layernorm_f32(w.z, nullptr, A + W.ln3_g, A + W.ln3_b, x, M, D, 0, st); CKL();            // layer output -> x
+  }
+  GemmP g = dense_gemm(x, M, D, A + h->gen_w, V, logits, V);
+  g.shift = A + h->gen_b;
+  launch_igemm_f32(g, st); CKL();
+  return 0;
 }
 
 // Test / micro-benchmark hook for the tcgen05 implicit-GEMM kernel (see include/frx.h).

@@ -45,6 +45,14 @@ struct Tap { float* data = nullptr; size_t capacity = 0; int shape[4] = {0, 0, 0
 typedef std::tuple<int, int, bool> GraphKey;
 struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; };
 
+struct BeamWs {
+  double *hscore = nullptr, *nlogp = nullptr;
+  int *hnode = nullptr, *nprev = nullptr, *ntok = nullptr, *nlen = nullptr, *nkv = nullptr, *chain = nullptr, *small = nullptr;
+  float* logits = nullptr;
+  int* host_flag = nullptr;
+};
+struct TfWs { float *x = nullptr, *y = nullptr, *z = nullptr, *qkv = nullptr, *ff = nullptr; unsigned char* mask = nullptr; };
+
 struct frx_handle {
   frx_config cfg{};
   std::string err;
@@ -93,6 +101,8 @@ struct frx_handle {
   std::map<std::string, Tap> taps;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[4] = {0, 0, 0, 0};
+  BeamWs beam;
+  TfWs tf;
   int step_idx = 0, step_batch = 0;
   bool timed_kernel = false;
 };
