@@ -130,6 +130,7 @@ struct TcGemmP {
   void* C;                  // bf16 or fp32 [M, ldc]
   int M, N, K, lda, ldw, ldc;
   int BN;                   // N tile (multiple of 16, <= 256); 0 = choose
+  int stages;               // smem ring depth (set by the launcher)
   int conv, H, Wd, Cin, OH, OW, KW, stride, pad_t, pad_l;
   const float* scale;       // per-N folded BatchNorm (v*scale + shift) or nullptr
   const float* shift;       // per-N bias when scale == nullptr

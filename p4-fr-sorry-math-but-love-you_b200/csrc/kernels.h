@@ -48,6 +48,10 @@ void launch_dwconv_bf16(const __nv_bfloat16* in, const float* w, const float* sc
                         int pad_l, int act, cudaStream_t st);
 void launch_se_scale_bf16(__nv_bfloat16* x, const float* w1, const float* b1, const float* w2, const float* b2,
                           int B, int HW, int C, int R, cudaStream_t st);
+void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const float* scale, const float* shift,
+                              __nv_bfloat16* out, float* mean, float* gate, const float* w1, const float* b1,
+                              const float* w2, const float* b2, int B, int H, int W, int C, int OH, int OW, int stride,
+                              int pad_t, int pad_l, int R, cudaStream_t st);
 void launch_layernorm_bf16out(const float* x, const float* res, const float* gamma, const float* beta,
                               __nv_bfloat16* out, int M, int C, int scramble_S, cudaStream_t st);
 void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st);

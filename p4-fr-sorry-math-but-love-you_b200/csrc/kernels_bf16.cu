@@ -178,4 +178,130 @@ void launch_se_scale_bf16(__nv_bfloat16* x, const float* w1, const float* b1, co
   se_scale_bf16_kernel<<<B, 256, (2 * C + R) * sizeof(float), st>>>(x, w1, b1, w2, b2, HW, C, R);
 }
 
+
+// ---------------------------------------------------------------------------
+// MBConv middle section, restructured for parallelism (the one-CTA-per-image SE
+// kernel above was latency-bound):
+//   1. dwconv_se_mean: depthwise 3x3 + BN + SiLU for one (image, 64-channel chunk)
+//      per CTA, which also owns that chunk's spatial mean -> deterministic, no atomics;
+//   2. se_fc: the two tiny FCs per image -> gate[B][C];
+//   3. se_apply: x *= gate, fully parallel 16-byte elementwise pass.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
+                                                             int H, int W, int C, int OH, int OW, int stride, int pad_t,
+                                                             int pad_l) {
+  __shared__ float red[32][64 + 1];
+  const int n = blockIdx.x, c0 = blockIdx.y * 64;
+  const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;  // 8 channels per thread, 32 pixel lanes
+  const int c = c0 + cg * 8;
+  const bool c_ok = c < C;
+  float wv[9][8], sc[8], sh[8], sum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sum[j] = 0.f; sc[j] = c_ok ? __ldg(scale + c + j) : 0.f; sh[j] = c_ok ? __ldg(shift + c + j) : 0.f; }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[t][j] = c_ok ? __ldg(w + t * C + c + j) : 0.f;
+  const __nv_bfloat16* ip = in + (long long)n * H * W * C;
+  __nv_bfloat16* op = out + (long long)n * OH * OW * C;
+  if (c_ok) {
+    for (int px = pl; px < OH * OW; px += 32) {
+      const int oh = px / OW, ow = px - oh * OW;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = oh * stride - pad_t + kh;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = ow * stride - pad_l + kw;
+          if (iw < 0 || iw >= W) continue;
+          float x[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(ip + ((long long)ih * W + iw) * C + c)), x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], wv[kh * 3 + kw][j], acc[j]);
+        }
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = fmaf(acc[j], sc[j], sh[j]);
+        o[j] = __fdividef(v, 1.f + __expf(-v));  // SiLU
+      }
+      const uint4 packed = pack8(o);
+      *reinterpret_cast<uint4*>(op + (long long)px * C + c) = packed;
+      float back[8];
+      unpack8(packed, back);  // the mean is taken over the stored (bf16-rounded) activations, like the 3-kernel version
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum[j] += back[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[pl][cg * 8 + j] = sum[j];
+  __syncthreads();
+  if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
+    mean[(long long)n * C + c0 + threadIdx.x] = s / (float)(OH * OW);
+  }
+}
+
+__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
+                                                    const float* __restrict__ b1, const float* __restrict__ w2,
+                                                    const float* __restrict__ b2, float* __restrict__ gate, int C, int R) {
+  extern __shared__ float sm[];
+  float* mv = sm;       // C
+  float* red = sm + C;  // R
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mv[c] = mean[(long long)n * C + c];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += 8) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w1 + (long long)r * C + c), mv[c], s);
+    s = warp_sum(s);
+    if (lane == 0) red[r] = act_apply(s + __ldg(b1 + r), ACT_SILU);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = __ldg(b2 + c);
+    const float* wr = w2 + (long long)c * R;
+    for (int r = 0; r < R; ++r) s = fmaf(__ldg(wr + r), red[r], s);
+    gate[(long long)n * C + c] = 1.f / (1.f + expf(-s));
+  }
+}
+
+__global__ void __launch_bounds__(256) se_apply_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ gate,
+                                                       long long total8, int HW, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int C8 = C >> 3;
+  const int c = (int)(i % C8) * 8;
+  const long long n = i / ((long long)C8 * HW);
+  uint4* ptr = reinterpret_cast<uint4*>(x) + i;
+  float v[8];
+  unpack8(*ptr, v);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + n * C + c));
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + n * C + c + 4));
+  v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+  v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+  *ptr = pack8(v);
+}
+
+void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const float* scale, const float* shift,
+                              __nv_bfloat16* out, float* mean, float* gate, const float* w1, const float* b1,
+                              const float* w2, const float* b2, int B, int H, int W, int C, int OH, int OW, int stride,
+                              int pad_t, int pad_l, int R, cudaStream_t st) {
+  dim3 g(B, (C + 63) / 64);
+  dwconv_se_mean_kernel<<<g, 256, 0, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l);
+  se_fc_kernel<<<B, 256, (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, C, R);
+  long long total8 = (long long)B * OH * OW * (C / 8);
+  se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(out, gate, total8, OH * OW, C);
+}
+
 }  // namespace frx

@@ -99,6 +99,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+// bf16-mode activations: fast intrinsics (2-ulp exp / division are far below bf16 output rounding)
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v) {
+  if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
+  if (ACT == ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-v));
+  return v;
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_affine_act(float (&v)[16], const float* __restrict__ scale,
+                                               const float* __restrict__ shift, int nb) {
+  if (scale) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(scale + nb + i));
+      const float4 h = __ldg(reinterpret_cast<const float4*>(shift + nb + i));
+      v[i] = act_fast<ACT>(fmaf(v[i], s.x, h.x));
+      v[i + 1] = act_fast<ACT>(fmaf(v[i + 1], s.y, h.y));
+      v[i + 2] = act_fast<ACT>(fmaf(v[i + 2], s.z, h.z));
+      v[i + 3] = act_fast<ACT>(fmaf(v[i + 3], s.w, h.w));
+    }
+  } else if (shift) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 h = __ldg(reinterpret_cast<const float4*>(shift + nb + i));
+      v[i] = act_fast<ACT>(v[i] + h.x);
+      v[i + 1] = act_fast<ACT>(v[i + 1] + h.y);
+      v[i + 2] = act_fast<ACT>(v[i + 2] + h.z);
+      v[i + 3] = act_fast<ACT>(v[i + 3] + h.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = act_fast<ACT>(v[i]);
+  }
+}
+
 }  // namespace
 
 template <int NCOLS>
@@ -112,6 +149,7 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
   const int BN = p.BN;
   const uint32_t b_bytes = (uint32_t)BN * (TC_BK * 2);
   const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+  const int NS = p.stages;  // ring depth (2 or 3), chosen by the launcher from the K extent
   const uint32_t smem0 = (smem_u32(dyn_smem) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
   const int KB = (p.K + TC_BK - 1) / TC_BK;
@@ -203,17 +241,16 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
   };
 
   // ---- main loop --------------------------------------------------------------------------
-#pragma unroll
-  for (int s = 0; s < TC_STAGES - 1; ++s) {
+  for (int s = 0; s < NS - 1; ++s) {
     if (s < KB) load_stage(s, s);
     cp_async_commit();
   }
   const uint32_t idesc = make_idesc(BN);
   for (int kb = 0; kb < KB; ++kb) {
-    cp_async_wait<TC_STAGES - 2>();                          // this thread's chunks of k-block kb have landed
+    if (NS == 3) cp_async_wait<1>(); else cp_async_wait<0>();  // this thread's chunks of k-block kb have landed
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the tensor core
     __syncthreads();
-    const int stage = kb % TC_STAGES;
+    const int stage = kb % NS;
     if (tid == 0) {
       tc_fence_after();
       const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
@@ -224,10 +261,10 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
       umma_commit(&mma_done[stage]);
       if (kb == KB - 1) umma_commit(&acc_done);
     }
-    const int nk = kb + TC_STAGES - 1;
+    const int nk = kb + NS - 1;
     if (nk < KB) {
-      if (kb >= 1) mbar_wait(&mma_done[(kb - 1) % TC_STAGES], (uint32_t)(((kb - 1) / TC_STAGES) & 1));
-      load_stage(nk, nk % TC_STAGES);
+      if (kb >= 1) mbar_wait(&mma_done[(kb - 1) % NS], (uint32_t)(((kb - 1) / NS) & 1));
+      load_stage(nk, nk % NS);
     }
     cp_async_commit();
   }
@@ -249,26 +286,48 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
       const bool full = nb + 16 <= p.N;
+      if (full) {  // vectorised scale/shift, activation resolved outside the element loop
+        if (p.act == ACT_SILU) epi_affine_act<ACT_SILU>(v, p.scale, p.shift, nb);
+        else if (p.act == ACT_RELU) epi_affine_act<ACT_RELU>(v, p.scale, p.shift, nb);
+        else epi_affine_act<ACT_NONE>(v, p.scale, p.shift, nb);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = nb + i;
-        if (full || n < p.N) {
-          if (p.scale) v[i] = v[i] * __ldg(p.scale + n) + __ldg(p.shift + n);
-          else if (p.shift) v[i] += __ldg(p.shift + n);
-          v[i] = act_apply(v[i], p.act);
+        for (int i = 0; i < 16; ++i) {
+          const int n = nb + i;
+          if (n < p.N) {
+            if (p.scale) v[i] = v[i] * __ldg(p.scale + n) + __ldg(p.shift + n);
+            else if (p.shift) v[i] += __ldg(p.shift + n);
+            v[i] = act_apply(v[i], p.act);
+          }
         }
       }
       if (p.res) {
         if (p.res_f32) {
           const float* rp = reinterpret_cast<const float*>(p.res) + (size_t)m * p.ldr + nb;
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (full || nb + i < p.N) v[i] += __ldg(rp + i);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(rp + i));
+              v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+            }
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.N) v[i] += __ldg(rp + i);
+          }
         } else {
           const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + (size_t)m * p.ldr + nb;
+          if (full) {
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp)), r1 = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (full || nb + i < p.N) v[i] += __bfloat162float(rp[i]);
+            for (int i = 0; i < 8; ++i) {
+              v[2 * i] += __uint_as_float(rw[i] << 16);
+              v[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
+            }
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.N) v[i] += __bfloat162float(rp[i]);
+          }
         }
       }
       if (p.out_f32) {
@@ -316,7 +375,7 @@ static int tc_pick_bn(int N) {
 
 template <int NCOLS>
 static int tc_launch(const TcGemmP& p, cudaStream_t st) {
-  const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
+  const size_t smem = (size_t)p.stages * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_igemm_kernel<NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -330,6 +389,7 @@ static int tc_launch(const TcGemmP& p, cudaStream_t st) {
 
 int launch_tc_igemm(TcGemmP p, cudaStream_t st) {
   if (p.BN == 0) p.BN = tc_pick_bn(p.N);
+  p.stages = (p.K + TC_BK - 1) / TC_BK <= 3 ? 2 : 3;
   if (p.BN <= 32) { p.BN = 32; return tc_launch<32>(p, st); }
   if (p.BN <= 64) return tc_launch<64>(p, st);
   if (p.BN <= 128) return tc_launch<128>(p, st);

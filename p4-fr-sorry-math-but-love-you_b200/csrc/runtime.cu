@@ -652,7 +652,7 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
     if (want_enc) {
       for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * act_max * 4)) return 1; h->act[i] = (float*)p; }
       for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * mid_max * 4)) return 1; h->mid[i] = (float*)p; }
-      if (dev_alloc(h, &p, B * 2048 * 4)) return 1;
+      if (dev_alloc(h, &p, B * 2048 * 4 * 2)) return 1;  // SE means + gates
       h->gate = (float*)p;
     }
     // ---- decoder state ----------------------------------------------------
@@ -872,10 +872,10 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
       int pt, pl;
       same_pad(H, b.k, b.stride, &OH, &pt);
       same_pad(W, b.k, b.stride, &OW, &pl);
-      launch_dwconv_bf16(m0, A + b.w_dw, A + b.sc_dw, A + b.sh_dw, m1, B, H, W, b.mid, OH, OW, b.stride, pt, pl, ACT_SILU, st);
-      CKL();
-      launch_se_scale_bf16(m1, A + b.se_w1, A + b.se_b1, A + b.se_w2, A + b.se_b2, B, OH * OW, b.mid, b.se_r, st);
-      CKL();
+      launch_mbconv_dw_se_bf16(m0, A + b.w_dw, A + b.sc_dw, A + b.sh_dw, m1, h->gate, h->gate + (size_t)B * 2048,
+                               A + b.se_w1, A + b.se_b1, A + b.se_w2, A + b.se_b2, B, H, W, b.mid, OH, OW, b.stride, pt, pl,
+                               b.se_r, st);
+      CKL(); h->launches += 2;
       TcGemmP g2 = tc_dense(m1, B * OH * OW, b.mid, A, b.wb_b, b.cout, y, 0);
       g2.scale = A + b.sc_b; g2.shift = A + b.sh_b;
       if (b.residual) { g2.res = x; g2.ldr = b.cout; }
