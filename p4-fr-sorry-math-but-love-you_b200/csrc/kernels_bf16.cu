@@ -212,19 +212,24 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      uint4 taps[9];  // all nine 16-byte loads in flight before any arithmetic
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int ih = oh * stride - pad_t + kh;
-        if (ih < 0 || ih >= H) continue;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const int iw = ow * stride - pad_l + kw;
-          if (iw < 0 || iw >= W) continue;
-          float x[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(ip + ((long long)ih * W + iw) * C + c)), x);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], wv[kh * 3 + kw][j], acc[j]);
+          const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+          taps[kh * 3 + kw] = ok ? __ldg(reinterpret_cast<const uint4*>(ip + ((long long)ih * W + iw) * C + c))
+                                 : make_uint4(0u, 0u, 0u, 0u);
         }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float x[8];
+        unpack8(taps[t], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], wv[t][j], acc[j]);
       }
       float o[8];
 #pragma unroll
@@ -270,8 +275,7 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ me
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = __ldg(b2 + c);
-    const float* wr = w2 + (long long)c * R;
-    for (int r = 0; r < R; ++r) s = fmaf(__ldg(wr + r), red[r], s);
+    for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2 + (long long)r * C + c), red[r], s);  // w2 is [R][C] (transposed at pack time)
     gate[(long long)n * C + c] = 1.f / (1.f + expf(-s));
   }
 }

@@ -389,7 +389,11 @@ static int tc_launch(const TcGemmP& p, cudaStream_t st) {
 
 int launch_tc_igemm(TcGemmP p, cudaStream_t st) {
   if (p.BN == 0) p.BN = tc_pick_bn(p.N);
-  p.stages = (p.K + TC_BK - 1) / TC_BK <= 3 ? 2 : 3;
+  {  // ring depth: 3 when three stages still leave room for >= 2 (3 for narrow tiles) CTAs per SM, else 2
+    const int kb = (p.K + TC_BK - 1) / TC_BK;
+    const size_t stage = TC_A_BYTES + (size_t)p.BN * TC_BK * 2;
+    p.stages = (kb > 3 && 3 * stage <= 72 * 1024) ? 3 : 2;
+  }
   if (p.BN <= 32) { p.BN = 32; return tc_launch<32>(p, st); }
   if (p.BN <= 64) return tc_launch<64>(p, st);
   if (p.BN <= 128) return tc_launch<128>(p, st);

@@ -298,6 +298,9 @@ static int pack_trunk_efficientnet(frx_handle* h, ArenaBuilder& ab) {
         b.se_w1 = ab.add(w1->f.data(), w1->f.size());
         b.se_b1 = ab.add(b1->f.data(), b1->f.size());
         b.se_w2 = ab.add(w2->f.data(), w2->f.size());
+        b.se_w2t = ab.add(nullptr, w2->f.size());  // [R][C] for the bf16 path's coalesced reads
+        for (int cc = 0; cc < b.mid; ++cc)
+          for (int rr = 0; rr < b.se_r; ++rr) ab.at(b.se_w2t)[(size_t)rr * b.mid + cc] = w2->f[(size_t)cc * b.se_r + rr];
         b.se_b2 = ab.add(b2->f.data(), b2->f.size());
         if (pack_conv(h, ab, p + ".conv_pwl.weight", b.cout, b.mid, 1, &b.w_b)) return 1;
         if (fold_bn(h, ab, p + ".bn3", b.cout, 1e-3f, nullptr, &b.sc_b, &b.sh_b)) return 1;
@@ -873,7 +876,7 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
       same_pad(H, b.k, b.stride, &OH, &pt);
       same_pad(W, b.k, b.stride, &OW, &pl);
       launch_mbconv_dw_se_bf16(m0, A + b.w_dw, A + b.sc_dw, A + b.sh_dw, m1, h->gate, h->gate + (size_t)B * 2048,
-                               A + b.se_w1, A + b.se_b1, A + b.se_w2, A + b.se_b2, B, H, W, b.mid, OH, OW, b.stride, pt, pl,
+                               A + b.se_w1, A + b.se_b1, A + b.se_w2t, A + b.se_b2, B, H, W, b.mid, OH, OW, b.stride, pt, pl,
                                b.se_r, st);
       CKL(); h->launches += 2;
       TcGemmP g2 = tc_dense(m1, B * OH * OW, b.mid, A, b.wb_b, b.cout, y, 0);

@@ -23,7 +23,7 @@ struct BlockW {
   std::string name;
   size_t w_a, sc_a, sh_a;      // first conv (3x3 for kinds 0/1, 1x1 expand for kind 2) + folded BN
   size_t w_dw, sc_dw, sh_dw;   // depthwise 3x3 + folded BN (kind 2)
-  size_t se_w1, se_b1, se_w2, se_b2;
+  size_t se_w1, se_b1, se_w2, se_b2, se_w2t = 0;
   size_t w_b, sc_b, sh_b;      // 1x1 projection + folded BN (kinds 1/2)
   size_t wb_a = 0, wb_b = 0;   // bf16 copies of w_a / w_b ([N][K], K contiguous) for the tcgen05 path
 };
