@@ -6,13 +6,17 @@
 //   * each CTA computes 1/8 of the output columns of every linear layer, with
 //     the bf16 weights streamed from L2 straight into tensor-core B fragments
 //     (pre-packed on the host in fragment order -> coalesced 16-byte loads);
-//   * the partial rows are all-gathered through distributed shared memory
-//     (each CTA stores its slice into all 8 CTAs' buffers) and a cluster
-//     barrier separates the stages -- no global-memory round trips, no grid sync;
+//   * the partial rows are all-gathered through distributed shared memory with
+//     st.async: each CTA stores its slice into all 8 CTAs' buffers and every store
+//     completes transaction bytes on the DESTINATION CTA's mbarrier, so a stage is
+//     over for a CTA exactly when all bytes it needs have landed -- no cluster
+//     barrier (whose release semantics cost a MEMBAR.ALL.GPU each), no fence, no
+//     global-memory round trips, no grid sync;
 //   * attention over the bf16 KV cache (head-major [L][B][H][T][32], 64 B rows)
 //     is done by one warp per (image, head) with 16-byte coalesced loads and
-//     warp-shuffle reductions; the step's K/V rows are written by the CTA that
-//     owns that head's columns.
+//     warp-shuffle reductions; the step's K/V rows are routed through DSMEM to
+//     the CTA that owns the image, which writes (and later reads) them itself, so
+//     no cross-CTA global-memory visibility is ever required.
 // Tensor cores are used through mma.sync (M=16 images per cluster); tcgen05's
 // minimum tile (M=64..128 rows) does not fit a 16-row per-step problem, and the
 // step is bandwidth/latency-bound, not MMA-bound.
@@ -92,6 +96,8 @@ struct Smem {
   __nv_bfloat16 abf2[IMG][DEC_FMAX + APAD];  // A operand of FFN linear1, K = F
   float red[4][32][4];             // K-split partial accumulators
   long long prof[16];
+  __nv_bfloat16 kvrow[IMG / 8][2][D];  // this step's K|V rows of the image(s) this CTA owns (sent by the 8 column owners)
+  unsigned long long bar[2];           // stage mbarriers (alternate by stage parity)
   DecClusterLayer lw[4];           // per-layer pointers (dynamic indexing of kernel params would spill them)
 };
 
@@ -194,18 +200,59 @@ __device__ __forceinline__ void gemm_stage(Smem& s, uint64_t pol, const __nv_bfl
   }
 }
 
-// All-gather stores: the same smem offset in every CTA of the cluster.
-__device__ __forceinline__ void ag_store_f2(cg::cluster_group& cl, float* local, float a, float b) {
-#pragma unroll
-  for (int r = 0; r < CL; ++r) *reinterpret_cast<float2*>(cl.map_shared_rank(local, r)) = make_float2(a, b);
+// ---- DSMEM all-gather with st.async + mbarrier transaction counting ------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
 }
-__device__ __forceinline__ void ag_store_u32(cg::cluster_group& cl, void* local, uint32_t v) {
-#pragma unroll
-  for (int r = 0; r < CL; ++r) *reinterpret_cast<uint32_t*>(cl.map_shared_rank(local, r)) = v;
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
 }
-__device__ __forceinline__ void ag_store_u4(cg::cluster_group& cl, void* local, uint4 v) {
+__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t a, uint32_t b, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n" ::"r"(raddr), "r"(a), "r"(b), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a byte-accounting bug traps (error reaches the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (int spins = 0; spins < (1 << 26); ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+// Store the same value at the same smem offset of every CTA of the cluster; each store
+// completes its byte count on the destination CTA's mbarrier `bar` (same offset everywhere).
+__device__ __forceinline__ void ag_store_f2(uint32_t bar, float* local, float a, float b) {
+  const uint32_t la = smem_u32(local);
 #pragma unroll
-  for (int r = 0; r < CL; ++r) *reinterpret_cast<uint4*>(cl.map_shared_rank(local, r)) = v;
+  for (int r = 0; r < CL; ++r) st_async_v2(mapa_u32(la, r), __float_as_uint(a), __float_as_uint(b), mapa_u32(bar, r));
+}
+__device__ __forceinline__ void ag_store_u32(uint32_t bar, void* local, uint32_t v) {
+  const uint32_t la = smem_u32(local);
+#pragma unroll
+  for (int r = 0; r < CL; ++r) st_async_b32(mapa_u32(la, r), v, mapa_u32(bar, r));
+}
+__device__ __forceinline__ void ag_store_u4(uint32_t bar, void* local, uint4 v) {
+  const uint32_t la = smem_u32(local);
+#pragma unroll
+  for (int r = 0; r < CL; ++r) st_async_v4(mapa_u32(la, r), v, mapa_u32(bar, r));
 }
 
 // LayerNorm of the 16 gathered rows (every CTA does all rows: the result is
@@ -377,8 +424,22 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
     s.xres[row][c] = v;
     s.abf[row][c] = __float2bfloat16_rn(v);
   }
+  const uint32_t bar0 = smem_u32(&s.bar[0]), bar1 = smem_u32(&s.bar[1]);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   __syncthreads();
-  cl.sync();  // every CTA of the cluster is resident before the first remote store
+  cl.sync();  // every CTA of the cluster is resident and its barriers initialised before the first remote store
+  // Stage protocol: thread 0 arms the stage's barrier with the bytes THIS CTA will receive, everybody
+  // computes and st.async-stores into all 8 CTAs, everybody waits for the local barrier phase.
+  int gstage = 0;
+  constexpr uint32_t R8 = NIMG / 8;  // row halves of the MMA tile that hold images
+  auto stage_bar = [&]() -> uint32_t { return (gstage & 1) ? bar1 : bar0; };
+  auto stage_begin = [&](uint32_t bytes) { if (tid == 0) mbar_expect_tx(stage_bar(), bytes); };
+  auto stage_end = [&]() { mbar_wait(stage_bar(), (uint32_t)((gstage >> 1) & 1)); ++gstage; };
+  float* const logit_s = reinterpret_cast<float*>(&s.abf2[0][0]);  // [IMG][256] fp32 view (abf2 is idle between S8 and S7)
 
   const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
   if (profiling) for (int i = 0; i < 16; ++i) s.prof[i] = 0;
@@ -395,28 +456,32 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       const DecClusterLayer& W = s.lw[l];
       // ---- S1 (layer 0 only): q | k | v of the embedded input -------------------------
       if (l == 0) {
+        stage_begin(NIMG * 2048u);
+        const uint32_t sb = stage_bar();
         const uint4* wp = p.w_first + (size_t)r * 12 * (D / 32) * 32;
         gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, wp, [&](int tile, float (&c)[4], int ln) {
           const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
           const float b0 = __ldg(p.b_first + col), b1 = __ldg(p.b_first + col + 1);
           if (seg == 0) {
-            ag_store_f2(cl, &s.q[row][col], c[0] + b0, c[1] + b1);
+            ag_store_f2(sb, &s.q[row][col], c[0] + b0, c[1] + b1);
             if (NIMG == 16) {
-            ag_store_f2(cl, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
+            ag_store_f2(sb, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
             }
           } else {
-            ag_store_u32(cl, &s.kv[row][col - D], pack_bf16(c[0] + b0, c[1] + b1));
+            ag_store_u32(sb, &s.kv[row][col - D], pack_bf16(c[0] + b0, c[1] + b1));
             if (NIMG == 16) {
-            ag_store_u32(cl, &s.kv[row + 8][col - D], pack_bf16(c[2] + b0, c[3] + b1));
+            ag_store_u32(sb, &s.kv[row + 8][col - D], pack_bf16(c[2] + b0, c[3] + b1));
             }
           }
         });
         mark(0);
-        cl.sync();
+        stage_end();
         mark(1);
       }
       // ---- S2: self attention over t cached rows + the current input row ------------------
       {
+        stage_begin(NIMG * 512u);
+        const uint32_t sb = stage_bar();
 #pragma unroll
         for (int pp = 0; pp < NIMG / 8; ++pp) {
           const int pair = warp * (NIMG / 8) + pp;
@@ -433,46 +498,52 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
           }
           if ((lane >> 2) == 0) {
             uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-            ag_store_u4(cl, &s.abf[li][hh * HD + (lane & 3) * 8], v);
+            ag_store_u4(sb, &s.abf[li][hh * HD + (lane & 3) * 8], v);
           }
         }
         mark(2);
-        cl.sync();
+        stage_end();
         mark(3);
       }
       // ---- S3: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
+      stage_begin(NIMG * 1024u);
+      uint32_t sb = stage_bar();
       gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o + (size_t)r * 4 * (D / 32) * 32,
                        [&](int tile, float (&c)[4], int ln) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_o + col), b1 = __ldg(W.b_o + col + 1);
-                         ag_store_f2(cl, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
+                         ag_store_f2(sb, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
                          if (NIMG == 16) {
-                         ag_store_f2(cl, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
+                         ag_store_f2(sb, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
                                      c[3] + b1 + s.xres[row + 8][col + 1]);
                          }
                        });
       mark(4);
       const LnParams lnp1 = load_ln(W.ln1_g, W.ln1_b);
-      cl.sync();
+      stage_end();
       mark(5);
       layernorm_rows<NIMG>(s, lnp1);
       __syncthreads();
       mark(6);
       // ---- S4: q2 = q_linear(u) ---------------------------------------------------------------
+      stage_begin(NIMG * 1024u);
+      sb = stage_bar();
       gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_q2 + (size_t)r * 4 * (D / 32) * 32,
                        [&](int tile, float (&c)[4], int ln) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_q2 + col), b1 = __ldg(W.b_q2 + col + 1);
-                         ag_store_f2(cl, &s.q[row][col], c[0] + b0, c[1] + b1);
+                         ag_store_f2(sb, &s.q[row][col], c[0] + b0, c[1] + b1);
                          if (NIMG == 16) {
-                         ag_store_f2(cl, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
+                         ag_store_f2(sb, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
                          }
                        });
       mark(4);
-      cl.sync();
+      stage_end();
       mark(5);
       // ---- S5: cross attention over the S memory tokens --------------------------------------------
       {
+        stage_begin(NIMG * 512u);
+        sb = stage_bar();
 #pragma unroll
         for (int pp = 0; pp < NIMG / 8; ++pp) {
           const int pair = warp * (NIMG / 8) + pp;
@@ -488,77 +559,84 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
           }
           if ((lane >> 2) == 0) {
             uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-            ag_store_u4(cl, &s.abf[li][hh * HD + (lane & 3) * 8], v);
+            ag_store_u4(sb, &s.abf[li][hh * HD + (lane & 3) * 8], v);
           }
         }
         mark(7);
-        cl.sync();
+        stage_end();
         mark(3);
       }
       // ---- S6: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
+      stage_begin(NIMG * 1024u);
+      sb = stage_bar();
       gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o2 + (size_t)r * 4 * (D / 32) * 32,
                        [&](int tile, float (&c)[4], int ln) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_o2 + col), b1 = __ldg(W.b_o2 + col + 1);
-                         ag_store_f2(cl, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
+                         ag_store_f2(sb, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
                          if (NIMG == 16) {
-                         ag_store_f2(cl, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
+                         ag_store_f2(sb, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
                                      c[3] + b1 + s.xres[row + 8][col + 1]);
                          }
                        });
       mark(4);
       const LnParams lnp2 = load_ln(W.ln2_g, W.ln2_b);
-      cl.sync();
+      stage_end();
       mark(5);
       layernorm_rows<NIMG>(s, lnp2);
       __syncthreads();
       mark(6);
       // ---- S7: ff = relu(linear0(w))  (F = 4 segments of D columns) --------------------------------
+      stage_begin(NIMG * 2048u);
+      sb = stage_bar();
       gemm_stage<D, 16>(s, pol, &s.abf[0][0], D + APAD, W.w_f0 + (size_t)r * 16 * (D / 32) * 32,
                         [&](int tile, float (&c)[4], int ln) {
                           const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
                           const float b0 = __ldg(W.b_f0 + col), b1 = __ldg(W.b_f0 + col + 1);
-                          ag_store_u32(cl, &s.abf2[row][col], pack_bf16(fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f)));
+                          ag_store_u32(sb, &s.abf2[row][col], pack_bf16(fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f)));
                           if (NIMG == 16) {
-                          ag_store_u32(cl, &s.abf2[row + 8][col], pack_bf16(fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f)));
+                          ag_store_u32(sb, &s.abf2[row + 8][col], pack_bf16(fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f)));
                           }
                         });
       mark(8);
-      cl.sync();
+      stage_end();
       mark(5);
       // ---- S8: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
+      stage_begin(NIMG * 1024u);
+      sb = stage_bar();
       gemm_stage<DEC_FMAX, 4>(s, pol, &s.abf2[0][0], DEC_FMAX + APAD, W.w_f1 + (size_t)r * 4 * (DEC_FMAX / 32) * 32,
                               [&](int tile, float (&c)[4], int ln) {
                                 const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                                 const float b0 = __ldg(W.b_f1 + col), b1 = __ldg(W.b_f1 + col + 1);
-                                ag_store_f2(cl, &s.pre[row][col], fmaxf(c[0] + b0, 0.f) + s.xres[row][col],
+                                ag_store_f2(sb, &s.pre[row][col], fmaxf(c[0] + b0, 0.f) + s.xres[row][col],
                                             fmaxf(c[1] + b1, 0.f) + s.xres[row][col + 1]);
                                 if (NIMG == 16) {
-                                ag_store_f2(cl, &s.pre[row + 8][col], fmaxf(c[2] + b0, 0.f) + s.xres[row + 8][col],
+                                ag_store_f2(sb, &s.pre[row + 8][col], fmaxf(c[2] + b0, 0.f) + s.xres[row + 8][col],
                                             fmaxf(c[3] + b1, 0.f) + s.xres[row + 8][col + 1]);
                                 }
                               });
       mark(9);
       const LnParams lnp3 = load_ln(W.ln3_g, W.ln3_b);
-      cl.sync();
+      stage_end();
       mark(5);
       layernorm_rows<NIMG>(s, lnp3);
       __syncthreads();
       mark(6);
       // ---- S9: K/V rows of y -> cache; next layer's q|k|v, or the vocabulary logits -------------------
+      stage_begin(NIMG * (l + 1 < L ? 2048u : 1024u) + NIMG * 128u);
+      sb = stage_bar();
       auto kv_store = [&](int tile, float (&c)[4], int ln) {
-        // tiles 0..3: K columns of head r; tiles 4..7: V columns of head r
+        // tiles 0..3: K columns of head r; tiles 4..7: V columns of head r.  The values go to the CTA that
+        // OWNS the image (it attends over that image's cache), which writes them to the global cache itself.
         const int seg = tile >> 2, dcol = (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
         const float* bias = W.b_next + seg * D + r * 32 + dcol;
         const float b0 = __ldg(bias), b1 = __ldg(bias + 1);
-        __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
 #pragma unroll
         for (int hrow = 0; hrow < NIMG / 8; ++hrow) {
-          const int b = img0 + row + hrow * 8;
-          if (b < B) {
-            const size_t off = (((((size_t)l * B + b) * H + r) * T) + t) * HD + dcol;
-            *reinterpret_cast<uint32_t*>(dst + off) = pack_bf16(c[hrow * 2] + b0, c[hrow * 2 + 1] + b1);
-          }
+          const int li = row + hrow * 8;                 // cluster-local image
+          const uint32_t owner = (uint32_t)(li / (NIMG / 8));
+          const uint32_t la = smem_u32(&s.kvrow[li % (NIMG / 8)][seg][r * 32 + dcol]);
+          st_async_b32(mapa_u32(la, owner), pack_bf16(c[hrow * 2] + b0, c[hrow * 2 + 1] + b1), mapa_u32(sb, owner));
         }
       };
       if (l + 1 < L) {
@@ -569,14 +647,14 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                             const int col = (seg - 2) * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
                             const float b0 = __ldg(W.b_next + 2 * D + col), b1 = __ldg(W.b_next + 2 * D + col + 1);
                             if (seg == 2) {
-                              ag_store_f2(cl, &s.q[row][col], c[0] + b0, c[1] + b1);
+                              ag_store_f2(sb, &s.q[row][col], c[0] + b0, c[1] + b1);
                               if (NIMG == 16) {
-                              ag_store_f2(cl, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
+                              ag_store_f2(sb, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
                               }
                             } else {
-                              ag_store_u32(cl, &s.kv[row][col - D], pack_bf16(c[0] + b0, c[1] + b1));
+                              ag_store_u32(sb, &s.kv[row][col - D], pack_bf16(c[0] + b0, c[1] + b1));
                               if (NIMG == 16) {
-                              ag_store_u32(cl, &s.kv[row + 8][col - D], pack_bf16(c[2] + b0, c[3] + b1));
+                              ag_store_u32(sb, &s.kv[row + 8][col - D], pack_bf16(c[2] + b0, c[3] + b1));
                               }
                             }
                           });
@@ -589,9 +667,9 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                             const float b0 = col < V ? __ldg(W.b_next + 2 * D + col) : 0.f;
                             const float b1 = col + 1 < V ? __ldg(W.b_next + 2 * D + col + 1) : 0.f;
                             const float v00 = c[0] + b0, v01 = c[1] + b1, v10 = c[2] + b0, v11 = c[3] + b1;
-                            ag_store_f2(cl, &s.q[row][col], v00, v01);
+                            ag_store_f2(sb, logit_s + row * 256 + col, v00, v01);
                             if (NIMG == 16) {
-                            ag_store_f2(cl, &s.q[row + 8][col], v10, v11);
+                            ag_store_f2(sb, logit_s + (row + 8) * 256 + col, v10, v11);
                             }
                             if (p.logits) {
                               const int bA = img0 + row, bB = img0 + row + 8;
@@ -609,7 +687,17 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                           });
       }
       mark(10);
-      cl.sync();
+      stage_end();
+      // write-out of the K/V rows this CTA owns: 16-byte stores, 64 contiguous bytes per (head, K|V)
+      if (tid < 64 * (NIMG / 8)) {
+        const int j = tid >> 6, rem = tid & 63, seg = rem >> 5, hh = (rem >> 2) & 7, ch = rem & 3;
+        const int b = img0 + r * (NIMG / 8) + j;
+        if (b < B) {
+          const uint4 v = *reinterpret_cast<const uint4*>(&s.kvrow[j][seg][hh * HD + ch * 8]);
+          __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
+          *reinterpret_cast<uint4*>(dst + (((((size_t)l * B + b) * H + hh) * T) + t) * HD + ch * 8) = v;
+        }
+      }
       mark(5);
     }  // layers
     // ---- greedy pick (first max index) + next input: every CTA does all 16 rows -------------------------
@@ -619,7 +707,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       float best = -INFINITY;
       int bi = 0x7fffffff;
       for (int i = lane; i < V; i += 32) {
-        float v = s.q[row][i];
+        float v = logit_s[row * 256 + i];
         if (v > best) { best = v; bi = i; }
       }
 #pragma unroll
@@ -648,11 +736,8 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
     }
     __syncthreads();
     mark(11);
-    // the next step's first remote stores (S1 -> qkv) must not overtake a peer that is still
-    // reading the logits out of its qkv buffer
-    cl.sync();
-    mark(5);
   }
+  cl.sync();  // nobody exits while a peer's stores to it may still be in flight
   if (profiling) for (int i = 0; i < 16; ++i) p.prof[i] = s.prof[i];
 }
 
