@@ -107,14 +107,60 @@ struct Smem {
 // NT >= 8: warp w owns tiles w, w+8, ...; NT == 4: two warps split K per tile.
 // Epi(tile, acc, lane) is called by the warp that holds the final accumulator.
 // ---------------------------------------------------------------------------
+// Weight prefetch: the first PF k-pairs of every tile a warp owns are loaded into registers BEFORE the
+// previous stage's barrier wait / LayerNorm, so their L2 latency overlaps that wait.  (Weights are static;
+// nothing orders these loads against the exchange.)
+template <int K, int NT>
+struct WPre {
+  static constexpr int TPW = NT >= 8 ? (NT + 7) / 8 : 1;
+  static constexpr int KP = K / 32;
+  static constexpr int KPW = NT >= 8 ? KP : KP / 2;  // k-pairs per warp task
+  static constexpr int PF = NT >= 8 ? 2 : 4;         // prefetched k-pairs
+  uint4 w[TPW][PF];
+};
+
+template <int K, int NT>
+__device__ __forceinline__ WPre<K, NT> prefetch_weights(const uint4* __restrict__ Wp, uint64_t pol) {
+  using P = WPre<K, NT>;
+  P pre;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if constexpr (NT >= 8) {
+#pragma unroll
+    for (int i = 0; i < P::TPW; ++i) {
+      const int tile = warp + 8 * i;
+#pragma unroll
+      for (int j = 0; j < P::PF; ++j)
+        pre.w[i][j] = tile < NT ? ldg_weights(Wp + ((size_t)tile * P::KP + j) * 32 + lane, pol) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  } else {
+    const int tile = warp & 3, half = warp >> 2;
+#pragma unroll
+    for (int j = 0; j < P::PF; ++j)
+      pre.w[0][j] = ldg_weights(Wp + ((size_t)tile * P::KP + half * P::KPW + j) * 32 + lane, pol);
+  }
+  return pre;
+}
+
 template <int K, int NT, typename Epi>
 __device__ __forceinline__ void gemm_stage(Smem& s, uint64_t pol, const __nv_bfloat16* A, int lda,
-                                           const uint4* __restrict__ Wp, Epi epi) {
+                                           const uint4* __restrict__ Wp, const WPre<K, NT>& pre, Epi epi) {
+  using P = WPre<K, NT>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   constexpr int KP = K / 32;
+  auto a_frags = [&](int kp, uint32_t (&a0)[4], uint32_t (&a1)[4]) {
+    const __nv_bfloat16* ap = A + gid * lda + kp * 32 + tig * 2;
+    a0[0] = *reinterpret_cast<const uint32_t*>(ap);
+    a0[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda);
+    a0[2] = *reinterpret_cast<const uint32_t*>(ap + 8);
+    a0[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 8);
+    a1[0] = *reinterpret_cast<const uint32_t*>(ap + 16);
+    a1[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 16);
+    a1[2] = *reinterpret_cast<const uint32_t*>(ap + 24);
+    a1[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 24);
+  };
   if constexpr (NT >= 8) {
-    constexpr int TPW = (NT + 7) / 8;
+    constexpr int TPW = P::TPW;
     float acc[TPW][2][4];
 #pragma unroll
     for (int i = 0; i < TPW; ++i)
@@ -122,8 +168,20 @@ __device__ __forceinline__ void gemm_stage(Smem& s, uint64_t pol, const __nv_bfl
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
-#pragma unroll 4
-    for (int kp = 0; kp < KP; ++kp) {
+#pragma unroll
+    for (int kp = 0; kp < P::PF; ++kp) {  // prefetched k-pairs
+      uint32_t a0[4], a1[4];
+      a_frags(kp, a0, a1);
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        if (warp + 8 * i < NT) {
+          mma_bf16(acc[i][0], a0, pre.w[i][kp].x, pre.w[i][kp].y);
+          mma_bf16(acc[i][1], a1, pre.w[i][kp].z, pre.w[i][kp].w);
+        }
+      }
+    }
+#pragma unroll 3
+    for (int kp = P::PF; kp < KP; ++kp) {
       uint4 w[TPW];
 #pragma unroll
       for (int i = 0; i < TPW; ++i) {
@@ -131,15 +189,7 @@ __device__ __forceinline__ void gemm_stage(Smem& s, uint64_t pol, const __nv_bfl
         if (tile < NT) w[i] = ldg_weights(Wp + ((size_t)tile * KP + kp) * 32 + lane, pol);
       }
       uint32_t a0[4], a1[4];
-      const __nv_bfloat16* ap = A + gid * lda + kp * 32 + tig * 2;
-      a0[0] = *reinterpret_cast<const uint32_t*>(ap);
-      a0[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda);
-      a0[2] = *reinterpret_cast<const uint32_t*>(ap + 8);
-      a0[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 8);
-      a1[0] = *reinterpret_cast<const uint32_t*>(ap + 16);
-      a1[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 16);
-      a1[2] = *reinterpret_cast<const uint32_t*>(ap + 24);
-      a1[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 24);
+      a_frags(kp, a0, a1);
 #pragma unroll
       for (int i = 0; i < TPW; ++i) {
         if (warp + 8 * i < NT) {
@@ -166,21 +216,20 @@ __device__ __forceinline__ void gemm_stage(Smem& s, uint64_t pol, const __nv_bfl
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-    constexpr int KH = KP / 2;
+    constexpr int KH = P::KPW;
+#pragma unroll
+    for (int kk = 0; kk < P::PF; ++kk) {
+      uint32_t a0[4], a1[4];
+      a_frags(half * KH + kk, a0, a1);
+      mma_bf16(acc[0], a0, pre.w[0][kk].x, pre.w[0][kk].y);
+      mma_bf16(acc[1], a1, pre.w[0][kk].z, pre.w[0][kk].w);
+    }
 #pragma unroll 4
-    for (int kk = 0; kk < KH; ++kk) {
+    for (int kk = P::PF; kk < KH; ++kk) {
       const int kp = half * KH + kk;
       uint4 w = ldg_weights(Wp + ((size_t)tile * KP + kp) * 32 + lane, pol);
       uint32_t a0[4], a1[4];
-      const __nv_bfloat16* ap = A + gid * lda + kp * 32 + tig * 2;
-      a0[0] = *reinterpret_cast<const uint32_t*>(ap);
-      a0[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda);
-      a0[2] = *reinterpret_cast<const uint32_t*>(ap + 8);
-      a0[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 8);
-      a1[0] = *reinterpret_cast<const uint32_t*>(ap + 16);
-      a1[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 16);
-      a1[2] = *reinterpret_cast<const uint32_t*>(ap + 24);
-      a1[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 24);
+      a_frags(kp, a0, a1);
       mma_bf16(acc[0], a0, w.x, w.y);
       mma_bf16(acc[1], a1, w.z, w.w);
     }
@@ -459,7 +508,8 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
         stage_begin(NIMG * 2048u);
         const uint32_t sb = stage_bar();
         const uint4* wp = p.w_first + (size_t)r * 12 * (D / 32) * 32;
-        gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, wp, [&](int tile, float (&c)[4], int ln) {
+        const auto pre_s1 = prefetch_weights<D, 12>(wp, pol);
+        gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, wp, pre_s1, [&](int tile, float (&c)[4], int ln) {
           const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
           const float b0 = __ldg(p.b_first + col), b1 = __ldg(p.b_first + col + 1);
           if (seg == 0) {
@@ -502,13 +552,14 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
           }
         }
         mark(2);
-        stage_end();
-        mark(3);
       }
+      const auto pre_s3 = prefetch_weights<D, 4>(W.w_o + (size_t)r * 4 * (D / 32) * 32, pol);
+      stage_end();
+      mark(3);
       // ---- S3: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
       stage_begin(NIMG * 1024u);
       uint32_t sb = stage_bar();
-      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o + (size_t)r * 4 * (D / 32) * 32,
+      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o + (size_t)r * 4 * (D / 32) * 32, pre_s3,
                        [&](int tile, float (&c)[4], int ln) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_o + col), b1 = __ldg(W.b_o + col + 1);
@@ -520,6 +571,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                        });
       mark(4);
       const LnParams lnp1 = load_ln(W.ln1_g, W.ln1_b);
+      const auto pre_s4 = prefetch_weights<D, 4>(W.w_q2 + (size_t)r * 4 * (D / 32) * 32, pol);
       stage_end();
       mark(5);
       layernorm_rows<NIMG>(s, lnp1);
@@ -528,7 +580,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       // ---- S4: q2 = q_linear(u) ---------------------------------------------------------------
       stage_begin(NIMG * 1024u);
       sb = stage_bar();
-      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_q2 + (size_t)r * 4 * (D / 32) * 32,
+      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_q2 + (size_t)r * 4 * (D / 32) * 32, pre_s4,
                        [&](int tile, float (&c)[4], int ln) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_q2 + col), b1 = __ldg(W.b_q2 + col + 1);
@@ -563,13 +615,14 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
           }
         }
         mark(7);
-        stage_end();
-        mark(3);
       }
+      const auto pre_s6 = prefetch_weights<D, 4>(W.w_o2 + (size_t)r * 4 * (D / 32) * 32, pol);
+      stage_end();
+      mark(3);
       // ---- S6: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
       stage_begin(NIMG * 1024u);
       sb = stage_bar();
-      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o2 + (size_t)r * 4 * (D / 32) * 32,
+      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o2 + (size_t)r * 4 * (D / 32) * 32, pre_s6,
                        [&](int tile, float (&c)[4], int ln) {
                          const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                          const float b0 = __ldg(W.b_o2 + col), b1 = __ldg(W.b_o2 + col + 1);
@@ -581,6 +634,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                        });
       mark(4);
       const LnParams lnp2 = load_ln(W.ln2_g, W.ln2_b);
+      const auto pre_s7 = prefetch_weights<D, 16>(W.w_f0 + (size_t)r * 16 * (D / 32) * 32, pol);
       stage_end();
       mark(5);
       layernorm_rows<NIMG>(s, lnp2);
@@ -589,7 +643,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       // ---- S7: ff = relu(linear0(w))  (F = 4 segments of D columns) --------------------------------
       stage_begin(NIMG * 2048u);
       sb = stage_bar();
-      gemm_stage<D, 16>(s, pol, &s.abf[0][0], D + APAD, W.w_f0 + (size_t)r * 16 * (D / 32) * 32,
+      gemm_stage<D, 16>(s, pol, &s.abf[0][0], D + APAD, W.w_f0 + (size_t)r * 16 * (D / 32) * 32, pre_s7,
                         [&](int tile, float (&c)[4], int ln) {
                           const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
                           const float b0 = __ldg(W.b_f0 + col), b1 = __ldg(W.b_f0 + col + 1);
@@ -599,12 +653,13 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                           }
                         });
       mark(8);
+      const auto pre_s8 = prefetch_weights<DEC_FMAX, 4>(W.w_f1 + (size_t)r * 4 * (DEC_FMAX / 32) * 32, pol);
       stage_end();
       mark(5);
       // ---- S8: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
       stage_begin(NIMG * 1024u);
       sb = stage_bar();
-      gemm_stage<DEC_FMAX, 4>(s, pol, &s.abf2[0][0], DEC_FMAX + APAD, W.w_f1 + (size_t)r * 4 * (DEC_FMAX / 32) * 32,
+      gemm_stage<DEC_FMAX, 4>(s, pol, &s.abf2[0][0], DEC_FMAX + APAD, W.w_f1 + (size_t)r * 4 * (DEC_FMAX / 32) * 32, pre_s8,
                               [&](int tile, float (&c)[4], int ln) {
                                 const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
                                 const float b0 = __ldg(W.b_f1 + col), b1 = __ldg(W.b_f1 + col + 1);
@@ -617,6 +672,12 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                               });
       mark(9);
       const LnParams lnp3 = load_ln(W.ln3_g, W.ln3_b);
+      const bool last_layer = l + 1 >= L;
+      // prefetch of S9's weights (two shapes: next-layer q|k|v or the generator) overlaps the S8 wait + LayerNorm
+      WPre<D, 20> pre_s9a;
+      WPre<D, 12> pre_s9b;
+      if (!last_layer) pre_s9a = prefetch_weights<D, 20>(W.w_next + (size_t)r * 20 * (D / 32) * 32, pol);
+      else pre_s9b = prefetch_weights<D, 12>(W.w_next + (size_t)r * 12 * (D / 32) * 32, pol);
       stage_end();
       mark(5);
       layernorm_rows<NIMG>(s, lnp3);
@@ -640,7 +701,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
         }
       };
       if (l + 1 < L) {
-        gemm_stage<D, 20>(s, pol, &s.abf[0][0], D + APAD, W.w_next + (size_t)r * 20 * (D / 32) * 32,
+        gemm_stage<D, 20>(s, pol, &s.abf[0][0], D + APAD, W.w_next + (size_t)r * 20 * (D / 32) * 32, pre_s9a,
                           [&](int tile, float (&c)[4], int ln) {
                             if (tile < 8) { kv_store(tile, c, ln); return; }
                             const int seg = tile >> 2;  // 2,3,4 -> q,k,v of layer l+1
@@ -660,7 +721,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                           });
       } else {
         // generator: V columns padded to 256; CTA r owns columns [32r, 32r+32) (tiles 8..11)
-        gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, W.w_next + (size_t)r * 12 * (D / 32) * 32,
+        gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, W.w_next + (size_t)r * 12 * (D / 32) * 32, pre_s9b,
                           [&](int tile, float (&c)[4], int ln) {
                             if (tile < 8) { kv_store(tile, c, ln); return; }
                             const int col = r * 32 + (tile - 8) * 8 + (ln & 3) * 2, row = ln >> 2;
