@@ -214,10 +214,9 @@ def run_frx(args, rank, world, local_rank):
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = t.tolist()
+    import frx
+    total_ms = frx.sharding.max_over_ranks(total_ms, dev)      # the job is as slow as its slowest rank
+    e2e_ms = frx.sharding.max_over_ranks(e2e_s * 1e3, dev)
     if rank != 0:
         return
     n_img = B * args.steps * world

@@ -198,12 +198,17 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
   const int c = c0 + cg * 8;
   const bool c_ok = c < C;
   float wv[9][8], sc[8], sh[8], sum[8];
+  auto ld8 = [&](const float* ptr, float (&dst)[8]) {  // two 16-byte loads (C % 8 == 0, arena 256-byte aligned)
+    const float4 a = c_ok ? __ldg(reinterpret_cast<const float4*>(ptr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b4 = c_ok ? __ldg(reinterpret_cast<const float4*>(ptr + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b4.x; dst[5] = b4.y; dst[6] = b4.z; dst[7] = b4.w;
+  };
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sum[j] = 0.f; sc[j] = c_ok ? __ldg(scale + c + j) : 0.f; sh[j] = c_ok ? __ldg(shift + c + j) : 0.f; }
+  for (int j = 0; j < 8; ++j) sum[j] = 0.f;
+  ld8(scale + c, sc);
+  ld8(shift + c, sh);
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wv[t][j] = c_ok ? __ldg(w + t * C + c + j) : 0.f;
+  for (int t = 0; t < 9; ++t) ld8(w + t * C + c, wv[t]);
   const __nv_bfloat16* ip = in + (long long)n * H * W * C;
   __nv_bfloat16* op = out + (long long)n * OH * OW * C;
   if (c_ok) {
@@ -273,8 +278,9 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ me
     if (lane == 0) red[r] = act_apply(s + __ldg(b1 + r), ACT_SILU);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {  // expand outputs split over gridDim.y CTAs
     float s = __ldg(b2 + c);
+#pragma unroll 8
     for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2 + (long long)r * C + c), red[r], s);  // w2 is [R][C] (transposed at pack time)
     gate[(long long)n * C + c] = 1.f / (1.f + expf(-s));
   }
@@ -303,7 +309,7 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
                               int pad_t, int pad_l, int R, cudaStream_t st) {
   dim3 g(B, (C + 63) / 64);
   dwconv_se_mean_kernel<<<g, 256, 0, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l);
-  se_fc_kernel<<<B, 256, (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, C, R);
+  se_fc_kernel<<<dim3(B, (C + 255) / 256), 256, (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, C, R);
   long long total8 = (long long)B * OH * OW * (C / 8);
   se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(out, gate, total8, OH * OW, C);
 }

@@ -362,7 +362,7 @@ void launch_maxpool2_f32(const float* in, float* out, int B, int H, int W, int C
 //    x NHWC [B, S=h*w, C]; gates = sigmoid(W1 relu(W0 mean + b0) + b1) [2C];
 //    out = x + g[c]*PEh[row][c] + g[C+c]*PEw[col][c]
 // ===========================================================================
-__global__ void __launch_bounds__(256) pe2d_f32_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(1024) pe2d_f32_kernel(const float* __restrict__ x,
                                                        const float* __restrict__ w0,  // [C/2][C]
                                                        const float* __restrict__ b0,
                                                        const float* __restrict__ w1,  // [2C][C/2]
@@ -384,14 +384,15 @@ __global__ void __launch_bounds__(256) pe2d_f32_kernel(const float* __restrict__
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < C / 2; r += 8) {
+  const int nwarps = blockDim.x >> 5;
+  for (int r = warp; r < C / 2; r += nwarps) {
     float s = 0.f;
     for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w0 + (long long)r * C + c), mean[c], s);
     s = warp_sum(s);
     if (lane == 0) hid[r] = fmaxf(s + __ldg(b0 + r), 0.f);
   }
   __syncthreads();
-  for (int r = warp; r < 2 * C; r += 8) {
+  for (int r = warp; r < 2 * C; r += nwarps) {
     float s = 0.f;
     for (int c = lane; c < C / 2; c += 32) s = fmaf(__ldg(w1 + (long long)r * (C / 2) + c), hid[c], s);
     s = warp_sum(s);
@@ -411,7 +412,7 @@ void launch_pe2d_f32(const float* x, const float* w0, const float* b0, const flo
                      const float* peh, const float* pew, float* out, int B, int h, int w, int C,
                      cudaStream_t st) {
   int smem = (C + C / 2 + 2 * C) * sizeof(float);
-  pe2d_f32_kernel<<<B, 256, smem, st>>>(x, w0, b0, w1, b1, peh, pew, out, h, w, C);
+  pe2d_f32_kernel<<<B, 1024, smem, st>>>(x, w0, b0, w1, b1, peh, pew, out, h, w, C);
 }
 
 // ===========================================================================
