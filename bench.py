@@ -32,6 +32,18 @@ ENCODE_FLOP_PER_IMAGE = 3.700e9 + 0.207e9
 TOTAL_FLOP_PER_IMAGE = 5.54e9
 
 
+def ncu_traffic(kernel, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json), or None when no capture matches this kernel / batch."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    for e in json.load(open(path)):
+        if e["kernel"] == kernel and e["batch"] == batch:
+            return e["dram_bytes_per_launch"]
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -54,7 +66,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -245,7 +257,7 @@ def run_frx(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(tokens_host.numel() * 8)},
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": None,
+                     "traffic": ncu_traffic("dec_cluster_bf16_kernel", B) if single_kernel else None,
                      "kernel": "dec_cluster_bf16_kernel (one launch = all 231 decode steps of the batch)" if single_kernel
                      else "greedy decode loop (CUDA graph of the fp32 step kernels)",
                      "algorithmic_bytes_per_launch": dec_bytes,
@@ -279,7 +291,7 @@ def run_frx(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="frx", choices=["frx", "reference"])
     ap.add_argument("--batch", type=int, default=256)
