@@ -73,6 +73,8 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -148,17 +150,17 @@ __device__ __forceinline__ void gemm_stage(Smem& s, uint64_t pol, const __nv_bfl
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   constexpr int KP = K / 32;
+  // A fragments of two k16 steps with two ldmatrix.x4 (instead of eight 32-bit LDS): lane -> row address of
+  // matrix (lane >> 3): {rows 0-7, k lo}, {rows 8-15, k lo}, {rows 0-7, k hi}, {rows 8-15, k hi} = a0..a3.
+  const uint32_t a_lane = smem_addr_u32(A + ((lane & 7) + ((lane >> 3) & 1) * 8) * lda + ((lane >> 4) & 1) * 8);
   auto a_frags = [&](int kp, uint32_t (&a0)[4], uint32_t (&a1)[4]) {
-    const __nv_bfloat16* ap = A + gid * lda + kp * 32 + tig * 2;
-    a0[0] = *reinterpret_cast<const uint32_t*>(ap);
-    a0[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda);
-    a0[2] = *reinterpret_cast<const uint32_t*>(ap + 8);
-    a0[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 8);
-    a1[0] = *reinterpret_cast<const uint32_t*>(ap + 16);
-    a1[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 16);
-    a1[2] = *reinterpret_cast<const uint32_t*>(ap + 24);
-    a1[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * lda + 24);
+    const uint32_t addr = a_lane + (uint32_t)kp * 64u;  // 32 bf16 per k-pair
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(a0[0]), "=r"(a0[1]), "=r"(a0[2]), "=r"(a0[3]) : "r"(addr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(a1[0]), "=r"(a1[1]), "=r"(a1[2]), "=r"(a1[3]) : "r"(addr + 32u));
   };
+  (void)gid; (void)tig;
   if constexpr (NT >= 8) {
     constexpr int TPW = P::TPW;
     float acc[TPW][2][4];
