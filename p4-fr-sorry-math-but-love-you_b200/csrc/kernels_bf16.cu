@@ -187,16 +187,26 @@ void launch_se_scale_bf16(__nv_bfloat16* x, const float* w1, const float* b1, co
 //   2. se_fc: the two tiny FCs per image -> gate[B][C];
 //   3. se_apply: x *= gate, fully parallel 16-byte elementwise pass.
 // ---------------------------------------------------------------------------
+// One CTA = one (image, 64-channel chunk).  The whole input tile of the chunk is staged in shared memory with
+// coalesced 16-byte loads issued up front (all in flight at once), then every output pixel reads its 9 taps
+// from shared memory; the CTA also owns the chunk's spatial mean (deterministic, no atomics).
 __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
                                                              int H, int W, int C, int OH, int OW, int stride, int pad_t,
                                                              int pad_l) {
-  __shared__ float red[32][64 + 1];
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  uint4* tile = reinterpret_cast<uint4*>(dw_smem);                                   // [H*W][8 channel groups] x 16 B
+  float (*red)[64 + 1] = reinterpret_cast<float (*)[64 + 1]>(dw_smem + (size_t)H * W * 8 * 16);  // [32][65]
   const int n = blockIdx.x, c0 = blockIdx.y * 64;
   const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;  // 8 channels per thread, 32 pixel lanes
   const int c = c0 + cg * 8;
   const bool c_ok = c < C;
+  const __nv_bfloat16* ip = in + (long long)n * H * W * C;
+  for (int i = threadIdx.x; i < H * W * 8; i += 256) {
+    const int px = i >> 3, g = i & 7;
+    tile[i] = (c0 + g * 8 < C) ? __ldg(reinterpret_cast<const uint4*>(ip + (long long)px * C + c0 + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+  }
   float wv[9][8], sc[8], sh[8], sum[8];
   auto ld8 = [&](const float* ptr, float (&dst)[8]) {  // two 16-byte loads (C % 8 == 0, arena 256-byte aligned)
     const float4 a = c_ok ? __ldg(reinterpret_cast<const float4*>(ptr)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
   ld8(shift + c, sh);
 #pragma unroll
   for (int t = 0; t < 9; ++t) ld8(w + t * C + c, wv[t]);
-  const __nv_bfloat16* ip = in + (long long)n * H * W * C;
+  __syncthreads();
   __nv_bfloat16* op = out + (long long)n * OH * OW * C;
   if (c_ok) {
     for (int px = pl; px < OH * OW; px += 32) {
@@ -217,24 +227,19 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      uint4 taps[9];  // all nine 16-byte loads in flight before any arithmetic
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int ih = oh * stride - pad_t + kh;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const int iw = ow * stride - pad_l + kw;
-          const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-          taps[kh * 3 + kw] = ok ? __ldg(reinterpret_cast<const uint4*>(ip + ((long long)ih * W + iw) * C + c))
-                                 : make_uint4(0u, 0u, 0u, 0u);
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            float x[8];
+            unpack8(tile[(ih * W + iw) * 8 + cg], x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], wv[kh * 3 + kw][j], acc[j]);
+          }
         }
-      }
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        float x[8];
-        unpack8(taps[t], x);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], wv[t][j], acc[j]);
       }
       float o[8];
 #pragma unroll
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
       const uint4 packed = pack8(o);
       *reinterpret_cast<uint4*>(op + (long long)px * C + c) = packed;
       float back[8];
-      unpack8(packed, back);  // the mean is taken over the stored (bf16-rounded) activations, like the 3-kernel version
+      unpack8(packed, back);  // the mean is taken over the stored (bf16-rounded) activations
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum[j] += back[j];
     }
@@ -308,7 +313,13 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
                               const float* w2, const float* b2, int B, int H, int W, int C, int OH, int OW, int stride,
                               int pad_t, int pad_l, int R, cudaStream_t st) {
   dim3 g(B, (C + 63) / 64);
-  dwconv_se_mean_kernel<<<g, 256, 0, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l);
+  const size_t smem = (size_t)H * W * 8 * 16 + 32 * 65 * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(dwconv_se_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dwconv_se_mean_kernel<<<g, 256, smem, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l);
   se_fc_kernel<<<dim3(B, (C + 255) / 256), 256, (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, C, R);
   long long total8 = (long long)B * OH * OW * (C / 8);
   se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(out, gate, total8, OH * OW, C);
