@@ -73,5 +73,32 @@ def main():
         print("wrote", path, os.path.getsize(path) // 1024, "KiB", "digest", out["digest"])
 
 
+LITE_SPEC = dict(network="LiteSATRN", enc_hidden=256, enc_filter=256, enc_layers=1, enc_heads=4,
+                 dec_src=256, dec_hidden=128, dec_filter=512, dec_layers=2, dec_heads=4)
+
+
+def main_lite():
+    """LiteSATRN (networks/LiteSATRN.py) greedy fixtures: 100 % reference code (no third-party arithmetic)."""
+    torch.set_grad_enabled(False)
+    ref = ref_shim.load_reference()
+    spec = satrn.ModelSpec(**LITE_SPEC)
+    sd = synth.synth_state_dict(spec, 0, calib_batch=4)
+    model = ref.networks.LiteSATRN(ref_shim.reference_flags("LiteSATRN"), ref_shim.reference_vocab()).eval()
+    model.load_state_dict(sd, strict=True)
+    batch, steps = 3, 120
+    images = synth.synth_images(spec, batch, 0)
+    expected = satrn.expected_tokens(batch, steps - 1)
+    logits = model(images, expected, False, 0.0)
+    tokens = ref.postprocessing.decode(model, images, expected=expected, method="greedy")
+    out = dict(digest=np.array(state_dict_digest(sd)), memory=model.encoder(images).contiguous().numpy(),
+               logits=logits.numpy(), tokens=tokens.numpy())
+    path = os.path.join(GOLDEN_DIR, "litesatrn_seed0.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if "--lite" in sys.argv:
+        main_lite()
+        sys.exit(0)
     main()

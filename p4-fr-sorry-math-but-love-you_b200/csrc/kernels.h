@@ -7,6 +7,9 @@ namespace frx {
 // fp32 kernel set (kernels_f32.cu)
 void launch_stem_conv(const float* in, const float* w, const float* scale, const float* shift, float* out,
                       int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st);
+void launch_direct_conv3x3(const float* in, const float* w, const float* scale, const float* shift, float* out, int B,
+                           int Cin, int H, int W, int OH, int OW, int Cout, int stride, int pad, int act,
+                           cudaStream_t st);
 void launch_igemm_f32(const GemmP& p, cudaStream_t st);
 void launch_dwconv_f32(const DwP& p, cudaStream_t st);
 void launch_se_gate_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,

@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ shift,
                                                         float* __restrict__ out, int B, int Cin, int H,
-                                                        int W, int OH, int OW, int Cout) {
+                                                        int W, int OH, int OW, int Cout, int stride, int pad,
+                                                        int act) {
   extern __shared__ float ws[];  // Cout*Cin*9 + 2*Cout
   for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) ws[i] = w[i];
   float* ssc = ws + Cout * Cin * 9;
@@ -37,23 +38,38 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
   int n = (int)(pix / ((long long)OW * OH));
   float acc = 0.f;
   for (int ci = 0; ci < Cin; ++ci) {
-    const float* ip = in + (((long long)n * Cin + ci) * H + oh * 2) * W + ow * 2;
+    const float* ip = in + ((long long)n * Cin + ci) * H * W;
     const float* wp = ws + (co * Cin + ci) * 9;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * stride - pad + kh;
+      if (ih < 0 || ih >= H) continue;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) acc = fmaf(__ldg(ip + kh * W + kw), wp[kh * 3 + kw], acc);
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * stride - pad + kw;
+        if (iw < 0 || iw >= W) continue;
+        acc = fmaf(__ldg(ip + (long long)ih * W + iw), wp[kh * 3 + kw], acc);
+      }
+    }
   }
-  out[idx] = act_apply(acc * ssc[co] + ssh[co], ACT_SILU);
+  out[idx] = act_apply(acc * ssc[co] + ssh[co], act);
 }
 
 void launch_stem_conv(const float* in, const float* w, const float* scale, const float* shift,
                       float* out, int B, int Cin, int H, int W, int OH, int OW, int Cout,
                       cudaStream_t st) {
+  launch_direct_conv3x3(in, w, scale, shift, out, B, Cin, H, W, OH, OW, Cout, 2, 0, ACT_SILU, st);
+}
+
+// Direct 3x3 convolution from an NCHW fp32 image (few input channels) to NHWC fp32:
+// EfficientSATRN stem (stride 2, padding 0, SiLU) and LiteSATRN conv0 (stride 1, padding 1, ReLU).
+void launch_direct_conv3x3(const float* in, const float* w, const float* scale, const float* shift, float* out, int B,
+                           int Cin, int H, int W, int OH, int OW, int Cout, int stride, int pad, int act,
+                           cudaStream_t st) {
   long long total = (long long)B * OH * OW * Cout;
   int smem = (Cout * Cin * 9 + 2 * Cout) * sizeof(float);
   stem_conv_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(in, w, scale, shift, out, B, Cin,
-                                                                      H, W, OH, OW, Cout);
+                                                                      H, W, OH, OW, Cout, stride, pad, act);
 }
 
 // ===========================================================================

@@ -184,6 +184,8 @@ extern "C" int frx_create(const frx_config* cfg, frx_handle** out) {
     return fail(h, "decoder head_dim must be 32 or 64");
   if (cfg->dec_hidden > 256) return fail(h, "decoder hidden_dim > 256 not supported yet");
   if (cfg->max_batch <= 0 || cfg->max_steps <= 0) return fail(h, "max_batch/max_steps must be positive");
+  if (cfg->network == FRX_NET_LITE_SATRN && cfg->precision != FRX_PREC_FP32)
+    return fail(h, "LiteSATRN is built for the fp32 mode only (the bf16 kernels are specialised for EfficientSATRN's dimensions)");
   return 0;
 }
 
@@ -930,19 +932,49 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
   return 0;
 }
 
+// LiteSATRN ShallowCNN (LiteSATRN.py:21-70): 4 x (conv3x3 p1 + BN + ReLU + maxpool2) -> H/16 x W/16 x hidden
+static int run_trunk_lite(frx_handle* h, const float* images, int B, float** out, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  const float* A = h->arena;
+  int H = c.height, W = c.width;
+  float* x = h->act[0];
+  float* y = h->act[1];
+  for (int i = 0; i < 4; ++i) {
+    const LiteConvW& L = h->lite[i];
+    if (i == 0) {
+      launch_direct_conv3x3(images, A + L.w, A + L.sc, A + L.sh, x, B, L.cin, H, W, H, W, L.cout, 1, 1, ACT_RELU, st);
+      CKL();
+    } else {
+      int OH, OW;
+      GemmP g = conv_gemm(y, B, H, W, L.cin, A + L.w, L.cout, 3, 1, x, &OH, &OW);
+      g.scale = A + L.sc; g.shift = A + L.sh; g.act = ACT_RELU;
+      launch_igemm_f32(g, st); CKL();
+    }
+    launch_maxpool2_f32(x, y, B, H, W, L.cout, st); CKL();
+    H /= 2; W /= 2;
+    if (tap(h, "lite_conv" + std::to_string(i), y, B, H, W, L.cout, st)) return 1;
+  }
+  if (H != h->feat_h || W != h->feat_w) return fail(h, "trunk output %dx%d != expected %dx%d", H, W, h->feat_h, h->feat_w);
+  *out = y;
+  return 0;
+}
+
 extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* memory, void* stream) {
   if (!h) return 1;
   if (!h->finalized) return fail(h, "frx_encode: weights not finalized");
   if (!(h->opt_parts & 1)) return fail(h, "frx_encode: handle was created without the encoder part");
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, "frx_encode: batch %d outside (0, %d]", B, h->cfg.max_batch);
-  if (h->cfg.network != FRX_NET_EFFICIENT_SATRN) return fail(h, "frx_encode: LiteSATRN trunk not implemented yet");
   const frx_config& c = h->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(c.device));
   if (c.precision == FRX_PREC_BF16 && !h->opt_enc_fp32) return encode_bf16(h, images, B, memory, st);
   const float* A = h->arena;
   float* t = nullptr;
-  if (run_trunk_efficientnet(h, images, B, &t, st)) return 1;
+  if (c.network == FRX_NET_LITE_SATRN) {
+    if (run_trunk_lite(h, images, B, &t, st)) return 1;
+  } else if (run_trunk_efficientnet(h, images, B, &t, st)) {
+    return 1;
+  }
   const int fh = h->feat_h, fw = h->feat_w, S = fh * fw, C = c.enc_hidden, F = c.enc_filter;
   if (tap(h, "trunk", t, B, fh, fw, C, st)) return 1;
   float* x = (t == h->act[0]) ? h->act[1] : h->act[0];

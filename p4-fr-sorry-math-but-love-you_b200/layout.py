@@ -44,6 +44,40 @@ def _mha(s, p, q_ch, k_ch, d):
     s[p + ".out_linear.bias"] = (q_ch,)
 
 
+def _satrn_encoder_tail(s, dims, prefix):
+    hidden, filt = dims["enc_hidden"], dims["enc_filter"]
+    pe = prefix + "positional_encoding."
+    s[pe + "dense0.weight"] = (hidden // 2, hidden)
+    s[pe + "dense0.bias"] = (hidden // 2,)
+    s[pe + "dense1.weight"] = (hidden * 2, hidden // 2)
+    s[pe + "dense1.bias"] = (hidden * 2,)
+    for i in range(dims["enc_layers"]):
+        p = "%sattention_layers.%d." % (prefix, i)
+        s[p + "norm.weight"] = (hidden,)
+        s[p + "norm.bias"] = (hidden,)
+        _mha(s, p + "attention_layer", hidden, hidden, hidden)
+        s[p + "conv0.weight"] = (filt, hidden, 1, 1)
+        _bn(s, p + "norm0", filt)
+        s[p + "depthwise.weight"] = (filt, 1, 3, 3)
+        s[p + "depthwise.bias"] = (filt,)
+        _bn(s, p + "depthwise_norm", filt)
+        s[p + "conv1.weight"] = (hidden, filt, 1, 1)
+        _bn(s, p + "norm1", hidden)
+
+
+def lite_encoder_shapes(dims, prefix="encoder."):
+    """LiteSATRN: ShallowCNN of 4 x (conv3x3 p1, BN, ReLU, maxpool2) (networks/LiteSATRN.py:21-70)
+    + the same positional encoding / encoder layers (:266-304)."""
+    s = collections.OrderedDict()
+    cnn = prefix + "shallow_cnn."
+    h = dims["enc_hidden"]
+    for i, (ci, co) in enumerate(((dims["in_ch"], h // 2), (h // 2, h), (h, h), (h, h))):
+        s["%sconv%d.weight" % (cnn, i)] = (co, ci, 3, 3)
+        _bn(s, "%sbatch_norm%d" % (cnn, i), co)
+    _satrn_encoder_tail(s, dims, prefix)
+    return s
+
+
 def encoder_shapes(dims, prefix="encoder."):
     s = collections.OrderedDict()
     cnn = prefix + "shallow_cnn."

@@ -52,9 +52,10 @@ def _stream(device):
 class _Engine:
     """One frx handle bound to (device, max_batch, max_steps, precision)."""
 
-    def __init__(self, dims, ids, device, max_batch, max_steps, precision, parts):
+    def __init__(self, dims, ids, device, max_batch, max_steps, precision, parts, network=0):
         cfg = _lib.FrxConfig()
-        cfg.network = 0
+        cfg.network = network
+        self.down = 16 if network == 1 else 32
         for k in ("height", "width", "in_ch", "enc_hidden", "enc_filter", "enc_layers", "enc_heads",
                   "dec_src", "dec_hidden", "dec_filter", "dec_layers", "dec_heads", "num_classes"):
             setattr(cfg, k, int(dims[k]))
@@ -81,8 +82,8 @@ class _Engine:
             if not name.endswith("num_batches_tracked"):
                 put(name, t)
         d = self.dims
-        put("pe2d.h", pe2d_table(d["height"] // 32, d["enc_hidden"]))
-        put("pe2d.w", pe2d_table(d["width"] // 32, d["enc_hidden"]))
+        put("pe2d.h", pe2d_table(d["height"] // self.down, d["enc_hidden"]))
+        put("pe2d.w", pe2d_table(d["width"] // self.down, d["enc_hidden"]))
         put("pe1d", pe1d_table(d["dec_hidden"]))
         self.h.call("frx_finalize_weights")
 
@@ -102,6 +103,8 @@ class _FrxModule(nn.Module):
     """Shared engine management (lazy creation, weight re-sync when dirty)."""
 
     _parts = 3  # bit0 encoder, bit1 decoder
+    _network = 0  # FRX_NET_EFFICIENT_SATRN
+    _down = 32
 
     def _setup(self, FLAGS, train_dataset, precision, max_batch, max_steps):
         self._dims = layout.dims_from_flags(FLAGS, len(train_dataset.id_to_token))
@@ -146,7 +149,7 @@ class _FrxModule(nn.Module):
             if e is not None:
                 need_b, need_t = max(need_b, e.max_batch), max(need_t, e.max_steps)
                 e.h.close()
-            e = _Engine(self._dims, self._ids, device, need_b, need_t, self._precision, self._parts)
+            e = _Engine(self._dims, self._ids, device, need_b, need_t, self._precision, self._parts, self._network)
             for k, v in self._options.items():
                 e.option(k, v)
             self._engine = e
@@ -209,7 +212,7 @@ class EfficientSATRN(_FrxModule):
 
     @property
     def memory_tokens(self):
-        return (self._dims["height"] // 32) * (self._dims["width"] // 32)
+        return (self._dims["height"] // self._down) * (self._dims["width"] // self._down)
 
     def encode(self, input):
         """SATRNEncoder.forward :311-323 -> src [B, h*w, C]."""
@@ -264,6 +267,35 @@ class EfficientSATRN(_FrxModule):
         out = torch.empty(tuple(shape), device=eng.device)
         eng.h.call("frx_read_tap", name.encode(), _ptr(out), n.value, ctypes.byref(n), shape, _stream(eng.device))
         return out  # NHWC
+
+
+class LiteSATRN(EfficientSATRN):
+    """networks/LiteSATRN.py:548-590 -- the knowledge-distillation student: a 4-conv ShallowCNN trunk (1/16
+    resolution, :21-70) in front of the same SATRN encoder / decoder classes; greedy decoding only (the
+    reference's LiteSATRN has no beam_search).  fp32 mode."""
+
+    _network = 1
+    _down = 16
+
+    def __init__(self, FLAGS, train_dataset, checkpoint=None, decoding_manager=None, *,
+                 precision="fp32", max_batch=None, max_steps=None):
+        nn.Module.__init__(self)
+        if precision != "fp32":
+            raise NotImplementedError("LiteSATRN runs in the fp32 mode only")
+        self._setup(FLAGS, train_dataset, precision, max_batch, max_steps)
+        self.encoder = layout.build_param_tree(layout.lite_encoder_shapes(self._dims), "encoder.")
+        self.decoder = layout.build_param_tree(layout.decoder_shapes(self._dims), "decoder.")
+        d = self.decoder
+        d.hidden_dim, d.filter_dim = self._dims["dec_hidden"], self._dims["dec_filter"]
+        d.num_classes, d.layer_num = self._dims["num_classes"], self._dims["dec_layers"]
+        d.pad_id, d.st_id = self._ids[2], self._ids[0]
+        d.manager = decoding_manager
+        self.criterion = nn.CrossEntropyLoss(ignore_index=self._ids[2])
+        if checkpoint:
+            self.load_state_dict(checkpoint)
+
+    def beam_search(self, *a, **k):
+        raise AttributeError("LiteSATRN has no beam_search (networks/LiteSATRN.py defines none)")
 
 
 class EfficientSATRN_encoder(_FrxModule):

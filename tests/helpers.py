@@ -38,3 +38,22 @@ def make_model(state_dict=None, precision="fp32", **kw):
     import frx
     flags = frx.Flags(flags_dict()).get()
     return frx.EfficientSATRN(flags, Vocab(), state_dict, None, precision=precision, **kw)
+
+
+def lite_flags_dict(height=128, width=256, rgb=1):
+    """configs/LiteSATRN.yaml with data.rgb overridden."""
+    return {
+        "network": "LiteSATRN",
+        "input_size": {"height": height, "width": width},
+        "SATRN": {
+            "encoder": {"hidden_dim": 256, "filter_dim": 256, "layer_num": 1, "head_num": 4},
+            "decoder": {"src_dim": 256, "hidden_dim": 128, "filter_dim": 512, "layer_num": 2, "head_num": 4},
+        },
+        "data": {"rgb": rgb},
+        "dropout_rate": 0.1,
+    }
+
+
+def make_lite_model(state_dict=None, **kw):
+    import frx
+    return frx.LiteSATRN(frx.Flags(lite_flags_dict()).get(), Vocab(), state_dict, None, **kw)

@@ -1,0 +1,65 @@
+"""LiteSATRN (networks/LiteSATRN.py): oracle pinned against reference fixtures (CPU) and the CUDA path
+against both (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, make_lite_model
+from oracle import satrn, synth
+from oracle.make_golden import LITE_SPEC, state_dict_digest
+
+TAU, LOGIT_TOL = 1e-4, 2e-4
+
+
+def _golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "litesatrn_seed0.npz"))
+
+
+@pytest.fixture(scope="module")
+def lite():
+    spec = satrn.ModelSpec(**LITE_SPEC)
+    return spec, synth.synth_state_dict(spec, 0, calib_batch=4)
+
+
+def test_lite_layout_and_oracle_match_reference(lite):
+    spec, sd = lite
+    g = _golden()
+    assert state_dict_digest(sd) == str(g["digest"])
+    model = make_lite_model()
+    assert list(model.state_dict().keys()) == list(sd.keys()) and len(sd) == 112
+    assert sum(p.numel() for p in model.parameters()) == 2_633_077
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        mem = satrn.encoder_forward(sd, spec, synth.synth_images(spec, 3, 0))
+        logits, tokens = satrn.decode_greedy(sd, spec, torch.from_numpy(g["memory"]), 120)
+    assert np.abs(mem.numpy() - g["memory"]).max() <= 2e-5
+    assert np.abs(logits.numpy() - g["logits"]).max() <= 1e-4
+    assert np.array_equal(tokens.numpy(), g["tokens"])
+
+
+@pytest.mark.gpu
+def test_lite_cuda_path_matches_reference_golden(lite):
+    spec, sd = lite
+    g = _golden()
+    model = make_lite_model(sd).cuda().eval()
+    x = synth.synth_images(spec, 3, 0).cuda()
+    with torch.no_grad():
+        mem = model.encode(x)
+        logits = model(x, satrn.expected_tokens(3, 119).cuda(), False, 0.0)
+    assert mem.shape == (3, 128, 256)
+    assert np.abs(mem.cpu().numpy() - g["memory"]).max() <= 1e-4 * np.abs(g["memory"]).max()
+    ref = torch.from_numpy(g["logits"])
+    ok = satrn.min_margins(ref) > TAU
+    assert ok.sum() >= 2
+    assert (logits.cpu()[ok] - ref[ok]).abs().max().item() <= LOGIT_TOL
+    assert torch.equal(logits.cpu().argmax(-1)[ok], torch.from_numpy(g["tokens"])[ok])
+    with pytest.raises(AttributeError):
+        model.beam_search(x)
+
+
+@pytest.mark.gpu
+def test_lite_bf16_is_rejected_loudly(lite):
+    with pytest.raises(NotImplementedError):
+        make_lite_model(lite[1], precision="bf16")
