@@ -43,6 +43,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 // Bounded spin: a protocol bug traps (error returned to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -137,6 +140,83 @@ __device__ __forceinline__ void epi_affine_act(float (&v)[16], const float* __re
 }
 
 }  // namespace
+
+// Epilogue of one 16-column chunk of one row: folded BN / bias, activation, residual, store.
+__device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_t (&r)[16], int m, int nb) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+      const bool full = nb + 16 <= p.N;
+      if (full) {  // vectorised scale/shift, activation resolved outside the element loop
+        if (p.act == ACT_SILU) epi_affine_act<ACT_SILU>(v, p.scale, p.shift, nb);
+        else if (p.act == ACT_RELU) epi_affine_act<ACT_RELU>(v, p.scale, p.shift, nb);
+        else epi_affine_act<ACT_NONE>(v, p.scale, p.shift, nb);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = nb + i;
+          if (n < p.N) {
+            if (p.scale) v[i] = v[i] * __ldg(p.scale + n) + __ldg(p.shift + n);
+            else if (p.shift) v[i] += __ldg(p.shift + n);
+            v[i] = act_apply(v[i], p.act);
+          }
+        }
+      }
+      if (p.res) {
+        if (p.res_f32) {
+          const float* rp = reinterpret_cast<const float*>(p.res) + (size_t)m * p.ldr + nb;
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(rp + i));
+              v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+            }
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.N) v[i] += __ldg(rp + i);
+          }
+        } else {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + (size_t)m * p.ldr + nb;
+          if (full) {
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp)), r1 = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[2 * i] += __uint_as_float(rw[i] << 16);
+              v[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
+            }
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.N) v[i] += __bfloat162float(rp[i]);
+          }
+        }
+      }
+      if (p.out_f32) {
+        float* cp = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + nb;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+          for (int i = 0; i < 16; ++i)
+            if (nb + i < p.N) cp[i] = v[i];
+        }
+      } else {
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + nb;
+        if (full) {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+          for (int i = 0; i < 16; ++i)
+            if (nb + i < p.N) cp[i] = __float2bfloat16_rn(v[i]);
+        }
+      }
+}
 
 template <int NCOLS>
 __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
@@ -281,86 +361,195 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
       uint32_t r[16];
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 16), r);
       const int nb = n0 + cc * 16;
-      if (m_ok && nb < p.N) {
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-      const bool full = nb + 16 <= p.N;
-      if (full) {  // vectorised scale/shift, activation resolved outside the element loop
-        if (p.act == ACT_SILU) epi_affine_act<ACT_SILU>(v, p.scale, p.shift, nb);
-        else if (p.act == ACT_RELU) epi_affine_act<ACT_RELU>(v, p.scale, p.shift, nb);
-        else epi_affine_act<ACT_NONE>(v, p.scale, p.shift, nb);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = nb + i;
-          if (n < p.N) {
-            if (p.scale) v[i] = v[i] * __ldg(p.scale + n) + __ldg(p.shift + n);
-            else if (p.shift) v[i] += __ldg(p.shift + n);
-            v[i] = act_apply(v[i], p.act);
-          }
-        }
-      }
-      if (p.res) {
-        if (p.res_f32) {
-          const float* rp = reinterpret_cast<const float*>(p.res) + (size_t)m * p.ldr + nb;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(rp + i));
-              v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
-            }
-          } else {
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.N) v[i] += __ldg(rp + i);
-          }
-        } else {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + (size_t)m * p.ldr + nb;
-          if (full) {
-            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp)), r1 = __ldg(reinterpret_cast<const uint4*>(rp + 8));
-            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[2 * i] += __uint_as_float(rw[i] << 16);
-              v[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
-            }
-          } else {
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.N) v[i] += __bfloat162float(rp[i]);
-          }
-        }
-      }
-      if (p.out_f32) {
-        float* cp = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + nb;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-          for (int i = 0; i < 16; ++i)
-            if (nb + i < p.N) cp[i] = v[i];
-        }
-      } else {
-        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + nb;
-        if (full) {
-          uint32_t w[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            w[i] = *reinterpret_cast<uint32_t*>(&t);
-          }
-          *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-        } else {
-          for (int i = 0; i < 16; ++i)
-            if (nb + i < p.N) cp[i] = __float2bfloat16_rn(v[i]);
-        }
-      }
-      }  // m_ok
+      if (m_ok && nb < p.N) epilogue_store16(p, r, m, nb);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(NCOLS) : "memory");
+  }
+}
+
+
+// ===========================================================================
+// Persistent, warp-specialised version (the default):
+//   warps 0-3  producers : cp.async gather of A (128 x 64) and W (BN x 64) into a 4-stage
+//                          swizzled ring; per stage: wait group -> fence.proxy.async -> arrive(full)
+//   warps 4-7  epilogue  : tcgen05.ld of the finished accumulator (TMEM buffer a) -> BN/bias, act,
+//                          residual -> global; arrive(acc_empty[a])
+//   warp  8    MMA       : one lane waits full[s], issues 4 x tcgen05.mma, commits to empty[s];
+//                          after the last k-block commits to acc_full[a]
+// Each CTA loops over output tiles (n-tile fastest, so concurrent CTAs share A tiles in L2); the
+// TMEM accumulator is double-buffered, so tile i's epilogue overlaps tile i+1's loads and MMAs.
+// ===========================================================================
+constexpr int WS_STAGES = 4;
+constexpr int WS_LAG = 2;            // cp.async groups kept in flight per producer thread
+constexpr int WS_THREADS = 288;
+
+template <int NCOLS>  // TMEM columns allocated = 2 accumulators of NCOLS/2 columns
+__global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p) {
+  extern __shared__ unsigned char dyn_smem[];
+  __shared__ __align__(8) uint64_t full_bar[WS_STAGES], empty_bar[WS_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)BN * (TC_BK * 2);
+  const uint32_t smem0 = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const int KB = (p.K + TC_BK - 1) / TC_BK;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + TC_BM - 1) / TC_BM;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 128); mbar_init(&acc_empty[1], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < 4) {
+    // ------------------------------ producers ------------------------------------------------
+    const int c = tid & 7, rbase = tid >> 3;  // 16-byte chunk, rows rbase + 16*i
+    const int nb_rows = (BN + 15) / 16;
+    int it = 0;   // flat k-block counter over all tiles of this CTA
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+      const __nv_bfloat16* a_ptr[8];
+      int a_ih0[8], a_iw0[8];
+      bool a_ok[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + rbase + 16 * i;
+        a_ok[i] = m < p.M;
+        a_ih0[i] = a_iw0[i] = 0;
+        a_ptr[i] = p.A;
+        if (a_ok[i]) {
+          if (p.conv) {
+            const int ow = m % p.OW;
+            const int tq = m / p.OW;
+            const int oh = tq % p.OH;
+            const int n = tq / p.OH;
+            a_ptr[i] = p.A + (size_t)n * p.H * p.Wd * p.Cin;
+            a_ih0[i] = oh * p.stride - p.pad_t;
+            a_iw0[i] = ow * p.stride - p.pad_l;
+          } else {
+            a_ptr[i] = p.A + (size_t)m * p.lda;
+          }
+        }
+      }
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int stage = it % WS_STAGES;
+        mbar_wait(&empty_bar[stage], (uint32_t)(((it / WS_STAGES) & 1) ^ 1));  // slot released by the MMA warp
+        const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes, sb = sa + TC_A_BYTES;
+        const int k = kb * TC_BK + c * 8;
+        int ci = k, kh = 0, kw = 0;
+        if (p.conv) {
+          const int tap = k / p.Cin;
+          ci = k - tap * p.Cin;
+          kh = tap / p.KW;
+          kw = tap - kh * p.KW;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rbase + 16 * i;
+          const uint32_t dst = sa + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+          const __nv_bfloat16* src = p.A;
+          uint32_t bytes = 0;
+          if (a_ok[i] && k < p.K) {
+            if (p.conv) {
+              const int ih = a_ih0[i] + kh, iw = a_iw0[i] + kw;
+              if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) {
+                src = a_ptr[i] + ((size_t)ih * p.Wd + iw) * p.Cin + ci;
+                bytes = 16;
+              }
+            } else {
+              src = a_ptr[i] + k;
+              bytes = 16;
+            }
+          }
+          cp_async16(dst, src, bytes);
+        }
+        for (int j = 0; j < nb_rows; ++j) {
+          const int row = rbase + 16 * j;
+          if (row < BN) {
+            const uint32_t dst = sb + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+            const int n = n0 + row;
+            const bool ok = n < p.N && k < p.K;
+            cp_async16(dst, ok ? p.W + (size_t)n * p.ldw + k : p.W, ok ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (it >= WS_LAG) {  // the group issued WS_LAG iterations ago has landed: publish that stage
+          cp_async_wait<WS_LAG>();
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          mbar_arrive(&full_bar[(it - WS_LAG) % WS_STAGES]);
+        }
+      }
+    }
+    // drain: publish the last WS_LAG stages
+    cp_async_wait<0>();
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    for (int j = (it >= WS_LAG ? it - WS_LAG : 0); j < it; ++j) mbar_arrive(&full_bar[j % WS_STAGES]);
+  } else if (warp == 8) {
+    // ------------------------------ MMA issuer ------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        const int a = ti & 1;
+        mbar_wait(&acc_empty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem + (uint32_t)(a * (NCOLS / 2));
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int stage = it % WS_STAGES;
+          mbar_wait(&full_bar[stage], (uint32_t)((it / WS_STAGES) & 1));
+          tc_fence_after();
+          const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes;
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int j = 0; j < TC_BK / 16; ++j)
+            umma_bf16(tacc, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
+          if (kb == KB - 1) umma_commit(&acc_full[a]);  // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 4..7) --------------------------------------
+    const int q = warp & 3;  // TMEM lane quarter
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      const int a = ti & 1;
+      const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+      mbar_wait(&acc_full[a], (uint32_t)((ti >> 1) & 1));
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool m_ok = m < p.M;
+      const uint32_t tacc = tmem + (uint32_t)(a * (NCOLS / 2)) + ((uint32_t)(q * 32) << 16);
+      for (int cc = 0; cc * 16 < BN; ++cc) {
+        uint32_t r[16];
+        tmem_ld16(tacc + (uint32_t)(cc * 16), r);
+        const int nb = n0 + cc * 16;
+        if (m_ok && nb < p.N) epilogue_store16(p, r, m, nb);
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[a]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(NCOLS) : "memory");
   }
 }
@@ -385,6 +574,34 @@ static int tc_launch(const TcGemmP& p, cudaStream_t st) {
   dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + p.BN - 1) / p.BN);
   tc_igemm_kernel<NCOLS><<<grid, 256, smem, st>>>(p);
   return 0;
+}
+
+template <int NCOLS>
+static int tc_launch_ws(const TcGemmP& p, int num_sms, cudaStream_t st) {
+  const size_t smem = (size_t)WS_STAGES * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_igemm_ws_kernel<NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  const int tiles = ((p.M + TC_BM - 1) / TC_BM) * ((p.N + p.BN - 1) / p.BN);
+  int per_sm = (int)((227 * 1024) / (smem + 2048));     // shared memory
+  if (per_sm > 512 / NCOLS) per_sm = 512 / NCOLS;       // tensor memory
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  const int grid = tiles < num_sms * per_sm ? tiles : num_sms * per_sm;
+  tc_igemm_ws_kernel<NCOLS><<<grid, WS_THREADS, smem, st>>>(p);
+  return 0;
+}
+
+// Persistent warp-specialised kernel; NCOLS = TMEM columns for the two accumulators.
+int launch_tc_igemm_ws(TcGemmP p, int num_sms, cudaStream_t st) {
+  if (p.BN == 0) p.BN = tc_pick_bn(p.N);
+  if (p.BN <= 32) { p.BN = 32; return tc_launch_ws<64>(p, num_sms, st); }
+  if (p.BN <= 64) return tc_launch_ws<128>(p, num_sms, st);
+  if (p.BN <= 128) return tc_launch_ws<256>(p, num_sms, st);
+  return tc_launch_ws<512>(p, num_sms, st);
 }
 
 int launch_tc_igemm(TcGemmP p, cudaStream_t st) {

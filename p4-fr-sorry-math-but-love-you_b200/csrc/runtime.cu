@@ -229,6 +229,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   else if (k == "timing") h->opt_timing = value != 0;
   else if (k == "cluster_images") h->opt_cluster_images = (value == 8 || value == 16) ? (int)value : 0;
   else if (k == "enc_fp32") h->opt_enc_fp32 = value != 0;
+  else if (k == "tc_ws") h->opt_tc_ws = value != 0;
   else if (k == "prof") {
     h->opt_prof = value != 0;
     if (h->opt_prof && !h->prof) { void* p; if (dev_alloc(h, &p, 16 * 8)) return 1; h->prof = (long long*)p; }
@@ -836,7 +837,7 @@ static TcGemmP tc_conv(const void* A, int B, int H, int W, int Cin, const float*
 
 #define TCL(g)                                                                                         \
   do {                                                                                                 \
-    int rc__ = launch_tc_igemm(g, st);                                                                 \
+    int rc__ = h->opt_tc_ws ? launch_tc_igemm_ws(g, h->num_sms, st) : launch_tc_igemm(g, st);          \
     if (rc__) return fail(h, "tcgen05 GEMM configuration failed: %s", cudaGetErrorString((cudaError_t)rc__)); \
     CKL();                                                                                             \
   } while (0)

@@ -62,6 +62,7 @@ struct frx_handle {
   bool opt_taps = false, opt_graphs = true, opt_timing = false;
   bool opt_prof = false;
   int opt_cluster_images = 0;  // 0 = auto
+  bool opt_tc_ws = true;       // persistent warp-specialised tcgen05 GEMM (false: one tile per CTA)
   bool opt_enc_fp32 = false;   // bf16 handle, but run the encoder on the fp32 SIMT path (debug)
   long long* prof = nullptr;
   int opt_parts = 3;  // bit0: encoder weights/workspaces, bit1: decoder

@@ -10,15 +10,17 @@ import frx
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def handle():
+@pytest.fixture(scope="module", params=["warp_specialised", "one_tile_per_cta"])
+def handle(request):
     cfg = frx._lib.FrxConfig()
     cfg.network, cfg.height, cfg.width, cfg.in_ch = 0, 128, 256, 1
     cfg.enc_hidden, cfg.enc_filter, cfg.enc_layers, cfg.enc_heads = 512, 512, 2, 8
     cfg.dec_src, cfg.dec_hidden, cfg.dec_filter, cfg.dec_layers, cfg.dec_heads = 512, 256, 1024, 3, 8
     cfg.num_classes, cfg.sos_id, cfg.eos_id, cfg.pad_id = 245, 0, 1, 2
     cfg.max_batch, cfg.max_steps, cfg.precision, cfg.device = 2, 4, 1, 0
-    return frx._lib.Handle(cfg)
+    h = frx._lib.Handle(cfg)
+    h.call("frx_set_option", b"tc_ws", 1 if request.param == "warp_specialised" else 0)
+    return h
 
 
 def _run(handle, a, w, m, n, k, conv=None, scale=None, shift=None, act=0, out_f32=True):
@@ -35,6 +37,17 @@ def _run(handle, a, w, m, n, k, conv=None, scale=None, shift=None, act=0, out_f3
                                    (128, 768, 128), (4096, 1536, 512), (130, 48, 96), (64, 512, 1536)])
 def test_dense_gemm(handle, m, n, k):
     g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    a = torch.randn(m, k, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).bfloat16()
+    c = _run(handle, a, w, m, n, k)
+    ref = a.float() @ w.float().t()
+    assert (c - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_many_tiles_per_cta(handle):
+    """More tiles than persistent CTAs: exercises the ring / accumulator phase wrap-around."""
+    m, n, k = 128 * 700, 96, 216
+    g = torch.Generator(device="cuda").manual_seed(5)
     a = torch.randn(m, k, device="cuda", generator=g).bfloat16()
     w = (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).bfloat16()
     c = _run(handle, a, w, m, n, k)
