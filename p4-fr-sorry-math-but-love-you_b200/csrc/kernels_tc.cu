@@ -19,6 +19,9 @@
 //
 // Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor /
 // InstrDescriptor) of the CUTLASS tree vendored in this image.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -42,6 +45,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: 2-D tiled bulk tensor copy global -> shared (128B-swizzled box), completion on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -376,19 +388,26 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
 // Persistent, warp-specialised version (the default):
 //   warps 0-3  producers : cp.async gather of A (128 x 64) and W (BN x 64) into a 4-stage
 //                          swizzled ring; per stage: wait group -> fence.proxy.async -> arrive(full)
-//   warps 4-7  epilogue  : tcgen05.ld of the finished accumulator (TMEM buffer a) -> BN/bias, act,
+//   warps 4-15 epilogue  : tcgen05.ld of the finished accumulator (TMEM buffer a) -> BN/bias, act,
 //                          residual -> global; arrive(acc_empty[a])
-//   warp  8    MMA       : one lane waits full[s], issues 4 x tcgen05.mma, commits to empty[s];
+//   warp  16   MMA       : one lane waits full[s], issues 4 x tcgen05.mma, commits to empty[s];
 //                          after the last k-block commits to acc_full[a]
 // Each CTA loops over output tiles (n-tile fastest, so concurrent CTAs share A tiles in L2); the
 // TMEM accumulator is double-buffered, so tile i's epilogue overlaps tile i+1's loads and MMAs.
 // ===========================================================================
 constexpr int WS_STAGES = 4;
 constexpr int WS_LAG = 2;            // cp.async groups kept in flight per producer thread
-constexpr int WS_THREADS = 288;
+constexpr int WS_PROD_WARPS = 8;     // address generation for the gather is instruction-latency bound: spread it
+constexpr int WS_EPI_WARPS = 8;      // 2 warps per TMEM lane quarter
+constexpr int WS_MMA_WARP = WS_PROD_WARPS + WS_EPI_WARPS;
+constexpr int WS_THREADS = (WS_MMA_WARP + 1) * 32;
+constexpr int WS_PROD_THREADS = WS_PROD_WARPS * 32;
+constexpr int WS_ROWS_PER_PASS = WS_PROD_THREADS / 8;   // rows covered by one pass of the producer threads
+constexpr int WS_A_PASSES = TC_BM / WS_ROWS_PER_PASS;
 
 template <int NCOLS>  // TMEM columns allocated = 2 accumulators of NCOLS/2 columns
-__global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p) {
+__global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p, const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmW) {
   extern __shared__ unsigned char dyn_smem[];
   __shared__ __align__(8) uint64_t full_bar[WS_STAGES], empty_bar[WS_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -402,15 +421,15 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
   const int tiles_m = (p.M + TC_BM - 1) / TC_BM;
   const int num_tiles = tiles_m * tiles_n;
 
-  if (warp == 8) {
+  if (warp == WS_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(NCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], (p.conv ? WS_PROD_THREADS : 0) + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], 128); mbar_init(&acc_empty[1], 128);
+    mbar_init(&acc_empty[0], WS_EPI_WARPS * 32); mbar_init(&acc_empty[1], WS_EPI_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   tc_fence_before();
@@ -418,24 +437,30 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < 4) {
+  if (warp < WS_PROD_WARPS) {
     // ------------------------------ producers ------------------------------------------------
-    const int c = tid & 7, rbase = tid >> 3;  // 16-byte chunk, rows rbase + 16*i
-    const int nb_rows = (BN + 15) / 16;
+    // W tiles (and A tiles of dense GEMMs) come by TMA from one elected thread; the implicit-GEMM
+    // gather of A for convolutions is done by all producer threads with 16-byte cp.async.
+    const bool tma_thread = tid == 0;
+    const uint32_t tma_bytes = (uint32_t)BN * (TC_BK * 2) + (p.conv ? 0u : (uint32_t)TC_A_BYTES);
+    if (!p.conv && !tma_thread) {
+      // dense GEMM: nothing to gather
+    } else {
+    const int c = tid & 7, rbase = tid >> 3;  // 16-byte chunk, rows rbase + WS_ROWS_PER_PASS*i
     int it = 0;   // flat k-block counter over all tiles of this CTA
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
-      const __nv_bfloat16* a_ptr[8];
-      int a_ih0[8], a_iw0[8];
-      bool a_ok[8];
+      const __nv_bfloat16* a_ptr[WS_A_PASSES];
+      int a_ih0[WS_A_PASSES], a_iw0[WS_A_PASSES];
+      bool a_ok[WS_A_PASSES];
+      if (p.conv) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + rbase + 16 * i;
-        a_ok[i] = m < p.M;
-        a_ih0[i] = a_iw0[i] = 0;
-        a_ptr[i] = p.A;
-        if (a_ok[i]) {
-          if (p.conv) {
+        for (int i = 0; i < WS_A_PASSES; ++i) {
+          const int m = m0 + rbase + WS_ROWS_PER_PASS * i;
+          a_ok[i] = m < p.M;
+          a_ih0[i] = a_iw0[i] = 0;
+          a_ptr[i] = p.A;
+          if (a_ok[i]) {
             const int ow = m % p.OW;
             const int tq = m / p.OW;
             const int oh = tq % p.OH;
@@ -443,8 +468,6 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
             a_ptr[i] = p.A + (size_t)n * p.H * p.Wd * p.Cin;
             a_ih0[i] = oh * p.stride - p.pad_t;
             a_iw0[i] = ow * p.stride - p.pad_l;
-          } else {
-            a_ptr[i] = p.A + (size_t)m * p.lda;
           }
         }
       }
@@ -452,56 +475,48 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
         const int stage = it % WS_STAGES;
         mbar_wait(&empty_bar[stage], (uint32_t)(((it / WS_STAGES) & 1) ^ 1));  // slot released by the MMA warp
         const uint32_t sa = smem0 + (uint32_t)stage * stage_bytes, sb = sa + TC_A_BYTES;
-        const int k = kb * TC_BK + c * 8;
-        int ci = k, kh = 0, kw = 0;
-        if (p.conv) {
-          const int tap = k / p.Cin;
-          ci = k - tap * p.Cin;
-          kh = tap / p.KW;
-          kw = tap - kh * p.KW;
+        if (tma_thread) {
+          mbar_arrive_expect_tx(&full_bar[stage], tma_bytes);
+          tma_load_2d(sb, &tmW, kb * TC_BK, n0, &full_bar[stage]);
+          if (!p.conv) tma_load_2d(sa, &tmA, kb * TC_BK, m0, &full_bar[stage]);
         }
+        if (p.conv) {
+          const int k = kb * TC_BK + c * 8;
+          const int tap = k / p.Cin;
+          const int ci = k - tap * p.Cin;
+          const int kh = tap / p.KW;
+          const int kw = tap - kh * p.KW;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = rbase + 16 * i;
-          const uint32_t dst = sa + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
-          const __nv_bfloat16* src = p.A;
-          uint32_t bytes = 0;
-          if (a_ok[i] && k < p.K) {
-            if (p.conv) {
+          for (int i = 0; i < WS_A_PASSES; ++i) {
+            const int row = rbase + WS_ROWS_PER_PASS * i;
+            const uint32_t dst = sa + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+            const __nv_bfloat16* src = p.A;
+            uint32_t bytes = 0;
+            if (a_ok[i] && k < p.K) {
               const int ih = a_ih0[i] + kh, iw = a_iw0[i] + kw;
               if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) {
                 src = a_ptr[i] + ((size_t)ih * p.Wd + iw) * p.Cin + ci;
                 bytes = 16;
               }
-            } else {
-              src = a_ptr[i] + k;
-              bytes = 16;
             }
+            cp_async16(dst, src, bytes);
           }
-          cp_async16(dst, src, bytes);
-        }
-        for (int j = 0; j < nb_rows; ++j) {
-          const int row = rbase + 16 * j;
-          if (row < BN) {
-            const uint32_t dst = sb + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
-            const int n = n0 + row;
-            const bool ok = n < p.N && k < p.K;
-            cp_async16(dst, ok ? p.W + (size_t)n * p.ldw + k : p.W, ok ? 16u : 0u);
+          cp_async_commit();
+          if (it >= WS_LAG) {  // the group issued WS_LAG iterations ago has landed: publish that stage
+            cp_async_wait<WS_LAG>();
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_arrive(&full_bar[(it - WS_LAG) % WS_STAGES]);
           }
-        }
-        cp_async_commit();
-        if (it >= WS_LAG) {  // the group issued WS_LAG iterations ago has landed: publish that stage
-          cp_async_wait<WS_LAG>();
-          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-          mbar_arrive(&full_bar[(it - WS_LAG) % WS_STAGES]);
         }
       }
     }
-    // drain: publish the last WS_LAG stages
-    cp_async_wait<0>();
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    for (int j = (it >= WS_LAG ? it - WS_LAG : 0); j < it; ++j) mbar_arrive(&full_bar[j % WS_STAGES]);
-  } else if (warp == 8) {
+    if (p.conv) {  // drain: publish the last WS_LAG stages
+      cp_async_wait<0>();
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      for (int j = (it >= WS_LAG ? it - WS_LAG : 0); j < it; ++j) mbar_arrive(&full_bar[j % WS_STAGES]);
+    }
+    }
+  } else if (warp == WS_MMA_WARP) {
     // ------------------------------ MMA issuer ------------------------------------------------
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BN);
@@ -526,8 +541,9 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 4..7) --------------------------------------
-    const int q = warp & 3;  // TMEM lane quarter
+    // ------------------------------ epilogue warps ----------------------------------------------
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int sub = (warp - WS_PROD_WARPS) >> 2;     // which share of the column chunks
     int ti = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       const int a = ti & 1;
@@ -537,7 +553,7 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
       const int m = m0 + q * 32 + lane;
       const bool m_ok = m < p.M;
       const uint32_t tacc = tmem + (uint32_t)(a * (NCOLS / 2)) + ((uint32_t)(q * 32) << 16);
-      for (int cc = 0; cc * 16 < BN; ++cc) {
+      for (int cc = sub; cc * 16 < BN; cc += WS_EPI_WARPS / 4) {
         uint32_t r[16];
         tmem_ld16(tacc + (uint32_t)(cc * 16), r);
         const int nb = n0 + cc * 16;
@@ -549,7 +565,7 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == WS_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(NCOLS) : "memory");
   }
 }
@@ -576,6 +592,34 @@ static int tc_launch(const TcGemmP& p, cudaStream_t st) {
   return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] matrix (row pitch ld elements), box = box_rows x 64 columns, 128-byte swizzle,
+// out-of-bounds elements read as zero (handles the K tail and ragged M / N edges).
+static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+  if (!enc) return (int)cudaErrorNotSupported;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
 template <int NCOLS>
 static int tc_launch_ws(const TcGemmP& p, int num_sms, cudaStream_t st) {
   const size_t smem = (size_t)WS_STAGES * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
@@ -591,7 +635,13 @@ static int tc_launch_ws(const TcGemmP& p, int num_sms, cudaStream_t st) {
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   const int grid = tiles < num_sms * per_sm ? tiles : num_sms * per_sm;
-  tc_igemm_ws_kernel<NCOLS><<<grid, WS_THREADS, smem, st>>>(p);
+  CUtensorMap tmA, tmW;
+  int rc = make_tmap_2d(&tmW, p.W, p.N, p.K, p.ldw, p.BN);
+  if (rc) return rc;
+  if (!p.conv) rc = make_tmap_2d(&tmA, p.A, p.M, p.K, p.lda, TC_BM);
+  else tmA = tmW;
+  if (rc) return rc;
+  tc_igemm_ws_kernel<NCOLS><<<grid, WS_THREADS, smem, st>>>(p, tmA, tmW);
   return 0;
 }
 
