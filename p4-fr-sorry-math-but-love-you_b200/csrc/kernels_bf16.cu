@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
   extern __shared__ __align__(16) unsigned char dw_smem[];
   uint4* tile = reinterpret_cast<uint4*>(dw_smem);                                   // [H*W][8 channel groups] x 16 B
   float (*red)[64 + 1] = reinterpret_cast<float (*)[64 + 1]>(dw_smem + (size_t)H * W * 8 * 16);  // [32][65]
+  float* wsm = reinterpret_cast<float*>(dw_smem + (size_t)H * W * 8 * 16 + 32 * 65 * sizeof(float));  // [11][64]: 9 taps, scale, shift
   const int n = blockIdx.x, c0 = blockIdx.y * 64;
   const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;  // 8 channels per thread, 32 pixel lanes
   const int c = c0 + cg * 8;
@@ -207,19 +208,23 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
     const int px = i >> 3, g = i & 7;
     tile[i] = (c0 + g * 8 < C) ? __ldg(reinterpret_cast<const uint4*>(ip + (long long)px * C + c0 + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
   }
-  float wv[9][8], sc[8], sh[8], sum[8];
-  auto ld8 = [&](const float* ptr, float (&dst)[8]) {  // two 16-byte loads (C % 8 == 0, arena 256-byte aligned)
-    const float4 a = c_ok ? __ldg(reinterpret_cast<const float4*>(ptr)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 b4 = c_ok ? __ldg(reinterpret_cast<const float4*>(ptr + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b4.x; dst[5] = b4.y; dst[6] = b4.z; dst[7] = b4.w;
-  };
+  float sum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = 0.f;
-  ld8(scale + c, sc);
-  ld8(shift + c, sh);
-#pragma unroll
-  for (int t = 0; t < 9; ++t) ld8(w + t * C + c, wv[t]);
+  for (int i = threadIdx.x; i < 11 * 64; i += 256) {
+    const int t = i >> 6, cc = c0 + (i & 63);
+    const float* src = t < 9 ? w + t * C : (t == 9 ? scale : shift);
+    wsm[i] = cc < C ? __ldg(src + cc) : 0.f;
+  }
   __syncthreads();
+  auto ld8s = [&](int t, float (&dst)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(wsm + t * 64 + cg * 8);
+    const float4 b4 = *reinterpret_cast<const float4*>(wsm + t * 64 + cg * 8 + 4);
+    dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b4.x; dst[5] = b4.y; dst[6] = b4.z; dst[7] = b4.w;
+  };
+  float sc[8], sh[8];
+  ld8s(9, sc);
+  ld8s(10, sh);
   __nv_bfloat16* op = out + (long long)n * OH * OW * C;
   if (c_ok) {
     for (int px = pl; px < OH * OW; px += 32) {
@@ -234,10 +239,11 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
         for (int kw = 0; kw < 3; ++kw) {
           const int iw = ow * stride - pad_l + kw;
           if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-            float x[8];
+            float x[8], wv[8];
             unpack8(tile[(ih * W + iw) * 8 + cg], x);
+            ld8s(kh * 3 + kw, wv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], wv[kh * 3 + kw][j], acc[j]);
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[j], wv[j], acc[j]);
           }
         }
       }
@@ -266,28 +272,56 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
   }
 }
 
+constexpr int SE_IMGS = 4;  // images per CTA: every FC weight is loaded once per 4 images
 __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
                                                     const float* __restrict__ b1, const float* __restrict__ w2,
-                                                    const float* __restrict__ b2, float* __restrict__ gate, int C, int R) {
+                                                    const float* __restrict__ b2, float* __restrict__ gate, int B, int C,
+                                                    int R) {
   extern __shared__ float sm[];
-  float* mv = sm;       // C
-  float* red = sm + C;  // R
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mv[c] = mean[(long long)n * C + c];
+  float* mv = sm;                  // [SE_IMGS][C]
+  float* red = sm + SE_IMGS * C;   // [SE_IMGS][R]
+  const int n0 = blockIdx.x * SE_IMGS;
+  for (int i = threadIdx.x; i < SE_IMGS * C; i += blockDim.x) {
+    const int im = i / C;
+    mv[i] = n0 + im < B ? mean[(long long)n0 * C + i] : 0.f;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < R; r += 8) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w1 + (long long)r * C + c), mv[c], s);
-    s = warp_sum(s);
-    if (lane == 0) red[r] = act_apply(s + __ldg(b1 + r), ACT_SILU);
+    float s[SE_IMGS];
+#pragma unroll
+    for (int im = 0; im < SE_IMGS; ++im) s[im] = 0.f;
+    const float4* wrow = reinterpret_cast<const float4*>(w1 + (long long)r * C);
+#pragma unroll 6
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {  // 16-byte loads, several in flight (C % 4 == 0)
+      const float4 wv = __ldg(wrow + c4);
+#pragma unroll
+      for (int im = 0; im < SE_IMGS; ++im) {
+        const float4 m4 = *reinterpret_cast<const float4*>(mv + im * C + c4 * 4);
+        s[im] = fmaf(wv.x, m4.x, fmaf(wv.y, m4.y, fmaf(wv.z, m4.z, fmaf(wv.w, m4.w, s[im]))));
+      }
+    }
+#pragma unroll
+    for (int im = 0; im < SE_IMGS; ++im) {
+      const float t = warp_sum(s[im]);
+      if (lane == 0) red[im * R + r] = act_apply(t + __ldg(b1 + r), ACT_SILU);
+    }
   }
   __syncthreads();
-  for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {  // expand outputs split over gridDim.y CTAs
-    float s = __ldg(b2 + c);
+  for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {  // expand outputs split over gridDim.y
+    float s[SE_IMGS];
+    const float bb = __ldg(b2 + c);
+#pragma unroll
+    for (int im = 0; im < SE_IMGS; ++im) s[im] = bb;
 #pragma unroll 8
-    for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2 + (long long)r * C + c), red[r], s);  // w2 is [R][C] (transposed at pack time)
-    gate[(long long)n * C + c] = 1.f / (1.f + expf(-s));
+    for (int r = 0; r < R; ++r) {
+      const float wv = __ldg(w2 + (long long)r * C + c);  // w2 is [R][C] (transposed at pack time)
+#pragma unroll
+      for (int im = 0; im < SE_IMGS; ++im) s[im] = fmaf(wv, red[im * R + r], s[im]);
+    }
+#pragma unroll
+    for (int im = 0; im < SE_IMGS; ++im)
+      if (n0 + im < B) gate[(long long)(n0 + im) * C + c] = 1.f / (1.f + expf(-s[im]));
   }
 }
 
@@ -313,14 +347,14 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
                               const float* w2, const float* b2, int B, int H, int W, int C, int OH, int OW, int stride,
                               int pad_t, int pad_l, int R, cudaStream_t st) {
   dim3 g(B, (C + 63) / 64);
-  const size_t smem = (size_t)H * W * 8 * 16 + 32 * 65 * sizeof(float);
+  const size_t smem = (size_t)H * W * 8 * 16 + 32 * 65 * sizeof(float) + 11 * 64 * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(dwconv_se_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
   dwconv_se_mean_kernel<<<g, 256, smem, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l);
-  se_fc_kernel<<<dim3(B, (C + 255) / 256), 256, (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, C, R);
+  se_fc_kernel<<<dim3((B + SE_IMGS - 1) / SE_IMGS, 4), 256, SE_IMGS * (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, B, C, R);
   long long total8 = (long long)B * OH * OW * (C / 8);
   se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(out, gate, total8, OH * OW, C);
 }
