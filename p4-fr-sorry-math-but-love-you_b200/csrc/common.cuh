@@ -132,6 +132,9 @@ struct TcGemmP {
   int BN;                   // N tile (multiple of 16, <= 256); 0 = choose
   int stages;               // smem ring depth (set by the launcher)
   int conv, H, Wd, Cin, OH, OW, KW, stride, pad_t, pad_l;
+  const __nv_bfloat16* Wpad; // conv only, optional: weights as [N][KW*KW][64] (channels zero-padded to 64) for the
+                             // TMA-im2col path (one filter tap = one 64-wide k-block); nullptr = cp.async gather
+  int im2col;               // set by the launcher when the im2col tensor map could be built
   const float* scale;       // per-N folded BatchNorm (v*scale + shift) or nullptr
   const float* shift;       // per-N bias when scale == nullptr
   int act;

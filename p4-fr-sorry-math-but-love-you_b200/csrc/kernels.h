@@ -43,6 +43,7 @@ void launch_beam_finish(const BeamP& p, cudaStream_t st);
 // tcgen05 implicit GEMM + bf16 trunk kernels (kernels_tc.cu, kernels_bf16.cu)
 int launch_tc_igemm(TcGemmP p, cudaStream_t st);                       // one tile per CTA (first version)
 int launch_tc_igemm_ws(TcGemmP p, int num_sms, cudaStream_t st);       // persistent, warp-specialised
+void launch_pad_conv_weights(const __nv_bfloat16* in, __nv_bfloat16* out, long long rows, int Cin, cudaStream_t st);
 void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);
 void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
 void launch_stem_conv_bf16(const float* in, const float* w, const float* scale, const float* shift,

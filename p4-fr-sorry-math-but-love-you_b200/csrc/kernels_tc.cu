@@ -22,6 +22,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -54,6 +57,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// TMA im2col mode: `pixelsPerColumn` output pixels starting at base pixel (w, h, n), filter tap (w_off, h_off),
+// `channelsPerPixel` channels from c -- one instruction stages a whole 128 x 64 implicit-GEMM A tile.
+__device__ __forceinline__ void tma_load_im2col(uint32_t smem_dst, const CUtensorMap* tmap, int c, int w, int h, int n,
+                                                uint16_t w_off, uint16_t h_off, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(w_off), "h"(h_off) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -416,10 +428,11 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
   const int BN = p.BN;
   const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)BN * (TC_BK * 2);
   const uint32_t smem0 = (smem_u32(dyn_smem) + 1023u) & ~1023u;
-  const int KB = (p.K + TC_BK - 1) / TC_BK;
+  const int KB = p.im2col ? p.KW * p.KW : (p.K + TC_BK - 1) / TC_BK;  // im2col: one k-block per filter tap
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + TC_BM - 1) / TC_BM;
   const int num_tiles = tiles_m * tiles_n;
+  const bool gather = p.conv && !p.im2col;  // A tiles gathered with cp.async by all producer threads
 
   if (warp == WS_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(NCOLS) : "memory");
@@ -427,7 +440,7 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
   }
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], (p.conv ? WS_PROD_THREADS : 0) + 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], (gather ? WS_PROD_THREADS : 0) + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_empty[0], WS_EPI_WARPS * 32); mbar_init(&acc_empty[1], WS_EPI_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -442,8 +455,8 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
     // W tiles (and A tiles of dense GEMMs) come by TMA from one elected thread; the implicit-GEMM
     // gather of A for convolutions is done by all producer threads with 16-byte cp.async.
     const bool tma_thread = tid == 0;
-    const uint32_t tma_bytes = (uint32_t)BN * (TC_BK * 2) + (p.conv ? 0u : (uint32_t)TC_A_BYTES);
-    if (!p.conv && !tma_thread) {
+    const uint32_t tma_bytes = (uint32_t)BN * (TC_BK * 2) + (gather ? 0u : (uint32_t)TC_A_BYTES);
+    if (!gather && !tma_thread) {
       // dense GEMM: nothing to gather
     } else {
     const int c = tid & 7, rbase = tid >> 3;  // 16-byte chunk, rows rbase + WS_ROWS_PER_PASS*i
@@ -453,7 +466,14 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
       const __nv_bfloat16* a_ptr[WS_A_PASSES];
       int a_ih0[WS_A_PASSES], a_iw0[WS_A_PASSES];
       bool a_ok[WS_A_PASSES];
-      if (p.conv) {
+      int bw = 0, bh = 0, bn = 0;  // im2col: base pixel of the tile's first output row
+      if (p.im2col) {
+        const int ow = m0 % p.OW, tq = m0 / p.OW;
+        bw = ow * p.stride - p.pad_l;
+        bh = (tq % p.OH) * p.stride - p.pad_t;
+        bn = tq / p.OH;
+      }
+      if (gather) {
 #pragma unroll
         for (int i = 0; i < WS_A_PASSES; ++i) {
           const int m = m0 + rbase + WS_ROWS_PER_PASS * i;
@@ -478,9 +498,10 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
         if (tma_thread) {
           mbar_arrive_expect_tx(&full_bar[stage], tma_bytes);
           tma_load_2d(sb, &tmW, kb * TC_BK, n0, &full_bar[stage]);
-          if (!p.conv) tma_load_2d(sa, &tmA, kb * TC_BK, m0, &full_bar[stage]);
+          if (p.im2col) tma_load_im2col(sa, &tmA, 0, bw, bh, bn, (uint16_t)(kb % p.KW), (uint16_t)(kb / p.KW), &full_bar[stage]);
+          else if (!p.conv) tma_load_2d(sa, &tmA, kb * TC_BK, m0, &full_bar[stage]);
         }
-        if (p.conv) {
+        if (gather) {
           const int k = kb * TC_BK + c * 8;
           const int tap = k / p.Cin;
           const int ci = k - tap * p.Cin;
@@ -510,7 +531,7 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
         }
       }
     }
-    if (p.conv) {  // drain: publish the last WS_LAG stages
+    if (gather) {  // drain: publish the last WS_LAG stages
       cp_async_wait<0>();
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       for (int j = (it >= WS_LAG ? it - WS_LAG : 0); j < it; ++j) mbar_arrive(&full_bar[j % WS_STAGES]);
@@ -620,8 +641,40 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long 
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
+static PFN_cuTensorMapEncodeIm2col_v12000 im2col_map_encoder() {
+  static PFN_cuTensorMapEncodeIm2col_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(ptr);
+  }
+  return fn;
+}
+
+// NHWC bf16 activation [B, H, W, C] as an im2col tensor map: 128 output pixels x 64 channels per load, the filter
+// tap is given per instruction.  Base-pixel bounding box per CUTLASS' convention (W, H order):
+// lower = -pad_before, upper = pad_after - (k - 1); traversal stride = convolution stride.
+static int make_tmap_im2col(CUtensorMap* tm, const TcGemmP& p) {
+  PFN_cuTensorMapEncodeIm2col_v12000 enc = im2col_map_encoder();
+  if (!enc) return (int)cudaErrorNotSupported;
+  const int B = p.M / (p.OH * p.OW), k = p.KW;
+  const int pad_r = (p.OW - 1) * p.stride + k - p.Wd - p.pad_l, pad_b = (p.OH - 1) * p.stride + k - p.H - p.pad_t;
+  cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wd, (cuuint64_t)p.H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Wd * p.Cin * 2, (cuuint64_t)p.H * p.Wd * p.Cin * 2};
+  int lower[2] = {-p.pad_l, -p.pad_t};
+  int upper[2] = {pad_r - (k - 1), pad_b - (k - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(p.A), dims, strides, lower, upper,
+                   (cuuint32_t)TC_BK, (cuuint32_t)TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
 template <int NCOLS>
-static int tc_launch_ws(const TcGemmP& p, int num_sms, cudaStream_t st) {
+static int tc_launch_ws(const TcGemmP& p_in, int num_sms, cudaStream_t st) {
+  TcGemmP p = p_in;
   const size_t smem = (size_t)WS_STAGES * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
@@ -636,11 +689,21 @@ static int tc_launch_ws(const TcGemmP& p, int num_sms, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   const int grid = tiles < num_sms * per_sm ? tiles : num_sms * per_sm;
   CUtensorMap tmA, tmW;
-  int rc = make_tmap_2d(&tmW, p.W, p.N, p.K, p.ldw, p.BN);
+  int rc;
+  p.im2col = 0;
+  if (p.conv && p.Wpad && p.Cin <= TC_BK && p.M % (p.OH * p.OW) == 0 && make_tmap_im2col(&tmA, p) == 0) {
+    p.im2col = 1;  // conv A tiles by TMA im2col; weights in the tap-major, 64-channel-padded layout
+    rc = make_tmap_2d(&tmW, p.Wpad, p.N, (long long)p.KW * p.KW * TC_BK, (long long)p.KW * p.KW * TC_BK, p.BN);
+  } else {
+    rc = make_tmap_2d(&tmW, p.W, p.N, p.K, p.ldw, p.BN);
+    if (rc) return rc;
+    if (!p.conv) rc = make_tmap_2d(&tmA, p.A, p.M, p.K, p.lda, TC_BM);
+    else tmA = tmW;
+  }
   if (rc) return rc;
-  if (!p.conv) rc = make_tmap_2d(&tmA, p.A, p.M, p.K, p.lda, TC_BM);
-  else tmA = tmW;
-  if (rc) return rc;
+  if (getenv("FRX_DEBUG"))
+    fprintf(stderr, "[frx] tc gemm M=%d N=%d K=%d BN=%d conv=%d Cin=%d stride=%d -> %s, grid %d\n", p.M, p.N, p.K, p.BN, p.conv,
+            p.Cin, p.stride, p.im2col ? "TMA im2col" : (p.conv ? "cp.async gather" : "TMA dense"), grid);
   tc_igemm_ws_kernel<NCOLS><<<grid, WS_THREADS, smem, st>>>(p, tmA, tmW);
   return 0;
 }
@@ -692,6 +755,19 @@ __global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* _
 }
 void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st) {
   bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+}
+
+
+// [N][taps][Cin] -> [N][taps][64] (zero padded) bf16, for the im2col path
+__global__ void __launch_bounds__(256) pad_conv_weights_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                               long long rows, int Cin) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 64) return;
+  const int ci = (int)(i & 63);
+  out[i] = ci < Cin ? in[(i >> 6) * Cin + ci] : __float2bfloat16_rn(0.f);
+}
+void launch_pad_conv_weights(const __nv_bfloat16* in, __nv_bfloat16* out, long long rows, int Cin, cudaStream_t st) {
+  pad_conv_weights_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, st>>>(in, out, rows, Cin);
 }
 
 }  // namespace frx

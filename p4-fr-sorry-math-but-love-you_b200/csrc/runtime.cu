@@ -230,6 +230,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   else if (k == "cluster_images") h->opt_cluster_images = (value == 8 || value == 16) ? (int)value : 0;
   else if (k == "enc_fp32") h->opt_enc_fp32 = value != 0;
   else if (k == "tc_ws") h->opt_tc_ws = value != 0;
+  else if (k == "tc_im2col") h->opt_tc_im2col = value != 0;
   else if (k == "prof") {
     h->opt_prof = value != 0;
     if (h->opt_prof && !h->prof) { void* p; if (dev_alloc(h, &p, 16 * 8)) return 1; h->prof = (long long*)p; }
@@ -526,9 +527,22 @@ static size_t pack_bf16_copy(ArenaBuilder& ab, size_t src_off, size_t n) {
   return off;
 }
 
+// bf16 [N][taps][64] copy (input channels zero-padded to 64) of a packed fp32 [N][taps][Cin] conv weight
+static size_t pack_bf16_conv_padded(ArenaBuilder& ab, size_t src_off, int N, int taps, int Cin) {
+  size_t n = (size_t)N * taps * 64;
+  size_t off = ab.add(nullptr, n / 2);
+  const float* s = ab.at(src_off);
+  uint16_t* d = reinterpret_cast<uint16_t*>(ab.at(off));
+  for (size_t row = 0; row < (size_t)N * taps; ++row)
+    for (int ci = 0; ci < 64; ++ci) d[row * 64 + ci] = ci < Cin ? (uint16_t)bf16_bits(s[row * Cin + ci]) : 0;
+  return off;
+}
+
 static void pack_encoder_bf16(frx_handle* h, ArenaBuilder& ab) {
   const frx_config& c = h->cfg;
   for (BlockW& b : h->blocks) {
+    if (b.kind <= 1 && b.cin <= 64)
+      b.wb_a_pad = pack_bf16_conv_padded(ab, b.w_a, b.kind == 0 ? b.cout : b.mid, b.k * b.k, b.cin);
     if (b.kind == 0) b.wb_a = pack_bf16_copy(ab, b.w_a, (size_t)b.cout * b.k * b.k * b.cin);
     else if (b.kind == 1) {
       b.wb_a = pack_bf16_copy(ab, b.w_a, (size_t)b.mid * b.k * b.k * b.cin);
@@ -860,11 +874,13 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
     int OH, OW;
     if (b.kind == 0) {
       TcGemmP g = tc_conv(x, B, H, W, b.cin, A, b.wb_a, b.cout, b.k, b.stride, y, &OH, &OW);
+      if (b.wb_a_pad && h->opt_tc_im2col) g.Wpad = (const __nv_bfloat16*)(A + b.wb_a_pad);
       g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
       if (b.residual) { g.res = x; g.ldr = b.cout; }
       TCL(g);
     } else if (b.kind == 1) {
       TcGemmP g = tc_conv(x, B, H, W, b.cin, A, b.wb_a, b.mid, b.k, b.stride, m0, &OH, &OW);
+      if (b.wb_a_pad && h->opt_tc_im2col) g.Wpad = (const __nv_bfloat16*)(A + b.wb_a_pad);
       g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
       TCL(g);
       TcGemmP g2 = tc_dense(m0, B * OH * OW, b.mid, A, b.wb_b, b.cout, y, 0);
@@ -1457,6 +1473,16 @@ extern "C" int frx_tc_gemm(frx_handle* h, const void* A, const void* W, void* C,
     else { OH = (H - k) / s + 1; OW = (Wd - k) / s + 1; }
     if (M != B * OH * OW || K != k * k * Cin) return fail(h, "frx_tc_gemm: conv shape mismatch (M %d vs %d, K %d vs %d)", M, B * OH * OW, K, k * k * Cin);
     g.conv = 1; g.H = H; g.Wd = Wd; g.Cin = Cin; g.OH = OH; g.OW = OW; g.KW = k; g.stride = s; g.pad_t = pt; g.pad_l = pl;
+    if (h->opt_tc_ws && h->opt_tc_im2col && Cin <= 64) {
+      size_t bytes = (size_t)N * k * k * 64 * 2;
+      if (h->hook_wpad_bytes < bytes) {
+        void* q;
+        if (dev_alloc(h, &q, bytes)) return 1;
+        h->hook_wpad = q; h->hook_wpad_bytes = bytes;
+      }
+      launch_pad_conv_weights((const __nv_bfloat16*)W, (__nv_bfloat16*)h->hook_wpad, (long long)N * k * k, Cin, st); CKL();
+      g.Wpad = (const __nv_bfloat16*)h->hook_wpad;
+    }
   }
   TCL(g);
   return 0;

@@ -26,6 +26,7 @@ struct BlockW {
   size_t se_w1, se_b1, se_w2, se_b2, se_w2t = 0;
   size_t w_b, sc_b, sh_b;      // 1x1 projection + folded BN (kinds 1/2)
   size_t wb_a = 0, wb_b = 0;   // bf16 copies of w_a / w_b ([N][K], K contiguous) for the tcgen05 path
+  size_t wb_a_pad = 0;         // 3x3 convs: bf16 [N][9][64] (channels zero-padded) for the TMA-im2col path
 };
 struct LiteConvW { int cin, cout; size_t w, sc, sh; };
 struct EncLayerW {
@@ -62,6 +63,8 @@ struct frx_handle {
   bool opt_taps = false, opt_graphs = true, opt_timing = false;
   bool opt_prof = false;
   int opt_cluster_images = 0;  // 0 = auto
+  bool opt_tc_im2col = true;   // 3x3 conv A tiles by TMA im2col (false: cp.async gather)
+  void* hook_wpad = nullptr; size_t hook_wpad_bytes = 0;
   bool opt_tc_ws = true;       // persistent warp-specialised tcgen05 GEMM (false: one tile per CTA)
   bool opt_enc_fp32 = false;   // bf16 handle, but run the encoder on the fp32 SIMT path (debug)
   long long* prof = nullptr;

@@ -10,7 +10,7 @@ import frx
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["warp_specialised", "one_tile_per_cta"])
+@pytest.fixture(scope="module", params=["ws_tma_im2col", "ws_cp_async_gather", "one_tile_per_cta"])
 def handle(request):
     cfg = frx._lib.FrxConfig()
     cfg.network, cfg.height, cfg.width, cfg.in_ch = 0, 128, 256, 1
@@ -19,7 +19,8 @@ def handle(request):
     cfg.num_classes, cfg.sos_id, cfg.eos_id, cfg.pad_id = 245, 0, 1, 2
     cfg.max_batch, cfg.max_steps, cfg.precision, cfg.device = 2, 4, 1, 0
     h = frx._lib.Handle(cfg)
-    h.call("frx_set_option", b"tc_ws", 1 if request.param == "warp_specialised" else 0)
+    h.call("frx_set_option", b"tc_ws", 0 if request.param == "one_tile_per_cta" else 1)
+    h.call("frx_set_option", b"tc_im2col", 1 if request.param == "ws_tma_im2col" else 0)
     return h
 
 
