@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
 }
 
 constexpr int SE_IMGS = 4;  // images per CTA: every FC weight is loaded once per 4 images
-__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
+__global__ void __launch_bounds__(1024) se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
                                                     const float* __restrict__ b1, const float* __restrict__ w2,
                                                     const float* __restrict__ b2, float* __restrict__ gate, int B, int C,
                                                     int R) {
@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ me
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < R; r += 8) {
+  const int nwarps = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nwarps) {
     float s[SE_IMGS];
 #pragma unroll
     for (int im = 0; im < SE_IMGS; ++im) s[im] = 0.f;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ me
     const float bb = __ldg(b2 + c);
 #pragma unroll
     for (int im = 0; im < SE_IMGS; ++im) s[im] = bb;
-#pragma unroll 8
+#pragma unroll 16
     for (int r = 0; r < R; ++r) {
       const float wv = __ldg(w2 + (long long)r * C + c);  // w2 is [R][C] (transposed at pack time)
 #pragma unroll
@@ -354,7 +355,7 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
     configured = smem;
   }
   dwconv_se_mean_kernel<<<g, 256, smem, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l);
-  se_fc_kernel<<<dim3((B + SE_IMGS - 1) / SE_IMGS, 4), 256, SE_IMGS * (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, B, C, R);
+  se_fc_kernel<<<dim3((B + SE_IMGS - 1) / SE_IMGS, 2), 1024, SE_IMGS * (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, B, C, R);
   long long total8 = (long long)B * OH * OW * (C / 8);
   se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(out, gate, total8, OH * OW, C);
 }
