@@ -642,6 +642,27 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       layernorm_rows<NIMG>(s, lnp2);
       __syncthreads();
       mark(6);
+      // L2 prefetch of the K/V history the NEXT self-attention of this warp will stream (next layer, or layer 0
+      // of the next step): late in the decode the 181 MB cache no longer fits L2, and these hints turn the
+      // attention's DRAM round trips into L2 hits without holding any registers.
+      if (t > 0) {
+        const int ln_next = (l + 1 < L) ? l + 1 : 0;
+        const int t_next = (l + 1 < L) ? t : t + 1;
+#pragma unroll
+        for (int pp = 0; pp < NIMG / 8; ++pp) {
+          const int pair = warp * (NIMG / 8) + pp;
+          const int li = r * (NIMG / 8) + (pair >> 3), hh = pair & 7;
+          const int b = img0 + li;
+          if (b < B) {
+            const size_t base = ((((size_t)ln_next * B + b) * H + hh) * T) * HD;
+            const int bytes = t_next * HD * 2;  // rows [0, t_next) of this (image, head)
+            for (int off = lane * 128; off < bytes; off += 32 * 128) {
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(reinterpret_cast<const char*>(p.kself + base) + off));
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(reinterpret_cast<const char*>(p.vself + base) + off));
+            }
+          }
+        }
+      }
       // ---- S7: ff = relu(linear0(w))  (F = 4 segments of D columns) --------------------------------
       stage_begin(NIMG * 2048u);
       sb = stage_bar();
