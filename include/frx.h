@@ -28,13 +28,14 @@ extern "C" {
 
 typedef struct frx_handle frx_handle;
 
-enum { FRX_NET_EFFICIENT_SATRN = 0, FRX_NET_LITE_SATRN = 1 };
+enum { FRX_NET_EFFICIENT_SATRN = 0, FRX_NET_LITE_SATRN = 1, FRX_NET_SWIN = 2 };
 enum { FRX_PREC_FP32 = 0, FRX_PREC_BF16 = 1 };
 enum { FRX_DTYPE_F32 = 0, FRX_DTYPE_I64 = 1 };
 
 /* Mirrors what the constructors read from FLAGS and the vocab:
  * networks/EfficientSATRN.py:664-692 (EfficientSATRN.__init__),
- * networks/LiteSATRN.py:548-576. */
+ * networks/LiteSATRN.py:548-576, networks/SWIN.py:1024-1049 (SWIN fixes the encoder to Swin-B/384:
+ * height = width = 384, in_ch = 3, enc_hidden = 1024; the enc_* SATRN fields are ignored). */
 typedef struct frx_config {
   int32_t network;      /* FRX_NET_* */
   int32_t height;       /* FLAGS.input_size.height */

@@ -97,7 +97,35 @@ def main_lite():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def main_swin():
+    """SwinTRN (networks/SWIN.py) greedy fixtures from the reference's own SWIN class (100 % reference code)."""
+    import yaml
+    from oracle import swin
+    torch.set_grad_enabled(False)
+    ref = ref_shim.load_reference()
+    torch.hub.load_state_dict_from_url = lambda *a, **k: {"model": {}}   # SWIN.py:1033 downloads ImageNet weights
+    d = yaml.safe_load(open(os.path.join(ref_shim.REFERENCE_ROOT, "configs", "SWIN.yaml")))
+    d["dropout_rate"] = 0.1
+    spec = swin.swin_spec()
+    sd = swin.synth_state_dict(spec, 0)
+    model = ref.networks.SWIN(ref.utils.Flags(d).get(), ref_shim.reference_vocab(), checkpoint=None).eval()
+    model.load_state_dict(sd, strict=True)
+    batch, steps = 2, 40
+    images = swin.synth_images(batch, 0)
+    expected = satrn.expected_tokens(batch, steps - 1)
+    logits = model(images, expected, False, 0.0)
+    memory = model.encoder(images)
+    out = dict(digest=np.array(state_dict_digest(sd)), memory_sub=memory[:, ::4].contiguous().numpy(),
+               logits=logits.numpy(), tokens=logits.argmax(-1).numpy())
+    path = os.path.join(GOLDEN_DIR, "swin_seed0.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if "--swin" in sys.argv:
+        main_swin()
+        sys.exit(0)
     if "--lite" in sys.argv:
         main_lite()
         sys.exit(0)

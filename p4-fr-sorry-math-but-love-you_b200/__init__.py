@@ -17,7 +17,7 @@ from . import _lib, decoding, flags, layout, networks, sharding, synthetic  # no
 from ._lib import library_path, load_library  # noqa: F401
 from .decoding import decode  # noqa: F401
 from .flags import Flags  # noqa: F401
-from .networks import EfficientSATRN, EfficientSATRN_decoder, EfficientSATRN_encoder, LiteSATRN  # noqa: F401
+from .networks import EfficientSATRN, EfficientSATRN_decoder, EfficientSATRN_encoder, LiteSATRN, SWIN  # noqa: F401
 
-__all__ = ["EfficientSATRN", "LiteSATRN", "EfficientSATRN_encoder", "EfficientSATRN_decoder", "decode", "Flags",
+__all__ = ["EfficientSATRN", "LiteSATRN", "SWIN", "EfficientSATRN_encoder", "EfficientSATRN_decoder", "decode", "Flags",
            "load_library", "library_path"]

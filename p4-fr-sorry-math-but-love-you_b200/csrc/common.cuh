@@ -10,13 +10,14 @@
 
 namespace frx {
 
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_SIGMOID = 3 };
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_SIGMOID = 3, ACT_GELU = 4 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(v, 0.f);
     case ACT_SILU: return v / (1.f + expf(-v));
     case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact GELU (SWIN.py:30)
     default: return v;
   }
 }

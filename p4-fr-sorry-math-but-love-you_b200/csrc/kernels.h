@@ -34,6 +34,13 @@ void launch_dec_argmax_embed(const float* logits, long long ld_logits, int V, lo
 
 void launch_pad_mask(const long long* text, unsigned char* mask, int B, int L, int pad_id, cudaStream_t st);
 
+// SwinTRN encoder pieces (kernels_swin.cu)
+void launch_swin_patch_embed(const float* img, const float* w, const float* bias, const float* g, const float* b,
+                             const float* ape, float* out, int B, int IMGS, int R, int E, cudaStream_t st);
+void launch_swin_window_attn(const float* qkv, const float* bias_table, float* out, int B, int R, int C, int heads, int ws,
+                             int shift, cudaStream_t st);
+void launch_swin_patch_merge(const float* x, float* out, int B, int R, int C, cudaStream_t st);
+
 // best-first search bookkeeping (kernels_beam.cu)
 void launch_beam_init(const BeamP& p, cudaStream_t st);
 void launch_beam_select(const BeamP& p, cudaStream_t st);

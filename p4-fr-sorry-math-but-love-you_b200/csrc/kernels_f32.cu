@@ -452,11 +452,11 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
   if (m >= M) return;
   const float* xp = x + (long long)m * C;
   const float* rp = res ? res + (long long)m * C : nullptr;
-  float v[32];  // C <= 1024
+  float v[64];  // C <= 2048
   const int per = C / 32;
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < 64; ++i) {
     if (i < per) {
       float t = __ldg(xp + i * 32 + lane);
       if (rp) t += __ldg(rp + i * 32 + lane);
@@ -467,11 +467,11 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
+  for (int i = 0; i < 64; ++i)
     if (i < per) { float d = v[i] - mean; q = fmaf(d, d, q); }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < 64; ++i) {
     if (i < per) {
       int ch = i * 32 + lane;
       float o = (v[i] - mean) * rstd * __ldg(gamma + ch) + __ldg(beta + ch);
@@ -574,10 +574,10 @@ void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S,
 //    residual and segmented output (KV-cache scatter).  Tile 32 x 32, the 8
 //    warps split K; lane = output column.
 // ===========================================================================
-constexpr int DG_BM = 32, DG_BN = 32, DG_KC = 256;
+constexpr int DG_BM = 32, DG_BN = 32, DG_KC = 512;  // K chunk = widest LayerNorm row (SwinTRN decoder: 512)
 
 __global__ void __launch_bounds__(256) dec_gemm_f32_kernel(const DecGemmP p) {
-  __shared__ __align__(16) float smem_raw[DG_BM * (DG_KC + 4)];
+  extern __shared__ __align__(16) float smem_raw[];  // DG_BM * (DG_KC + 4) floats
   float (*As)[DG_KC + 4] = reinterpret_cast<float (*)[DG_KC + 4]>(smem_raw);
   float (*red)[DG_BM][DG_BN] = reinterpret_cast<float (*)[DG_BM][DG_BN]>(smem_raw);  // reused after the K loop
   static_assert(8 * DG_BM * DG_BN <= DG_BM * (DG_KC + 4), "partials must fit in the A buffer");
@@ -661,7 +661,13 @@ __global__ void __launch_bounds__(256) dec_gemm_f32_kernel(const DecGemmP p) {
 
 void launch_dec_gemm_f32(const DecGemmP& p, cudaStream_t st) {
   dim3 g((p.M + DG_BM - 1) / DG_BM, (p.N + DG_BN - 1) / DG_BN);
-  dec_gemm_f32_kernel<<<g, 256, 0, st>>>(p);
+  static bool configured = false;
+  const int smem = DG_BM * (DG_KC + 4) * (int)sizeof(float);
+  if (!configured) {
+    cudaFuncSetAttribute(dec_gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  dec_gemm_f32_kernel<<<g, 256, smem, st>>>(p);
 }
 
 // ===========================================================================

@@ -178,14 +178,16 @@ extern "C" int frx_create(const frx_config* cfg, frx_handle** out) {
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) return fail(h, "device is sm_%d%d; frx is built for sm_100a (B200) only", prop.major, prop.minor);
   h->num_sms = prop.multiProcessorCount;
-  if (cfg->network != FRX_NET_EFFICIENT_SATRN && cfg->network != FRX_NET_LITE_SATRN)
+  if (cfg->network != FRX_NET_EFFICIENT_SATRN && cfg->network != FRX_NET_LITE_SATRN && cfg->network != FRX_NET_SWIN)
     return fail(h, "unknown network %d", cfg->network);
+  if (cfg->network == FRX_NET_SWIN && (cfg->height != 384 || cfg->width != 384 || cfg->in_ch != 3 || cfg->enc_hidden != 1024))
+    return fail(h, "SWIN is fixed to Swin-B/384: 384x384x3 input, 1024-wide memory (networks/SWIN.py:1028-1031)");
   if (cfg->dec_hidden % cfg->dec_heads || (cfg->dec_hidden / cfg->dec_heads != 32 && cfg->dec_hidden / cfg->dec_heads != 64))
     return fail(h, "decoder head_dim must be 32 or 64");
-  if (cfg->dec_hidden > 256) return fail(h, "decoder hidden_dim > 256 not supported yet");
+  if (cfg->dec_hidden > 512) return fail(h, "decoder hidden_dim > 512 not supported");
   if (cfg->max_batch <= 0 || cfg->max_steps <= 0) return fail(h, "max_batch/max_steps must be positive");
-  if (cfg->network == FRX_NET_LITE_SATRN && cfg->precision != FRX_PREC_FP32)
-    return fail(h, "LiteSATRN is built for the fp32 mode only (the bf16 kernels are specialised for EfficientSATRN's dimensions)");
+  if (cfg->network != FRX_NET_EFFICIENT_SATRN && cfg->precision != FRX_PREC_FP32)
+    return fail(h, "LiteSATRN / SWIN are built for the fp32 mode only (the bf16 kernels are specialised for EfficientSATRN's dimensions)");
   return 0;
 }
 
@@ -336,6 +338,56 @@ static int pack_trunk_lite(frx_handle* h, ArenaBuilder& ab) {
       return 1;
     }
     if (fold_bn(h, ab, e + "batch_norm" + std::to_string(i), L.cout, 1e-5f, nullptr, &L.sc, &L.sh)) return 1;
+  }
+  return 0;
+}
+
+// SwinTRN encoder (networks/SWIN.py:590-741): Swin-B/384, patch 4, window 12, depths 2-2-18-2, heads 4-8-16-32.
+static int pack_swin(frx_handle* h, ArenaBuilder& ab) {
+  const std::string e = "encoder.";
+  const int E = 128, R0 = 96, WS = 12;
+  const int depths[4] = {2, 2, 18, 2}, heads[4] = {4, 8, 16, 32};
+  auto vec = [&](const std::string& name, std::initializer_list<int64_t> shape, size_t* off) -> int {
+    const HostTensor* t;
+    if (need(h, name, shape, &t)) return 1;
+    *off = ab.add(t->f.data(), t->f.size());
+    return 0;
+  };
+  if (vec(e + "patch_embed.proj.weight", {E, 3, 4, 4}, &h->sw_pe_w) || vec(e + "patch_embed.proj.bias", {E}, &h->sw_pe_b) ||
+      vec(e + "patch_embed.norm.weight", {E}, &h->sw_pe_g) || vec(e + "patch_embed.norm.bias", {E}, &h->sw_pe_beta) ||
+      vec(e + "absolute_pos_embed", {1, R0 * R0, E}, &h->sw_ape) || vec(e + "norm.weight", {8 * E}, &h->sw_norm_g) ||
+      vec(e + "norm.bias", {8 * E}, &h->sw_norm_b))
+    return 1;
+  h->sw_blocks.clear();
+  h->sw_merges.clear();
+  for (int i = 0; i < 4; ++i) {
+    const int dim = E << i, res = R0 >> i;
+    for (int j = 0; j < depths[i]; ++j) {
+      SwinBlockW b{};
+      b.dim = dim; b.res = res; b.heads = heads[i];
+      b.ws = WS; b.shift = (j % 2 == 0) ? 0 : WS / 2;
+      if (res <= WS) { b.ws = res; b.shift = 0; }  // :262-265
+      const std::string p = e + "layers." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
+      const int T = (2 * b.ws - 1) * (2 * b.ws - 1);
+      if (vec(p + "norm1.weight", {dim}, &b.n1_g) || vec(p + "norm1.bias", {dim}, &b.n1_b) ||
+          vec(p + "attn.relative_position_bias_table", {T, b.heads}, &b.bias_table) ||
+          vec(p + "attn.qkv.weight", {3 * dim, dim}, &b.qkv_w) || vec(p + "attn.qkv.bias", {3 * dim}, &b.qkv_b) ||
+          vec(p + "attn.proj.weight", {dim, dim}, &b.proj_w) || vec(p + "attn.proj.bias", {dim}, &b.proj_b) ||
+          vec(p + "norm2.weight", {dim}, &b.n2_g) || vec(p + "norm2.bias", {dim}, &b.n2_b) ||
+          vec(p + "mlp.fc1.weight", {4 * dim, dim}, &b.fc1_w) || vec(p + "mlp.fc1.bias", {4 * dim}, &b.fc1_b) ||
+          vec(p + "mlp.fc2.weight", {dim, 4 * dim}, &b.fc2_w) || vec(p + "mlp.fc2.bias", {dim}, &b.fc2_b))
+        return 1;
+      h->sw_blocks.push_back(b);
+    }
+    if (i < 3) {
+      SwinMergeW m{};
+      m.dim = dim; m.res = res;
+      const std::string p = e + "layers." + std::to_string(i) + ".downsample.";
+      if (vec(p + "reduction.weight", {2 * dim, 4 * dim}, &m.red_w) || vec(p + "norm.weight", {4 * dim}, &m.n_g) ||
+          vec(p + "norm.bias", {4 * dim}, &m.n_b))
+        return 1;
+      h->sw_merges.push_back(m);
+    }
   }
   return 0;
 }
@@ -621,12 +673,16 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
   ArenaBuilder ab;
   const bool want_enc = h->opt_parts & 1, want_dec = h->opt_parts & 2;
   if (want_enc) {
-    if (c.network == FRX_NET_EFFICIENT_SATRN) {
-      if (pack_trunk_efficientnet(h, ab)) return 1;
-    } else if (pack_trunk_lite(h, ab)) {
-      return 1;
+    if (c.network == FRX_NET_SWIN) {
+      if (pack_swin(h, ab)) return 1;
+    } else {
+      if (c.network == FRX_NET_EFFICIENT_SATRN) {
+        if (pack_trunk_efficientnet(h, ab)) return 1;
+      } else if (pack_trunk_lite(h, ab)) {
+        return 1;
+      }
+      if (pack_encoder(h, ab)) return 1;
     }
-    if (pack_encoder(h, ab)) return 1;
   }
   if (want_dec && pack_decoder(h, ab)) return 1;
   if (want_dec && c.precision == FRX_PREC_BF16 && pack_decoder_bf16(h, ab)) return 1;
@@ -669,7 +725,13 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
     if (enc_act > mid_max) mid_max = enc_act;
     if (S * C > act_max) act_max = S * C;
     void* p;
-    if (want_enc) {
+    if (want_enc && c.network == FRX_NET_SWIN) {
+      const size_t tok = 96 * 96;  // per image: x [tok,128], LN copy, q|k|v [tok,384], MLP hidden [tok,512] (largest at stage 0)
+      for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * tok * 128 * 4)) return 1; h->sw_x[i] = (float*)p; }
+      if (dev_alloc(h, &p, B * tok * 128 * 4)) return 1; h->sw_a = (float*)p;
+      if (dev_alloc(h, &p, B * tok * 384 * 4)) return 1; h->sw_qkv = (float*)p;
+      if (dev_alloc(h, &p, B * tok * 512 * 4)) return 1; h->sw_hid = (float*)p;
+    } else if (want_enc) {
       for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * act_max * 4)) return 1; h->act[i] = (float*)p; }
       for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * mid_max * 4)) return 1; h->mid[i] = (float*)p; }
       if (dev_alloc(h, &p, B * 2048 * 4 * 2)) return 1;  // SE means + gates
@@ -949,6 +1011,52 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
   return 0;
 }
 
+// SwinTransformer.forward_features (SWIN.py:725-736) -> memory [B, 144, 1024]
+static int encode_swin(frx_handle* h, const float* images, int B, float* memory, cudaStream_t st) {
+  const float* A = h->arena;
+  float* x = h->sw_x[0];
+  float* y = h->sw_x[1];
+  launch_swin_patch_embed(images, A + h->sw_pe_w, A + h->sw_pe_b, A + h->sw_pe_g, A + h->sw_pe_beta, A + h->sw_ape, x, B, 384,
+                          96, 128, st);
+  CKL();
+  if (tap(h, "embed", x, B, 96, 96, 128, st)) return 1;
+  size_t bi = 0;
+  const int depths[4] = {2, 2, 18, 2};
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < depths[i]; ++j, ++bi) {
+      const SwinBlockW& b = h->sw_blocks[bi];
+      const int M = B * b.res * b.res, C = b.dim;
+      launch_layernorm_f32(x, nullptr, A + b.n1_g, A + b.n1_b, h->sw_a, M, C, 0, st); CKL();
+      GemmP g = dense_gemm(h->sw_a, M, C, A + b.qkv_w, 3 * C, h->sw_qkv, 3 * C);
+      g.shift = A + b.qkv_b;
+      launch_igemm_f32(g, st); CKL();
+      launch_swin_window_attn(h->sw_qkv, A + b.bias_table, h->sw_a, B, b.res, C, b.heads, b.ws, b.shift, st); CKL();
+      GemmP gp = dense_gemm(h->sw_a, M, C, A + b.proj_w, C, y, C);   // y = x + proj(attn)
+      gp.shift = A + b.proj_b; gp.res = x; gp.ldr = C;
+      launch_igemm_f32(gp, st); CKL();
+      launch_layernorm_f32(y, nullptr, A + b.n2_g, A + b.n2_b, h->sw_a, M, C, 0, st); CKL();
+      GemmP g1 = dense_gemm(h->sw_a, M, C, A + b.fc1_w, 4 * C, h->sw_hid, 4 * C);
+      g1.shift = A + b.fc1_b; g1.act = ACT_GELU;
+      launch_igemm_f32(g1, st); CKL();
+      GemmP g2 = dense_gemm(h->sw_hid, M, 4 * C, A + b.fc2_w, C, x, C);  // x = y + fc2(gelu(fc1(ln(y))))
+      g2.shift = A + b.fc2_b; g2.res = y; g2.ldr = C;
+      launch_igemm_f32(g2, st); CKL();
+      if (tap(h, "block" + std::to_string(i) + "." + std::to_string(j), x, B, b.res, b.res, C, st)) return 1;
+    }
+    if (i < 3) {  // PatchMerging (:404-421)
+      const SwinMergeW& m = h->sw_merges[i];
+      const int M2 = B * (m.res / 2) * (m.res / 2);
+      launch_swin_patch_merge(x, h->sw_hid, B, m.res, m.dim, st); CKL();
+      launch_layernorm_f32(h->sw_hid, nullptr, A + m.n_g, A + m.n_b, h->sw_qkv, M2, 4 * m.dim, 0, st); CKL();
+      GemmP g = dense_gemm(h->sw_qkv, M2, 4 * m.dim, A + m.red_w, 2 * m.dim, x, 2 * m.dim);
+      launch_igemm_f32(g, st); CKL();
+      if (tap(h, "merge" + std::to_string(i), x, B, m.res / 2, m.res / 2, 2 * m.dim, st)) return 1;
+    }
+  }
+  launch_layernorm_f32(x, nullptr, A + h->sw_norm_g, A + h->sw_norm_b, memory, B * 144, 1024, 0, st); CKL();
+  return 0;
+}
+
 // LiteSATRN ShallowCNN (LiteSATRN.py:21-70): 4 x (conv3x3 p1 + BN + ReLU + maxpool2) -> H/16 x W/16 x hidden
 static int run_trunk_lite(frx_handle* h, const float* images, int B, float** out, cudaStream_t st) {
   const frx_config& c = h->cfg;
@@ -984,6 +1092,7 @@ extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* 
   const frx_config& c = h->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(c.device));
+  if (c.network == FRX_NET_SWIN) return encode_swin(h, images, B, memory, st);
   if (c.precision == FRX_PREC_BF16 && !h->opt_enc_fp32) return encode_bf16(h, images, B, memory, st);
   const float* A = h->arena;
   float* t = nullptr;

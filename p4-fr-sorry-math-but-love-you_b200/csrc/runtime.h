@@ -40,6 +40,11 @@ struct DecLayerW {
   size_t ln1_g, ln1_b, ln2_g, ln2_b, ln3_g, ln3_b;
 };
 struct FusedW { size_t wt, b; int N; };
+struct SwinBlockW {
+  int dim, res, heads, ws, shift;
+  size_t n1_g, n1_b, bias_table, qkv_w, qkv_b, proj_w, proj_b, n2_g, n2_b, fc1_w, fc1_b, fc2_w, fc2_b;
+};
+struct SwinMergeW { int dim, res; size_t red_w, n_g, n_b; };
 // fragment-packed bf16 weights of the persistent decode kernel (offsets in floats = u32 words)
 struct DecPackW { size_t w_o, w_q2, w_o2, w_f0, w_f1, w_next; };
 struct Tap { float* data = nullptr; size_t capacity = 0; int shape[4] = {0, 0, 0, 0}; };
@@ -82,6 +87,11 @@ struct frx_handle {
   // encoder
   size_t pe_w0 = 0, pe_b0 = 0, pe_w1 = 0, pe_b1 = 0, pe_h = 0, pe_w = 0;
   std::vector<EncLayerW> enc;
+  // SwinTRN encoder
+  size_t sw_pe_w = 0, sw_pe_b = 0, sw_pe_g = 0, sw_pe_beta = 0, sw_ape = 0, sw_norm_g = 0, sw_norm_b = 0;
+  std::vector<SwinBlockW> sw_blocks;
+  std::vector<SwinMergeW> sw_merges;   // merge i follows the last block of stage i
+  float *sw_x[2] = {nullptr, nullptr}, *sw_a = nullptr, *sw_qkv = nullptr, *sw_hid = nullptr;
   // decoder
   size_t emb = 0, pe1d = 0, gen_w = 0, gen_b = 0, w_cross = 0, b_cross = 0;
   size_t last_wb = 0, cross_wb = 0;   // bf16 copies of conv_last / cross K|V weights

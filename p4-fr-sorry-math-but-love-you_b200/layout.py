@@ -155,6 +155,98 @@ def decoder_shapes(dims, prefix="decoder."):
     return s
 
 
+# SwinTRN encoder is hard-wired in the reference (networks/SWIN.py:1028-1031): Swin-B/384
+SWIN_IMG, SWIN_PATCH, SWIN_EMBED, SWIN_WINDOW = 384, 4, 128, 12
+SWIN_DEPTHS, SWIN_HEADS, SWIN_HEAD_CLASSES = (2, 2, 18, 2), (4, 8, 16, 32), 21841
+
+
+def swin_relative_position_index(ws):
+    """networks/SWIN.py:116-135"""
+    coords = torch.stack(torch.meshgrid([torch.arange(ws), torch.arange(ws)], indexing="ij"))
+    cf = torch.flatten(coords, 1)
+    rel = (cf[:, :, None] - cf[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws - 1
+    rel[:, :, 1] += ws - 1
+    rel[:, :, 0] *= 2 * ws - 1
+    return rel.sum(-1)
+
+
+def swin_attn_mask(res, ws, shift):
+    """networks/SWIN.py:286-310"""
+    img = torch.zeros((1, res, res, 1))
+    cnt = 0
+    for h in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+        for w in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            img[:, h, w, :] = cnt
+            cnt += 1
+    mw = img.view(1, res // ws, ws, res // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, ws * ws)
+    m = mw.unsqueeze(1) - mw.unsqueeze(2)
+    return m.masked_fill(m != 0, float(-100.0)).masked_fill(m == 0, float(0.0))
+
+
+def swin_encoder_entries(prefix="encoder."):
+    """(name, shape, kind) in the reference's registration order; kind in {"param", "rel_index", "attn_mask"}."""
+    out = []
+    e = prefix
+    r0 = SWIN_IMG // SWIN_PATCH
+    out.append((e + "absolute_pos_embed", (1, r0 * r0, SWIN_EMBED), "param"))
+    out.append((e + "patch_embed.proj.weight", (SWIN_EMBED, 3, SWIN_PATCH, SWIN_PATCH), "param"))
+    out.append((e + "patch_embed.proj.bias", (SWIN_EMBED,), "param"))
+    out.append((e + "patch_embed.norm.weight", (SWIN_EMBED,), "param"))
+    out.append((e + "patch_embed.norm.bias", (SWIN_EMBED,), "param"))
+    for i, (depth, heads) in enumerate(zip(SWIN_DEPTHS, SWIN_HEADS)):
+        dim, res = SWIN_EMBED * 2 ** i, r0 // 2 ** i
+        for j in range(depth):
+            ws, shift = SWIN_WINDOW, (0 if j % 2 == 0 else SWIN_WINDOW // 2)
+            if res <= ws:
+                ws, shift = res, 0
+            p = "%slayers.%d.blocks.%d." % (e, i, j)
+            if shift > 0:
+                out.append((p + "attn_mask", (res, ws, shift), "attn_mask"))
+            for n, s in (("norm1.weight", (dim,)), ("norm1.bias", (dim,)),
+                         ("attn.relative_position_bias_table", ((2 * ws - 1) ** 2, heads))):
+                out.append((p + n, s, "param"))
+            out.append((p + "attn.relative_position_index", (ws,), "rel_index"))
+            for n, s in (("attn.qkv.weight", (3 * dim, dim)), ("attn.qkv.bias", (3 * dim,)),
+                         ("attn.proj.weight", (dim, dim)), ("attn.proj.bias", (dim,)),
+                         ("norm2.weight", (dim,)), ("norm2.bias", (dim,)),
+                         ("mlp.fc1.weight", (4 * dim, dim)), ("mlp.fc1.bias", (4 * dim,)),
+                         ("mlp.fc2.weight", (dim, 4 * dim)), ("mlp.fc2.bias", (dim,))):
+                out.append((p + n, s, "param"))
+        if i < len(SWIN_DEPTHS) - 1:
+            p = "%slayers.%d.downsample." % (e, i)
+            out.append((p + "reduction.weight", (2 * dim, 4 * dim), "param"))
+            out.append((p + "norm.weight", (4 * dim,), "param"))
+            out.append((p + "norm.bias", (4 * dim,), "param"))
+    out.append((e + "norm.weight", (SWIN_EMBED * 8,), "param"))
+    out.append((e + "norm.bias", (SWIN_EMBED * 8,), "param"))
+    out.append((e + "head.weight", (SWIN_HEAD_CLASSES, SWIN_EMBED * 8), "param"))
+    out.append((e + "head.bias", (SWIN_HEAD_CLASSES,), "param"))
+    return out
+
+
+def build_swin_encoder_tree():
+    tree = ParamTree()
+    for name, shape, kind in swin_encoder_entries():
+        short = name[len("encoder."):]
+        if kind == "rel_index":
+            tree.add(short, swin_relative_position_index(shape[0]), True)
+        elif kind == "attn_mask":
+            tree.add(short, swin_attn_mask(*shape), True)
+        else:
+            tree.add(short, _init_tensor(name, shape), False)
+    return tree
+
+
+def swin_decoder_shapes(dims, prefix="decoder."):
+    """SWIN's Feedforward is an nn.Sequential (networks/SWIN.py:827-841): layers.0 / layers.3."""
+    s = collections.OrderedDict()
+    for k, v in decoder_shapes(dims, prefix).items():
+        s[k.replace("feedforward_layer.linear0", "feedforward_layer.layers.0")
+           .replace("feedforward_layer.linear1", "feedforward_layer.layers.3")] = v
+    return s
+
+
 def dims_from_flags(FLAGS, num_classes):
     """The fields the constructors read (networks/EfficientSATRN.py:667-688)."""
     enc, dec = FLAGS.SATRN.encoder, FLAGS.SATRN.decoder

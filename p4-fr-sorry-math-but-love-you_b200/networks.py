@@ -55,6 +55,7 @@ class _Engine:
     def __init__(self, dims, ids, device, max_batch, max_steps, precision, parts, network=0):
         cfg = _lib.FrxConfig()
         cfg.network = network
+        self.network = network
         self.down = 16 if network == 1 else 32
         for k in ("height", "width", "in_ch", "enc_hidden", "enc_filter", "enc_layers", "enc_heads",
                   "dec_src", "dec_hidden", "dec_filter", "dec_layers", "dec_heads", "num_classes"):
@@ -78,12 +79,17 @@ class _Engine:
             shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
             self.h.call("frx_load_tensor", name.encode(), _ptr(t), shape, t.dim(), dt)
 
+        skip = ("num_batches_tracked", "relative_position_index", "attn_mask")  # derived constants, recomputed in-kernel
         for name, t in state_dict.items():
-            if not name.endswith("num_batches_tracked"):
-                put(name, t)
+            if name.endswith(skip) or name.startswith("encoder.head."):  # Swin's classification head is never used
+                continue
+            # SWIN names its FFN linears layers.0 / layers.3 (networks/SWIN.py:831-838); the C side uses one naming
+            put(name.replace("feedforward_layer.layers.0", "feedforward_layer.linear0")
+                    .replace("feedforward_layer.layers.3", "feedforward_layer.linear1"), t)
         d = self.dims
-        put("pe2d.h", pe2d_table(d["height"] // self.down, d["enc_hidden"]))
-        put("pe2d.w", pe2d_table(d["width"] // self.down, d["enc_hidden"]))
+        if self.network != 2:
+            put("pe2d.h", pe2d_table(d["height"] // self.down, d["enc_hidden"]))
+            put("pe2d.w", pe2d_table(d["width"] // self.down, d["enc_hidden"]))
         put("pe1d", pe1d_table(d["dec_hidden"]))
         self.h.call("frx_finalize_weights")
 
@@ -296,6 +302,37 @@ class LiteSATRN(EfficientSATRN):
 
     def beam_search(self, *a, **k):
         raise AttributeError("LiteSATRN has no beam_search (networks/LiteSATRN.py defines none)")
+
+
+class SWIN(EfficientSATRN):
+    """networks/SWIN.py:1024-1063 -- Swin-B/384 encoder (patch 4, window 12, depths 2-2-18-2, absolute position
+    embedding; hard-wired in the reference, the yaml's SATRN.encoder block is ignored) + the transformer decoder
+    of configs/SWIN.yaml.  Input [B, 3, 384, 384]; greedy decoding only; fp32 mode.  Unlike the reference the
+    constructor does not download ImageNet weights (there is no network): pass a checkpoint dict."""
+
+    _network = 2
+    _down = 32
+
+    def __init__(self, FLAGS, train_dataset, checkpoint=None, *, precision="fp32", max_batch=None, max_steps=None):
+        nn.Module.__init__(self)
+        if precision != "fp32":
+            raise NotImplementedError("SWIN runs in the fp32 mode only")
+        self._setup(FLAGS, train_dataset, precision, max_batch, max_steps)
+        self._dims.update(height=layout.SWIN_IMG, width=layout.SWIN_IMG, in_ch=3, enc_hidden=layout.SWIN_EMBED * 8,
+                          enc_filter=0, enc_layers=0, enc_heads=0)
+        self.encoder = layout.build_swin_encoder_tree()
+        self.decoder = layout.build_param_tree(layout.swin_decoder_shapes(self._dims), "decoder.")
+        d = self.decoder
+        d.hidden_dim, d.filter_dim = self._dims["dec_hidden"], self._dims["dec_filter"]
+        d.num_classes, d.layer_num = self._dims["num_classes"], self._dims["dec_layers"]
+        d.pad_id, d.st_id = self._ids[2], self._ids[0]
+        d.manager = None
+        self.criterion = nn.CrossEntropyLoss(ignore_index=self._ids[2])
+        if isinstance(checkpoint, dict):
+            self.load_state_dict(checkpoint)
+
+    def beam_search(self, *a, **k):
+        raise AttributeError("SWIN has no usable beam_search (the reference's is dead code, SURVEY App. A.6)")
 
 
 class EfficientSATRN_encoder(_FrxModule):

@@ -57,3 +57,22 @@ def lite_flags_dict(height=128, width=256, rgb=1):
 def make_lite_model(state_dict=None, **kw):
     import frx
     return frx.LiteSATRN(frx.Flags(lite_flags_dict()).get(), Vocab(), state_dict, None, **kw)
+
+
+def swin_flags_dict():
+    """configs/SWIN.yaml (the SATRN.encoder block is ignored by SWIN)."""
+    return {
+        "network": "SWIN",
+        "input_size": {"height": 384, "width": 384},
+        "SATRN": {
+            "encoder": {"hidden_dim": 300, "filter_dim": 600, "layer_num": 6, "head_num": 8},
+            "decoder": {"src_dim": 1024, "hidden_dim": 512, "filter_dim": 512, "layer_num": 4, "head_num": 8},
+        },
+        "data": {"rgb": 3},
+        "dropout_rate": 0.1,
+    }
+
+
+def make_swin_model(state_dict=None, **kw):
+    import frx
+    return frx.SWIN(frx.Flags(swin_flags_dict()).get(), Vocab(), state_dict, **kw)
