@@ -103,6 +103,15 @@ def synthetic_images(batch, seed):
     return torch.randn(batch, 1, 128, 256, generator=g)
 
 
+def workload_config(batch, precision):
+    return {"workload": "EfficientSATRN greedy inference, batch %d per GPU, 128x256x1 randn images, "
+                        "max_sequence 230 (231 decode steps), random-init weights, image batch sharded "
+                        "over ranks (no collective)" % batch,
+            "batch_per_gpu": batch, "decode_steps": STEPS_PER_IMAGE, "precision": precision,
+            "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
+                  "(KV cache + activations) also exceeds the 126 MB L2"}
+
+
 def build_model(precision, batch):
     import frx
     from helpers import Vocab, flags_dict
@@ -148,10 +157,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "EfficientSATRN greedy, 128x256x1 randn images, max_sequence 230 (231 steps), "
-                               "random-init weights; reference arm = the reference's CPU algorithm "
-                               "(oracle port, op-for-op) on a bounded sample",
-                   "batch_per_step": sample},
+        "config": dict(workload_config(args.batch, args.precision),
+                       reference_arm="the reference's CPU algorithm (oracle port, op for op, fp32) on the host cores; "
+                                     "each step is a bounded sample of %d images of the same workload" % sample),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": "%d step(s) x %d images x 231 decode steps, torch %s CPU fp32, %d threads"
                                    % (max(1, args.steps), sample, torch.__version__, cores)},
@@ -247,12 +255,7 @@ def run_frx(args, rank, world, local_rank):
         "warmup": max(args.warmup, 1), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
         "data": "synthetic",
-        "config": {"workload": "EfficientSATRN greedy inference, batch %d per GPU, 128x256x1 randn images, "
-                               "max_sequence 230 (231 decode steps), random-init weights, image batch sharded "
-                               "over ranks (no collective)" % B,
-                   "batch_per_gpu": B, "decode_steps": T, "precision": args.precision,
-                   "l2": "256 MiB buffer written between timed iterations (L2 flush); per-step working set "
-                         "(KV cache + activations) also exceeds the 126 MB L2"},
+        "config": workload_config(B, args.precision),
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(images_host.numel() * 4),
                 "d2h_bytes_per_step": int(tokens_host.numel() * 8)},
         "gpu_launches": int(gpu_launches),
@@ -276,7 +279,7 @@ def run_frx(args, rank, world, local_rank):
         import frx
         from helpers import Vocab, flags_dict
         sd_cal = o_synth.synth_state_dict(o_satrn.ModelSpec(), 0)
-        ips, cores, cpu_tok, dt = cpu_reference_throughput(sd_cal, args.cpu_sample, 1)
+        ips, cores, cpu_tok, dt = cpu_reference_throughput(sd_cal, args.cpu_sample, args.cpu_runs)
         xs = synthetic_images(args.cpu_sample, 0).to(dev)
         agree = {}
         with torch.no_grad():
@@ -288,9 +291,9 @@ def run_frx(args, rank, world, local_rank):
                 del m
         line["cpu_baseline"] = {
             "value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "1 batch of %d images x 231 decode steps (%.1f s), oracle port of the reference's "
+            "sample": "%d batches of %d images x 231 decode steps (%.1f s), oracle port of the reference's "
                       "as-written CPU algorithm, torch %s fp32, BN-calibrated synthetic checkpoint"
-                      % (args.cpu_sample, dt, torch.__version__),
+                      % (args.cpu_runs, args.cpu_sample, dt, torch.__version__),
             "gpu_fp32_mode_token_agreement": agree["fp32"],
             "gpu_bf16_mode_token_agreement": agree["bf16"]}
     print(json.dumps(line), flush=True)
@@ -305,6 +308,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--precision", default=os.environ.get("FRX_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=32)
+    ap.add_argument("--cpu-runs", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
