@@ -147,10 +147,10 @@ struct TcGemmP {
 // bf16 persistent decode kernel (kernels_decode_bf16.cu)
 // ---------------------------------------------------------------------------
 constexpr int DEC_CLUSTER = 8;   // CTAs per cluster
-constexpr int DEC_IMG = 16;      // images per cluster (= M of mma.m16n8k16)
+constexpr int DEC_IMG = 8;       // images per cluster (rows 0..7 of the mma.m16n8k16 tile)
 constexpr int DEC_FMAX = 1024;   // decoder filter_dim the kernel is specialised for
 constexpr int DEC_TMAX = 232;    // max decode steps
-constexpr int DEC_MAX_CLUSTERS_8 = 32;  // co-resident 8-CTA clusters at 2 CTAs/SM (measured: 33 on B200)
+constexpr int DEC_MAX_CLUSTERS = 32;  // clusters per launch; 33 8-CTA clusters are co-resident at 2 CTAs/SM on B200
 
 struct DecClusterLayer {
   const uint4 *w_o, *w_q2, *w_o2, *w_f0, *w_f1, *w_next;   // fragment-packed bf16, per-CTA blocks
@@ -160,6 +160,7 @@ struct DecClusterLayer {
 
 struct DecClusterP {
   int B, steps, T, L, V, S, sos;
+  int img_base;                  // first image of this launch (set by the launcher)
   const uint4* w_first;          // layer-0 q|k|v
   const float* b_first;
   DecClusterLayer layer[4];

@@ -70,7 +70,7 @@ void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S,
 
 // bf16 persistent decode (kernels_decode_bf16.cu)
 size_t dec_cluster_smem_bytes();
-int launch_dec_cluster_bf16(const DecClusterP& p, int images_per_cluster, cudaStream_t st);
+int launch_dec_cluster_bf16(const DecClusterP& p, cudaStream_t st);
 void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc, int B, int S, int L, int Dm,
                           cudaStream_t st);
 

@@ -1,29 +1,29 @@
 // kernels_decode_bf16.cu -- the whole greedy decode loop as ONE persistent kernel.
 //
-// Design (DESIGN.md "decode"): every operation of the decoder step is local to
-// an image, so there is no reason for grid-wide synchronisation.  A thread-block
-// CLUSTER of 8 CTAs owns 16 images (the M of one mma.m16n8k16) for all steps:
-//   * each CTA computes 1/8 of the output columns of every linear layer, with
-//     the bf16 weights streamed from L2 straight into tensor-core B fragments
-//     (pre-packed on the host in fragment order -> coalesced 16-byte loads);
-//   * the partial rows are all-gathered through distributed shared memory with
-//     st.async: each CTA stores its slice into all 8 CTAs' buffers and every store
-//     completes transaction bytes on the DESTINATION CTA's mbarrier, so a stage is
-//     over for a CTA exactly when all bytes it needs have landed -- no cluster
-//     barrier (whose release semantics cost a MEMBAR.ALL.GPU each), no fence, no
-//     global-memory round trips, no grid sync;
-//   * attention over the bf16 KV cache (head-major [L][B][H][T][32], 64 B rows)
-//     is done by one warp per (image, head) with 16-byte coalesced loads and
-//     warp-shuffle reductions; the step's K/V rows are routed through DSMEM to
-//     the CTA that owns the image, which writes (and later reads) them itself, so
-//     no cross-CTA global-memory visibility is ever required.
-// Tensor cores are used through mma.sync (M=16 images per cluster); tcgen05's
-// minimum tile (M=64..128 rows) does not fit a 16-row per-step problem, and the
-// step is bandwidth/latency-bound, not MMA-bound.
+// A thread-block CLUSTER of 8 CTAs owns 8 images for all steps; CTA r of the cluster owns
+// attention HEAD r of those images and 1/8 of the output columns of every other linear layer:
+//   * q|k|v of head r are computed by CTA r (the 96 columns of the fused projection that belong to the
+//     head) and consumed by CTA r's own attention warps (warp w <-> image w) straight from shared memory:
+//     q, k, v never cross a CTA boundary, and the K/V cache of (image, head r) is written and read by one
+//     CTA only, so no cross-CTA global-memory visibility is needed anywhere;
+//   * what does cross CTA boundaries is all-gathered through distributed shared memory with st.async: the
+//     attention outputs (2x per layer), the pre-LayerNorm rows (3x) and the FFN hidden row (1x) = 6
+//     exchanges per layer + the logits = 19 per step.  Every store completes transaction bytes on the
+//     DESTINATION CTA's mbarrier; a stage is over for a CTA when the bytes it expects have landed -- no
+//     cluster barrier, no fence;
+//   * linear layers run on mma.sync.m16n8k16 (bf16 -> fp32) with the weights streamed from L2 in
+//     B-fragment order (packed on the host).  Every warp requests the weight fragments of its share of a
+//     stage before the wait that precedes the stage (weights are static), so a stage costs one L2 round
+//     trip at most; every stage is K-split over two warps, the partial fragments meet in shared memory and
+//     the epilogue works on 8-column row pieces so that all DSMEM / global stores are 16 bytes wide;
+//   * work that nobody waits for in this step -- the K/V cache rows of the layer OUTPUT (the
+//     reference caches layer outputs) -- runs between a stage's stores and its wait.
+// LayerNorm / residual are recomputed redundantly per CTA on the gathered rows (cheaper than another
+// exchange).  tcgen05 is not used here on purpose: M is 8..16 rows per cluster.
 //
-// Implements the recurrence of SURVEY App. A.4 (networks/EfficientSATRN.py:374-397,
-// :539-558): cached layer OUTPUTS, current layer INPUT as the last key, scores
-// divided by sqrt(d_model), post-LN, ReLU after both FFN linears.
+// Implements the recurrence of SURVEY App. A.4 (networks/EfficientSATRN.py:374-397, :539-558): cached
+// layer OUTPUTS, current layer INPUT as the last key, scores divided by sqrt(d_model), post-LN, ReLU
+// after both FFN linears.
 #include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
@@ -37,17 +37,21 @@ namespace frx {
 
 namespace {
 
-constexpr int CL = DEC_CLUSTER;   // CTAs per cluster
-constexpr int IMG = DEC_IMG;      // smem rows per cluster (= M of the MMA); NIMG <= IMG of them hold images
-constexpr int D = 256;            // decoder width this kernel is specialised for
+constexpr int CL = DEC_CLUSTER;  // CTAs per cluster
+constexpr int D = 256;           // decoder width this kernel is specialised for
 constexpr int HD = 32;
-constexpr int H = D / HD;         // 8 heads
-constexpr int NTHR = 256;
-constexpr int APAD = 8;           // bf16 padding of the A-operand rows (bank-conflict-free fragments)
+constexpr int H = D / HD;        // 8 heads = CL
+constexpr int FF = DEC_FMAX;
+constexpr int APAD = 8;          // bf16 padding of the A-operand rows (conflict-free ldmatrix)
+constexpr int FPAD = 4;          // fp32 padding of rows that are accessed 16 bytes per lane, 8 rows at a time
+constexpr int NIMG = DEC_IMG;    // images per cluster = warps per CTA (warp w <-> image w)
+constexpr int NTHR = NIMG * 32;
+constexpr int RED_FLOATS = 2048;  // K-split reduction region: KS * NT * 32 lanes * 2 floats, NT <= 16
+static_assert(NIMG == 8, "the kernel maps MMA rows 0..7 to the cluster's images");
+static_assert(H == CL, "one head per CTA of the cluster");
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -61,11 +65,11 @@ __device__ __forceinline__ uint64_t make_evict_last_policy() {
 __device__ __forceinline__ uint4 ldg_weights(const uint4* p, uint64_t pol) {
   uint4 v;  // weights are re-read every step by every cluster: ask L2 to keep them
   asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;\n"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
   return v;
 }
 
-// KV-cache rows are written by other SMs earlier in this kernel: coherent (L2) load, L1 bypassed.
+// KV-cache rows were written earlier in this kernel by this CTA: L2 load, L1 bypassed.
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 v;
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
@@ -73,7 +77,7 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -90,179 +94,120 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 struct Smem {
-  float xres[IMG][D];              // residual stream (fp32)
-  float pre[IMG][D];               // gathered pre-LayerNorm rows
-  float q[IMG][D];                 // q of the current layer input (also q2, logits)
-  __nv_bfloat16 kv[IMG][2 * D];    // k | v of the current layer input (the extra "current" key/value)
-  __nv_bfloat16 abf[IMG][D + APAD];        // A operand (bf16) of the next GEMM, K = D
-  __nv_bfloat16 abf2[IMG][DEC_FMAX + APAD];  // A operand of FFN linear1, K = F
-  float red[4][32][4];             // K-split partial accumulators
+  // row strides are padded by 16 bytes wherever a quarter-warp touches 8 rows with 16-byte accesses
+  float xres[NIMG][D + FPAD];           // residual stream (fp32), full rows in every CTA
+  float pre[NIMG][D + FPAD];            // gathered pre-LayerNorm rows
+  __nv_bfloat16 abf[NIMG][D + APAD];    // A operand: LayerNorm output / embedded input
+  __nv_bfloat16 obf[NIMG][D + APAD];    // A operand: gathered attention outputs (all heads)
+  __nv_bfloat16 abf2[NIMG][FF + APAD];  // A operand: gathered FFN hidden row (also the fp32 logits view)
+  float red[2][RED_FLOATS];             // K-split partial fragments (two alternating regions)
+  float qh[NIMG][HD + FPAD];            // q of head r (this CTA's head)
+  __nv_bfloat16 kcur[NIMG][HD + APAD];  // k, v of the current layer input, head r (the extra "current" key)
+  __nv_bfloat16 vcur[NIMG][HD + APAD];
   long long prof[16];
-  __nv_bfloat16 kvrow[IMG / 8][2][D];  // this step's K|V rows of the image(s) this CTA owns (sent by the 8 column owners)
-  unsigned long long bar[2];           // stage mbarriers (alternate by stage parity)
-  DecClusterLayer lw[4];           // per-layer pointers (dynamic indexing of kernel params would spill them)
+  unsigned long long bar[2];            // stage mbarriers (alternate by stage parity)
+  DecClusterLayer lw[4];                // per-layer pointers (dynamic indexing of kernel params would spill them)
 };
 
 // ---------------------------------------------------------------------------
-// One GEMM stage: out[16, NT*8 columns of this CTA] = A[16, K] * W^T, A in smem
-// (bf16), W pre-packed for this CTA: [NT tiles][K/32][32 lanes] uint4.
-// NT >= 8: warp w owns tiles w, w+8, ...; NT == 4: two warps split K per tile.
-// Epi(tile, acc, lane) is called by the warp that holds the final accumulator.
+// GEMM stage: out[8 images, NT*8 columns of this CTA] = A[8, K] * W^T; A bf16 in smem (rows 8..15 of the
+// MMA tile alias rows 0..7), W fragment-packed [tile][K/32][32 lanes] uint4.  The K range is split over
+// KS warps (warp w: k-slice w % KS, tiles (w / KS) + j*TG); the partial fragments meet in shared memory and
+// the epilogue runs on (tile, row) units of 8 consecutive columns so that everything it stores is 16 bytes
+// wide: epi(tile, row, v[8], sub) with sub in [0, NTHR / (NT*8)) distinguishing the threads that share a unit
+// (they split the destinations of an all-gather between them).
 // ---------------------------------------------------------------------------
-// Weight prefetch: the first PF k-pairs of every tile a warp owns are loaded into registers BEFORE the
-// previous stage's barrier wait / LayerNorm, so their L2 latency overlaps that wait.  (Weights are static;
-// nothing orders these loads against the exchange.)
-template <int K, int NT>
-struct WPre {
-  static constexpr int TPW = NT >= 8 ? (NT + 7) / 8 : 1;
-  static constexpr int KP = K / 32;
-  static constexpr int KPW = NT >= 8 ? KP : KP / 2;  // k-pairs per warp task
-  static constexpr int PF = NT >= 8 ? 2 : 4;         // prefetched k-pairs
-  uint4 w[TPW][PF];
+template <int NT, int KP, int KS>
+struct GC {
+  static constexpr int NW = NTHR / 32, TG = NW / KS, TPW = NT / TG, KPW = KP / KS, TOT = TPW * KPW;
+  static constexpr int UNITS = NT * 8, NSUB = NTHR / UNITS;
+  static_assert(NW % KS == 0 && NT % TG == 0 && KP % KS == 0 && NSUB >= 1, "bad GEMM split");
+  static_assert(KS * NT * 64 <= RED_FLOATS, "reduction region too small");
 };
 
-template <int K, int NT>
-__device__ __forceinline__ WPre<K, NT> prefetch_weights(const uint4* __restrict__ Wp, uint64_t pol) {
-  using P = WPre<K, NT>;
-  P pre;
+template <int N>
+struct WPre { uint4 w[N > 0 ? N : 1]; };
+
+template <int NT, int KP, int KS, int PF>
+__device__ __forceinline__ WPre<PF> prefetch_w(const uint4* __restrict__ Wp, uint64_t pol) {
+  using C = GC<NT, KP, KS>;
+  WPre<PF> pre;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if constexpr (NT >= 8) {
+  const int ks = warp % KS, tg = warp / KS;
 #pragma unroll
-    for (int i = 0; i < P::TPW; ++i) {
-      const int tile = warp + 8 * i;
-#pragma unroll
-      for (int j = 0; j < P::PF; ++j)
-        pre.w[i][j] = tile < NT ? ldg_weights(Wp + ((size_t)tile * P::KP + j) * 32 + lane, pol) : make_uint4(0u, 0u, 0u, 0u);
-    }
-  } else {
-    const int tile = warp & 3, half = warp >> 2;
-#pragma unroll
-    for (int j = 0; j < P::PF; ++j)
-      pre.w[0][j] = ldg_weights(Wp + ((size_t)tile * P::KP + half * P::KPW + j) * 32 + lane, pol);
+  for (int idx = 0; idx < PF; ++idx) {
+    const int kk = idx / C::TPW, j = idx % C::TPW;
+    pre.w[idx] = ldg_weights(Wp + ((size_t)(tg + j * C::TG) * KP + ks * C::KPW + kk) * 32 + lane, pol);
   }
   return pre;
 }
 
-template <int K, int NT, typename Epi>
-__device__ __forceinline__ void gemm_stage(Smem& s, uint64_t pol, const __nv_bfloat16* A, int lda,
-                                           const uint4* __restrict__ Wp, const WPre<K, NT>& pre, Epi epi) {
-  using P = WPre<K, NT>;
+template <int NT, int KP, int KS, int PF, typename Epi>
+__device__ __forceinline__ void gemm2(float* __restrict__ red, const __nv_bfloat16* A, int lda,
+                                      const uint4* __restrict__ Wp, uint64_t pol, const WPre<PF>& pre, Epi epi) {
+  using C = GC<NT, KP, KS>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gid = lane >> 2, tig = lane & 3;
-  constexpr int KP = K / 32;
-  // A fragments of two k16 steps with two ldmatrix.x4 (instead of eight 32-bit LDS): lane -> row address of
-  // matrix (lane >> 3): {rows 0-7, k lo}, {rows 8-15, k lo}, {rows 0-7, k hi}, {rows 8-15, k hi} = a0..a3.
-  const uint32_t a_lane = smem_addr_u32(A + ((lane & 7) + ((lane >> 3) & 1) * 8) * lda + ((lane >> 4) & 1) * 8);
-  auto a_frags = [&](int kp, uint32_t (&a0)[4], uint32_t (&a1)[4]) {
-    const uint32_t addr = a_lane + (uint32_t)kp * 64u;  // 32 bf16 per k-pair
+  const int ks = warp % KS, tg = warp / KS;
+  uint4 w[C::TOT];
+#pragma unroll
+  for (int idx = 0; idx < C::TOT; ++idx) {
+    const int kk = idx / C::TPW, j = idx % C::TPW;
+    if (idx < PF) w[idx] = pre.w[idx];
+    else w[idx] = ldg_weights(Wp + ((size_t)(tg + j * C::TG) * KP + ks * C::KPW + kk) * 32 + lane, pol);
+  }
+  // A fragments of two k16 steps with two ldmatrix.x4: lane -> row address of matrix (lane >> 3):
+  // {rows 0-7, k lo}, {rows 8-15, k lo}, {rows 0-7, k hi}, {rows 8-15, k hi}; rows 8-15 alias rows 0-7.
+  const uint32_t a_lane = smem_u32(A + (lane & 7) * lda + ((lane >> 4) & 1) * 8);
+  float acc[C::TPW][2][4];
+#pragma unroll
+  for (int j = 0; j < C::TPW; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][h][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < C::KPW; ++kk) {
+    const uint32_t addr = a_lane + (uint32_t)(ks * C::KPW + kk) * 64u;  // 32 bf16 per k-pair
+    uint32_t a0[4], a1[4];
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                  : "=r"(a0[0]), "=r"(a0[1]), "=r"(a0[2]), "=r"(a0[3]) : "r"(addr));
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                  : "=r"(a1[0]), "=r"(a1[1]), "=r"(a1[2]), "=r"(a1[3]) : "r"(addr + 32u));
-  };
-  (void)gid; (void)tig;
-  if constexpr (NT >= 8) {
-    constexpr int TPW = P::TPW;
-    float acc[TPW][2][4];
 #pragma unroll
-    for (int i = 0; i < TPW; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
-#pragma unroll
-    for (int kp = 0; kp < P::PF; ++kp) {  // prefetched k-pairs
-      uint32_t a0[4], a1[4];
-      a_frags(kp, a0, a1);
-#pragma unroll
-      for (int i = 0; i < TPW; ++i) {
-        if (warp + 8 * i < NT) {
-          mma_bf16(acc[i][0], a0, pre.w[i][kp].x, pre.w[i][kp].y);
-          mma_bf16(acc[i][1], a1, pre.w[i][kp].z, pre.w[i][kp].w);
-        }
-      }
+    for (int j = 0; j < C::TPW; ++j) {
+      const uint4 ww = w[kk * C::TPW + j];
+      mma_bf16(acc[j][0], a0, ww.x, ww.y);
+      mma_bf16(acc[j][1], a1, ww.z, ww.w);
     }
-#pragma unroll 3
-    for (int kp = P::PF; kp < KP; ++kp) {
-      uint4 w[TPW];
+  }
+  // partial fragments -> red[ks][tile][lane] (float2: row lane>>2, columns (lane&3)*2 + {0,1})
 #pragma unroll
-      for (int i = 0; i < TPW; ++i) {
-        int tile = warp + 8 * i;
-        if (tile < NT) w[i] = ldg_weights(Wp + ((size_t)tile * KP + kp) * 32 + lane, pol);
-      }
-      uint32_t a0[4], a1[4];
-      a_frags(kp, a0, a1);
+  for (int j = 0; j < C::TPW; ++j)
+    *reinterpret_cast<float2*>(red + ((size_t)(ks * NT + tg + j * C::TG) * 32 + lane) * 2) =
+        make_float2(acc[j][0][0] + acc[j][1][0], acc[j][0][1] + acc[j][1][1]);
+  __syncthreads();
+  if (threadIdx.x < C::UNITS * C::NSUB) {
+    const int u = threadIdx.x % C::UNITS, sub = threadIdx.x / C::UNITS;
+    const int tile = u >> 3, row = u & 7;
+    float v[8];
 #pragma unroll
-      for (int i = 0; i < TPW; ++i) {
-        if (warp + 8 * i < NT) {
-          mma_bf16(acc[i][0], a0, w[i].x, w[i].y);
-          mma_bf16(acc[i][1], a1, w[i].z, w[i].w);
-        }
-      }
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int k2 = 0; k2 < KS; ++k2) {
+      const float4* src = reinterpret_cast<const float4*>(red + ((size_t)(k2 * NT + tile) * 32 + row * 4) * 2);
+      const float4 lo = src[0], hi = src[1];
+      v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w;
+      v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
     }
-#pragma unroll
-    for (int i = 0; i < TPW; ++i) {
-      int tile = warp + 8 * i;
-      if (tile < NT) {
-        float c[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) c[e] = acc[i][0][e] + acc[i][1][e];
-        epi(tile, c, lane);
-      }
-    }
-  } else {
-    static_assert(NT == 4, "NT must be 4 or >= 8");
-    const int tile = warp & 3, half = warp >> 2;
-    float acc[2][4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-    constexpr int KH = P::KPW;
-#pragma unroll
-    for (int kk = 0; kk < P::PF; ++kk) {
-      uint32_t a0[4], a1[4];
-      a_frags(half * KH + kk, a0, a1);
-      mma_bf16(acc[0], a0, pre.w[0][kk].x, pre.w[0][kk].y);
-      mma_bf16(acc[1], a1, pre.w[0][kk].z, pre.w[0][kk].w);
-    }
-#pragma unroll 4
-    for (int kk = P::PF; kk < KH; ++kk) {
-      const int kp = half * KH + kk;
-      uint4 w = ldg_weights(Wp + ((size_t)tile * KP + kp) * 32 + lane, pol);
-      uint32_t a0[4], a1[4];
-      a_frags(kp, a0, a1);
-      mma_bf16(acc[0], a0, w.x, w.y);
-      mma_bf16(acc[1], a1, w.z, w.w);
-    }
-    float c[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) c[e] = acc[0][e] + acc[1][e];
-    if (half == 1) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s.red[tile][lane][e] = c[e];
-    }
-    __syncthreads();
-    if (half == 0) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) c[e] += s.red[tile][lane][e];
-      epi(tile, c, lane);
-    }
+    epi(tile, row, v, sub);
   }
 }
 
 // ---- DSMEM all-gather with st.async + mbarrier transaction counting ------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
-}
-__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
-}
-__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t a, uint32_t b, uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n" ::"r"(raddr), "r"(a), "r"(b), "r"(rbar) : "memory");
 }
 __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar) : "memory");
@@ -288,66 +233,53 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
-// Store the same value at the same smem offset of every CTA of the cluster; each store
-// completes its byte count on the destination CTA's mbarrier `bar` (same offset everywhere).
-__device__ __forceinline__ void ag_store_f2(uint32_t bar, float* local, float a, float b) {
-  const uint32_t la = smem_u32(local);
-#pragma unroll
-  for (int r = 0; r < CL; ++r) st_async_v2(mapa_u32(la, r), __float_as_uint(a), __float_as_uint(b), mapa_u32(bar, r));
-}
-__device__ __forceinline__ void ag_store_u32(uint32_t bar, void* local, uint32_t v) {
-  const uint32_t la = smem_u32(local);
-#pragma unroll
-  for (int r = 0; r < CL; ++r) st_async_b32(mapa_u32(la, r), v, mapa_u32(bar, r));
-}
+// Store the same value at the same smem offset of every CTA of the cluster; each store completes its
+// byte count on the destination CTA's mbarrier `bar` (same offset everywhere).
 __device__ __forceinline__ void ag_store_u4(uint32_t bar, void* local, uint4 v) {
   const uint32_t la = smem_u32(local);
 #pragma unroll
   for (int r = 0; r < CL; ++r) st_async_v4(mapa_u32(la, r), v, mapa_u32(bar, r));
 }
 
-// LayerNorm of the 16 gathered rows (every CTA does all rows: the result is
-// needed everywhere and recomputing is cheaper than another exchange).
 struct LnParams { float g[D / 32], b[D / 32]; };
 __device__ __forceinline__ LnParams load_ln(const float* __restrict__ g, const float* __restrict__ b) {
-  LnParams o;  // issued BEFORE the cluster barrier so the L2 latency overlaps the wait
+  LnParams o;  // issued BEFORE the stage wait so the load latency overlaps it
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < D / 32; ++i) { o.g[i] = __ldg(g + i * 32 + lane); o.b[i] = __ldg(b + i * 32 + lane); }
   return o;
 }
 
-template <int NIMG>
+// LayerNorm of the gathered rows: warp w <-> row w (every CTA does all rows).
 __device__ __forceinline__ void layernorm_rows(Smem& s, const LnParams& P) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float v[D / 32];
+  float sum = 0.f;
 #pragma unroll
-  for (int rr = 0; rr < NIMG / 8; ++rr) {
-    const int row = warp * (NIMG / 8) + rr;
-    float v[D / 32];
-    float sum = 0.f;
+  for (int i = 0; i < D / 32; ++i) { v[i] = s.pre[row][i * 32 + lane]; sum += v[i]; }
+  const float mean = warp_sum(sum) * (1.f / D);
+  float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < D / 32; ++i) { v[i] = s.pre[row][i * 32 + lane]; sum += v[i]; }
-    const float mean = warp_sum(sum) * (1.f / D);
-    float q = 0.f;
+  for (int i = 0; i < D / 32; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < D / 32; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < D / 32; ++i) {
-      const int c = i * 32 + lane;
-      float o = (v[i] - mean) * rstd * P.g[i] + P.b[i];
-      s.xres[row][c] = o;
-      s.abf[row][c] = __float2bfloat16_rn(o);
-    }
+  for (int i = 0; i < D / 32; ++i) {
+    const int c = i * 32 + lane;
+    const float o = (v[i] - mean) * rstd * P.g[i] + P.b[i];
+    s.xres[row][c] = o;
+    s.abf[row][c] = __float2bfloat16_rn(o);
   }
 }
 
+// ---------------------------------------------------------------------------
 // Attention of one (image, head) pair by one warp, single pass (online softmax).
-// Lane (g = lane>>2, c = lane&3) handles keys j = g (mod 8) and head dims [8c, 8c+8).
-// K/V rows are 32 bf16 (64 B), contiguous over keys -> each warp load covers 512
-// contiguous bytes; 4 K rows + 4 V rows are in flight per lane before any math.
-// Every lane group keeps its own running (max, sum, acc) and the 8 groups are
-// merged with shuffles at the end.  All lanes return the 8 output dims [8c, 8c+8).
+// Lane (g = lane>>2, c = lane&3) handles keys j = g (mod 8) and head dims [8c, 8c+8).  K/V rows are 32
+// bf16 (64 B), contiguous over keys -> each warp load covers 512 contiguous bytes; U K rows + U V rows
+// (8*U keys) are in flight per lane before any arithmetic.  Every lane group keeps its own running
+// (max, sum, acc); the 8 groups are merged with shuffles at the end, then the extra "current input" key
+// of the reference recurrence.  All lanes return the 8 output dims [8c, 8c+8).
+// ---------------------------------------------------------------------------
+template <int U>
 __device__ __forceinline__ void attend_pair(const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
                                             const __nv_bfloat16* __restrict__ Vc, int n_hist,
                                             const __nv_bfloat16* __restrict__ kx,
@@ -361,22 +293,22 @@ __device__ __forceinline__ void attend_pair(const float* __restrict__ q, const _
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  for (int j0 = 0; j0 < n_hist; j0 += 32) {
-    uint4 kk[4], vv[4];
+  for (int j0 = 0; j0 < n_hist; j0 += 8 * U) {
+    uint4 kk[U], vv[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int j = j0 + u * 8 + g;
       kk[u] = j < n_hist ? ldg_stream(Kc + (size_t)j * HD + c * 8) : zero;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int j = j0 + u * 8 + g;
       vv[u] = j < n_hist ? ldg_stream(Vc + (size_t)j * HD + c * 8) : zero;
     }
-    float sv[4];
+    float sv[U];
     float cm = m;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       float kf[8];
       unpack8(kk[u], kf);
       float part = 0.f;
@@ -392,7 +324,7 @@ __device__ __forceinline__ void attend_pair(const float* __restrict__ q, const _
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] *= scale;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const float pj = (sv[u] == -INFINITY) ? 0.f : __expf(sv[u] - cm);
       float vf[8];
       unpack8(vv[u], vf);
@@ -445,31 +377,42 @@ __device__ __forceinline__ void attend_pair(const float* __restrict__ q, const _
   for (int i = 0; i < 8; ++i) o[i] = acc[i] * inv;
 }
 
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
 }  // namespace
 
 // ===========================================================================
 // The persistent decode kernel
 // ===========================================================================
-template <int NIMG>
-__global__ void __cluster_dims__(DEC_CLUSTER, 1, 1) __launch_bounds__(256, 2)
+__global__ void __cluster_dims__(DEC_CLUSTER, 1, 1) __launch_bounds__(NTHR, 2)
 dec_cluster_bf16_kernel(const DecClusterP p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   cg::cluster_group cl = cg::this_cluster();
-  const int r = (int)cl.block_rank();
-  const int img0 = (blockIdx.x / CL) * NIMG;  // first image of this cluster
+  const int r = (int)cl.block_rank();                        // CTA rank = head index = column slice
+  const int img0 = p.img_base + (blockIdx.x / CL) * NIMG;    // first image of this cluster
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint64_t pol = make_evict_last_policy();
   const float inv_temp = 1.f / sqrtf((float)D);  // D = 256: exact reciprocal of 16
   const float emb_scale = sqrtf((float)D);
   const int L = p.L, T = p.T, V = p.V, B = p.B;
+  constexpr int LDA = D + APAD, LDA2 = FF + APAD;
+  constexpr int KPD = D / 32, KPF = FF / 32;
+  constexpr size_t WT = (size_t)KPD * 32;   // uint4 per tile for K = D
+  constexpr int KS = 2;                     // every stage splits K over two warps
+  // weight fragments (uint4 per lane) requested before the wait that precedes a stage
+  constexpr int PF_A = 6;                      // of 12
+  constexpr int PF_S = GC<4, KPD, KS>::TOT;    // 4
+  constexpr int PF_E = 8;                      // of 16
+  constexpr int PF_F = 8;                      // of 16
 
   if (tid == 0) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) s.lw[l] = p.layer[l];
   }
   // ---- step 0 input: <SOS> embedding + position 0 --------------------------------
-  for (int i = tid; i < IMG * D; i += NTHR) {
+  for (int i = tid; i < NIMG * D; i += NTHR) {
     const int row = i / D, c = i % D;
     float v = __ldg(p.emb + (size_t)p.sos * D + c) * emb_scale + __ldg(p.pe + c);
     s.xres[row][c] = v;
@@ -484,13 +427,16 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
   __syncthreads();
   cl.sync();  // every CTA of the cluster is resident and its barriers initialised before the first remote store
   // Stage protocol: thread 0 arms the stage's barrier with the bytes THIS CTA will receive, everybody
-  // computes and st.async-stores into all 8 CTAs, everybody waits for the local barrier phase.
+  // computes and st.async-stores into all 8 CTAs, everybody waits for the local barrier phase.  A CTA can
+  // run at most one exchange ahead of its slowest peer, and consecutive exchanges never share a buffer.
   int gstage = 0;
-  constexpr uint32_t R8 = NIMG / 8;  // row halves of the MMA tile that hold images
   auto stage_bar = [&]() -> uint32_t { return (gstage & 1) ? bar1 : bar0; };
   auto stage_begin = [&](uint32_t bytes) { if (tid == 0) mbar_expect_tx(stage_bar(), bytes); };
   auto stage_end = [&]() { mbar_wait(stage_bar(), (uint32_t)((gstage >> 1) & 1)); ++gstage; };
-  float* const logit_s = reinterpret_cast<float*>(&s.abf2[0][0]);  // [IMG][256] fp32 view (abf2 is idle between S8 and S7)
+  int rsel = 0;
+  auto next_red = [&]() -> float* { rsel ^= 1; return s.red[rsel]; };
+  float* const logit_s = reinterpret_cast<float*>(&s.abf2[0][0]);  // [NIMG][LGS] fp32 view (abf2 is idle then)
+  constexpr int LGS = 256 + FPAD;
 
   const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
   if (profiling) for (int i = 0; i < 16; ++i) s.prof[i] = 0;
@@ -502,296 +448,229 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       tprev = now;
     }
   };
+  const int b_mine = img0 + warp;            // the image this warp attends for / normalises
+  const bool mine = b_mine < B;
+
+  // all-gather of this warp's attention output (head r, image `warp`) into every CTA's obf
+  auto store_attn = [&](uint32_t sb, const float (&o)[8]) {
+    if ((lane >> 2) == 0) {
+      uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      ag_store_u4(sb, &s.obf[warp][r * HD + (lane & 3) * 8], v);
+    }
+  };
+  // epilogue of a "pre-LayerNorm" stage: 8 columns of row `row`, + bias (+ ReLU) + residual, sent to CTA `sub`
+  auto pre_epi = [&](uint32_t sb, const float* bias, bool relu) {
+    return [&, sb, bias, relu](int tile, int row, float (&v)[8], int sub) {
+      const int col = r * 32 + tile * 8;
+      const float4 b0 = ldg4(bias + col), b1 = ldg4(bias + col + 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(&s.xres[row][col]), x1 = *reinterpret_cast<const float4*>(&s.xres[row][col + 4]);
+      float o[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+      }
+      const uint32_t la = mapa_u32(smem_u32(&s.pre[row][col]), (uint32_t)sub), rb = mapa_u32(sb, (uint32_t)sub);
+      st_async_v4(la, make_uint4(__float_as_uint(o[0] + x0.x), __float_as_uint(o[1] + x0.y), __float_as_uint(o[2] + x0.z),
+                                 __float_as_uint(o[3] + x0.w)), rb);
+      st_async_v4(la + 16, make_uint4(__float_as_uint(o[4] + x1.x), __float_as_uint(o[5] + x1.y), __float_as_uint(o[6] + x1.z),
+                                      __float_as_uint(o[7] + x1.w)), rb);
+    };
+  };
+  // q|k|v of head r (tiles: q 0-3, k 4-7, v 8-11), biases at `bias` in natural [q|k|v] column order
+  auto qkv_epi = [&](const float* bias) {
+    return [&, bias](int tile, int row, float (&v)[8], int sub) {
+      if (sub != 0) return;
+      const int seg = tile >> 2, col = (tile & 3) * 8;
+      const float4 b0 = ldg4(bias + seg * D + r * HD + col), b1 = ldg4(bias + seg * D + r * HD + col + 4);
+      const float o[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
+      if (seg == 0) {
+        *reinterpret_cast<float4*>(&s.qh[row][col]) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(&s.qh[row][col + 4]) = make_float4(o[4], o[5], o[6], o[7]);
+      } else {
+        __nv_bfloat16(*dst)[HD + APAD] = seg == 1 ? s.kcur : s.vcur;
+        *reinterpret_cast<uint4*>(&dst[row][col]) =
+            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      }
+    };
+  };
+  // K/V cache rows (layer lc, position t) of the rows in abf: tiles 0-3 = K of head r, 4-7 = V of head r
+  auto cache_rows = [&](int lc, int t, const uint4* wp, const float* bias) {
+    gemm2<8, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, WPre<0>{}, [&](int tile, int row, float (&v)[8], int sub) {
+      const int b = img0 + row;
+      if (sub != 0 || b >= B) return;
+      const int seg = tile >> 2, col = (tile & 3) * 8;
+      const float4 b0 = ldg4(bias + seg * D + r * HD + col), b1 = ldg4(bias + seg * D + r * HD + col + 4);
+      __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
+      *reinterpret_cast<uint4*>(dst + (((((size_t)lc * B + b) * H + r) * T) + t) * HD + col) =
+          make_uint4(pack_bf16(v[0] + b0.x, v[1] + b0.y), pack_bf16(v[2] + b0.z, v[3] + b0.w),
+                     pack_bf16(v[4] + b1.x, v[5] + b1.y), pack_bf16(v[6] + b1.z, v[7] + b1.w));
+    });
+  };
+
+  auto pre_a = prefetch_w<12, KPD, KS, PF_A>(p.w_first + (size_t)r * 12 * WT, pol);
   for (int t = 0; t < p.steps; ++t) {
     for (int l = 0; l < L; ++l) {
       const DecClusterLayer& W = s.lw[l];
-      // ---- S1 (layer 0 only): q | k | v of the embedded input -------------------------
-      if (l == 0) {
-        stage_begin(NIMG * 2048u);
-        const uint32_t sb = stage_bar();
-        const uint4* wp = p.w_first + (size_t)r * 12 * (D / 32) * 32;
-        const auto pre_s1 = prefetch_weights<D, 12>(wp, pol);
-        gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, wp, pre_s1, [&](int tile, float (&c)[4], int ln) {
-          const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
-          const float b0 = __ldg(p.b_first + col), b1 = __ldg(p.b_first + col + 1);
-          if (seg == 0) {
-            ag_store_f2(sb, &s.q[row][col], c[0] + b0, c[1] + b1);
-            if (NIMG == 16) {
-            ag_store_f2(sb, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
-            }
-          } else {
-            ag_store_u32(sb, &s.kv[row][col - D], pack_bf16(c[0] + b0, c[1] + b1));
-            if (NIMG == 16) {
-            ag_store_u32(sb, &s.kv[row + 8][col - D], pack_bf16(c[2] + b0, c[3] + b1));
-            }
-          }
-        });
+      // ---- A: q|k|v of head r from the layer input, then self attention of (image warp, head r) -------
+      {
+        const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + r) * T) * HD;
+        const int n_hist = mine ? t : 0;
+        const uint4* wp = l == 0 ? p.w_first + (size_t)r * 12 * WT : s.lw[l - 1].w_next + ((size_t)r * 20 + 8) * WT;
+        const float* bias = l == 0 ? p.b_first : s.lw[l - 1].b_next + 2 * D;
+        gemm2<12, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
+        __syncthreads();
         mark(0);
-        stage_end();
+        stage_begin(NIMG * 512u);
+        const uint32_t sb = stage_bar();
+        float o[8];
+        attend_pair<4>(&s.qh[warp][0], p.kself + base, p.vself + base, n_hist, &s.kcur[warp][0], &s.vcur[warp][0], inv_temp, o);
+        store_attn(sb, o);
         mark(1);
       }
-      // ---- S2: self attention over t cached rows + the current input row ------------------
-      {
-        stage_begin(NIMG * 512u);
-        const uint32_t sb = stage_bar();
-#pragma unroll
-        for (int pp = 0; pp < NIMG / 8; ++pp) {
-          const int pair = warp * (NIMG / 8) + pp;
-          const int li = r * (NIMG / 8) + (pair >> 3), hh = pair & 7;  // cluster-local image, head
-          const int b = img0 + li;
-          float o[8];
-          if (b < B) {
-            const size_t base = ((((size_t)l * B + b) * H + hh) * T) * HD;
-            attend_pair(&s.q[li][hh * HD], p.kself + base, p.vself + base, t, &s.kv[li][hh * HD],
-                        &s.kv[li][D + hh * HD], inv_temp, o);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = 0.f;
-          }
-          if ((lane >> 2) == 0) {
-            uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-            ag_store_u4(sb, &s.abf[li][hh * HD + (lane & 3) * 8], v);
-          }
-        }
-        mark(2);
-      }
-      const auto pre_s3 = prefetch_weights<D, 4>(W.w_o + (size_t)r * 4 * (D / 32) * 32, pol);
+      const auto pre_b = prefetch_w<4, KPD, KS, PF_S>(W.w_o + (size_t)r * 4 * WT, pol);
+      // nobody waits for this in the current step: cache rows of the previous layer's output (= this input)
+      if (l > 0) cache_rows(l - 1, t, s.lw[l - 1].w_next + (size_t)r * 20 * WT, s.lw[l - 1].b_next);
+      mark(2);
       stage_end();
       mark(3);
-      // ---- S3: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
+      // ---- B: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
       stage_begin(NIMG * 1024u);
-      uint32_t sb = stage_bar();
-      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o + (size_t)r * 4 * (D / 32) * 32, pre_s3,
-                       [&](int tile, float (&c)[4], int ln) {
-                         const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
-                         const float b0 = __ldg(W.b_o + col), b1 = __ldg(W.b_o + col + 1);
-                         ag_store_f2(sb, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
-                         if (NIMG == 16) {
-                         ag_store_f2(sb, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
-                                     c[3] + b1 + s.xres[row + 8][col + 1]);
-                         }
-                       });
+      gemm2<4, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o + (size_t)r * 4 * WT, pol, pre_b, pre_epi(stage_bar(), W.b_o, false));
       mark(4);
       const LnParams lnp1 = load_ln(W.ln1_g, W.ln1_b);
-      const auto pre_s4 = prefetch_weights<D, 4>(W.w_q2 + (size_t)r * 4 * (D / 32) * 32, pol);
+      const auto pre_c = prefetch_w<4, KPD, KS, PF_S>(W.w_q2 + (size_t)r * 4 * WT, pol);
       stage_end();
       mark(5);
-      layernorm_rows<NIMG>(s, lnp1);
+      layernorm_rows(s, lnp1);
       __syncthreads();
       mark(6);
-      // ---- S4: q2 = q_linear(u) ---------------------------------------------------------------
-      stage_begin(NIMG * 1024u);
-      sb = stage_bar();
-      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_q2 + (size_t)r * 4 * (D / 32) * 32, pre_s4,
-                       [&](int tile, float (&c)[4], int ln) {
-                         const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
-                         const float b0 = __ldg(W.b_q2 + col), b1 = __ldg(W.b_q2 + col + 1);
-                         ag_store_f2(sb, &s.q[row][col], c[0] + b0, c[1] + b1);
-                         if (NIMG == 16) {
-                         ag_store_f2(sb, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
-                         }
-                       });
-      mark(4);
-      stage_end();
-      mark(5);
-      // ---- S5: cross attention over the S memory tokens --------------------------------------------
+      // ---- C: q2 of head r, cross attention of (image warp, head r) over the S memory tokens -------
       {
+        const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + r) * p.S) * HD;
+        const int n_keys = mine ? p.S : 0;
+        gemm2<4, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_q2 + (size_t)r * 4 * WT, pol, pre_c,
+                          [&](int tile, int row, float (&v)[8], int sub) {
+                            if (sub != 0) return;
+                            const int col = tile * 8;
+                            const float4 b0 = ldg4(W.b_q2 + r * HD + col), b1 = ldg4(W.b_q2 + r * HD + col + 4);
+                            *reinterpret_cast<float4*>(&s.qh[row][col]) = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
+                            *reinterpret_cast<float4*>(&s.qh[row][col + 4]) = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
+                          });
+        __syncthreads();
+        mark(4);
         stage_begin(NIMG * 512u);
-        sb = stage_bar();
+        const uint32_t sb = stage_bar();
+        float o[8];
+        if (mine) {
+          attend_pair<4>(&s.qh[warp][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, inv_temp, o);
+        } else {
 #pragma unroll
-        for (int pp = 0; pp < NIMG / 8; ++pp) {
-          const int pair = warp * (NIMG / 8) + pp;
-          const int li = r * (NIMG / 8) + (pair >> 3), hh = pair & 7;
-          const int b = img0 + li;
-          float o[8];
-          if (b < B) {
-            const size_t base = ((((size_t)l * B + b) * H + hh) * p.S) * HD;
-            attend_pair(&s.q[li][hh * HD], p.kcross + base, p.vcross + base, p.S, nullptr, nullptr, inv_temp, o);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = 0.f;
-          }
-          if ((lane >> 2) == 0) {
-            uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-            ag_store_u4(sb, &s.abf[li][hh * HD + (lane & 3) * 8], v);
-          }
+          for (int i = 0; i < 8; ++i) o[i] = 0.f;
         }
+        store_attn(sb, o);
         mark(7);
       }
-      const auto pre_s6 = prefetch_weights<D, 4>(W.w_o2 + (size_t)r * 4 * (D / 32) * 32, pol);
+      const auto pre_d = prefetch_w<4, KPD, KS, PF_S>(W.w_o2 + (size_t)r * 4 * WT, pol);
       stage_end();
       mark(3);
-      // ---- S6: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
+      // ---- D: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
       stage_begin(NIMG * 1024u);
-      sb = stage_bar();
-      gemm_stage<D, 4>(s, pol, &s.abf[0][0], D + APAD, W.w_o2 + (size_t)r * 4 * (D / 32) * 32, pre_s6,
-                       [&](int tile, float (&c)[4], int ln) {
-                         const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
-                         const float b0 = __ldg(W.b_o2 + col), b1 = __ldg(W.b_o2 + col + 1);
-                         ag_store_f2(sb, &s.pre[row][col], c[0] + b0 + s.xres[row][col], c[1] + b1 + s.xres[row][col + 1]);
-                         if (NIMG == 16) {
-                         ag_store_f2(sb, &s.pre[row + 8][col], c[2] + b0 + s.xres[row + 8][col],
-                                     c[3] + b1 + s.xres[row + 8][col + 1]);
-                         }
-                       });
+      gemm2<4, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o2 + (size_t)r * 4 * WT, pol, pre_d, pre_epi(stage_bar(), W.b_o2, false));
       mark(4);
       const LnParams lnp2 = load_ln(W.ln2_g, W.ln2_b);
-      const auto pre_s7 = prefetch_weights<D, 16>(W.w_f0 + (size_t)r * 16 * (D / 32) * 32, pol);
+      const auto pre_e = prefetch_w<16, KPD, KS, PF_E>(W.w_f0 + (size_t)r * 16 * WT, pol);
       stage_end();
       mark(5);
-      layernorm_rows<NIMG>(s, lnp2);
+      layernorm_rows(s, lnp2);
       __syncthreads();
       mark(6);
       // L2 prefetch of the K/V history the NEXT self-attention of this warp will stream (next layer, or layer 0
-      // of the next step): late in the decode the 181 MB cache no longer fits L2, and these hints turn the
+      // of the next step): late in the decode the cache no longer fits L2, and these hints turn the
       // attention's DRAM round trips into L2 hits without holding any registers.
-      if (t > 0) {
+      if (t > 0 && mine) {
         const int ln_next = (l + 1 < L) ? l + 1 : 0;
         const int t_next = (l + 1 < L) ? t : t + 1;
-#pragma unroll
-        for (int pp = 0; pp < NIMG / 8; ++pp) {
-          const int pair = warp * (NIMG / 8) + pp;
-          const int li = r * (NIMG / 8) + (pair >> 3), hh = pair & 7;
-          const int b = img0 + li;
-          if (b < B) {
-            const size_t base = ((((size_t)ln_next * B + b) * H + hh) * T) * HD;
-            const int bytes = t_next * HD * 2;  // rows [0, t_next) of this (image, head)
-            for (int off = lane * 128; off < bytes; off += 32 * 128) {
-              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(reinterpret_cast<const char*>(p.kself + base) + off));
-              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(reinterpret_cast<const char*>(p.vself + base) + off));
-            }
-          }
+        const size_t base = ((((size_t)ln_next * B + b_mine) * H + r) * T) * HD;
+        const int bytes = t_next * HD * 2;  // rows [0, t_next) of this (image, head)
+        for (int off = lane * 128; off < bytes; off += 32 * 128) {
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(reinterpret_cast<const char*>(p.kself + base) + off));
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(reinterpret_cast<const char*>(p.vself + base) + off));
         }
       }
-      // ---- S7: ff = relu(linear0(w))  (F = 4 segments of D columns) --------------------------------
-      stage_begin(NIMG * 2048u);
-      sb = stage_bar();
-      gemm_stage<D, 16>(s, pol, &s.abf[0][0], D + APAD, W.w_f0 + (size_t)r * 16 * (D / 32) * 32, pre_s7,
-                        [&](int tile, float (&c)[4], int ln) {
-                          const int seg = tile >> 2, col = seg * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
-                          const float b0 = __ldg(W.b_f0 + col), b1 = __ldg(W.b_f0 + col + 1);
-                          ag_store_u32(sb, &s.abf2[row][col], pack_bf16(fmaxf(c[0] + b0, 0.f), fmaxf(c[1] + b1, 0.f)));
-                          if (NIMG == 16) {
-                          ag_store_u32(sb, &s.abf2[row + 8][col], pack_bf16(fmaxf(c[2] + b0, 0.f), fmaxf(c[3] + b1, 0.f)));
-                          }
-                        });
-      mark(8);
-      const auto pre_s8 = prefetch_weights<DEC_FMAX, 4>(W.w_f1 + (size_t)r * 4 * (DEC_FMAX / 32) * 32, pol);
+      // ---- E: ff = relu(linear0(w)); CTA r owns hidden units [128r, 128r+128) ------------------------
+      {
+        stage_begin(NIMG * 2048u);
+        const uint32_t sb = stage_bar();
+        gemm2<16, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_f0 + (size_t)r * 16 * WT, pol, pre_e,
+                           [&](int tile, int row, float (&v)[8], int sub) {
+                             const int col = r * 128 + tile * 8;
+                             const float4 b0 = ldg4(W.b_f0 + col), b1 = ldg4(W.b_f0 + col + 4);
+                             const uint4 o = make_uint4(pack_bf16(fmaxf(v[0] + b0.x, 0.f), fmaxf(v[1] + b0.y, 0.f)),
+                                                        pack_bf16(fmaxf(v[2] + b0.z, 0.f), fmaxf(v[3] + b0.w, 0.f)),
+                                                        pack_bf16(fmaxf(v[4] + b1.x, 0.f), fmaxf(v[5] + b1.y, 0.f)),
+                                                        pack_bf16(fmaxf(v[6] + b1.z, 0.f), fmaxf(v[7] + b1.w, 0.f)));
+                             const uint32_t la = smem_u32(&s.abf2[row][col]);
+#pragma unroll
+                             for (int d = 0; d < 4; ++d)
+                               st_async_v4(mapa_u32(la, (uint32_t)(sub * 4 + d)), o, mapa_u32(sb, (uint32_t)(sub * 4 + d)));
+                           });
+        mark(8);
+      }
+      const auto pre_f = prefetch_w<4, KPF, KS, PF_F>(W.w_f1 + (size_t)r * 4 * KPF * 32, pol);
       stage_end();
       mark(5);
-      // ---- S8: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
+      // ---- F: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
       stage_begin(NIMG * 1024u);
-      sb = stage_bar();
-      gemm_stage<DEC_FMAX, 4>(s, pol, &s.abf2[0][0], DEC_FMAX + APAD, W.w_f1 + (size_t)r * 4 * (DEC_FMAX / 32) * 32, pre_s8,
-                              [&](int tile, float (&c)[4], int ln) {
-                                const int col = r * 32 + tile * 8 + (ln & 3) * 2, row = ln >> 2;
-                                const float b0 = __ldg(W.b_f1 + col), b1 = __ldg(W.b_f1 + col + 1);
-                                ag_store_f2(sb, &s.pre[row][col], fmaxf(c[0] + b0, 0.f) + s.xres[row][col],
-                                            fmaxf(c[1] + b1, 0.f) + s.xres[row][col + 1]);
-                                if (NIMG == 16) {
-                                ag_store_f2(sb, &s.pre[row + 8][col], fmaxf(c[2] + b0, 0.f) + s.xres[row + 8][col],
-                                            fmaxf(c[3] + b1, 0.f) + s.xres[row + 8][col + 1]);
-                                }
-                              });
+      gemm2<4, KPF, KS>(next_red(), &s.abf2[0][0], LDA2, W.w_f1 + (size_t)r * 4 * KPF * 32, pol, pre_f, pre_epi(stage_bar(), W.b_f1, true));
       mark(9);
       const LnParams lnp3 = load_ln(W.ln3_g, W.ln3_b);
       const bool last_layer = l + 1 >= L;
-      // prefetch of S9's weights (two shapes: next-layer q|k|v or the generator) overlaps the S8 wait + LayerNorm
-      WPre<D, 20> pre_s9a;
-      WPre<D, 12> pre_s9b;
-      if (!last_layer) pre_s9a = prefetch_weights<D, 20>(W.w_next + (size_t)r * 20 * (D / 32) * 32, pol);
-      else pre_s9b = prefetch_weights<D, 12>(W.w_next + (size_t)r * 12 * (D / 32) * 32, pol);
+      // next consumer of y: the next layer's q|k|v (12 tiles), or the generator (4 tiles); both sit behind
+      // the 8 cache tiles in w_next
+      WPre<PF_S> pre_g;
+      if (!last_layer) pre_a = prefetch_w<12, KPD, KS, PF_A>(W.w_next + ((size_t)r * 20 + 8) * WT, pol);
+      else pre_g = prefetch_w<4, KPD, KS, PF_S>(W.w_next + ((size_t)r * 12 + 8) * WT, pol);
       stage_end();
       mark(5);
-      layernorm_rows<NIMG>(s, lnp3);
+      layernorm_rows(s, lnp3);
       __syncthreads();
       mark(6);
-      // ---- S9: K/V rows of y -> cache; next layer's q|k|v, or the vocabulary logits -------------------
-      stage_begin(NIMG * (l + 1 < L ? 2048u : 1024u) + NIMG * 128u);
-      sb = stage_bar();
-      auto kv_store = [&](int tile, float (&c)[4], int ln) {
-        // tiles 0..3: K columns of head r; tiles 4..7: V columns of head r.  The values go to the CTA that
-        // OWNS the image (it attends over that image's cache), which writes them to the global cache itself.
-        const int seg = tile >> 2, dcol = (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
-        const float* bias = W.b_next + seg * D + r * 32 + dcol;
-        const float b0 = __ldg(bias), b1 = __ldg(bias + 1);
+      if (last_layer) {
+        // ---- G: vocabulary logits (V columns padded to 256; CTA r owns [32r, 32r+32)) ------------------
+        stage_begin(NIMG * 1024u);
+        const uint32_t sb = stage_bar();
+        gemm2<4, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_next + ((size_t)r * 12 + 8) * WT, pol, pre_g,
+                          [&](int tile, int row, float (&v)[8], int sub) {
+                            const int col = r * 32 + tile * 8;
+                            const float* gb = W.b_next + 2 * D;
 #pragma unroll
-        for (int hrow = 0; hrow < NIMG / 8; ++hrow) {
-          const int li = row + hrow * 8;                 // cluster-local image
-          const uint32_t owner = (uint32_t)(li / (NIMG / 8));
-          const uint32_t la = smem_u32(&s.kvrow[li % (NIMG / 8)][seg][r * 32 + dcol]);
-          st_async_b32(mapa_u32(la, owner), pack_bf16(c[hrow * 2] + b0, c[hrow * 2 + 1] + b1), mapa_u32(sb, owner));
-        }
-      };
-      if (l + 1 < L) {
-        gemm_stage<D, 20>(s, pol, &s.abf[0][0], D + APAD, W.w_next + (size_t)r * 20 * (D / 32) * 32, pre_s9a,
-                          [&](int tile, float (&c)[4], int ln) {
-                            if (tile < 8) { kv_store(tile, c, ln); return; }
-                            const int seg = tile >> 2;  // 2,3,4 -> q,k,v of layer l+1
-                            const int col = (seg - 2) * D + r * 32 + (tile & 3) * 8 + (ln & 3) * 2, row = ln >> 2;
-                            const float b0 = __ldg(W.b_next + 2 * D + col), b1 = __ldg(W.b_next + 2 * D + col + 1);
-                            if (seg == 2) {
-                              ag_store_f2(sb, &s.q[row][col], c[0] + b0, c[1] + b1);
-                              if (NIMG == 16) {
-                              ag_store_f2(sb, &s.q[row + 8][col], c[2] + b0, c[3] + b1);
-                              }
-                            } else {
-                              ag_store_u32(sb, &s.kv[row][col - D], pack_bf16(c[0] + b0, c[1] + b1));
-                              if (NIMG == 16) {
-                              ag_store_u32(sb, &s.kv[row + 8][col - D], pack_bf16(c[2] + b0, c[3] + b1));
-                              }
+                            for (int i = 0; i < 8; ++i) v[i] += col + i < V ? __ldg(gb + col + i) : 0.f;
+                            const uint32_t la = mapa_u32(smem_u32(logit_s + row * LGS + col), (uint32_t)sub), rb = mapa_u32(sb, (uint32_t)sub);
+                            st_async_v4(la, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])), rb);
+                            st_async_v4(la + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])), rb);
+                            const int b = img0 + row;
+                            if (sub == 1 && p.logits && b < B) {
+                              float* lp = p.logits + ((size_t)b * p.steps + t) * V + col;
+#pragma unroll
+                              for (int i = 0; i < 8; ++i)
+                                if (col + i < V) lp[i] = v[i];
                             }
                           });
-      } else {
-        // generator: V columns padded to 256; CTA r owns columns [32r, 32r+32) (tiles 8..11)
-        gemm_stage<D, 12>(s, pol, &s.abf[0][0], D + APAD, W.w_next + (size_t)r * 12 * (D / 32) * 32, pre_s9b,
-                          [&](int tile, float (&c)[4], int ln) {
-                            if (tile < 8) { kv_store(tile, c, ln); return; }
-                            const int col = r * 32 + (tile - 8) * 8 + (ln & 3) * 2, row = ln >> 2;
-                            const float b0 = col < V ? __ldg(W.b_next + 2 * D + col) : 0.f;
-                            const float b1 = col + 1 < V ? __ldg(W.b_next + 2 * D + col + 1) : 0.f;
-                            const float v00 = c[0] + b0, v01 = c[1] + b1, v10 = c[2] + b0, v11 = c[3] + b1;
-                            ag_store_f2(sb, logit_s + row * 256 + col, v00, v01);
-                            if (NIMG == 16) {
-                            ag_store_f2(sb, logit_s + (row + 8) * 256 + col, v10, v11);
-                            }
-                            if (p.logits) {
-                              const int bA = img0 + row, bB = img0 + row + 8;
-                              if (bA < B) {
-                                float* lp = p.logits + ((size_t)bA * p.steps + t) * V;
-                                if (col < V) lp[col] = v00;
-                                if (col + 1 < V) lp[col + 1] = v01;
-                              }
-                              if (NIMG == 16 && bB < B) {
-                                float* lp = p.logits + ((size_t)bB * p.steps + t) * V;
-                                if (col < V) lp[col] = v10;
-                                if (col + 1 < V) lp[col + 1] = v11;
-                              }
-                            }
-                          });
+        mark(4);
+        pre_a = prefetch_w<12, KPD, KS, PF_A>(p.w_first + (size_t)r * 12 * WT, pol);
+        cache_rows(l, t, W.w_next + (size_t)r * 12 * WT, W.b_next);
+        mark(2);
+        stage_end();
+        mark(5);
       }
-      mark(10);
-      stage_end();
-      // write-out of the K/V rows this CTA owns: 16-byte stores, 64 contiguous bytes per (head, K|V)
-      if (tid < 64 * (NIMG / 8)) {
-        const int j = tid >> 6, rem = tid & 63, seg = rem >> 5, hh = (rem >> 2) & 7, ch = rem & 3;
-        const int b = img0 + r * (NIMG / 8) + j;
-        if (b < B) {
-          const uint4 v = *reinterpret_cast<const uint4*>(&s.kvrow[j][seg][hh * HD + ch * 8]);
-          __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
-          *reinterpret_cast<uint4*>(dst + (((((size_t)l * B + b) * H + hh) * T) + t) * HD + ch * 8) = v;
-        }
-      }
-      mark(5);
     }  // layers
-    // ---- greedy pick (first max index) + next input: every CTA does all 16 rows -------------------------
-#pragma unroll
-    for (int rr = 0; rr < NIMG / 8; ++rr) {
-      const int row = warp * (NIMG / 8) + rr;
+    // ---- greedy pick (first max index) + next input: warp w <-> row w, every CTA does all rows ----------
+    {
+      const int row = warp;
       float best = -INFINITY;
       int bi = 0x7fffffff;
       for (int i = lane; i < V; i += 32) {
-        float v = logit_s[row * 256 + i];
+        float v = logit_s[row * LGS + i];
         if (v > best) { best = v; bi = i; }
       }
 #pragma unroll
@@ -801,11 +680,10 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
       if (bi < 0 || bi >= V) bi = 0;
-      const int b = img0 + row;
       int nxt = bi;
-      if (b < B) {
-        if (p.forced) nxt = (int)p.forced[(size_t)b * p.steps + t];
-        if (r == 0 && lane == 0 && p.tokens) p.tokens[(size_t)b * p.steps + t] = bi;
+      if (mine) {
+        if (p.forced) nxt = (int)p.forced[(size_t)b_mine * p.steps + t];
+        if (r == 0 && lane == 0 && p.tokens) p.tokens[(size_t)b_mine * p.steps + t] = bi;
       }
       if (t + 1 < p.steps) {
         const float* pe = p.pe + (size_t)(t + 1) * D;
@@ -819,7 +697,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       }
     }
     __syncthreads();
-    mark(11);
+    mark(10);
   }
   cl.sync();  // nobody exits while a peer's stores to it may still be in flight
   if (profiling) for (int i = 0; i < 16; ++i) p.prof[i] = s.prof[i];
@@ -827,38 +705,35 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
 
 size_t dec_cluster_smem_bytes() { return sizeof(Smem); }
 
-template <int NIMG>
-static int launch_variant(const DecClusterP& p, cudaStream_t st) {
+// One launch decodes up to DEC_MAX_CLUSTERS clusters (all co-resident: two CTAs per SM); larger batches
+// are decoded in consecutive launches over image ranges.
+int launch_dec_cluster_bf16(const DecClusterP& p0, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dec_cluster_bf16_kernel<NIMG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(Smem));
+    cudaError_t e = cudaFuncSetAttribute(dec_cluster_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int clusters = (p.B + NIMG - 1) / NIMG;
   if (getenv("FRX_DEBUG")) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = sizeof(Smem);
+    cfg.gridDim = dim3(DEC_MAX_CLUSTERS * CL); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = sizeof(Smem);
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, dec_cluster_bf16_kernel<NIMG>, &cfg);
-    fprintf(stderr, "[frx] decode kernel: %d clusters of %d CTAs requested, max co-resident clusters = %d (%s), smem %zu B\n",
-            clusters, CL, n, cudaGetErrorString(e), sizeof(Smem));
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, dec_cluster_bf16_kernel, &cfg);
+    fprintf(stderr, "[frx] decode kernel: clusters of %d CTAs x %d threads, max co-resident clusters = %d (%s), smem %zu B\n",
+            CL, NTHR, n, cudaGetErrorString(e), sizeof(Smem));
   }
-  dec_cluster_bf16_kernel<NIMG><<<clusters * CL, NTHR, sizeof(Smem), st>>>(p);
+  for (int base = 0; base < p0.B; base += DEC_MAX_CLUSTERS * NIMG) {
+    DecClusterP p = p0;
+    p.img_base = base;
+    const int n = p0.B - base < DEC_MAX_CLUSTERS * NIMG ? p0.B - base : DEC_MAX_CLUSTERS * NIMG;
+    const int clusters = (n + NIMG - 1) / NIMG;
+    dec_cluster_bf16_kernel<<<clusters * CL, NTHR, sizeof(Smem), st>>>(p);
+  }
   return 0;
-}
-
-// 8 images per cluster while all clusters can be co-resident (two CTAs per SM: the
-// second CTA's latency chains fill the first one's stalls); 16 per cluster beyond.
-int launch_dec_cluster_bf16(const DecClusterP& p, int images_per_cluster, cudaStream_t st) {
-  int n = images_per_cluster;
-  if (n == 0) n = (p.B + 7) / 8 <= DEC_MAX_CLUSTERS_8 ? 8 : 16;
-  return n == 8 ? launch_variant<8>(p, st) : launch_variant<16>(p, st);
 }
 
 // ===========================================================================

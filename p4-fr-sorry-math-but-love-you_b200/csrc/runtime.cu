@@ -229,7 +229,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   if (k == "taps") h->opt_taps = value != 0;
   else if (k == "graphs") h->opt_graphs = value != 0;
   else if (k == "timing") h->opt_timing = value != 0;
-  else if (k == "cluster_images") h->opt_cluster_images = (value == 8 || value == 16) ? (int)value : 0;
+  else if (k == "cluster_images") {}  // accepted for compatibility: clusters always own 8 images
   else if (k == "enc_fp32") h->opt_enc_fp32 = value != 0;
   else if (k == "tc_ws") h->opt_tc_ws = value != 0;
   else if (k == "tc_im2col") h->opt_tc_im2col = value != 0;
@@ -639,8 +639,8 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
     P.w_o2 = square("attention_layer.out_linear", D);
     P.w_f1 = square("feedforward_layer.linear1", F);
     const float* f0 = W(l, "feedforward_layer.linear0");
-    P.w_f0 = pack_frag_stage(ab, 16, D, [=](int r, int tile, int gid) {
-      return f0 + (size_t)((tile >> 2) * 256 + r * 32 + (tile & 3) * 8 + gid) * D;
+    P.w_f0 = pack_frag_stage(ab, 16, D, [=](int r, int tile, int gid) {  // CTA r: hidden units [128r, 128r+128)
+      return f0 + (size_t)(r * 128 + tile * 8 + gid) * D;
     });
     const float* wk = W(l, "self_attention_layer.k_linear");
     const float* wv = W(l, "self_attention_layer.v_linear");
@@ -1312,7 +1312,7 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
   p.prof = h->opt_prof ? h->prof : nullptr;
   if (p.prof) CK(cudaMemsetAsync(h->prof, 0, 16 * 8, st));
   if (h->opt_timing) CK(cudaEventRecord(h->ev[3], st));
-  int rc = launch_dec_cluster_bf16(p, h->opt_cluster_images, st);
+  int rc = launch_dec_cluster_bf16(p, st);
   if (rc) return fail(h, "decode cluster kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
   CKL();
   if (h->opt_timing) CK(cudaEventRecord(h->ev[4], st));

@@ -67,7 +67,6 @@ struct frx_handle {
   bool finalized = false, ws_ready = false;
   bool opt_taps = false, opt_graphs = true, opt_timing = false;
   bool opt_prof = false;
-  int opt_cluster_images = 0;  // 0 = auto
   bool opt_tc_im2col = true;   // 3x3 conv A tiles by TMA im2col (false: cp.async gather)
   void* hook_wpad = nullptr; size_t hook_wpad_bytes = 0;
   bool opt_tc_ws = true;       // persistent warp-specialised tcgen05 GEMM (false: one tile per CTA)
