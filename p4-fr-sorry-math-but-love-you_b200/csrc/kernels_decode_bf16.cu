@@ -16,6 +16,9 @@
 //     stage before the wait that precedes the stage (weights are static), so a stage costs one L2 round
 //     trip at most; every stage is K-split over two warps, the partial fragments meet in shared memory and
 //     the epilogue works on 8-column row pieces so that all DSMEM / global stores are 16 bytes wide;
+//   * attention of (image w, head r) is one warp on the tensor cores (q replicated over the MMA rows), K/V
+//     rows staged global -> shared by cp.async one 32-key block ahead (block 0 is requested before the
+//     projection GEMM that produces q) and turned into B fragments with ldmatrix / ldmatrix.trans;
 //   * work that nobody waits for in this step -- the K/V cache rows of the layer OUTPUT (the
 //     reference caches layer outputs) -- runs between a stage's stores and its wait.
 // LayerNorm / residual are recomputed redundantly per CTA on the gathered rows (cheaper than another
@@ -69,14 +72,6 @@ __device__ __forceinline__ uint4 ldg_weights(const uint4* p, uint64_t pol) {
   return v;
 }
 
-// KV-cache rows were written earlier in this kernel by this CTA: L2 load, L1 bypassed.
-__device__ __forceinline__ uint4 ldg_stream(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -104,6 +99,7 @@ struct Smem {
   float qh[NIMG][HD + FPAD];            // q of head r (this CTA's head)
   __nv_bfloat16 kcur[NIMG][HD + APAD];  // k, v of the current layer input, head r (the extra "current" key)
   __nv_bfloat16 vcur[NIMG][HD + APAD];
+  __nv_bfloat16 kvst[NIMG][2][32][HD];  // per-warp staging of one 32-key K/V block (KVStage)
   long long prof[16];
   unsigned long long bar[2];            // stage mbarriers (alternate by stage parity)
   DecClusterLayer lw[4];                // per-layer pointers (dynamic indexing of kernel params would spill them)
@@ -209,6 +205,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
 __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar) : "memory");
 }
@@ -233,13 +232,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
-// Store the same value at the same smem offset of every CTA of the cluster; each store completes its
-// byte count on the destination CTA's mbarrier `bar` (same offset everywhere).
-__device__ __forceinline__ void ag_store_u4(uint32_t bar, void* local, uint4 v) {
-  const uint32_t la = smem_u32(local);
-#pragma unroll
-  for (int r = 0; r < CL; ++r) st_async_v4(mapa_u32(la, r), v, mapa_u32(bar, r));
-}
 
 struct LnParams { float g[D / 32], b[D / 32]; };
 __device__ __forceinline__ LnParams load_ln(const float* __restrict__ g, const float* __restrict__ b) {
@@ -250,18 +242,26 @@ __device__ __forceinline__ LnParams load_ln(const float* __restrict__ g, const f
   return o;
 }
 
-// LayerNorm of the gathered rows: warp w <-> row w (every CTA does all rows).
+// LayerNorm of the gathered rows: warp w <-> row w (every CTA does all rows).  Mean and centred second
+// moment are taken around the lane's own first element (a shift that keeps the single-pass form
+// var = E[(x-s)^2] - (E[x-s])^2 well conditioned) so one butterfly carries both sums.
 __device__ __forceinline__ void layernorm_rows(Smem& s, const LnParams& P) {
   const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float v[D / 32];
-  float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < D / 32; ++i) { v[i] = s.pre[row][i * 32 + lane]; sum += v[i]; }
-  const float mean = warp_sum(sum) * (1.f / D);
-  float q = 0.f;
+  for (int i = 0; i < D / 32; ++i) v[i] = s.pre[row][i * 32 + lane];
+  const float shift = __shfl_sync(0xffffffffu, v[0], 0);
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < D / 32; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+  for (int i = 0; i < D / 32; ++i) { const float d = v[i] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float md = s1 * (1.f / D);
+  const float mean = shift + md;
+  const float rstd = rsqrtf(fmaxf(s2 * (1.f / D) - md * md, 0.f) + 1e-5f);
 #pragma unroll
   for (int i = 0; i < D / 32; ++i) {
     const int c = i * 32 + lane;
@@ -272,111 +272,144 @@ __device__ __forceinline__ void layernorm_rows(Smem& s, const LnParams& P) {
 }
 
 // ---------------------------------------------------------------------------
-// Attention of one (image, head) pair by one warp, single pass (online softmax).
-// Lane (g = lane>>2, c = lane&3) handles keys j = g (mod 8) and head dims [8c, 8c+8).  K/V rows are 32
-// bf16 (64 B), contiguous over keys -> each warp load covers 512 contiguous bytes; U K rows + U V rows
-// (8*U keys) are in flight per lane before any arithmetic.  Every lane group keeps its own running
-// (max, sum, acc); the 8 groups are merged with shuffles at the end, then the extra "current input" key
-// of the reference recurrence.  All lanes return the 8 output dims [8c, 8c+8).
+// Attention of one (image, head) pair by one warp on the tensor cores, single pass (online softmax),
+// 32 keys per iteration.  The query is one row, so the MMA tile carries it in rows 0..7 (replicated) and
+// nothing in rows 8..15; what the tensor core buys here is instruction count (16 HMMA + ~100 other
+// instructions per 32 keys instead of ~260 FFMA/shuffle instructions) in an issue-bound phase.
+//   * K/V rows ([key][32] bf16, 64 B) travel global -> shared with cp.async (16 B per lane, 512 contiguous
+//     bytes per instruction, zero-fill past the history), so a block can be requested long before it is
+//     needed without holding registers: block 0 is requested BEFORE the projection GEMM that produces q,
+//     block i+1 while block i is being reduced;
+//   * B fragments come from shared memory with ldmatrix (K: plain, V: .trans); rows are XOR-swizzled by
+//     16-byte chunk so that both the cp.async writes and the ldmatrix reads are bank-conflict-free;
+//   * after the loop the extra "current input" key of the reference recurrence is merged.
+// Lane (gid, tig) returns dims 8 nt + 2 tig + {0, 1}, nt = 0..3, in o[2 nt + {0, 1}]; the eight gid groups
+// hold identical copies.
 // ---------------------------------------------------------------------------
-template <int U>
-__device__ __forceinline__ void attend_pair(const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
-                                            const __nv_bfloat16* __restrict__ Vc, int n_hist,
-                                            const __nv_bfloat16* __restrict__ kx,
-                                            const __nv_bfloat16* __restrict__ vx, float inv_temp,
-                                            float (&o)[8]) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
-  float qv[8];
+struct KVStage { __nv_bfloat16 k[32][HD], v[32][HD]; };  // one 32-key block of one warp (4 KB)
+
+__device__ __forceinline__ uint32_t kv_swz(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc,
+                                           int kb, int n_hist) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) qv[i] = q[c * 8 + i];
-  float m = -INFINITY, l = 0.f, acc[8];
+  for (int i = 0; i < 4; ++i) {
+    const int id = lane + 32 * i, row = id >> 2, chunk = id & 3;
+    const int key = kb + row;
+    const uint32_t bytes = key < n_hist ? 16u : 0u;   // zero-fill past the history (also keeps V finite)
+    const size_t off = (size_t)(key < n_hist ? key : 0) * HD + chunk * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ks + kv_swz(row, chunk)), "l"(Kc + off), "r"(bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(vs + kv_swz(row, chunk)), "l"(Vc + off), "r"(bytes) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+// Block 0 must have been requested with kv_request(st, Kc, Vc, 0, n_hist) (when n_hist > 0).
+__device__ __forceinline__ void attend_mma(KVStage& st, const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
+                                           const __nv_bfloat16* __restrict__ Vc, int n_hist,
+                                           const __nv_bfloat16* __restrict__ kx,
+                                           const __nv_bfloat16* __restrict__ vx, float inv_temp,
+                                           float (&o)[8]) {
+  const int lane = threadIdx.x & 31, tig = lane & 3;
+  uint32_t aq0[4], aq1[4];
+  {
+    const float2 qa = *reinterpret_cast<const float2*>(q + 2 * tig), qb = *reinterpret_cast<const float2*>(q + 8 + 2 * tig);
+    const float2 qc = *reinterpret_cast<const float2*>(q + 16 + 2 * tig), qd = *reinterpret_cast<const float2*>(q + 24 + 2 * tig);
+    aq0[0] = pack_bf16(qa.x, qa.y); aq0[1] = 0u; aq0[2] = pack_bf16(qb.x, qb.y); aq0[3] = 0u;
+    aq1[0] = pack_bf16(qc.x, qc.y); aq1[1] = 0u; aq1[2] = pack_bf16(qd.x, qd.y); aq1[3] = 0u;
+  }
+  float m = -INFINITY, l = 0.f;
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  for (int j0 = 0; j0 < n_hist; j0 += 8 * U) {
-    uint4 kk[U], vv[U];
+  for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * 8 + g;
-      kk[u] = j < n_hist ? ldg_stream(Kc + (size_t)j * HD + c * 8) : zero;
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+  const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
+  const int lrow = lane & 7, lmat = lane >> 3;
+  for (int kb = 0; kb < n_hist; kb += 32) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    uint32_t kf[4][4], vf[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // score tile j: keys 8j..8j+7; matrices = dim chunks 0..3
+      const int key = 8 * j + lrow;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(kf[j][0]), "=r"(kf[j][1]), "=r"(kf[j][2]), "=r"(kf[j][3]) : "r"(ks + kv_swz(key, lmat)));
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * 8 + g;
-      vv[u] = j < n_hist ? ldg_stream(Vc + (size_t)j * HD + c * 8) : zero;
+    for (int x = 0; x < 4; ++x) {  // x = 2 * (16-key k-step) + (pair of 8-dim n-tiles)
+      const int key = 16 * (x >> 1) + (lmat & 1) * 8 + lrow, chunk = 2 * (x & 1) + (lmat >> 1);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(vf[x][0]), "=r"(vf[x][1]), "=r"(vf[x][2]), "=r"(vf[x][3]) : "r"(vs + kv_swz(key, chunk)));
     }
-    float sv[U];
+    __syncwarp();
+    if (kb + 32 < n_hist) kv_request(st, Kc, Vc, kb + 32, n_hist);
+    float sc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
+      mma_bf16(sc[j], aq0, kf[j][0], kf[j][1]);
+      mma_bf16(sc[j], aq1, kf[j][2], kf[j][3]);
+    }
     float cm = m;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float kf[8];
-      unpack8(kk[u], kf);
-      float part = 0.f;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) part = fmaf(qv[i], kf[i], part);
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      sv[u] = (j0 + u * 8 + g < n_hist) ? part * inv_temp : -INFINITY;
-      cm = fmaxf(cm, sv[u]);
-    }
+      for (int e = 0; e < 2; ++e) {
+        const int key = kb + 8 * j + 2 * tig + e;
+        sc[j][e] = key < n_hist ? sc[j][e] * inv_temp : -INFINITY;
+        cm = fmaxf(cm, sc[j][e]);
+      }
+    cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+    cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
     const float scale = (m == -INFINITY) ? 0.f : __expf(m - cm);
     l *= scale;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= scale;
+    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] *= scale; acc[nt][1] *= scale; }
+    float pr[4][2];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float pj = (sv[u] == -INFINITY) ? 0.f : __expf(sv[u] - cm);
-      float vf[8];
-      unpack8(vv[u], vf);
-      l += pj;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, vf[i], acc[i]);
+      for (int e = 0; e < 2; ++e) { pr[j][e] = __expf(sc[j][e] - cm); l += pr[j][e]; }
+#pragma unroll
+    for (int ks2 = 0; ks2 < 2; ++ks2) {  // 16 keys per k-step: score tiles 2 ks2 (k lo) and 2 ks2 + 1 (k hi)
+      const uint32_t ap[4] = {pack_bf16(pr[2 * ks2][0], pr[2 * ks2][1]), 0u, pack_bf16(pr[2 * ks2 + 1][0], pr[2 * ks2 + 1][1]), 0u};
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        mma_bf16(acc[2 * np], ap, vf[2 * ks2 + np][0], vf[2 * ks2 + np][1]);
+        mma_bf16(acc[2 * np + 1], ap, vf[2 * ks2 + np][2], vf[2 * ks2 + np][3]);
+      }
     }
     m = cm;
   }
-  // ---- merge the 8 lane groups (+ the current key) --------------------------------
-  float M = m;
-  M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 4));
-  M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 8));
-  M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
-  float s_cur = -INFINITY;
-  float vcur[8];
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
   if (kx) {
+    const float4 q0 = *reinterpret_cast<const float4*>(q + 8 * tig), q1 = *reinterpret_cast<const float4*>(q + 8 * tig + 4);
     float kf[8];
-    unpack8(*reinterpret_cast<const uint4*>(kx + c * 8), kf);
-    unpack8(*reinterpret_cast<const uint4*>(vx + c * 8), vcur);
-    float part = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) part = fmaf(qv[i], kf[i], part);
+    unpack8(*reinterpret_cast<const uint4*>(kx + tig * 8), kf);
+    float part = q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] + q1.z * kf[6] + q1.w * kf[7];
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
-    s_cur = part * inv_temp;
-    M = fmaxf(M, s_cur);
-  }
-  const float gs = (m == -INFINITY) ? 0.f : __expf(m - M);
-  l *= gs;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] *= gs;
-  l += __shfl_xor_sync(0xffffffffu, l, 4);
-  l += __shfl_xor_sync(0xffffffffu, l, 8);
-  l += __shfl_xor_sync(0xffffffffu, l, 16);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-  }
-  if (kx) {
+    const float s_cur = part * inv_temp;
+    const float M = fmaxf(m, s_cur);
+    const float gs = (m == -INFINITY) ? 0.f : __expf(m - M);
     const float pc = __expf(s_cur - M);
-    l += pc;
+    l = l * gs + pc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pc, vcur[i], acc[i]);
+    for (int nt = 0; nt < 4; ++nt) {
+      const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vx + 8 * nt + 2 * tig);
+      acc[nt][0] = fmaf(pc, __low2float(v2), acc[nt][0] * gs);
+      acc[nt][1] = fmaf(pc, __high2float(v2), acc[nt][1] * gs);
+    }
   }
   const float inv = __fdividef(1.f, l);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = acc[i] * inv;
+  for (int nt = 0; nt < 4; ++nt) { o[2 * nt] = acc[nt][0] * inv; o[2 * nt + 1] = acc[nt][1] * inv; }
 }
-
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -450,13 +483,15 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
   };
   const int b_mine = img0 + warp;            // the image this warp attends for / normalises
   const bool mine = b_mine < B;
+  KVStage& kvst = *reinterpret_cast<KVStage*>(&s.kvst[warp][0][0][0]);  // this warp's K/V staging block
 
-  // all-gather of this warp's attention output (head r, image `warp`) into every CTA's obf
+  // all-gather of this warp's attention output (head r, image `warp`) into every CTA's obf: the eight gid
+  // groups of the warp hold identical copies, group g serves destination CTA g
   auto store_attn = [&](uint32_t sb, const float (&o)[8]) {
-    if ((lane >> 2) == 0) {
-      uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-      ag_store_u4(sb, &s.obf[warp][r * HD + (lane & 3) * 8], v);
-    }
+    const uint32_t dst = (uint32_t)(lane >> 2), rb = mapa_u32(sb, dst);
+    const uint32_t la = mapa_u32(smem_u32(&s.obf[warp][r * HD + 2 * (lane & 3)]), dst);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) st_async_b32(la + nt * 16, pack_bf16(o[2 * nt], o[2 * nt + 1]), rb);
   };
   // epilogue of a "pre-LayerNorm" stage: 8 columns of row `row`, + bias (+ ReLU) + residual, sent to CTA `sub`
   auto pre_epi = [&](uint32_t sb, const float* bias, bool relu) {
@@ -515,6 +550,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + r) * T) * HD;
         const int n_hist = mine ? t : 0;
+        if (n_hist > 0) kv_request(kvst, p.kself + base, p.vself + base, 0, n_hist);  // lands during the projection
         const uint4* wp = l == 0 ? p.w_first + (size_t)r * 12 * WT : s.lw[l - 1].w_next + ((size_t)r * 20 + 8) * WT;
         const float* bias = l == 0 ? p.b_first : s.lw[l - 1].b_next + 2 * D;
         gemm2<12, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
@@ -523,7 +559,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
         stage_begin(NIMG * 512u);
         const uint32_t sb = stage_bar();
         float o[8];
-        attend_pair<4>(&s.qh[warp][0], p.kself + base, p.vself + base, n_hist, &s.kcur[warp][0], &s.vcur[warp][0], inv_temp, o);
+        attend_mma(kvst, &s.qh[warp][0], p.kself + base, p.vself + base, n_hist, &s.kcur[warp][0], &s.vcur[warp][0], inv_temp, o);
         store_attn(sb, o);
         mark(1);
       }
@@ -548,6 +584,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + r) * p.S) * HD;
         const int n_keys = mine ? p.S : 0;
+        if (n_keys > 0) kv_request(kvst, p.kcross + base, p.vcross + base, 0, n_keys);
         gemm2<4, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_q2 + (size_t)r * 4 * WT, pol, pre_c,
                           [&](int tile, int row, float (&v)[8], int sub) {
                             if (sub != 0) return;
@@ -562,7 +599,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
         const uint32_t sb = stage_bar();
         float o[8];
         if (mine) {
-          attend_pair<4>(&s.qh[warp][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, inv_temp, o);
+          attend_mma(kvst, &s.qh[warp][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, inv_temp, o);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -584,19 +621,6 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       layernorm_rows(s, lnp2);
       __syncthreads();
       mark(6);
-      // L2 prefetch of the K/V history the NEXT self-attention of this warp will stream (next layer, or layer 0
-      // of the next step): late in the decode the cache no longer fits L2, and these hints turn the
-      // attention's DRAM round trips into L2 hits without holding any registers.
-      if (t > 0 && mine) {
-        const int ln_next = (l + 1 < L) ? l + 1 : 0;
-        const int t_next = (l + 1 < L) ? t : t + 1;
-        const size_t base = ((((size_t)ln_next * B + b_mine) * H + r) * T) * HD;
-        const int bytes = t_next * HD * 2;  // rows [0, t_next) of this (image, head)
-        for (int off = lane * 128; off < bytes; off += 32 * 128) {
-          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(reinterpret_cast<const char*>(p.kself + base) + off));
-          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(reinterpret_cast<const char*>(p.vself + base) + off));
-        }
-      }
       // ---- E: ff = relu(linear0(w)); CTA r owns hidden units [128r, 128r+128) ------------------------
       {
         stage_begin(NIMG * 2048u);
