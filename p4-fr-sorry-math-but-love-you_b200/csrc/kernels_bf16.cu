@@ -194,8 +194,16 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
                                                              int H, int W, int C, int OH, int OW, int stride, int pad_t,
-                                                             int pad_l) {
+                                                             int pad_l, const float* __restrict__ se_w1,
+                                                             const float* __restrict__ se_w2, int se_floats) {
   extern __shared__ __align__(16) unsigned char dw_smem[];
+  {  // the SE FC weights are read once per forward pass: pull them into L2 now so that se_fc does not wait on DRAM
+    const long long line = ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x) * 32;  // 128 B
+    if (line < se_floats) {
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(se_w1 + line));
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(se_w2 + line));
+    }
+  }
   uint4* tile = reinterpret_cast<uint4*>(dw_smem);                                   // [H*W][8 channel groups] x 16 B
   float (*red)[64 + 1] = reinterpret_cast<float (*)[64 + 1]>(dw_smem + (size_t)H * W * 8 * 16);  // [32][65]
   float* wsm = reinterpret_cast<float*>(dw_smem + (size_t)H * W * 8 * 16 + 32 * 65 * sizeof(float));  // [11][64]: 9 taps, scale, shift
@@ -272,11 +280,15 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
   }
 }
 
-constexpr int SE_IMGS = 4;  // images per CTA: every FC weight is loaded once per 4 images
-__global__ void __launch_bounds__(1024) se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
-                                                    const float* __restrict__ b1, const float* __restrict__ w2,
-                                                    const float* __restrict__ b2, float* __restrict__ gate, int B, int C,
-                                                    int R) {
+constexpr int SE_IMGS = 4;  // images per CTA
+constexpr int SE_ROWS = 4;  // FC1 rows per warp: each 16-byte weight load meets 4 images, each 16-byte mean load 4 rows
+// One CTA = 4 images.  FC1 (C -> R, SiLU): warp w owns rows [4w, 4w+4), lanes stride over C in float4 steps, so the
+// shared-memory traffic for the means (the previous version's limit) is amortised over 4 rows; FC2 (R -> C,
+// sigmoid): one thread per output channel, outputs split over gridDim.y CTAs.
+__global__ void __launch_bounds__(512, 1) se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
+                                                       const float* __restrict__ b1, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, float* __restrict__ gate, int B, int C,
+                                                       int R) {
   extern __shared__ float sm[];
   float* mv = sm;                  // [SE_IMGS][C]
   float* red = sm + SE_IMGS * C;   // [SE_IMGS][R]
@@ -288,25 +300,33 @@ __global__ void __launch_bounds__(1024) se_fc_kernel(const float* __restrict__ m
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
-  for (int r = warp; r < R; r += nwarps) {
-    float s[SE_IMGS];
+  for (int r0 = warp * SE_ROWS; r0 < R; r0 += nwarps * SE_ROWS) {
+    float s[SE_ROWS][SE_IMGS];
 #pragma unroll
-    for (int im = 0; im < SE_IMGS; ++im) s[im] = 0.f;
-    const float4* wrow = reinterpret_cast<const float4*>(w1 + (long long)r * C);
-#pragma unroll 6
-    for (int c4 = lane; c4 < C / 4; c4 += 32) {  // 16-byte loads, several in flight (C % 4 == 0)
-      const float4 wv = __ldg(wrow + c4);
+    for (int j = 0; j < SE_ROWS; ++j)
+#pragma unroll
+      for (int im = 0; im < SE_IMGS; ++im) s[j][im] = 0.f;
+#pragma unroll 3
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {  // C % 4 == 0
+      float4 wv[SE_ROWS], m4[SE_IMGS];
+#pragma unroll
+      for (int j = 0; j < SE_ROWS; ++j)
+        wv[j] = r0 + j < R ? __ldg(reinterpret_cast<const float4*>(w1 + (long long)(r0 + j) * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int im = 0; im < SE_IMGS; ++im) m4[im] = *reinterpret_cast<const float4*>(mv + im * C + c4 * 4);
+#pragma unroll
+      for (int j = 0; j < SE_ROWS; ++j)
+#pragma unroll
+        for (int im = 0; im < SE_IMGS; ++im)
+          s[j][im] = fmaf(wv[j].x, m4[im].x, fmaf(wv[j].y, m4[im].y, fmaf(wv[j].z, m4[im].z, fmaf(wv[j].w, m4[im].w, s[j][im]))));
+    }
+#pragma unroll
+    for (int j = 0; j < SE_ROWS; ++j)
 #pragma unroll
       for (int im = 0; im < SE_IMGS; ++im) {
-        const float4 m4 = *reinterpret_cast<const float4*>(mv + im * C + c4 * 4);
-        s[im] = fmaf(wv.x, m4.x, fmaf(wv.y, m4.y, fmaf(wv.z, m4.z, fmaf(wv.w, m4.w, s[im]))));
+        const float t = warp_sum(s[j][im]);
+        if (lane == 0 && r0 + j < R) red[im * R + r0 + j] = act_apply(t + __ldg(b1 + r0 + j), ACT_SILU);
       }
-    }
-#pragma unroll
-    for (int im = 0; im < SE_IMGS; ++im) {
-      const float t = warp_sum(s[im]);
-      if (lane == 0) red[im * R + r] = act_apply(t + __ldg(b1 + r), ACT_SILU);
-    }
   }
   __syncthreads();
   for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < C; c += gridDim.y * blockDim.x) {  // expand outputs split over gridDim.y
@@ -314,7 +334,7 @@ __global__ void __launch_bounds__(1024) se_fc_kernel(const float* __restrict__ m
     const float bb = __ldg(b2 + c);
 #pragma unroll
     for (int im = 0; im < SE_IMGS; ++im) s[im] = bb;
-#pragma unroll 16
+#pragma unroll 32
     for (int r = 0; r < R; ++r) {
       const float wv = __ldg(w2 + (long long)r * C + c);  // w2 is [R][C] (transposed at pack time)
 #pragma unroll
@@ -354,8 +374,8 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
     cudaFuncSetAttribute(dwconv_se_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  dwconv_se_mean_kernel<<<g, 256, smem, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l);
-  se_fc_kernel<<<dim3((B + SE_IMGS - 1) / SE_IMGS, 2), 1024, SE_IMGS * (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, B, C, R);
+  dwconv_se_mean_kernel<<<g, 256, smem, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l, w1, w2, R * C);
+  se_fc_kernel<<<dim3((B + SE_IMGS - 1) / SE_IMGS, 2), 512, SE_IMGS * (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, B, C, R);
   long long total8 = (long long)B * OH * OW * (C / 8);
   se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(out, gate, total8, OH * OW, C);
 }

@@ -492,8 +492,59 @@ void launch_layernorm_f32(const float* x, const float* res, const float* gamma, 
   layernorm_f32_kernel<float><<<(M + 7) / 8, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
 }
 
+// Scrambled store (the reference's raw reshape) for the bf16 path: one CTA per image normalises its S
+// rows into shared memory laid out as the flat index f = token * C + ch seen as [f / S][f % S], then writes
+// out[(f % S) * C + f / S] with consecutive lanes on consecutive addresses -- a tiled transpose instead of
+// S * C scattered 2-byte stores.
+__global__ void __launch_bounds__(256) layernorm_scramble_bf16_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                                      const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta,
+                                                                      __nv_bfloat16* __restrict__ out, int S, int C) {
+  extern __shared__ __nv_bfloat16 ln_tile[];  // [C][S + 2]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = C / 32, LD = S + 2;
+  for (int qd = warp; qd < S; qd += 8) {
+    const float* xp = x + ((long long)b * S + qd) * C;
+    const float* rp = res ? res + ((long long)b * S + qd) * C : nullptr;
+    float v[16];  // C <= 512
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < per) {
+        float t = __ldg(xp + i * 32 + lane);
+        if (rp) t += __ldg(rp + i * 32 + lane);
+        v[i] = t;
+        s += t;
+      }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < per) { float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < per) {
+        const int ch = i * 32 + lane;
+        const int f = qd * C + ch;
+        ln_tile[(f / S) * LD + f % S] = __float2bfloat16_rn((v[i] - mean) * rstd * __ldg(gamma + ch) + __ldg(beta + ch));
+      }
+  }
+  __syncthreads();
+  __nv_bfloat16* op = out + (long long)b * S * C;
+  for (int g = threadIdx.x; g < S * C; g += 256) {  // g = pp * C + cc
+    const int pp = g / C, cc = g - pp * C;
+    op[g] = ln_tile[cc * LD + pp];
+  }
+}
+
 void launch_layernorm_bf16out(const float* x, const float* res, const float* gamma, const float* beta,
                               __nv_bfloat16* out, int M, int C, int scramble_S, cudaStream_t st) {
+  if (scramble_S > 0 && C <= 512 && C % 32 == 0 && M % scramble_S == 0 && (size_t)C * (scramble_S + 2) * 2 <= 48 * 1024) {
+    layernorm_scramble_bf16_kernel<<<M / scramble_S, 256, (size_t)C * (scramble_S + 2) * 2, st>>>(x, res, gamma, beta, out,
+                                                                                               scramble_S, C);
+    return;
+  }
   layernorm_f32_kernel<__nv_bfloat16><<<(M + 7) / 8, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
 }
 

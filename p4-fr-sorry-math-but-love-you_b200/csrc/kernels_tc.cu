@@ -710,7 +710,12 @@ static int tc_launch_ws(const TcGemmP& p_in, int num_sms, cudaStream_t st) {
 
 // Persistent warp-specialised kernel; NCOLS = TMEM columns for the two accumulators.
 int launch_tc_igemm_ws(TcGemmP p, int num_sms, cudaStream_t st) {
-  if (p.BN == 0) p.BN = tc_pick_bn(p.N);
+  if (p.BN == 0) {
+    p.BN = tc_pick_bn(p.N);
+    // few M tiles (the 4x8 maps of the last trunk stage, the encoder tokens): narrower N tiles until every SM has one
+    const int tiles_m = (p.M + TC_BM - 1) / TC_BM;
+    while (p.BN > 64 && p.BN % 32 == 0 && p.N % (p.BN / 2) == 0 && tiles_m * ((p.N + p.BN - 1) / p.BN) < num_sms) p.BN /= 2;
+  }
   if (p.BN <= 32) { p.BN = 32; return tc_launch_ws<64>(p, num_sms, st); }
   if (p.BN <= 64) return tc_launch_ws<128>(p, num_sms, st);
   if (p.BN <= 128) return tc_launch_ws<256>(p, num_sms, st);
