@@ -53,16 +53,20 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    The sampler process is started before the warm-up (nvidia-smi needs a few hundred ms to produce its first
+    line on an 8-GPU box); every line is time-stamped on arrival and only the lines that fall inside
+    [window_begin(), window_end()] are summarised."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -75,9 +79,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def window_begin(self):
+        self.t0 = time.monotonic()
+
+    def window_end(self):
+        self.t1 = time.monotonic()
+
+    def stop(self):
         if self.proc:
             self.proc.terminate()
             self.thread.join(timeout=2)
@@ -85,7 +95,9 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if self.t0 is not None and not (self.t0 <= t <= self.t1 + 0.02):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -199,10 +211,10 @@ def run_frx(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    clocks = ClockSampler(local_rank).start()
     for _ in range(max(args.warmup, 1)):
         step_device()
     torch.cuda.synchronize(dev)
-    lt = (torch.zeros(3) if False else None)
     import ctypes
     ms3 = (ctypes.c_float * 4)()
 
@@ -211,16 +223,18 @@ def run_frx(args, rank, world, local_rank):
     launches0 = eng.launches
     enc_ms, dec_ms, kern_ms = [], [], []
     barrier()
-    with ClockSampler(local_rank) as clocks:
-        for s, e in ev:
-            flush.zero_()            # L2 flush between timed iterations (outside the event pair)
-            s.record()
-            step_device()
-            e.record()
-            e.synchronize()
-            eng.h.lib.frx_last_timing(eng.h.ptr, ms3)
-            enc_ms.append(ms3[0]); dec_ms.append(ms3[1]); kern_ms.append(ms3[3])
-        barrier()
+    clocks.window_begin()
+    for s, e in ev:
+        flush.zero_()            # L2 flush between timed iterations (outside the event pair)
+        s.record()
+        step_device()
+        e.record()
+        e.synchronize()
+        eng.h.lib.frx_last_timing(eng.h.ptr, ms3)
+        enc_ms.append(ms3[0]); dec_ms.append(ms3[1]); kern_ms.append(ms3[3])
+    barrier()
+    clocks.window_end()
+    clocks.stop()
     gpu_launches = eng.launches - launches0
     total_ms = sum(s.elapsed_time(e) for s, e in ev)
 
