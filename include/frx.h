@@ -121,7 +121,8 @@ int frx_beam_search(frx_handle* h, const float* memory, int32_t batch, int32_t b
                     int32_t max_sequence, int64_t* tokens, void* stream);
 
 /* SATRNDecoder.forward, teacher-forced branch (EfficientSATRN.py:488-495) in
- * eval mode (dropout = identity).
+ * eval mode (dropout = identity).  In bf16 mode every linear layer (M = B*L rows) and the vocabulary
+ * projection run on the tcgen05 GEMM (bf16 operands, fp32 accumulation / residual stream / LayerNorm).
  * text    : device int64 [B, L] (= expected[:, :-1])
  * logits  : device fp32 [B, L, num_classes] */
 int frx_decode_teacher_forced(frx_handle* h, const float* memory, const int64_t* text,

@@ -217,7 +217,7 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
       }
       if (p.out_f32) {
         float* cp = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + nb;
-        if (full) {
+        if (full && (p.ldc & 3) == 0) {  // 16-byte stores need a 16-byte-aligned row stride (the logits' is 245 floats)
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
@@ -226,7 +226,7 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
         }
       } else {
         __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + nb;
-        if (full) {
+        if (full && (p.ldc & 7) == 0) {
           uint32_t w[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {

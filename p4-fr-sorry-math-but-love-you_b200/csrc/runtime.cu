@@ -623,6 +623,17 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
     return find(h, "decoder.attention_layers." + std::to_string(l) + "." + name + ".weight")->f.data();
   };
   const float* gen = find(h, "decoder.generator.weight")->f.data();
+  // row-major bf16 copies for the teacher-forced path (tcgen05 GEMMs want [N][K])
+  h->gen_wb = pack_bf16_copy(ab, h->gen_w, (size_t)V * D);
+  for (int l = 0; l < L; ++l) {
+    DecLayerW& Wl = h->dec[l];
+    Wl.wb_o = pack_bf16_copy(ab, Wl.w_o, (size_t)D * D);
+    Wl.wb_q2 = pack_bf16_copy(ab, Wl.w_q2, (size_t)D * D);
+    Wl.wb_o2 = pack_bf16_copy(ab, Wl.w_o2, (size_t)D * D);
+    Wl.wb_f0 = pack_bf16_copy(ab, Wl.w_f0, (size_t)F * D);
+    Wl.wb_f1 = pack_bf16_copy(ab, Wl.w_f1, (size_t)D * F);
+    Wl.wb_sqkv = pack_bf16_copy(ab, Wl.w_sqkv, (size_t)3 * D * D);
+  }
   h->dpack.assign(L, DecPackW{});
   h->dpack_first = pack_frag_stage(ab, 12, D, [&](int r, int tile, int gid) {
     const char* names[3] = {"self_attention_layer.q_linear", "self_attention_layer.k_linear", "self_attention_layer.v_linear"};
@@ -1532,6 +1543,54 @@ extern "C" int frx_decode_teacher_forced(frx_handle* h, const float* memory, con
     return g;
   };
   float* x = w.x;
+  if (c.precision == FRX_PREC_BF16 && h->gen_wb) {
+    // bf16 mode: every linear layer (M = B*L rows) on the tcgen05 GEMM -- bf16 operands, fp32 accumulation, fp32
+    // residual stream / LayerNorm / softmax; the attention kernels are the fp32 ones (K/V history = the fp32 qkv rows).
+    if (ws_alloc(h, &w.xb, Mm * D * 2) || ws_alloc(h, &w.ffb, Mm * F * 2)) return 1;
+    auto tlin = [&](const void* in, int K, size_t wo, size_t bo, int N, void* out, int out_f32, int act, const float* res) {
+      TcGemmP g = tc_dense(in, M, K, A, wo, N, out, out_f32);
+      g.shift = A + bo; g.act = act;
+      if (res) { g.res = res; g.res_f32 = 1; g.ldr = N; }
+      return g;
+    };
+    auto to_bf16 = [&](const float* src) { launch_f32_to_bf16(src, (__nv_bfloat16*)w.xb, (long long)M * D, st); };
+    for (int l = 0; l < NL; ++l) {
+      const DecLayerW& W = h->dec[l];
+      to_bf16(x); CKL();
+      { TcGemmP g = tlin(w.xb, D, W.wb_sqkv, W.b_sqkv, 3 * D, w.qkv, 1, ACT_NONE, nullptr); TCL(g); }
+      {
+        AttnP a{};
+        a.q = w.qkv; a.ldq = 3 * D; a.kcache = w.qkv + D; a.vcache = w.qkv + 2 * D; a.rows_per_img = L; a.D = 3 * D;
+        a.causal_L = L; a.key_mask = w.mask; a.q_per_img = L; a.temperature = temp; a.out = w.y; a.ldo = D; a.M = M;
+        a.heads = c.dec_heads;
+        launch_dec_attn_f32(a, HD, st); CKL();
+      }
+      to_bf16(w.y); CKL();
+      { TcGemmP g = tlin(w.xb, D, W.wb_o, W.b_o, D, w.z, 1, ACT_NONE, x); TCL(g); }
+      launch_layernorm_f32(w.z, nullptr, A + W.ln1_g, A + W.ln1_b, w.y, M, D, 0, st); CKL();          // u -> y
+      to_bf16(w.y); CKL();
+      { TcGemmP g = tlin(w.xb, D, W.wb_q2, W.b_q2, D, w.z, 1, ACT_NONE, nullptr); TCL(g); }            // q2 -> z
+      {
+        AttnP a{};
+        a.q = w.z; a.ldq = D; a.kcache = h->cross + (size_t)l * 2 * D; a.vcache = h->cross + (size_t)l * 2 * D + D;
+        a.rows_per_img = S; a.D = NL * 2 * D; a.n_hist = S; a.q_per_img = L; a.temperature = temp; a.out = x; a.ldo = D;
+        a.M = M; a.heads = c.dec_heads;
+        launch_dec_attn_f32(a, HD, st); CKL();                                                          // c -> x (x is dead)
+      }
+      to_bf16(x); CKL();
+      { TcGemmP g = tlin(w.xb, D, W.wb_o2, W.b_o2, D, w.z, 1, ACT_NONE, w.y); TCL(g); }
+      launch_layernorm_f32(w.z, nullptr, A + W.ln2_g, A + W.ln2_b, w.y, M, D, 0, st); CKL();          // w -> y
+      to_bf16(w.y); CKL();
+      { TcGemmP g = tlin(w.xb, D, W.wb_f0, W.b_f0, F, w.ffb, 0, ACT_RELU, nullptr); TCL(g); }
+      { TcGemmP g = tlin(w.ffb, F, W.wb_f1, W.b_f1, D, w.z, 1, ACT_RELU, w.y); TCL(g); }
+      launch_layernorm_f32(w.z, nullptr, A + W.ln3_g, A + W.ln3_b, x, M, D, 0, st); CKL();            // layer output -> x
+    }
+    to_bf16(x); CKL();
+    TcGemmP g = tc_dense(w.xb, M, D, A, h->gen_wb, V, logits, 1);
+    g.shift = A + h->gen_b;
+    TCL(g);
+    return 0;
+  }
   for (int l = 0; l < NL; ++l) {
     const DecLayerW& W = h->dec[l];
     { GemmP g = lin(x, D, W.w_sqkv, W.b_sqkv, 3 * D, w.qkv, ACT_NONE, nullptr); launch_igemm_f32(g, st); CKL(); }

@@ -37,6 +37,7 @@ struct EncLayerW {
 struct DecLayerW {
   size_t wt_o, b_o, wt_q2, b_q2, wt_o2, b_o2, wt_f0, b_f0, wt_f1, b_f1;   // [K][N] for the step kernels
   size_t w_o, w_q2, w_o2, w_f0, w_f1, w_sqkv, b_sqkv;                     // [N][K] for the teacher-forced path
+  size_t wb_o = 0, wb_q2 = 0, wb_o2 = 0, wb_f0 = 0, wb_f1 = 0, wb_sqkv = 0;  // bf16 copies of the above (bf16 mode)
   size_t ln1_g, ln1_b, ln2_g, ln2_b, ln3_g, ln3_b;
 };
 struct FusedW { size_t wt, b; int N; };
@@ -57,7 +58,11 @@ struct BeamWs {
   float* logits = nullptr;
   int* host_flag = nullptr;
 };
-struct TfWs { float *x = nullptr, *y = nullptr, *z = nullptr, *qkv = nullptr, *ff = nullptr; unsigned char* mask = nullptr; };
+struct TfWs {
+  float *x = nullptr, *y = nullptr, *z = nullptr, *qkv = nullptr, *ff = nullptr;
+  unsigned char* mask = nullptr;
+  void *xb = nullptr, *ffb = nullptr;  // bf16 A operands of the tcgen05 GEMMs (bf16 mode)
+};
 
 struct frx_handle {
   frx_config cfg{};
@@ -93,6 +98,7 @@ struct frx_handle {
   float *sw_x[2] = {nullptr, nullptr}, *sw_a = nullptr, *sw_qkv = nullptr, *sw_hid = nullptr;
   // decoder
   size_t emb = 0, pe1d = 0, gen_w = 0, gen_b = 0, w_cross = 0, b_cross = 0;
+  size_t gen_wb = 0;  // bf16 copy of the generator weight (teacher-forced path, bf16 mode)
   size_t last_wb = 0, cross_wb = 0;   // bf16 copies of conv_last / cross K|V weights
   std::vector<DecLayerW> dec;
   std::vector<FusedW> fused;

@@ -81,3 +81,39 @@ def test_bf16_deterministic_and_batch_invariant(model_bf16, spec):
         ls, ts = model_bf16.greedy(x[16:23].contiguous(), 60)
     assert torch.equal(l1, l2) and torch.equal(t1, t2)
     assert torch.equal(l1[16:23], ls) and torch.equal(t1[16:23], ts)
+
+
+def test_bf16_teacher_forced_within_tolerance(model_bf16):
+    """Teacher-forced branch (EfficientSATRN.py:488-495) with every linear layer on the tcgen05 GEMM."""
+    g = load_golden(0)
+    mem = torch.from_numpy(g["memory"]).cuda()
+    text = torch.from_numpy(g["tf_text"]).cuda()
+    b, L = text.shape
+    eng = model_bf16.engine(mem.device, b, 231)
+    logits = torch.empty(b, L, 245, device="cuda")
+    eng.h.call("frx_decode_teacher_forced", mem.data_ptr(), text.data_ptr(), b, L, logits.data_ptr(),
+               torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["tf_logits"])
+    rel = ((logits.cpu() - ref).abs().max() / ref.abs().max()).item()
+    print("bf16 teacher-forced max rel logit error: %.4f" % rel)
+    assert rel <= BF16_REL_TOL
+    agree = (logits.cpu().argmax(-1) == ref.argmax(-1)).float().mean().item()
+    print("bf16 teacher-forced per-position argmax agreement: %.4f" % agree)
+    assert agree >= 0.95
+
+
+def test_bf16_decode_batch_larger_than_one_launch(ckpt0):
+    """More than 256 images: the decode kernel is launched over consecutive image ranges; every image must decode
+    exactly as it does in a small batch (clusters own 8 images, nothing depends on the batch size)."""
+    model = make_model(ckpt0, precision="bf16", max_batch=272, max_steps=24).cuda().eval()
+    g = load_golden(0)
+    mem8 = torch.from_numpy(g["memory"]).cuda()
+    reps = 272 // mem8.size(0)
+    mem = mem8.repeat(reps, 1, 1).contiguous()
+    logits_big, tokens_big = _decode(model, mem, 24)
+    logits_small, tokens_small = _decode(model, mem8, 24)
+    for r in range(reps):
+        sl = slice(r * mem8.size(0), (r + 1) * mem8.size(0))
+        assert torch.equal(tokens_big[sl], tokens_small)
+        assert torch.equal(logits_big[sl], logits_small)
