@@ -67,6 +67,7 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
 void launch_layernorm_bf16out(const float* x, const float* res, const float* gamma, const float* beta,
                               __nv_bfloat16* out, int M, int C, int scramble_S, cudaStream_t st);
 void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st);
+bool launch_enc_attn_mma_bf16(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st);
 
 // bf16 persistent decode (kernels_decode_bf16.cu)
 size_t dec_cluster_smem_bytes();

@@ -380,4 +380,104 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
   se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(out, gate, total8, OH * OW, C);
 }
 
+// ---------------------------------------------------------------------------
+// Encoder self-attention for the bf16 path (EfficientSATRN.py:164-172,:198-228): S = 32 tokens, head dim 64,
+// scores divided by sqrt(d_model).  One warp = 16 query rows of one (image, head) on mma.sync.m16n8k16:
+// S = Q K^T (4 key tiles x 4 k-steps), softmax in the accumulator layout, O = P V (8 dim tiles x 2 k-steps) with
+// the probabilities re-used as the A fragment.  Operands are converted fp32 -> bf16 while the fragments are loaded
+// (the qkv rows are the fp32 output of the projection GEMM); 64 HMMA per warp instead of ~16k scalar instructions.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restrict__ qkv,       // [B*32, 3*D]
+                                                          __nv_bfloat16* __restrict__ out,     // [B*32, D]
+                                                          int D, int heads, float inv_temp) {
+  constexpr int S = 32, HD = 64;
+  const int b = blockIdx.x / heads, hh = blockIdx.x % heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int ld = 3 * D;
+  const float* qb = qkv + (long long)b * S * ld + hh * HD;  // q of token 0; k at +D, v at +2D
+  const int i0 = warp * 16;
+  float sacc[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const float* q0 = qb + (long long)(i0 + gid) * ld + 16 * ks + 2 * tig;
+    const float* q1 = q0 + 8 * ld;
+    const float2 a00 = __ldg(reinterpret_cast<const float2*>(q0)), a10 = __ldg(reinterpret_cast<const float2*>(q1));
+    const float2 a01 = __ldg(reinterpret_cast<const float2*>(q0 + 8)), a11 = __ldg(reinterpret_cast<const float2*>(q1 + 8));
+    const uint32_t a[4] = {pack2(a00.x, a00.y), pack2(a10.x, a10.y), pack2(a01.x, a01.y), pack2(a11.x, a11.y)};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float* kp = qb + D + (long long)(8 * nt + gid) * ld + 16 * ks + 2 * tig;
+      const float2 k0 = __ldg(reinterpret_cast<const float2*>(kp)), k1 = __ldg(reinterpret_cast<const float2*>(kp + 8));
+      mma16816(sacc[nt], a, pack2(k0.x, k0.y), pack2(k1.x, k1.y));
+    }
+  }
+  // softmax over the 32 keys of rows gid (c0, c1) and gid + 8 (c2, c3)
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sacc[nt][e] *= inv_temp;
+    mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    sacc[nt][0] = __expf(sacc[nt][0] - mx0); sacc[nt][1] = __expf(sacc[nt][1] - mx0);
+    sacc[nt][2] = __expf(sacc[nt][2] - mx1); sacc[nt][3] = __expf(sacc[nt][3] - mx1);
+    sum0 += sacc[nt][0] + sacc[nt][1];
+    sum1 += sacc[nt][2] + sacc[nt][3];
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  float oacc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[n][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {  // 16 keys per k-step = score tiles 2kk (k lo) and 2kk + 1 (k hi)
+    const uint32_t a[4] = {pack2(sacc[2 * kk][0], sacc[2 * kk][1]), pack2(sacc[2 * kk][2], sacc[2 * kk][3]),
+                           pack2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]), pack2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3])};
+    const float* vp = qb + 2 * D + (long long)(16 * kk + 2 * tig) * ld + gid;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float v00 = __ldg(vp + 8 * n), v01 = __ldg(vp + ld + 8 * n);
+      const float v10 = __ldg(vp + 8 * ld + 8 * n), v11 = __ldg(vp + 9 * ld + 8 * n);
+      mma16816(oacc[n], a, pack2(v00, v01), pack2(v10, v11));
+    }
+  }
+  const float r0 = __fdividef(1.f, sum0), r1 = __fdividef(1.f, sum1);
+  __nv_bfloat16* o0 = out + ((long long)b * S + i0 + gid) * D + hh * HD + 2 * tig;
+  __nv_bfloat16* o1 = o0 + (long long)8 * D;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    *reinterpret_cast<uint32_t*>(o0 + 8 * n) = pack2(oacc[n][0] * r0, oacc[n][1] * r0);
+    *reinterpret_cast<uint32_t*>(o1 + 8 * n) = pack2(oacc[n][2] * r1, oacc[n][3] * r1);
+  }
+}
+
+// returns false when the shape is not the one the kernel is specialised for (the caller then uses the generic kernel)
+bool launch_enc_attn_mma_bf16(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st) {
+  if (S != 32 || D / heads != 64 || D % heads != 0) return false;
+  enc_attn_mma_kernel<<<B * heads, 64, 0, st>>>(qkv, out, D, heads, 1.f / sqrtf((float)D));
+  return true;
+}
+
 }  // namespace frx

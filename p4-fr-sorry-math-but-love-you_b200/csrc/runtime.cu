@@ -1001,7 +1001,8 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
     TcGemmP g = tc_dense(m0, M, C, A, L.wb_qkv, 3 * C, qkv, 1);
     g.shift = A + L.b_qkv;
     TCL(g);
-    launch_enc_attn_bf16out(qkv, m0, B, S, C, c.enc_heads, st); CKL();
+    if (!launch_enc_attn_mma_bf16(qkv, m0, B, S, C, c.enc_heads, st)) launch_enc_attn_bf16out(qkv, m0, B, S, C, c.enc_heads, st);
+    CKL();
     float* proj = (float*)m1;
     TcGemmP go = tc_dense(m0, M, C, A, L.wb_o, C, proj, 1);
     go.shift = A + L.b_o;
