@@ -480,4 +480,104 @@ bool launch_enc_attn_mma_bf16(const float* qkv, __nv_bfloat16* out, int B, int S
   return true;
 }
 
+// ---------------------------------------------------------------------------
+// Narrow 3x3 convolution (the two 24 -> 24 blocks of trunk stage 0, 63 x 127 maps): out = silu(bn(conv(x))) (+ x).
+// With 24 channels a per-tap im2col feed re-reads every input pixel 9x from L2 in 48-byte pieces and pads K
+// from 216 to 576 and N from 24 to 32; this kernel stages an 8 x 32 output tile's halo ((8+2) x (32+2) pixels x
+// 24 channels, 16 KB) in shared memory ONCE, and runs the implicit GEMM [256 pixels x 216] x [216 x 24] on
+// mma.sync.m16n8k16 with A fragments gathered straight from the halo tile (k = tap * 24 + channel; an 8-aligned
+// k group never straddles a tap, so every fragment register is one 4-byte shared load).  Warp w owns tile row w.
+// Weights: B fragments pre-packed on the host, [14 k-steps][3 n-tiles][32 lanes] x {b0, b1}, staged in smem.
+// ---------------------------------------------------------------------------
+constexpr int C24 = 24, C24_TH = 8, C24_TW = 32, C24_KS = 14;  // K = 216 padded to 224
+
+__global__ void __launch_bounds__(256) conv3x3_c24_mma_kernel(const __nv_bfloat16* __restrict__ in, const uint2* __restrict__ wfrag,
+                                                              const float* __restrict__ scale, const float* __restrict__ shift,
+                                                              __nv_bfloat16* __restrict__ out, int H, int W, int add_res) {
+  constexpr int PW = C24_TW + 2, PH = C24_TH + 2;
+  __shared__ __align__(16) __nv_bfloat16 halo[PH * PW * C24];   // 16320 B
+  __shared__ uint2 wsm[C24_KS * 3 * 32];                        // 10752 B
+  const int tiles_x = (W + C24_TW - 1) / C24_TW, tiles_y = (H + C24_TH - 1) / C24_TH;
+  const int n = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
+  const int y0 = (t / tiles_x) * C24_TH, x0 = (t % tiles_x) * C24_TW;
+  const __nv_bfloat16* ip = in + (long long)n * H * W * C24;
+  // halo: 3 x 16-byte chunks per pixel; a halo row is contiguous in global memory (NHWC, 48 B per pixel)
+  for (int i = threadIdx.x; i < PH * PW * 3; i += 256) {
+    const int pix = i / 3, ch = i - pix * 3;
+    const int py = pix / PW, px = pix - py * PW;
+    const int y = y0 + py - 1, x = x0 + px - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const uint4*>(ip + ((long long)y * W + x) * C24) + ch);
+    reinterpret_cast<uint4*>(halo)[i] = v;
+  }
+  for (int i = threadIdx.x; i < C24_KS * 3 * 32; i += 256) wsm[i] = __ldg(wfrag + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  float acc[2][3][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+  const uint32_t* hw = reinterpret_cast<const uint32_t*>(halo);  // 12 words per pixel
+#pragma unroll
+  for (int s = 0; s < C24_KS; ++s) {
+    const int klo = 16 * s, khi = 16 * s + 8;
+    const int tap_lo = klo / C24, ch_lo = klo % C24, tap_hi = khi / C24, ch_hi = khi % C24;  // compile-time after unrolling
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int px = mt * 16 + gid;  // tile column of fragment rows gid (a0, a2); +8 for a1, a3
+      const int p_lo = ((warp + tap_lo / 3) * PW + px + tap_lo % 3) * 12 + (ch_lo >> 1) + tig;
+      a[mt][0] = hw[p_lo];
+      a[mt][1] = hw[p_lo + 8 * 12];
+      if (tap_hi < 9) {
+        const int p_hi = ((warp + tap_hi / 3) * PW + px + tap_hi % 3) * 12 + (ch_hi >> 1) + tig;
+        a[mt][2] = hw[p_hi];
+        a[mt][3] = hw[p_hi + 8 * 12];
+      } else {
+        a[mt][2] = 0u; a[mt][3] = 0u;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      const uint2 b = wsm[(s * 3 + nt) * 32 + lane];
+      mma16816(acc[0][nt], a[0], b.x, b.y);
+      mma16816(acc[1][nt], a[1], b.x, b.y);
+    }
+  }
+  // epilogue: folded BN, SiLU, residual (the centre tap of the halo), bf16 pairs
+  const int y = y0 + warp;
+  if (y >= H) return;
+  __nv_bfloat16* op = out + ((long long)n * H + y) * W * C24;
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) {
+    const int ch = nt * 8 + 2 * tig;
+    const float s0 = __ldg(scale + ch), s1 = __ldg(scale + ch + 1), h0 = __ldg(shift + ch), h1 = __ldg(shift + ch + 1);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        const int px = mt * 16 + gid + hr * 8, x = x0 + px;
+        if (x >= W) continue;
+        float v0 = fmaf(acc[mt][nt][2 * hr], s0, h0), v1 = fmaf(acc[mt][nt][2 * hr + 1], s1, h1);
+        v0 = __fdividef(v0, 1.f + __expf(-v0));
+        v1 = __fdividef(v1, 1.f + __expf(-v1));
+        if (add_res) {
+          const uint32_t r = hw[((warp + 1) * PW + px + 1) * 12 + (ch >> 1)];
+          v0 += __uint_as_float(r << 16);
+          v1 += __uint_as_float(r & 0xffff0000u);
+        }
+        *reinterpret_cast<uint32_t*>(op + (long long)x * C24 + ch) = pack2(v0, v1);
+      }
+  }
+}
+
+void launch_conv3x3_c24_bf16(const __nv_bfloat16* in, const void* wfrag, const float* scale, const float* shift,
+                             __nv_bfloat16* out, int B, int H, int W, int add_res, cudaStream_t st) {
+  const int tiles = ((W + C24_TW - 1) / C24_TW) * ((H + C24_TH - 1) / C24_TH);
+  conv3x3_c24_mma_kernel<<<B * tiles, 256, 0, st>>>(in, reinterpret_cast<const uint2*>(wfrag), scale, shift, out, H, W, add_res);
+}
+
 }  // namespace frx

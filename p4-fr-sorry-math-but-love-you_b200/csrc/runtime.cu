@@ -230,6 +230,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   else if (k == "graphs") h->opt_graphs = value != 0;
   else if (k == "timing") h->opt_timing = value != 0;
   else if (k == "cluster_images") {}  // accepted for compatibility: clusters always own 8 images
+  else if (k == "conv24") h->opt_conv24 = value != 0;  // 0: stage-0 convs through the tcgen05 im2col GEMM instead
   else if (k == "enc_fp32") h->opt_enc_fp32 = value != 0;
   else if (k == "tc_ws") h->opt_tc_ws = value != 0;
   else if (k == "tc_im2col") h->opt_tc_im2col = value != 0;
@@ -590,12 +591,33 @@ static size_t pack_bf16_conv_padded(ArenaBuilder& ab, size_t src_off, int N, int
   return off;
 }
 
+// B fragments of a 24 -> 24 3x3 convolution for conv3x3_c24_mma_kernel: k = tap * 24 + channel (216, zero-padded to
+// 224), [k-step s][n-tile nt][lane] -> {b0 = W[n][16s + 2tig, +1], b1 = W[n][16s + 8 + 2tig, +1]}, n = 8 nt + gid.
+static size_t pack_frag_conv24(ArenaBuilder& ab, size_t w_off) {
+  const int K = 216;
+  size_t off = ab.add(nullptr, (size_t)14 * 3 * 32 * 2);
+  const float* w = ab.at(w_off);  // [24][216]
+  uint32_t* d = reinterpret_cast<uint32_t*>(ab.at(off));
+  for (int s = 0; s < 14; ++s)
+    for (int nt = 0; nt < 3; ++nt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int gid = lane >> 2, tig = lane & 3, n = 8 * nt + gid;
+        for (int q = 0; q < 2; ++q) {
+          const int k = 16 * s + 8 * q + 2 * tig;
+          const uint32_t lo = k < K ? bf16_bits(w[(size_t)n * K + k]) : 0u, hi = k + 1 < K ? bf16_bits(w[(size_t)n * K + k + 1]) : 0u;
+          d[((size_t)(s * 3 + nt) * 32 + lane) * 2 + q] = lo | (hi << 16);
+        }
+      }
+  return off;
+}
+
 static void pack_encoder_bf16(frx_handle* h, ArenaBuilder& ab) {
   const frx_config& c = h->cfg;
   for (BlockW& b : h->blocks) {
     if (b.kind <= 1 && b.cin <= 64)
       b.wb_a_pad = pack_bf16_conv_padded(ab, b.w_a, b.kind == 0 ? b.cout : b.mid, b.k * b.k, b.cin);
     if (b.kind == 0) b.wb_a = pack_bf16_copy(ab, b.w_a, (size_t)b.cout * b.k * b.k * b.cin);
+    if (b.kind == 0 && b.cin == 24 && b.cout == 24 && b.k == 3 && b.stride == 1) b.w_frag24 = pack_frag_conv24(ab, b.w_a);
     else if (b.kind == 1) {
       b.wb_a = pack_bf16_copy(ab, b.w_a, (size_t)b.mid * b.k * b.k * b.cin);
       b.wb_b = pack_bf16_copy(ab, b.w_b, (size_t)b.cout * b.mid);
@@ -945,7 +967,11 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
   if (tap_bf16(h, "stem", x, B, H, W, 24, st)) return 1;
   for (const BlockW& b : h->blocks) {
     int OH, OW;
-    if (b.kind == 0) {
+    if (b.kind == 0 && b.w_frag24 && h->opt_conv24) {
+      OH = H; OW = W;  // 3x3, stride 1, "same"
+      launch_conv3x3_c24_bf16(x, A + b.w_frag24, A + b.sc_a, A + b.sh_a, y, B, H, W, b.residual ? 1 : 0, st);
+      CKL();
+    } else if (b.kind == 0) {
       TcGemmP g = tc_conv(x, B, H, W, b.cin, A, b.wb_a, b.cout, b.k, b.stride, y, &OH, &OW);
       if (b.wb_a_pad && h->opt_tc_im2col) g.Wpad = (const __nv_bfloat16*)(A + b.wb_a_pad);
       g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;

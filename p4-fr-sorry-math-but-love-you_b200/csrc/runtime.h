@@ -27,6 +27,7 @@ struct BlockW {
   size_t w_b, sc_b, sh_b;      // 1x1 projection + folded BN (kinds 1/2)
   size_t wb_a = 0, wb_b = 0;   // bf16 copies of w_a / w_b ([N][K], K contiguous) for the tcgen05 path
   size_t wb_a_pad = 0;         // 3x3 convs: bf16 [N][9][64] (channels zero-padded) for the TMA-im2col path
+  size_t w_frag24 = 0;         // 24 -> 24 3x3 convs: mma.m16n8k16 B fragments [14][3][32] x {b0, b1} (conv3x3_c24_mma_kernel)
 };
 struct LiteConvW { int cin, cout; size_t w, sc, sh; };
 struct EncLayerW {
@@ -75,6 +76,7 @@ struct frx_handle {
   bool opt_tc_im2col = true;   // 3x3 conv A tiles by TMA im2col (false: cp.async gather)
   void* hook_wpad = nullptr; size_t hook_wpad_bytes = 0;
   bool opt_tc_ws = true;       // persistent warp-specialised tcgen05 GEMM (false: one tile per CTA)
+  bool opt_conv24 = true;      // stage-0 24 -> 24 convs on the halo-tile mma.sync kernel (false: tcgen05 im2col GEMM)
   bool opt_enc_fp32 = false;   // bf16 handle, but run the encoder on the fp32 SIMT path (debug)
   long long* prof = nullptr;
   int opt_parts = 3;  // bit0: encoder weights/workspaces, bit1: decoder

@@ -117,3 +117,27 @@ def test_bf16_decode_batch_larger_than_one_launch(ckpt0):
         sl = slice(r * mem8.size(0), (r + 1) * mem8.size(0))
         assert torch.equal(tokens_big[sl], tokens_small)
         assert torch.equal(logits_big[sl], logits_small)
+
+
+def test_bf16_stage0_conv_kernel_matches_oracle_and_gemm_path(ckpt0, spec):
+    """The halo-tile mma.sync kernel of the two 24 -> 24 stage-0 convs: bf16-rounding distance from the fp32
+    oracle, and agreement with the tcgen05 im2col GEMM it replaces (both bf16), on an odd batch."""
+    x = synth.synth_images(spec, 3, 11)
+    taps = {}
+    with torch.no_grad():
+        satrn.encoder_forward(ckpt0, spec, x, taps=taps)
+    got = {}
+    for conv24 in (1, 0):
+        m = make_model(ckpt0, precision="bf16").cuda().eval()
+        m.set_option("taps", 1)
+        m.set_option("conv24", conv24)
+        m.encode(x.cuda())
+        torch.cuda.synchronize()
+        got[conv24] = {n: m.read_tap(n).permute(0, 3, 1, 2).contiguous().cpu() for n in ("eff_block.0.0", "eff_block.0.1")}
+    for name in ("eff_block.0.0", "eff_block.0.1"):
+        ref = taps[name]
+        scale = ref.abs().max().item()
+        err = (got[1][name] - ref).abs().max().item() / scale
+        gap = (got[1][name] - got[0][name]).abs().max().item() / scale
+        print("%s: halo-tile kernel vs oracle %.4f, vs im2col GEMM %.4f" % (name, err, gap))
+        assert err <= 1.5e-2 and gap <= 1.5e-2
