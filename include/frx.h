@@ -128,6 +128,29 @@ int frx_beam_search(frx_handle* h, const float* memory, int32_t batch, int32_t b
 int frx_decode_teacher_forced(frx_handle* h, const float* memory, const int64_t* text,
                               int32_t batch, int32_t length, float* logits, void* stream);
 
+/* DecodingManager (postprocessing/postprocessing.py:182-405; built by get_decoding_manager, :158-180, and attached
+ * to the model by inference_single.py:80-95): rule-constrained greedy decoding.  The host compiles the manager's
+ * `rules` dict against its `tokens` list into per-class tables:
+ *   flags[v] : bit 0 cannot_initial, 1 next_underbar, 2 next_lbracket, 3 cannot_next_underbar, 4 cannot_next_lbracket
+ *   limit[v] : limit_params[token] where limit_series[token] is true, else 0
+ *   ids6     : ids of "<SOS>", "<EOS>", "" (the empty token), "{", "}", "_"
+ * Host pointers; the library keeps device copies. */
+int frx_set_decoding_rules(frx_handle* h, const int32_t* flags, const int32_t* limit, int32_t num_classes,
+                           const int32_t* ids6);
+
+/* SATRNDecoder.forward inference branch with a manager attached (EfficientSATRN.py:536-564): every step's logits
+ * row goes through DecodingManager.sift (:193-233) -- softmax, black-listed classes (MemoryNode._look_back,
+ * :327-391) zeroed, argmax = next input token, MemoryNode.record (:303-325).
+ * probs   : device fp32 [B, steps, num_classes] MASKED SOFTMAX rows (what the reference's forward returns) or NULL
+ * tokens  : device int64 [B, steps] or NULL
+ * (The reference itself raises TypeError after its last step: it calls manager.reset() without the required
+ * argument, :564 vs postprocessing.py:237.  These entry points return the loop's results.)
+ * The step kernels are the fp32 ones in either precision mode. */
+int frx_decode_greedy_managed(frx_handle* h, const float* memory, int32_t batch, int32_t steps, float* probs,
+                              int64_t* tokens, void* stream);
+int frx_forward_greedy_managed(frx_handle* h, const float* images, int32_t batch, int32_t steps, float* probs,
+                               int64_t* tokens, void* stream);
+
 /* Introspection for bench.py / tests: number of kernel launches the library
  * has enqueued since creation (nodes of replayed CUDA graphs included), and the
  * bytes currently allocated by the handle. */

@@ -122,7 +122,63 @@ def main_swin():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+
+def compile_rules(rules, tokens):
+    """Per-token tables equivalent to the reference's RULES dict (postprocessing/postprocessing.py:12-156) for a
+    given token list: bit 0 cannot_initial, 1 next_underbar, 2 next_lbracket, 3 cannot_next_underbar,
+    4 cannot_next_lbracket; limit[v] = limit_params[token] where limit_series[token] is true, else 0."""
+    V = len(tokens)
+    flags = np.zeros(V, np.int32)
+    limit = np.zeros(V, np.int32)
+    for bit, key in enumerate(("cannot_initial", "next_underbar", "next_lbracket", "cannot_next_underbar",
+                               "cannot_next_lbracket")):
+        for t in rules[key]:
+            flags[tokens.index(t)] |= 1 << bit
+    for v, t in enumerate(tokens):
+        if rules["limit_series"].get(t, False):
+            limit[v] = rules["limit_params"][t]
+    return flags, limit
+
+
+def main_manager():
+    """Greedy decode under the reference's DecodingManager (postprocessing/postprocessing.py:182-405,
+    EfficientSATRN.py:536-564): masked-softmax outputs and tokens of the REAL reference."""
+    import importlib
+    torch.set_grad_enabled(False)
+    ref = ref_shim.load_reference()
+    pp = importlib.import_module("postprocessing.postprocessing")
+    spec = satrn.ModelSpec()
+    batch = 4
+    manager = pp.get_decoding_manager(os.path.join(ref_shim.REFERENCE_ROOT, "configs", "tokens.txt"), batch_size=batch)
+    # The reference calls `self.manager.reset()` after the loop (:564) although reset() requires `sequence_length`
+    # (postprocessing.py:237) -- a TypeError once all steps are done.  The wrapper supplies the missing argument;
+    # nothing the loop produced depends on it.
+    _reset = manager.reset
+    manager.reset = lambda sequence_length=None: _reset(sequence_length)
+    sd = synth.synth_state_dict(spec, 0)
+    model = ref.networks.EfficientSATRN(ref_shim.reference_flags(), ref_shim.reference_vocab(), None, manager).eval()
+    model.load_state_dict(sd, strict=True)
+    images = synth.synth_images(spec, batch, 0)
+    expected = satrn.expected_tokens(batch)
+    with ref_shim.cpu_get_device():
+        probs = model(images, expected, False, 0.0)            # [B, 231, 245] masked softmax (:553-555)
+    tokens = probs.argmax(-1)
+    flags, limit = compile_rules(manager.rules, manager.tokens)
+    keep = np.array([0, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 230])
+    out = dict(digest=np.array(state_dict_digest(sd)), tokens=tokens.numpy(), probs_steps=keep,
+               probs=probs[:, keep].numpy().astype(np.float32), probs_max=probs.max(-1).values.numpy().astype(np.float32),
+               vocab=np.array(manager.tokens), flags=flags, limit=limit)
+    path = os.path.join(GOLDEN_DIR, "efficientsatrn_seed0_manager.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    plain = np.load(os.path.join(GOLDEN_DIR, "efficientsatrn_seed0.npz"))["tokens"]
+    print("tokens changed by the manager: %.1f %%" % (100.0 * (plain != tokens.numpy()).mean()))
+
+
 if __name__ == "__main__":
+    if "--manager" in sys.argv:
+        main_manager()
+        sys.exit(0)
     if "--swin" in sys.argv:
         main_swin()
         sys.exit(0)

@@ -13,6 +13,7 @@ SYMBOLS = [
     "frx_forward_greedy_host", "frx_decode_begin", "frx_decode_step", "frx_beam_search",
     "frx_decode_teacher_forced", "frx_launch_count", "frx_device_bytes", "frx_set_option",
     "frx_read_tap", "frx_last_timing", "frx_read_prof", "frx_tc_gemm",
+    "frx_set_decoding_rules", "frx_decode_greedy_managed", "frx_forward_greedy_managed",
 ]
 
 
@@ -67,6 +68,9 @@ def load_library():
     lib.frx_read_prof.argtypes = [vp, ctypes.POINTER(i64)]
     lib.frx_tc_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, ctypes.POINTER(i32), vp, vp, i32, i32, vp]
     lib.frx_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    lib.frx_set_decoding_rules.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, ctypes.POINTER(i32)]
+    lib.frx_decode_greedy_managed.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    lib.frx_forward_greedy_managed.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     _LIB = lib
     return lib
 

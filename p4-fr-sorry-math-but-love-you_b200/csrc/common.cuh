@@ -143,6 +143,9 @@ struct TcGemmP {
   int res_f32, ldr, out_f32;
 };
 
+// ids of the tokens the DecodingManager rules single out (dec_sift_embed_kernel)
+struct SiftIds { int sos, eos, empty, lbrace, rbrace, underbar; };
+
 // ---------------------------------------------------------------------------
 // bf16 persistent decode kernel (kernels_decode_bf16.cu)
 // ---------------------------------------------------------------------------

@@ -32,6 +32,10 @@ void launch_dec_argmax_embed(const float* logits, long long ld_logits, int V, lo
                              cudaStream_t st);
 
 
+void launch_dec_sift_embed(float* logits, long long ld_logits, int V, long long* tokens_out, long long ld_tok, int4* state,
+                           const int* flags, const int* limit, const SiftIds& ids, int* cur_tok, const float* emb,
+                           const float* pe_next, float scale, float* x, int M, int D, cudaStream_t st);
+void launch_sift_state_init(int4* state, int M, int sos, cudaStream_t st);
 void launch_pad_mask(const long long* text, unsigned char* mask, int B, int L, int pad_id, cudaStream_t st);
 
 // SwinTRN encoder pieces (kernels_swin.cu)

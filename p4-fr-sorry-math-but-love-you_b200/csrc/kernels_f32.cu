@@ -887,4 +887,91 @@ void launch_pad_mask(const long long* text, unsigned char* mask, int B, int L, i
   pad_mask_kernel<<<(B * L + 255) / 256, 256, 0, st>>>(text, mask, B, L, pad_id);
 }
 
+// ===========================================================================
+// DecodingManager.sift + MemoryNode.record/_look_back (postprocessing/postprocessing.py:193-233,
+// :303-391) fused with the next step's embedding: one warp per row.  In place: the row of logits becomes the
+// row of masked softmax probabilities (what the reference's forward returns when a manager is attached,
+// EfficientSATRN.py:553-555); the constrained argmax (first maximum, like torch.argmax) is the next input token.
+// state[m] = {current token, run length, #'{', #'}'} (MemoryNode.__init__: <SOS>, 1, 0, 0).
+// ===========================================================================
+__global__ void __launch_bounds__(256) dec_sift_embed_kernel(float* __restrict__ logits, long long ld_logits, int V,
+                                                             long long* __restrict__ tokens_out, long long ld_tok,
+                                                             int4* __restrict__ state, const int* __restrict__ flags,
+                                                             const int* __restrict__ limit, SiftIds ids,
+                                                             int* __restrict__ cur_tok, const float* __restrict__ emb,
+                                                             const float* __restrict__ pe_next, float scale,
+                                                             float* __restrict__ x, int M, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  float* lp = logits + (long long)m * ld_logits;
+  int4 stt = state[m];  // x = current token, y = run length, z = '{' count, w = '}' count
+  const int cur = stt.x;
+  const int cf = (cur >= 0 && cur < V) ? __ldg(flags + cur) : 0;
+  const int clim = (cur >= 0 && cur < V) ? __ldg(limit + cur) : 0;
+  // softmax (F.softmax, :216)
+  float mx = -INFINITY;
+  for (int i = lane; i < V; i += 32) mx = fmaxf(mx, lp[i]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < V; i += 32) sum += expf(lp[i] - mx);
+  sum = warp_sum(sum);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < V; i += 32) {
+    // MemoryNode._look_back (:327-391)
+    bool black = (i == ids.sos) || (i == ids.empty) || (i == ids.rbrace && stt.z == stt.w);
+    if (cur == ids.eos) {
+    } else if (cur == ids.sos) {
+      black = black || (__ldg(flags + i) & 1);
+    } else if (cf & 2) {
+      black = black || (i != ids.underbar);
+    } else if (cf & 4) {
+      black = black || (i != ids.lbrace);
+    } else {
+      if ((cf & 8) && i == ids.underbar) black = true;
+      if ((cf & 16) && i == ids.lbrace) black = true;
+      if (clim > 0 && stt.y >= clim && i == cur) black = true;
+    }
+    const float pv = black ? 0.f : expf(lp[i] - mx) / sum;
+    lp[i] = pv;
+    if (pv > best) { best = pv; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (bi < 0 || bi >= V) bi = 0;
+  if (lane == 0) {  // MemoryNode.record (:303-325)
+    stt.y = (bi == cur) ? stt.y + 1 : 1;
+    if (bi == ids.lbrace) stt.z += 1;
+    else if (bi == ids.rbrace) stt.w += 1;
+    stt.x = bi;
+    state[m] = stt;
+    if (tokens_out) tokens_out[(long long)m * ld_tok] = bi;
+    cur_tok[m] = bi;
+  }
+  if (pe_next) {
+    for (int d = lane; d < D; d += 32)
+      x[(long long)m * D + d] = __ldg(emb + (long long)bi * D + d) * scale + __ldg(pe_next + d);
+  }
+}
+
+void launch_dec_sift_embed(float* logits, long long ld_logits, int V, long long* tokens_out, long long ld_tok, int4* state,
+                           const int* flags, const int* limit, const SiftIds& ids, int* cur_tok, const float* emb,
+                           const float* pe_next, float scale, float* x, int M, int D, cudaStream_t st) {
+  dec_sift_embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(logits, ld_logits, V, tokens_out, ld_tok, state, flags, limit, ids,
+                                                     cur_tok, emb, pe_next, scale, x, M, D);
+}
+
+__global__ void sift_state_init_kernel(int4* state, int M, int sos) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) state[i] = make_int4(sos, 1, 0, 0);
+}
+void launch_sift_state_init(int4* state, int M, int sos, cudaStream_t st) {
+  sift_state_init_kernel<<<(M + 255) / 256, 256, 0, st>>>(state, M, sos);
+}
+
 }  // namespace frx

@@ -1300,20 +1300,27 @@ static int run_decode_step(frx_handle* h, int B, int t, float* logits_dst, long 
   return 0;
 }
 
-static int run_greedy_loop(frx_handle* h, int B, int steps, bool forced, cudaStream_t st) {
+// mode 0: greedy, 1: forced tokens, 2: DecodingManager (the logits rows become masked softmax rows, :553-555)
+static int run_greedy_loop(frx_handle* h, int B, int steps, int mode, cudaStream_t st) {
   const frx_config& c = h->cfg;
   const float* A = h->arena;
   const int D = c.dec_hidden, V = c.num_classes;
   const float scale = sqrtf((float)D);
   launch_dec_embed_f32(nullptr, nullptr, c.sos_id, A + h->emb, A + h->pe1d, 0, nullptr, 0, scale, h->dx, B, D, st);
   CKL();
+  const SiftIds sids{h->sift_ids[0], h->sift_ids[1], h->sift_ids[2], h->sift_ids[3], h->sift_ids[4], h->sift_ids[5]};
+  if (mode == 2) { launch_sift_state_init(h->sift_state, B, sids.sos, st); CKL(); }  // manager.reset (:536-537)
   for (int t = 0; t < steps; ++t) {
     float* lg = h->logits_int + (size_t)t * V;
     if (run_decode_step(h, B, t, lg, (long long)steps * V, st)) return 1;
     const float* pe_next = (t + 1 < steps) ? A + h->pe1d + (size_t)(t + 1) * D : nullptr;
-    launch_dec_argmax_embed(lg, (long long)steps * V, V, h->tokens_int + t, steps,
-                            forced ? h->forced_int + t : nullptr, steps, h->cur_tok, A + h->emb, pe_next, scale,
-                            h->dx, B, D, st);
+    if (mode == 2)
+      launch_dec_sift_embed(lg, (long long)steps * V, V, h->tokens_int + t, steps, h->sift_state, h->sift_flags,
+                            h->sift_limit, sids, h->cur_tok, A + h->emb, pe_next, scale, h->dx, B, D, st);
+    else
+      launch_dec_argmax_embed(lg, (long long)steps * V, V, h->tokens_int + t, steps,
+                              mode == 1 ? h->forced_int + t : nullptr, steps, h->cur_tok, A + h->emb, pe_next, scale,
+                              h->dx, B, D, st);
     CKL();
   }
   return 0;
@@ -1359,7 +1366,7 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
 }
 
 static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int steps, float* logits,
-                              int64_t* tokens, const int64_t* forced, cudaStream_t st) {
+                              int64_t* tokens, const int64_t* forced, cudaStream_t st, bool managed = false) {
   const frx_config& c = h->cfg;
   if (!h->finalized) return fail(h, "decode: weights not finalized");
   if (!(h->opt_parts & 2)) return fail(h, "decode: handle was created without the decoder part");
@@ -1368,19 +1375,22 @@ static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int ste
   if (steps > 500) return fail(h, "decode: steps exceed the 1-D positional table (500)");
   CK(cudaSetDevice(c.device));
   if (run_cross_kv(h, memory, B, st)) return 1;
-  if (c.precision == FRX_PREC_BF16)  // one persistent kernel; writes the caller's buffers directly
+  if (managed && !h->have_rules) return fail(h, "managed decode: frx_set_decoding_rules has not been called");
+  if (managed && forced) return fail(h, "managed decode: forced tokens are not supported");
+  const int mode = managed ? 2 : (forced ? 1 : 0);
+  if (c.precision == FRX_PREC_BF16 && !managed)  // one persistent kernel; writes the caller's buffers directly
     return decode_greedy_bf16(h, B, steps, logits, (long long*)(tokens ? tokens : (int64_t*)h->tokens_int),
                               (const long long*)forced, st);
   if (forced) CK(cudaMemcpyAsync(h->forced_int, forced, (size_t)B * steps * 8, cudaMemcpyDeviceToDevice, st));
   if (h->opt_graphs) {
-    GraphKey key{B, steps, forced != nullptr};
+    GraphKey key{B, steps, mode};
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
       cudaStream_t cs;
       CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
       int64_t before = h->launches;
       CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      int rc = run_greedy_loop(h, B, steps, forced != nullptr, cs);
+      int rc = run_greedy_loop(h, B, steps, mode, cs);
       cudaGraph_t graph = nullptr;
       cudaError_t e = cudaStreamEndCapture(cs, &graph);
       cudaStreamDestroy(cs);
@@ -1396,7 +1406,7 @@ static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int ste
     }
     CK(cudaGraphLaunch(it->second.exec, st));
     h->launches += it->second.nodes;
-  } else if (run_greedy_loop(h, B, steps, forced != nullptr, st)) {
+  } else if (run_greedy_loop(h, B, steps, mode, st)) {
     return 1;
   }
   if (logits) CK(cudaMemcpyAsync(logits, h->logits_int, (size_t)B * steps * c.num_classes * 4, cudaMemcpyDeviceToDevice, st));
@@ -1408,6 +1418,46 @@ extern "C" int frx_decode_greedy(frx_handle* h, const float* memory, int32_t B, 
                                  int64_t* tokens, const int64_t* forced, void* stream) {
   if (!h) return 1;
   return decode_greedy_impl(h, memory, B, steps, logits, tokens, forced, (cudaStream_t)stream);
+}
+
+// DecodingManager (postprocessing/postprocessing.py:182-405): upload the per-token rule tables.
+extern "C" int frx_set_decoding_rules(frx_handle* h, const int32_t* flags, const int32_t* limit, int32_t num_classes,
+                                      const int32_t* ids6) {
+  if (!h) return 1;
+  const frx_config& c = h->cfg;
+  if (num_classes != c.num_classes) return fail(h, "decoding rules: %d classes, the model has %d", num_classes, c.num_classes);
+  for (int i = 0; i < 6; ++i)
+    if (ids6[i] < 0 || ids6[i] >= num_classes) return fail(h, "decoding rules: special token id %d out of range", ids6[i]);
+  CK(cudaSetDevice(c.device));
+  if (!h->sift_flags) {
+    void* p;
+    if (dev_alloc(h, &p, (size_t)num_classes * 4)) return 1; h->sift_flags = (int*)p;
+    if (dev_alloc(h, &p, (size_t)num_classes * 4)) return 1; h->sift_limit = (int*)p;
+    if (dev_alloc(h, &p, (size_t)c.max_batch * sizeof(int4))) return 1; h->sift_state = (int4*)p;
+  }
+  CK(cudaMemcpy(h->sift_flags, flags, (size_t)num_classes * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->sift_limit, limit, (size_t)num_classes * 4, cudaMemcpyHostToDevice));
+  for (int i = 0; i < 6; ++i) h->sift_ids[i] = ids6[i];
+  h->have_rules = true;
+  for (auto it = h->graphs.begin(); it != h->graphs.end();) {  // captured graphs embed the special-token ids
+    if (std::get<2>(it->first) == 2) { cudaGraphExecDestroy(it->second.exec); it = h->graphs.erase(it); }
+    else ++it;
+  }
+  return 0;
+}
+
+// SATRNDecoder.forward inference branch with a DecodingManager attached (EfficientSATRN.py:536-564).
+extern "C" int frx_decode_greedy_managed(frx_handle* h, const float* memory, int32_t B, int32_t steps, float* probs,
+                                         int64_t* tokens, void* stream) {
+  if (!h) return 1;
+  return decode_greedy_impl(h, memory, B, steps, probs, tokens, nullptr, (cudaStream_t)stream, true);
+}
+
+extern "C" int frx_forward_greedy_managed(frx_handle* h, const float* images, int32_t B, int32_t steps, float* probs,
+                                          int64_t* tokens, void* stream) {
+  if (!h) return 1;
+  if (frx_encode(h, images, B, h->memory_int, stream)) return 1;
+  return decode_greedy_impl(h, h->memory_int, B, steps, probs, tokens, nullptr, (cudaStream_t)stream, true);
 }
 
 extern "C" int frx_forward_greedy(frx_handle* h, const float* images, int32_t B, int32_t steps, float* logits,

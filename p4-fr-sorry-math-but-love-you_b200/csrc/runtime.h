@@ -50,7 +50,7 @@ struct SwinMergeW { int dim, res; size_t red_w, n_g, n_b; };
 // fragment-packed bf16 weights of the persistent decode kernel (offsets in floats = u32 words)
 struct DecPackW { size_t w_o, w_q2, w_o2, w_f0, w_f1, w_next; };
 struct Tap { float* data = nullptr; size_t capacity = 0; int shape[4] = {0, 0, 0, 0}; };
-typedef std::tuple<int, int, bool> GraphKey;
+typedef std::tuple<int, int, int> GraphKey;  // batch, steps, mode (0 greedy, 1 forced, 2 DecodingManager)
 struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; };
 
 struct BeamWs {
@@ -125,5 +125,10 @@ struct frx_handle {
   BeamWs beam;
   TfWs tf;
   int step_idx = 0, step_batch = 0;
+  // DecodingManager rule tables (frx_set_decoding_rules) and per-row state of the constrained greedy decode
+  int *sift_flags = nullptr, *sift_limit = nullptr;
+  int4* sift_state = nullptr;
+  int sift_ids[6] = {0, 0, 0, 0, 0, 0};  // <SOS>, <EOS>, "", "{", "}", "_"
+  bool have_rules = false;
   bool timed_kernel = false;
 };

@@ -18,3 +18,31 @@ def decode(model, input, data_loader=None, expected=None, method="greedy", beam_
     else:
         raise NotImplementedError(f"There's no '{method}' type yet.")
     return sequence
+
+
+RULE_BITS = ("cannot_initial", "next_underbar", "next_lbracket", "cannot_next_underbar", "cannot_next_lbracket")
+
+
+def compile_decoding_rules(manager):
+    """Per-class tables for ``frx_set_decoding_rules`` from a reference-style DecodingManager
+    (postprocessing/postprocessing.py:182-191: ``.rules`` is the RULES dict, ``.tokens`` the 245 class names).
+
+    Returns (flags, limit, ids6) as Python int lists: flags bit i <-> ``rules[RULE_BITS[i]]`` contains the token;
+    limit[v] = ``limit_params[token]`` where ``limit_series[token]`` is true (MemoryNode._look_back, :327-391);
+    ids6 = ids of "<SOS>", "<EOS>", "" (the empty class), "{", "}", "_"."""
+    tokens = list(manager.tokens)
+    index = {t: i for i, t in enumerate(tokens)}
+    flags, limit = [0] * len(tokens), [0] * len(tokens)
+    for bit, key in enumerate(RULE_BITS):
+        for t in manager.rules.get(key, ()):
+            if t not in index:
+                raise KeyError("decoding rule %r names the unknown token %r" % (key, t))
+            flags[index[t]] |= 1 << bit
+    series, params = manager.rules.get("limit_series", {}), manager.rules.get("limit_params", {})
+    for t, on in series.items():
+        if on and t in index:
+            if t not in params:
+                raise KeyError("limit_series enables %r but limit_params has no entry for it" % t)
+            limit[index[t]] = int(params[t])
+    ids6 = [index[t] for t in ("<SOS>", "<EOS>", "", "{", "}", "_")]
+    return flags, limit, ids6

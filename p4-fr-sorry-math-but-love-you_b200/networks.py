@@ -188,11 +188,15 @@ class EfficientSATRN(_FrxModule):
         if checkpoint:
             self.load_state_dict(checkpoint)
 
-    def _check_manager(self):
-        if self.decoder.manager is not None:
-            raise NotImplementedError(
-                "DecodingManager rule masks (postprocessing/postprocessing.py:182-404) are not part of "
-                "the accelerated path yet (SURVEY 8f-1); construct with decoding_manager=None")
+    def _attach_manager(self, eng):
+        """Upload the DecodingManager's rule tables (postprocessing/postprocessing.py:182-405) once per engine."""
+        if getattr(eng, "_rules_of", None) is not self.decoder.manager:
+            from .decoding import compile_decoding_rules
+            flags, limit, ids6 = compile_decoding_rules(self.decoder.manager)
+            n = len(flags)
+            eng.h.call("frx_set_decoding_rules", (ctypes.c_int32 * n)(*flags), (ctypes.c_int32 * n)(*limit), n,
+                       (ctypes.c_int32 * 6)(*ids6))
+            eng._rules_of = self.decoder.manager
 
     def forward(self, input, expected, is_train, teacher_forcing_ratio):
         """:697-706 -> logits [B, expected.size(1)-1, num_classes] fp32 on input's device."""
@@ -211,8 +215,11 @@ class EfficientSATRN(_FrxModule):
             eng.h.call("frx_encode", _ptr(x), b, _ptr(memory), st)
             eng.h.call("frx_decode_teacher_forced", _ptr(memory), _ptr(text), b, steps, _ptr(logits), st)
             return logits
-        self._check_manager()
         logits = torch.empty(b, steps, v, device=x.device)
+        if self.decoder.manager is not None:  # :536-564: every row is the manager's masked softmax, not logits
+            self._attach_manager(eng)
+            eng.h.call("frx_forward_greedy_managed", _ptr(x), b, steps, _ptr(logits), None, _stream(x.device))
+            return logits
         eng.h.call("frx_forward_greedy", _ptr(x), b, steps, _ptr(logits), None, _stream(x.device))
         return logits
 

@@ -33,3 +33,9 @@ def ckpt1(spec):
 def load_golden(seed):
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "efficientsatrn_seed%d.npz" % seed))
+
+
+def load_manager_golden():
+    """Reference greedy decode under its DecodingManager (oracle/make_golden.py --manager) + the compiled rule tables."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "efficientsatrn_seed0_manager.npz"))

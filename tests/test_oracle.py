@@ -82,3 +82,19 @@ def test_teacher_forced_matches_reference(spec, ckpt0):
 def test_expected_contract():
     e = satrn.expected_tokens(3)
     assert e.shape == (3, 232) and e[0, 0] == 0 and e[0, -1] == 1 and e[0, 1] == 158
+
+
+def test_decoding_manager_matches_reference(spec, ckpt0):
+    """Rule-constrained greedy decode (postprocessing.py:182-405, EfficientSATRN.py:536-564): tokens identical to
+    the reference's, masked-softmax rows to 2e-6."""
+    from conftest import load_manager_golden
+    from oracle import manager
+    g = load_manager_golden()
+    rules = manager.Rules([str(t) for t in g["vocab"]], g["flags"], g["limit"])
+    with torch.no_grad():
+        mem = torch.from_numpy(load_golden(0)["memory"])
+        probs, tokens = manager.decode_greedy_managed(ckpt0, spec, mem, 231, rules)
+    assert np.array_equal(tokens.numpy(), g["tokens"])
+    keep = g["probs_steps"]
+    assert np.abs(probs[:, keep].numpy() - g["probs"]).max() <= 2e-6
+    assert np.abs(probs.max(-1).values.numpy() - g["probs_max"]).max() <= 2e-6
