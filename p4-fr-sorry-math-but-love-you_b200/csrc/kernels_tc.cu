@@ -132,6 +132,7 @@ __device__ __forceinline__ float act_fast(float v) {
   if (ACT == ACT_RELU) return fmaxf(v, 0.f);
   if (ACT == ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
   if (ACT == ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-v));
+  if (ACT == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact GELU (SWIN.py:30)
   return v;
 }
 
@@ -174,6 +175,7 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
       if (full) {  // vectorised scale/shift, activation resolved outside the element loop
         if (p.act == ACT_SILU) epi_affine_act<ACT_SILU>(v, p.scale, p.shift, nb);
         else if (p.act == ACT_RELU) epi_affine_act<ACT_RELU>(v, p.scale, p.shift, nb);
+        else if (p.act == ACT_GELU) epi_affine_act<ACT_GELU>(v, p.scale, p.shift, nb);
         else epi_affine_act<ACT_NONE>(v, p.scale, p.shift, nb);
       } else {
 #pragma unroll

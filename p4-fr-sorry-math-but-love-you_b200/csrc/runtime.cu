@@ -186,8 +186,8 @@ extern "C" int frx_create(const frx_config* cfg, frx_handle** out) {
     return fail(h, "decoder head_dim must be 32 or 64");
   if (cfg->dec_hidden > 512) return fail(h, "decoder hidden_dim > 512 not supported");
   if (cfg->max_batch <= 0 || cfg->max_steps <= 0) return fail(h, "max_batch/max_steps must be positive");
-  if (cfg->network != FRX_NET_EFFICIENT_SATRN && cfg->precision != FRX_PREC_FP32)
-    return fail(h, "LiteSATRN / SWIN are built for the fp32 mode only (the bf16 kernels are specialised for EfficientSATRN's dimensions)");
+  if (cfg->network == FRX_NET_LITE_SATRN && cfg->precision != FRX_PREC_FP32)
+    return fail(h, "LiteSATRN is built for the fp32 mode only (the bf16 kernels are specialised for EfficientSATRN's dimensions)");
   return 0;
 }
 
@@ -639,8 +639,8 @@ static void pack_encoder_bf16(frx_handle* h, ArenaBuilder& ab) {
 static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
   const frx_config& c = h->cfg;
   const int D = c.dec_hidden, F = c.dec_filter, V = c.num_classes, L = c.dec_layers;
-  if (D != 256 || F != DEC_FMAX || c.dec_heads != 8 || L > 4 || V > 256)
-    return fail(h, "bf16 decode kernel is specialised for hidden 256 / filter 1024 / 8 heads / <=4 layers / <=256 classes");
+  h->dec_cluster_ok = !(D != 256 || F != DEC_FMAX || c.dec_heads != 8 || L > 4 || V > 256);
+  if (!h->dec_cluster_ok) return 0;  // e.g. SwinTRN (512 / 512 / 4 layers): the greedy loop stays on the fp32 step kernels
   auto W = [&](int l, const char* name) -> const float* {
     return find(h, "decoder.attention_layers." + std::to_string(l) + "." + name + ".weight")->f.data();
   };
@@ -721,6 +721,16 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
   if (want_dec && c.precision == FRX_PREC_BF16 && pack_decoder_bf16(h, ab)) return 1;
   if (c.precision == FRX_PREC_BF16) {
     if (want_enc && c.network == FRX_NET_EFFICIENT_SATRN) pack_encoder_bf16(h, ab);
+    if (want_enc && c.network == FRX_NET_SWIN) {
+      for (SwinBlockW& b : h->sw_blocks) {
+        const size_t C = b.dim;
+        b.qkv_wb = pack_bf16_copy(ab, b.qkv_w, 3 * C * C);
+        b.proj_wb = pack_bf16_copy(ab, b.proj_w, C * C);
+        b.fc1_wb = pack_bf16_copy(ab, b.fc1_w, 4 * C * C);
+        b.fc2_wb = pack_bf16_copy(ab, b.fc2_w, 4 * C * C);
+      }
+      for (SwinMergeW& m : h->sw_merges) m.red_wb = pack_bf16_copy(ab, m.red_w, (size_t)8 * m.dim * m.dim);
+    }
     if (want_dec) h->cross_wb = pack_bf16_copy(ab, h->w_cross, (size_t)c.dec_layers * 2 * c.dec_hidden * c.dec_src);
   }
   // upload (re-finalize re-uses the arena when the size is unchanged)
@@ -764,6 +774,10 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
       if (dev_alloc(h, &p, B * tok * 128 * 4)) return 1; h->sw_a = (float*)p;
       if (dev_alloc(h, &p, B * tok * 384 * 4)) return 1; h->sw_qkv = (float*)p;
       if (dev_alloc(h, &p, B * tok * 512 * 4)) return 1; h->sw_hid = (float*)p;
+      if (c.precision == FRX_PREC_BF16) {
+        if (dev_alloc(h, &p, B * tok * 128 * 2)) return 1; h->sw_ab = p;
+        if (dev_alloc(h, &p, B * tok * 512 * 2)) return 1; h->sw_hidb = p;
+      }
     } else if (want_enc) {
       for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * act_max * 4)) return 1; h->act[i] = (float*)p; }
       for (int i = 0; i < 2; ++i) { if (dev_alloc(h, &p, B * mid_max * 4)) return 1; h->mid[i] = (float*)p; }
@@ -1064,6 +1078,21 @@ static int encode_swin(frx_handle* h, const float* images, int B, float* memory,
     for (int j = 0; j < depths[i]; ++j, ++bi) {
       const SwinBlockW& b = h->sw_blocks[bi];
       const int M = B * b.res * b.res, C = b.dim;
+      if (h->cfg.precision == FRX_PREC_BF16) {
+        // bf16 mode: the four linear layers of the block on the tcgen05 GEMM (bf16 operands, fp32 accumulation);
+        // residual stream, LayerNorm statistics and the window attention (softmax) stay fp32
+        __nv_bfloat16* ab16 = (__nv_bfloat16*)h->sw_ab;
+        launch_layernorm_bf16out(x, nullptr, A + b.n1_g, A + b.n1_b, ab16, M, C, 0, st); CKL();
+        { TcGemmP g = tc_dense(ab16, M, C, A, b.qkv_wb, 3 * C, h->sw_qkv, 1); g.shift = A + b.qkv_b; TCL(g); }
+        launch_swin_window_attn(h->sw_qkv, A + b.bias_table, h->sw_a, B, b.res, C, b.heads, b.ws, b.shift, st); CKL();
+        launch_f32_to_bf16(h->sw_a, ab16, (long long)M * C, st); CKL();
+        { TcGemmP g = tc_dense(ab16, M, C, A, b.proj_wb, C, y, 1); g.shift = A + b.proj_b; g.res = x; g.res_f32 = 1; g.ldr = C; TCL(g); }
+        launch_layernorm_bf16out(y, nullptr, A + b.n2_g, A + b.n2_b, ab16, M, C, 0, st); CKL();
+        { TcGemmP g = tc_dense(ab16, M, C, A, b.fc1_wb, 4 * C, h->sw_hidb, 0); g.shift = A + b.fc1_b; g.act = ACT_GELU; TCL(g); }
+        { TcGemmP g = tc_dense(h->sw_hidb, M, 4 * C, A, b.fc2_wb, C, x, 1); g.shift = A + b.fc2_b; g.res = y; g.res_f32 = 1; g.ldr = C; TCL(g); }
+        if (tap(h, "block" + std::to_string(i) + "." + std::to_string(j), x, B, b.res, b.res, C, st)) return 1;
+        continue;
+      }
       launch_layernorm_f32(x, nullptr, A + b.n1_g, A + b.n1_b, h->sw_a, M, C, 0, st); CKL();
       GemmP g = dense_gemm(h->sw_a, M, C, A + b.qkv_w, 3 * C, h->sw_qkv, 3 * C);
       g.shift = A + b.qkv_b;
@@ -1085,6 +1114,13 @@ static int encode_swin(frx_handle* h, const float* images, int B, float* memory,
       const SwinMergeW& m = h->sw_merges[i];
       const int M2 = B * (m.res / 2) * (m.res / 2);
       launch_swin_patch_merge(x, h->sw_hid, B, m.res, m.dim, st); CKL();
+      if (h->cfg.precision == FRX_PREC_BF16) {
+        launch_layernorm_bf16out(h->sw_hid, nullptr, A + m.n_g, A + m.n_b, (__nv_bfloat16*)h->sw_hidb, M2, 4 * m.dim, 0, st); CKL();
+        TcGemmP g = tc_dense(h->sw_hidb, M2, 4 * m.dim, A, m.red_wb, 2 * m.dim, x, 1);
+        TCL(g);
+        if (tap(h, "merge" + std::to_string(i), x, B, m.res / 2, m.res / 2, 2 * m.dim, st)) return 1;
+        continue;
+      }
       launch_layernorm_f32(h->sw_hid, nullptr, A + m.n_g, A + m.n_b, h->sw_qkv, M2, 4 * m.dim, 0, st); CKL();
       GemmP g = dense_gemm(h->sw_qkv, M2, 4 * m.dim, A + m.red_w, 2 * m.dim, x, 2 * m.dim);
       launch_igemm_f32(g, st); CKL();
@@ -1378,7 +1414,7 @@ static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int ste
   if (managed && !h->have_rules) return fail(h, "managed decode: frx_set_decoding_rules has not been called");
   if (managed && forced) return fail(h, "managed decode: forced tokens are not supported");
   const int mode = managed ? 2 : (forced ? 1 : 0);
-  if (c.precision == FRX_PREC_BF16 && !managed)  // one persistent kernel; writes the caller's buffers directly
+  if (c.precision == FRX_PREC_BF16 && h->dec_cluster_ok && !managed)  // one persistent kernel; writes the caller's buffers directly
     return decode_greedy_bf16(h, B, steps, logits, (long long*)(tokens ? tokens : (int64_t*)h->tokens_int),
                               (const long long*)forced, st);
   if (forced) CK(cudaMemcpyAsync(h->forced_int, forced, (size_t)B * steps * 8, cudaMemcpyDeviceToDevice, st));
@@ -1620,7 +1656,7 @@ extern "C" int frx_decode_teacher_forced(frx_handle* h, const float* memory, con
     return g;
   };
   float* x = w.x;
-  if (c.precision == FRX_PREC_BF16 && h->gen_wb) {
+  if (c.precision == FRX_PREC_BF16 && h->dec_cluster_ok && h->gen_wb) {
     // bf16 mode: every linear layer (M = B*L rows) on the tcgen05 GEMM -- bf16 operands, fp32 accumulation, fp32
     // residual stream / LayerNorm / softmax; the attention kernels are the fp32 ones (K/V history = the fp32 qkv rows).
     if (ws_alloc(h, &w.xb, Mm * D * 2) || ws_alloc(h, &w.ffb, Mm * F * 2)) return 1;

@@ -45,8 +45,9 @@ struct FusedW { size_t wt, b; int N; };
 struct SwinBlockW {
   int dim, res, heads, ws, shift;
   size_t n1_g, n1_b, bias_table, qkv_w, qkv_b, proj_w, proj_b, n2_g, n2_b, fc1_w, fc1_b, fc2_w, fc2_b;
+  size_t qkv_wb = 0, proj_wb = 0, fc1_wb = 0, fc2_wb = 0;  // bf16 copies (bf16 mode)
 };
-struct SwinMergeW { int dim, res; size_t red_w, n_g, n_b; };
+struct SwinMergeW { int dim, res; size_t red_w, n_g, n_b; size_t red_wb = 0; };
 // fragment-packed bf16 weights of the persistent decode kernel (offsets in floats = u32 words)
 struct DecPackW { size_t w_o, w_q2, w_o2, w_f0, w_f1, w_next; };
 struct Tap { float* data = nullptr; size_t capacity = 0; int shape[4] = {0, 0, 0, 0}; };
@@ -131,4 +132,6 @@ struct frx_handle {
   int sift_ids[6] = {0, 0, 0, 0, 0, 0};  // <SOS>, <EOS>, "", "{", "}", "_"
   bool have_rules = false;
   bool timed_kernel = false;
+  bool dec_cluster_ok = false;   // bf16 mode: the persistent cluster decode kernel fits this decoder's dimensions
+  void *sw_ab = nullptr, *sw_hidb = nullptr;  // SwinTRN bf16 mode: bf16 A operands (LayerNorm / attention output, MLP hidden)
 };

@@ -314,7 +314,8 @@ class LiteSATRN(EfficientSATRN):
 class SWIN(EfficientSATRN):
     """networks/SWIN.py:1024-1063 -- Swin-B/384 encoder (patch 4, window 12, depths 2-2-18-2, absolute position
     embedding; hard-wired in the reference, the yaml's SATRN.encoder block is ignored) + the transformer decoder
-    of configs/SWIN.yaml.  Input [B, 3, 384, 384]; greedy decoding only; fp32 mode.  Unlike the reference the
+    of configs/SWIN.yaml.  Input [B, 3, 384, 384]; greedy decoding only.  precision="bf16" runs the encoder's linear
+    layers on the tcgen05 GEMM (the 512-wide, 4-layer decoder keeps the fp32 step kernels).  Unlike the reference the
     constructor does not download ImageNet weights (there is no network): pass a checkpoint dict."""
 
     _network = 2
@@ -322,8 +323,6 @@ class SWIN(EfficientSATRN):
 
     def __init__(self, FLAGS, train_dataset, checkpoint=None, *, precision="fp32", max_batch=None, max_steps=None):
         nn.Module.__init__(self)
-        if precision != "fp32":
-            raise NotImplementedError("SWIN runs in the fp32 mode only")
         self._setup(FLAGS, train_dataset, precision, max_batch, max_steps)
         self._dims.update(height=layout.SWIN_IMG, width=layout.SWIN_IMG, in_ch=3, enc_hidden=layout.SWIN_EMBED * 8,
                           enc_filter=0, enc_layers=0, enc_heads=0)
