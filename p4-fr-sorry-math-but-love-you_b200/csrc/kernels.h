@@ -43,6 +43,8 @@ void launch_swin_patch_embed(const float* img, const float* w, const float* bias
                              const float* ape, float* out, int B, int IMGS, int R, int E, cudaStream_t st);
 void launch_swin_window_attn(const float* qkv, const float* bias_table, float* out, int B, int R, int C, int heads, int ws,
                              int shift, cudaStream_t st);
+bool launch_swin_window_attn_mma(const float* qkv, const float* bias_table, __nv_bfloat16* out, int B, int R, int C, int heads,
+                                 int ws, int shift, cudaStream_t st);
 void launch_swin_patch_merge(const float* x, float* out, int B, int R, int C, cudaStream_t st);
 
 // best-first search bookkeeping (kernels_beam.cu)

@@ -153,4 +153,153 @@ void launch_swin_patch_merge(const float* x, float* out, int B, int R, int C, cu
   swin_patch_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, out, B, R, C);
 }
 
+// ---------------------------------------------------------------------------
+// bf16-mode (shifted-)window attention on mma.sync.m16n8k16: same indexing as swin_window_attn_kernel (one block per
+// (image, window, head), cyclic shift / window partition / reverse as index arithmetic), window 12 x 12 = 144 tokens =
+// 9 query tiles x 18 key tiles, head dim 32.  q*hd^-0.5, k (row-major) and v (transposed) are staged in shared memory
+// as bf16; S = Q K^T (36 HMMA per query tile), + relative-position bias + (-100 across shifted regions), softmax in
+// the accumulator layout, O = P V (36 HMMA) with P re-used as the A fragment; output bf16 (the A operand of the
+// projection GEMM) in the ORIGINAL token order.
+// ---------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ uint32_t sw_pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void sw_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+}  // namespace
+
+constexpr int SWA_N = 144, SWA_WS = 12, SWA_LDK = 40, SWA_LDV = 152, SWA_NB = (2 * SWA_WS - 1) * (2 * SWA_WS - 1);
+
+__global__ void __launch_bounds__(128) swin_window_attn_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ bias_table,
+                                                                   __nv_bfloat16* __restrict__ out, int R, int C, int heads, int shift) {
+  __shared__ __align__(16) __nv_bfloat16 Qb[SWA_N * SWA_LDK];
+  __shared__ __align__(16) __nv_bfloat16 Kb[SWA_N * SWA_LDK];
+  __shared__ __align__(16) __nv_bfloat16 Vt[32 * SWA_LDV];
+  __shared__ float bias_h[SWA_NB];
+  __shared__ int tokidx[SWA_N];
+  __shared__ int colinfo[SWA_N];  // y | x << 8 | region << 16 of window position j
+  constexpr int ws = SWA_WS, N = SWA_N;
+  const int nWr = R / ws;
+  const int hh = blockIdx.x % heads;
+  const int win = (blockIdx.x / heads) % (nWr * nWr);
+  const int n = blockIdx.x / (heads * nWr * nWr);
+  const int wh = win / nWr, ww = win % nWr;
+  for (int i = threadIdx.x; i < N; i += 128) {
+    const int hs = wh * ws + i / ws, wsft = ww * ws + i % ws;     // coordinates in the shifted image
+    const int h = (hs + shift) % R, w = (wsft + shift) % R;       // roll(x, -shift): shifted[hs] = x[hs + shift]
+    tokidx[i] = h * R + w;
+    int rid = 0;
+    if (shift > 0) {
+      const int hr = hs < R - ws ? 0 : (hs < R - shift ? 1 : 2);
+      const int wr = wsft < R - ws ? 0 : (wsft < R - shift ? 1 : 2);
+      rid = hr * 3 + wr;
+    }
+    colinfo[i] = (i / ws) | ((i % ws) << 8) | (rid << 16);
+  }
+  for (int i = threadIdx.x; i < SWA_NB; i += 128) bias_h[i] = __ldg(bias_table + (long long)i * heads + hh);
+  __syncthreads();
+  const float scale = rsqrtf(32.f);
+  const float* base = qkv + (long long)n * R * R * 3 * C + hh * 32;
+  for (int i = threadIdx.x; i < N * 32; i += 128) {
+    const int r = i >> 5, c = i & 31;
+    const float* rp = base + (long long)tokidx[r] * 3 * C + c;
+    Qb[r * SWA_LDK + c] = __float2bfloat16_rn(__ldg(rp) * scale);
+    Kb[r * SWA_LDK + c] = __float2bfloat16_rn(__ldg(rp + C));
+    Vt[c * SWA_LDV + r] = __float2bfloat16_rn(__ldg(rp + 2 * C));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const uint32_t* Qw = reinterpret_cast<const uint32_t*>(Qb);
+  const uint32_t* Kw = reinterpret_cast<const uint32_t*>(Kb);
+  const uint32_t* Vw = reinterpret_cast<const uint32_t*>(Vt);
+  for (int mt = warp; mt < N / 16; mt += 4) {
+    const int r0 = mt * 16 + gid, r1 = r0 + 8;
+    uint32_t a[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      a[ks][0] = Qw[(r0 * SWA_LDK + 16 * ks + 2 * tig) >> 1];
+      a[ks][1] = Qw[(r1 * SWA_LDK + 16 * ks + 2 * tig) >> 1];
+      a[ks][2] = Qw[(r0 * SWA_LDK + 16 * ks + 8 + 2 * tig) >> 1];
+      a[ks][3] = Qw[(r1 * SWA_LDK + 16 * ks + 8 + 2 * tig) >> 1];
+    }
+    float sacc[18][4];
+#pragma unroll
+    for (int nt = 0; nt < 18; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int kb = ((8 * nt + gid) * SWA_LDK + 16 * ks + 2 * tig) >> 1;
+        sw_mma(sacc[nt], a[ks], Kw[kb], Kw[kb + 4]);
+      }
+    }
+    // relative-position bias + shifted-window mask, then softmax over the 144 keys of rows r0 (c0, c1) and r1 (c2, c3)
+    const int i0 = colinfo[r0], i1 = colinfo[r1];
+    const int y0 = i0 & 255, x0 = (i0 >> 8) & 255, g0 = i0 >> 16, y1 = i1 & 255, x1 = (i1 >> 8) & 255, g1 = i1 >> 16;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 18; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cj = colinfo[8 * nt + 2 * tig + e];
+        const int yj = cj & 255, xj = (cj >> 8) & 255, gj = cj >> 16;
+        float s0 = sacc[nt][e] + bias_h[(y0 - yj + ws - 1) * (2 * ws - 1) + (x0 - xj + ws - 1)];
+        float s1 = sacc[nt][2 + e] + bias_h[(y1 - yj + ws - 1) * (2 * ws - 1) + (x1 - xj + ws - 1)];
+        if (gj != g0) s0 += -100.f;
+        if (gj != g1) s1 += -100.f;
+        sacc[nt][e] = s0; sacc[nt][2 + e] = s1;
+        mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 18; ++nt) {
+      sacc[nt][0] = __expf(sacc[nt][0] - mx0); sacc[nt][1] = __expf(sacc[nt][1] - mx0);
+      sacc[nt][2] = __expf(sacc[nt][2] - mx1); sacc[nt][3] = __expf(sacc[nt][3] - mx1);
+      sum0 += sacc[nt][0] + sacc[nt][1];
+      sum1 += sacc[nt][2] + sacc[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    float oacc[4][4];
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[nd][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 9; ++kk) {  // 16 keys per k-step = score tiles 2kk (k lo) and 2kk + 1 (k hi)
+      const uint32_t pa[4] = {sw_pack2(sacc[2 * kk][0], sacc[2 * kk][1]), sw_pack2(sacc[2 * kk][2], sacc[2 * kk][3]),
+                              sw_pack2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]), sw_pack2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3])};
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) {
+        const int vb = ((8 * nd + gid) * SWA_LDV + 16 * kk + 2 * tig) >> 1;
+        sw_mma(oacc[nd], pa, Vw[vb], Vw[vb + 4]);
+      }
+    }
+    const float q0 = __fdividef(1.f, sum0), q1 = __fdividef(1.f, sum1);
+    __nv_bfloat16* o0 = out + ((long long)n * R * R + tokidx[r0]) * C + hh * 32 + 2 * tig;
+    __nv_bfloat16* o1 = out + ((long long)n * R * R + tokidx[r1]) * C + hh * 32 + 2 * tig;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      *reinterpret_cast<uint32_t*>(o0 + 8 * nd) = sw_pack2(oacc[nd][0] * q0, oacc[nd][1] * q0);
+      *reinterpret_cast<uint32_t*>(o1 + 8 * nd) = sw_pack2(oacc[nd][2] * q1, oacc[nd][3] * q1);
+    }
+  }
+}
+
+// returns false when the window is not 12 x 12 with 32-wide heads (the caller then uses the fp32 kernel)
+bool launch_swin_window_attn_mma(const float* qkv, const float* bias_table, __nv_bfloat16* out, int B, int R, int C, int heads,
+                                 int ws, int shift, cudaStream_t st) {
+  if (ws != SWA_WS || C != heads * 32 || R % ws != 0) return false;
+  const int nW = (R / ws) * (R / ws);
+  swin_window_attn_mma_kernel<<<B * nW * heads, 128, 0, st>>>(qkv, bias_table, out, R, C, heads, shift);
+  return true;
+}
+
 }  // namespace frx

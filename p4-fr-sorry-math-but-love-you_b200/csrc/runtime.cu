@@ -1084,8 +1084,11 @@ static int encode_swin(frx_handle* h, const float* images, int B, float* memory,
         __nv_bfloat16* ab16 = (__nv_bfloat16*)h->sw_ab;
         launch_layernorm_bf16out(x, nullptr, A + b.n1_g, A + b.n1_b, ab16, M, C, 0, st); CKL();
         { TcGemmP g = tc_dense(ab16, M, C, A, b.qkv_wb, 3 * C, h->sw_qkv, 1); g.shift = A + b.qkv_b; TCL(g); }
-        launch_swin_window_attn(h->sw_qkv, A + b.bias_table, h->sw_a, B, b.res, C, b.heads, b.ws, b.shift, st); CKL();
-        launch_f32_to_bf16(h->sw_a, ab16, (long long)M * C, st); CKL();
+        if (!launch_swin_window_attn_mma(h->sw_qkv, A + b.bias_table, ab16, B, b.res, C, b.heads, b.ws, b.shift, st)) {
+          launch_swin_window_attn(h->sw_qkv, A + b.bias_table, h->sw_a, B, b.res, C, b.heads, b.ws, b.shift, st); CKL();
+          launch_f32_to_bf16(h->sw_a, ab16, (long long)M * C, st);
+        }
+        CKL();
         { TcGemmP g = tc_dense(ab16, M, C, A, b.proj_wb, C, y, 1); g.shift = A + b.proj_b; g.res = x; g.res_f32 = 1; g.ldr = C; TCL(g); }
         launch_layernorm_bf16out(y, nullptr, A + b.n2_g, A + b.n2_b, ab16, M, C, 0, st); CKL();
         { TcGemmP g = tc_dense(ab16, M, C, A, b.fc1_wb, 4 * C, h->sw_hidb, 0); g.shift = A + b.fc1_b; g.act = ACT_GELU; TCL(g); }

@@ -67,7 +67,7 @@ def test_swin_cuda_path_matches_reference_golden(ckpt):
 
 
 SWIN_BF16_REL_TOL = 8e-2  # bf16 mode: 24 blocks x 4 linear layers on the tcgen05 GEMM (bf16 operands), fp32 residual
-                          # stream; measured on the synthetic checkpoint: memory 0.047, logits 0.031, tokens identical
+                          # stream; measured on the synthetic checkpoint: memory 0.064, logits 0.034, tokens identical
 
 
 @pytest.mark.gpu
