@@ -167,6 +167,8 @@ __device__ __forceinline__ void epi_affine_act(float (&v)[16], const float* __re
 }  // namespace
 
 // Epilogue of one 16-column chunk of one row: folded BN / bias, activation, residual, store.
+// GELU (erff) is compiled only into the instantiation SwinTRN uses: it costs registers every other layer would pay for.
+template <bool GELU>
 __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_t (&r)[16], int m, int nb) {
       float v[16];
 #pragma unroll
@@ -175,7 +177,7 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
       if (full) {  // vectorised scale/shift, activation resolved outside the element loop
         if (p.act == ACT_SILU) epi_affine_act<ACT_SILU>(v, p.scale, p.shift, nb);
         else if (p.act == ACT_RELU) epi_affine_act<ACT_RELU>(v, p.scale, p.shift, nb);
-        else if (p.act == ACT_GELU) epi_affine_act<ACT_GELU>(v, p.scale, p.shift, nb);
+        else if (GELU && p.act == ACT_GELU) epi_affine_act<ACT_GELU>(v, p.scale, p.shift, nb);
         else epi_affine_act<ACT_NONE>(v, p.scale, p.shift, nb);
       } else {
 #pragma unroll
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
       uint32_t r[16];
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 16), r);
       const int nb = n0 + cc * 16;
-      if (m_ok && nb < p.N) epilogue_store16(p, r, m, nb);
+      if (m_ok && nb < p.N) epilogue_store16<false>(p, r, m, nb);
     }
   }
   tc_fence_before();
@@ -419,7 +421,7 @@ constexpr int WS_PROD_THREADS = WS_PROD_WARPS * 32;
 constexpr int WS_ROWS_PER_PASS = WS_PROD_THREADS / 8;   // rows covered by one pass of the producer threads
 constexpr int WS_A_PASSES = TC_BM / WS_ROWS_PER_PASS;
 
-template <int NCOLS>  // TMEM columns allocated = 2 accumulators of NCOLS/2 columns
+template <int NCOLS, bool GELU>  // TMEM columns allocated = 2 accumulators of NCOLS/2 columns
 __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p, const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW) {
   extern __shared__ unsigned char dyn_smem[];
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(WS_THREADS) tc_igemm_ws_kernel(const TcGemmP p
         uint32_t r[16];
         tmem_ld16(tacc + (uint32_t)(cc * 16), r);
         const int nb = n0 + cc * 16;
-        if (m_ok && nb < p.N) epilogue_store16(p, r, m, nb);
+        if (m_ok && nb < p.N) epilogue_store16<GELU>(p, r, m, nb);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[a]);
@@ -680,7 +682,9 @@ static int tc_launch_ws(const TcGemmP& p_in, int num_sms, cudaStream_t st) {
   const size_t smem = (size_t)WS_STAGES * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_igemm_ws_kernel<NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_igemm_ws_kernel<NCOLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_igemm_ws_kernel<NCOLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
@@ -706,7 +710,8 @@ static int tc_launch_ws(const TcGemmP& p_in, int num_sms, cudaStream_t st) {
   if (getenv("FRX_DEBUG"))
     fprintf(stderr, "[frx] tc gemm M=%d N=%d K=%d BN=%d conv=%d Cin=%d stride=%d -> %s, grid %d\n", p.M, p.N, p.K, p.BN, p.conv,
             p.Cin, p.stride, p.im2col ? "TMA im2col" : (p.conv ? "cp.async gather" : "TMA dense"), grid);
-  tc_igemm_ws_kernel<NCOLS><<<grid, WS_THREADS, smem, st>>>(p, tmA, tmW);
+  if (p.act == ACT_GELU) tc_igemm_ws_kernel<NCOLS, true><<<grid, WS_THREADS, smem, st>>>(p, tmA, tmW);
+  else tc_igemm_ws_kernel<NCOLS, false><<<grid, WS_THREADS, smem, st>>>(p, tmA, tmW);
   return 0;
 }
 
@@ -725,6 +730,12 @@ int launch_tc_igemm_ws(TcGemmP p, int num_sms, cudaStream_t st) {
 }
 
 int launch_tc_igemm(TcGemmP p, cudaStream_t st) {
+  if (p.act == ACT_GELU) {  // only the persistent kernel carries the GELU epilogue
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return launch_tc_igemm_ws(p, sms, st);
+  }
   if (p.BN == 0) p.BN = tc_pick_bn(p.N);
   {  // ring depth: 3 when three stages still leave room for >= 2 (3 for narrow tiles) CTAs per SM, else 2
     const int kb = (p.K + TC_BK - 1) / TC_BK;
