@@ -1,5 +1,7 @@
 // kernels_bf16.cu -- bandwidth-bound kernels of the bf16 trunk (NHWC bf16
 // activations, fp32 arithmetic): stem conv, depthwise 3x3, squeeze-excite.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -280,6 +282,112 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
   }
 }
 
+// Default MBConv depthwise kernel: 4 channels per thread, 32-channel chunks per CTA (8 channel groups x 16 pixel lanes =
+// 128 threads, 8 KB tile).  The generic kernel above is bound by shared-memory load wavefronts (78 % of the L1/TEX
+// peak, 40 % of them bank-conflict replays of the per-pixel tap re-reads) and its 256-thread CTAs keep too few tile
+// loads in flight; here
+//   * the 9 taps of the thread's channels live in registers, a tap costs one 8-byte shared load;
+//   * the small CTAs keep 6-8 CTAs per SM resident, so the tile loads of some overlap the arithmetic of others;
+//   * the 9-tap sum, the folded BN and the SiLU run on PACKED HALF PAIRS: the tile is converted bf16 -> fp16 once while
+//     it is staged, SiLU(v) = v (0.5 tanh(v/2) + 0.5) costs one tanh.approx.f16x2 per pair.  fp16 carries 11 significand
+//     bits through the 9-term sum -- more than the 8 bits the bf16 store keeps; activations and folded-BN outputs are
+//     O(1..100), far from the fp16 range limit.
+template <int CH>
+__global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                 __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
+                                                                 int H, int W, int C, int OH, int OW, int stride, int pad_t,
+                                                                 int pad_l, const float* __restrict__ se_w1,
+                                                                 const float* __restrict__ se_w2, int se_floats) {
+  constexpr int NT = CH * 4, G8 = CH / 8, G4 = CH / 4;
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  {  // SE FC weights -> L2 (see dwconv_se_mean_kernel)
+    const long long line = ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * NT + threadIdx.x) * 32;
+    if (line < se_floats) {
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(se_w1 + line));
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(se_w2 + line));
+    }
+  }
+  uint4* tile = reinterpret_cast<uint4*>(dw_smem);                                               // [H*W][CH/8] x 16 B
+  float (*red)[CH + 1] = reinterpret_cast<float (*)[CH + 1]>(dw_smem + (size_t)H * W * G8 * 16);  // [16][CH + 1]
+  const int n = blockIdx.x, c0 = blockIdx.y * CH;
+  const __nv_bfloat16* ip = in + (long long)n * H * W * C;
+  for (int i = threadIdx.x; i < H * W * G8; i += NT) {
+    const int px = i / G8, g = i - px * G8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c0 + g * 8 < C) {
+      float x[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(ip + (long long)px * C + c0 + g * 8)), x);
+      const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+      const __half2 h2 = __floats2half2_rn(x[4], x[5]), h3 = __floats2half2_rn(x[6], x[7]);
+      v = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                     *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+    }
+    tile[i] = v;
+  }
+  const int cg = threadIdx.x % G4, pl = threadIdx.x / G4;  // 4 channels per thread, 16 pixel lanes
+  const int c = c0 + cg * 4;
+  const bool c_ok = c < C;
+  __half2 wt[9][2], sc[2], sh[2];
+  {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 f = c_ok ? __ldg(reinterpret_cast<const float4*>(w + t * C + c)) : z;
+      wt[t][0] = __floats2half2_rn(f.x, f.y); wt[t][1] = __floats2half2_rn(f.z, f.w);
+    }
+    const float4 a = c_ok ? __ldg(reinterpret_cast<const float4*>(scale + c)) : z;
+    const float4 d = c_ok ? __ldg(reinterpret_cast<const float4*>(shift + c)) : z;
+    sc[0] = __floats2half2_rn(a.x, a.y); sc[1] = __floats2half2_rn(a.z, a.w);
+    sh[0] = __floats2half2_rn(d.x, d.y); sh[1] = __floats2half2_rn(d.z, d.w);
+  }
+  const __half2 half_ = __floats2half2_rn(0.5f, 0.5f);
+  __syncthreads();
+  const uint2* tile2 = reinterpret_cast<const uint2*>(tile);  // [H*W][CH/4] x 8 B
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  __nv_bfloat16* op = out + (long long)n * OH * OW * C;
+  if (c_ok) {
+    for (int px = pl; px < OH * OW; px += 16) {
+      const int oh = px / OW, ow = px - oh * OW;
+      __half2 acc0 = __floats2half2_rn(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = oh * stride - pad_t + kh;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = ow * stride - pad_l + kw;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            const uint2 u = tile2[(ih * W + iw) * G4 + cg];
+            acc0 = __hfma2(*reinterpret_cast<const __half2*>(&u.x), wt[kh * 3 + kw][0], acc0);
+            acc1 = __hfma2(*reinterpret_cast<const __half2*>(&u.y), wt[kh * 3 + kw][1], acc1);
+          }
+        }
+      }
+      const __half2 v0 = __hfma2(acc0, sc[0], sh[0]), v1 = __hfma2(acc1, sc[1], sh[1]);       // folded BN
+      const __half2 o0 = __hmul2(v0, __hfma2(h2tanh_approx(__hmul2(v0, half_)), half_, half_));  // SiLU = v (0.5 tanh(v/2) + 0.5)
+      const __half2 o1 = __hmul2(v1, __hfma2(h2tanh_approx(__hmul2(v1, half_)), half_, half_));
+      const float2 f0 = __half22float2(o0), f1 = __half22float2(o1);
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(f0.x, f0.y), p1 = __floats2bfloat162_rn(f1.x, f1.y);
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&p0);
+      packed.y = *reinterpret_cast<const uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(op + (long long)px * C + c) = packed;
+      // the mean is taken over the stored (bf16-rounded) activations
+      sum[0] += __uint_as_float(packed.x << 16); sum[1] += __uint_as_float(packed.x & 0xffff0000u);
+      sum[2] += __uint_as_float(packed.y << 16); sum[3] += __uint_as_float(packed.y & 0xffff0000u);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[pl][cg * 4 + j] = sum[j];
+  __syncthreads();
+  if (threadIdx.x < CH && c0 + threadIdx.x < C) {
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s2 += red[i][threadIdx.x];
+    mean[(long long)n * C + c0 + threadIdx.x] = s2 / (float)(OH * OW);
+  }
+}
+
 constexpr int SE_IMGS = 4;  // images per CTA
 constexpr int SE_ROWS = 4;  // FC1 rows per warp: each 16-byte weight load meets 4 images, each 16-byte mean load 4 rows
 // One CTA = 4 images.  FC1 (C -> R, SiLU): warp w owns rows [4w, 4w+4), lanes stride over C in float4 steps, so the
@@ -374,7 +482,19 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
     cudaFuncSetAttribute(dwconv_se_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  dwconv_se_mean_kernel<<<g, 256, smem, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l, w1, w2, R * C);
+  if (C % 8 == 0) {  // 4 channels per thread, 32-channel chunks: small CTAs, taps in registers, packed-half arithmetic
+    constexpr int CH = 32;
+    const size_t sm4 = (size_t)H * W * (CH / 8) * 16 + 16 * (CH + 1) * sizeof(float);
+    static size_t configured4 = 0;
+    if (sm4 > 48 * 1024 && sm4 > configured4) {
+      cudaFuncSetAttribute(dwconv4_se_mean_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+      configured4 = sm4;
+    }
+    dwconv4_se_mean_kernel<CH><<<dim3(B, (C + CH - 1) / CH), CH * 4, sm4, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW,
+                                                                             stride, pad_t, pad_l, w1, w2, R * C);
+  } else {
+    dwconv_se_mean_kernel<<<g, 256, smem, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW, stride, pad_t, pad_l, w1, w2, R * C);
+  }
   se_fc_kernel<<<dim3((B + SE_IMGS - 1) / SE_IMGS, 2), 512, SE_IMGS * (C + R) * sizeof(float), st>>>(mean, w1, b1, w2, b2, gate, B, C, R);
   long long total8 = (long long)B * OH * OW * (C / 8);
   se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(out, gate, total8, OH * OW, C);
