@@ -141,3 +141,22 @@ def test_bf16_stage0_conv_kernel_matches_oracle_and_gemm_path(ckpt0, spec):
         gap = (got[1][name] - got[0][name]).abs().max().item() / scale
         print("%s: halo-tile kernel vs oracle %.4f, vs im2col GEMM %.4f" % (name, err, gap))
         assert err <= 1.5e-2 and gap <= 1.5e-2
+
+
+@pytest.mark.parametrize("b,steps", [(1, 1), (1, 7), (9, 1), (17, 3)])
+def test_bf16_edge_shapes(ckpt0, model_bf16, spec, b, steps):
+    """Ragged batches (clusters with idle image slots) and single-step decodes against the fp32 mode of the same
+    library under forced decoding (bf16 rounding apart, nothing may depend on the shape)."""
+    x = synth.synth_images(spec, b, 31).cuda()
+    m32 = make_model(ckpt0).cuda().eval()
+    with torch.no_grad():
+        mem = m32.encode(x)
+        eng = m32.engine(x.device, b, steps)
+        l32 = torch.empty(b, steps, 245, device="cuda")
+        t32 = torch.empty(b, steps, dtype=torch.int64, device="cuda")
+        eng.h.call("frx_decode_greedy", mem.data_ptr(), b, steps, l32.data_ptr(), t32.data_ptr(), None,
+                   torch.cuda.current_stream().cuda_stream)
+        l16, t16 = _decode(model_bf16, mem, steps, forced=t32.cpu())
+    rel = ((l16 - l32.cpu()).abs().max() / l32.abs().max().cpu()).item()
+    assert l16.shape == (b, steps, 245) and t16.shape == (b, steps)
+    assert rel <= BF16_REL_TOL, rel
