@@ -63,3 +63,26 @@ def test_lite_cuda_path_matches_reference_golden(lite):
 def test_lite_bf16_is_rejected_loudly(lite):
     with pytest.raises(NotImplementedError):
         make_lite_model(lite[1], precision="bf16")
+
+
+@pytest.mark.gpu
+def test_lite_with_decoding_manager_matches_oracle(lite):
+    """LiteSATRN.forward with a manager attached (LiteSATRN.py:516-543) vs the oracle's restatement of the rule
+    machine (itself pinned against the reference's DecodingManager on EfficientSATRN, tests/test_oracle.py)."""
+    from conftest import load_manager_golden
+    from oracle import manager
+    spec, sd = lite
+    mg = load_manager_golden()
+    rules = manager.Rules([str(t) for t in mg["vocab"]], mg["flags"], mg["limit"])
+    model = make_lite_model(sd).cuda().eval()
+    model.decoder.manager = rules.as_manager()
+    x = synth.synth_images(spec, 3, 0)
+    with torch.no_grad():
+        mem = satrn.encoder_forward(sd, spec, x)
+        ref_probs, ref_tokens = manager.decode_greedy_managed(sd, spec, mem, 60, rules)
+        out = model(x.cuda(), satrn.expected_tokens(3, 59).cuda(), False, 0.0).cpu()
+    assert out.shape == (3, 60, 245)
+    agree = (out.argmax(-1) == ref_tokens).float().mean().item()
+    assert agree >= 0.98, agree          # a near-tie may legitimately flip (fp32 on two devices)
+    if agree == 1.0:
+        assert (out - ref_probs).abs().max().item() <= 5e-5
