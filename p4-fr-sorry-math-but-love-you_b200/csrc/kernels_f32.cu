@@ -670,17 +670,30 @@ __global__ void __launch_bounds__(256) dec_gemm_f32_kernel(const DecGemmP p) {
     const int ks = kn / 8;  // multiple of 4
     const int kb = warp * ks;
     if (n_ok) {
+      // the weight rows of the NEXT two k-groups are requested before the current group's FMAs: the loop is a chain of
+      // L2 round trips otherwise (16 per warp at K = 512).  Accumulation order is unchanged.
+      const float* wbase = p.Wt + (long long)kc * p.N + n;
+      auto ldw = [&](int k, float (&w)[4]) {
+        if (k < kb + ks) {
+          const float* wp = wbase + (long long)k * p.N;
+          w[0] = __ldg(wp); w[1] = __ldg(wp + p.N); w[2] = __ldg(wp + 2LL * p.N); w[3] = __ldg(wp + 3LL * p.N);
+        }
+      };
+      float wa[4] = {0.f, 0.f, 0.f, 0.f}, wb[4] = {0.f, 0.f, 0.f, 0.f}, wc[4] = {0.f, 0.f, 0.f, 0.f};
+      ldw(kb, wa);
+      ldw(kb + 4, wb);
       for (int k = kb; k < kb + ks; k += 4) {
-        const float* wp = p.Wt + (long long)(kc + k) * p.N + n;
-        float w0 = __ldg(wp), w1 = __ldg(wp + p.N), w2 = __ldg(wp + 2LL * p.N), w3 = __ldg(wp + 3LL * p.N);
+        ldw(k + 8, wc);
 #pragma unroll
         for (int r = 0; r < DG_BM; ++r) {
           float4 a = *reinterpret_cast<const float4*>(&As[r][k]);
-          acc[r] = fmaf(a.x, w0, acc[r]);
-          acc[r] = fmaf(a.y, w1, acc[r]);
-          acc[r] = fmaf(a.z, w2, acc[r]);
-          acc[r] = fmaf(a.w, w3, acc[r]);
+          acc[r] = fmaf(a.x, wa[0], acc[r]);
+          acc[r] = fmaf(a.y, wa[1], acc[r]);
+          acc[r] = fmaf(a.z, wa[2], acc[r]);
+          acc[r] = fmaf(a.w, wa[3], acc[r]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { wa[i] = wb[i]; wb[i] = wc[i]; }
       }
     }
     __syncthreads();
