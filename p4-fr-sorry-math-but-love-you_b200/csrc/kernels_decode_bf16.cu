@@ -40,18 +40,28 @@ namespace frx {
 
 namespace {
 
-constexpr int CL = DEC_CLUSTER;  // CTAs per cluster
-constexpr int D = 256;           // decoder width this kernel is specialised for
+// The kernel is specialised at compile time for one decoder geometry; the default is EfficientSATRN's (hidden 256,
+// 8 heads, filter 1024 -> clusters of 8 CTAs).  kernels_decode_bf16_d128.cu re-includes this file for LiteSATRN's
+// (hidden 128, 4 heads, filter 512 -> clusters of 4).  Head width is 32 and one CTA owns one head in both.
+#ifndef FRX_DEC_D
+#define FRX_DEC_D 256
+#define FRX_DEC_FF 1024
+#define FRX_DEC_NAME(x) x
+#endif
+constexpr int D = FRX_DEC_D;     // decoder width
 constexpr int HD = 32;
-constexpr int H = D / HD;        // 8 heads = CL
-constexpr int FF = DEC_FMAX;
+constexpr int H = D / HD;        // heads = CTAs per cluster
+constexpr int CL = H;
+constexpr int FF = FRX_DEC_FF;
+constexpr int VP = 256;          // vocabulary columns, padded
+constexpr int NG = VP / CL / 8;  // generator tiles per CTA
+static_assert(D / CL == 32 && FF / CL == 128 && CL <= 8 && (8 % CL) == 0, "column slices: 32 of D, 128 of FF per CTA");
 constexpr int APAD = 8;          // bf16 padding of the A-operand rows (conflict-free ldmatrix)
 constexpr int FPAD = 4;          // fp32 padding of rows that are accessed 16 bytes per lane, 8 rows at a time
 constexpr int NIMG = DEC_IMG;    // images per cluster = warps per CTA (warp w <-> image w)
 constexpr int NTHR = NIMG * 32;
 constexpr int RED_FLOATS = 2048;  // K-split reduction region: KS * NT * 32 lanes * 2 floats, NT <= 16
 static_assert(NIMG == 8, "the kernel maps MMA rows 0..7 to the cluster's images");
-static_assert(H == CL, "one head per CTA of the cluster");
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -418,8 +428,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // ===========================================================================
 // The persistent decode kernel
 // ===========================================================================
-__global__ void __cluster_dims__(DEC_CLUSTER, 1, 1) __launch_bounds__(NTHR, 2)
-dec_cluster_bf16_kernel(const DecClusterP p) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 2)
+FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   cg::cluster_group cl = cg::this_cluster();
@@ -435,10 +445,10 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
   constexpr size_t WT = (size_t)KPD * 32;   // uint4 per tile for K = D
   constexpr int KS = 2;                     // every stage splits K over two warps
   // weight fragments (uint4 per lane) requested before the wait that precedes a stage
-  constexpr int PF_A = 6;                      // of 12
+  constexpr int PF_A = 6;                      // of 12 (D = 256) / 6 (D = 128)
   constexpr int PF_S = GC<4, KPD, KS>::TOT;    // 4
-  constexpr int PF_E = 8;                      // of 16
-  constexpr int PF_F = 8;                      // of 16
+  constexpr int PF_E = GC<16, KPD, KS>::TOT < 8 ? GC<16, KPD, KS>::TOT : 8;
+  constexpr int PF_F = GC<4, KPF, KS>::TOT < 8 ? GC<4, KPF, KS>::TOT : 8;
 
   if (tid == 0) {
 #pragma unroll
@@ -469,7 +479,8 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
   int rsel = 0;
   auto next_red = [&]() -> float* { rsel ^= 1; return s.red[rsel]; };
   float* const logit_s = reinterpret_cast<float*>(&s.abf2[0][0]);  // [NIMG][LGS] fp32 view (abf2 is idle then)
-  constexpr int LGS = 256 + FPAD;
+  constexpr int LGS = VP + FPAD;
+  static_assert(NIMG * LGS * 4 <= NIMG * (FF + APAD) * 2, "the fp32 logits view must fit in abf2");
 
   const bool profiling = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
   if (profiling) for (int i = 0; i < 16; ++i) s.prof[i] = 0;
@@ -488,14 +499,18 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
   // all-gather of this warp's attention output (head r, image `warp`) into every CTA's obf: the eight gid
   // groups of the warp hold identical copies, group g serves destination CTA g
   auto store_attn = [&](uint32_t sb, const float (&o)[8]) {
-    const uint32_t dst = (uint32_t)(lane >> 2), rb = mapa_u32(sb, dst);
-    const uint32_t la = mapa_u32(smem_u32(&s.obf[warp][r * HD + 2 * (lane & 3)]), dst);
+    const uint32_t dst = (uint32_t)(lane >> 2);
+    if (dst < (uint32_t)CL) {
+      const uint32_t rb = mapa_u32(sb, dst);
+      const uint32_t la = mapa_u32(smem_u32(&s.obf[warp][r * HD + 2 * (lane & 3)]), dst);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) st_async_b32(la + nt * 16, pack_bf16(o[2 * nt], o[2 * nt + 1]), rb);
+      for (int nt = 0; nt < 4; ++nt) st_async_b32(la + nt * 16, pack_bf16(o[2 * nt], o[2 * nt + 1]), rb);
+    }
   };
   // epilogue of a "pre-LayerNorm" stage: 8 columns of row `row`, + bias (+ ReLU) + residual, sent to CTA `sub`
   auto pre_epi = [&](uint32_t sb, const float* bias, bool relu) {
     return [&, sb, bias, relu](int tile, int row, float (&v)[8], int sub) {
+      if (sub >= CL) return;  // 8 threads share a unit, one per destination CTA
       const int col = r * 32 + tile * 8;
       const float4 b0 = ldg4(bias + col), b1 = ldg4(bias + col + 4);
       const float4 x0 = *reinterpret_cast<const float4*>(&s.xres[row][col]), x1 = *reinterpret_cast<const float4*>(&s.xres[row][col + 4]);
@@ -556,7 +571,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
         gemm2<12, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
         __syncthreads();
         mark(0);
-        stage_begin(NIMG * 512u);
+        stage_begin(NIMG * D * 2u);
         const uint32_t sb = stage_bar();
         float o[8];
         attend_mma(kvst, &s.qh[warp][0], p.kself + base, p.vself + base, n_hist, &s.kcur[warp][0], &s.vcur[warp][0], inv_temp, o);
@@ -570,7 +585,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       stage_end();
       mark(3);
       // ---- B: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
-      stage_begin(NIMG * 1024u);
+      stage_begin(NIMG * D * 4u);
       gemm2<4, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o + (size_t)r * 4 * WT, pol, pre_b, pre_epi(stage_bar(), W.b_o, false));
       mark(4);
       const LnParams lnp1 = load_ln(W.ln1_g, W.ln1_b);
@@ -595,7 +610,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                           });
         __syncthreads();
         mark(4);
-        stage_begin(NIMG * 512u);
+        stage_begin(NIMG * D * 2u);
         const uint32_t sb = stage_bar();
         float o[8];
         if (mine) {
@@ -611,7 +626,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       stage_end();
       mark(3);
       // ---- D: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
-      stage_begin(NIMG * 1024u);
+      stage_begin(NIMG * D * 4u);
       gemm2<4, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o2 + (size_t)r * 4 * WT, pol, pre_d, pre_epi(stage_bar(), W.b_o2, false));
       mark(4);
       const LnParams lnp2 = load_ln(W.ln2_g, W.ln2_b);
@@ -623,7 +638,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       mark(6);
       // ---- E: ff = relu(linear0(w)); CTA r owns hidden units [128r, 128r+128) ------------------------
       {
-        stage_begin(NIMG * 2048u);
+        stage_begin(NIMG * FF * 2u);
         const uint32_t sb = stage_bar();
         gemm2<16, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_f0 + (size_t)r * 16 * WT, pol, pre_e,
                            [&](int tile, int row, float (&v)[8], int sub) {
@@ -635,8 +650,8 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                                                         pack_bf16(fmaxf(v[6] + b1.z, 0.f), fmaxf(v[7] + b1.w, 0.f)));
                              const uint32_t la = smem_u32(&s.abf2[row][col]);
 #pragma unroll
-                             for (int d = 0; d < 4; ++d)
-                               st_async_v4(mapa_u32(la, (uint32_t)(sub * 4 + d)), o, mapa_u32(sb, (uint32_t)(sub * 4 + d)));
+                             for (int d = 0; d < CL / 2; ++d)
+                               st_async_v4(mapa_u32(la, (uint32_t)(sub * (CL / 2) + d)), o, mapa_u32(sb, (uint32_t)(sub * (CL / 2) + d)));
                            });
         mark(8);
       }
@@ -644,16 +659,17 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       stage_end();
       mark(5);
       // ---- F: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
-      stage_begin(NIMG * 1024u);
+      stage_begin(NIMG * D * 4u);
       gemm2<4, KPF, KS>(next_red(), &s.abf2[0][0], LDA2, W.w_f1 + (size_t)r * 4 * KPF * 32, pol, pre_f, pre_epi(stage_bar(), W.b_f1, true));
       mark(9);
       const LnParams lnp3 = load_ln(W.ln3_g, W.ln3_b);
       const bool last_layer = l + 1 >= L;
       // next consumer of y: the next layer's q|k|v (12 tiles), or the generator (4 tiles); both sit behind
       // the 8 cache tiles in w_next
-      WPre<PF_S> pre_g;
+      constexpr int PF_G = GC<NG, KPD, KS>::TOT;
+      WPre<PF_G> pre_g;
       if (!last_layer) pre_a = prefetch_w<12, KPD, KS, PF_A>(W.w_next + ((size_t)r * 20 + 8) * WT, pol);
-      else pre_g = prefetch_w<4, KPD, KS, PF_S>(W.w_next + ((size_t)r * 12 + 8) * WT, pol);
+      else pre_g = prefetch_w<NG, KPD, KS, PF_G>(W.w_next + ((size_t)r * (8 + NG) + 8) * WT, pol);
       stage_end();
       mark(5);
       layernorm_rows(s, lnp3);
@@ -661,11 +677,12 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
       mark(6);
       if (last_layer) {
         // ---- G: vocabulary logits (V columns padded to 256; CTA r owns [32r, 32r+32)) ------------------
-        stage_begin(NIMG * 1024u);
+        stage_begin(NIMG * VP * 4u);
         const uint32_t sb = stage_bar();
-        gemm2<4, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_next + ((size_t)r * 12 + 8) * WT, pol, pre_g,
+        gemm2<NG, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_next + ((size_t)r * (8 + NG) + 8) * WT, pol, pre_g,
                           [&](int tile, int row, float (&v)[8], int sub) {
-                            const int col = r * 32 + tile * 8;
+                            if (sub >= CL) return;
+                            const int col = r * (VP / CL) + tile * 8;
                             const float* gb = W.b_next + 2 * D;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] += col + i < V ? __ldg(gb + col + i) : 0.f;
@@ -682,7 +699,7 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
                           });
         mark(4);
         pre_a = prefetch_w<12, KPD, KS, PF_A>(p.w_first + (size_t)r * 12 * WT, pol);
-        cache_rows(l, t, W.w_next + (size_t)r * 12 * WT, W.b_next);
+        cache_rows(l, t, W.w_next + (size_t)r * (8 + NG) * WT, W.b_next);
         mark(2);
         stage_end();
         mark(5);
@@ -727,14 +744,14 @@ dec_cluster_bf16_kernel(const DecClusterP p) {
   if (profiling) for (int i = 0; i < 16; ++i) p.prof[i] = s.prof[i];
 }
 
-size_t dec_cluster_smem_bytes() { return sizeof(Smem); }
+size_t FRX_DEC_NAME(dec_cluster_smem_bytes)() { return sizeof(Smem); }
 
 // One launch decodes up to DEC_MAX_CLUSTERS clusters (all co-resident: two CTAs per SM); larger batches
 // are decoded in consecutive launches over image ranges.
-int launch_dec_cluster_bf16(const DecClusterP& p0, cudaStream_t st) {
+int FRX_DEC_NAME(launch_dec_cluster_bf16)(const DecClusterP& p0, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dec_cluster_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaError_t e = cudaFuncSetAttribute(FRX_DEC_NAME(dec_cluster_bf16_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -746,7 +763,7 @@ int launch_dec_cluster_bf16(const DecClusterP& p0, cudaStream_t st) {
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, dec_cluster_bf16_kernel, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, FRX_DEC_NAME(dec_cluster_bf16_kernel), &cfg);
     fprintf(stderr, "[frx] decode kernel: clusters of %d CTAs x %d threads, max co-resident clusters = %d (%s), smem %zu B\n",
             CL, NTHR, n, cudaGetErrorString(e), sizeof(Smem));
   }
@@ -755,11 +772,12 @@ int launch_dec_cluster_bf16(const DecClusterP& p0, cudaStream_t st) {
     p.img_base = base;
     const int n = p0.B - base < DEC_MAX_CLUSTERS * NIMG ? p0.B - base : DEC_MAX_CLUSTERS * NIMG;
     const int clusters = (n + NIMG - 1) / NIMG;
-    dec_cluster_bf16_kernel<<<clusters * CL, NTHR, sizeof(Smem), st>>>(p);
+    FRX_DEC_NAME(dec_cluster_bf16_kernel)<<<clusters * CL, NTHR, sizeof(Smem), st>>>(p);
   }
   return 0;
 }
 
+#ifndef FRX_DEC_VARIANT
 // ===========================================================================
 // cross K/V: fp32 [B*S][L*2*D] (k_l | v_l per layer) -> bf16 head-major
 // [L][B][H][S][32] caches
@@ -784,5 +802,7 @@ void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc
   long long total = (long long)B * S * L * 2 * Dm;
   cross_to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, kc, vc, B, S, L, Dm);
 }
+
+#endif  // FRX_DEC_VARIANT
 
 }  // namespace frx

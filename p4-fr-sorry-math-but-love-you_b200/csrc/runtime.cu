@@ -186,8 +186,6 @@ extern "C" int frx_create(const frx_config* cfg, frx_handle** out) {
     return fail(h, "decoder head_dim must be 32 or 64");
   if (cfg->dec_hidden > 512) return fail(h, "decoder hidden_dim > 512 not supported");
   if (cfg->max_batch <= 0 || cfg->max_steps <= 0) return fail(h, "max_batch/max_steps must be positive");
-  if (cfg->network == FRX_NET_LITE_SATRN && cfg->precision != FRX_PREC_FP32)
-    return fail(h, "LiteSATRN is built for the fp32 mode only (the bf16 kernels are specialised for EfficientSATRN's dimensions)");
   return 0;
 }
 
@@ -552,11 +550,11 @@ static inline uint32_t bf16_bits(float f) {  // round-to-nearest-even, like __fl
 // [cta r][tile][k-pair kp][lane] -> uint4 {b0b1(k-step 2kp), b2b3(2kp), b0b1(2kp+1), b2b3(2kp+1)}.
 // rowptr(r, tile, gid) returns the K-float weight row of output column (tile, gid) of CTA r, or nullptr.
 template <class F>
-static size_t pack_frag_stage(ArenaBuilder& ab, int NT, int K, F rowptr) {
+static size_t pack_frag_stage(ArenaBuilder& ab, int CL, int NT, int K, F rowptr) {
   const int KP = K / 32;
-  size_t off = ab.add(nullptr, (size_t)DEC_CLUSTER * NT * KP * 32 * 4);
+  size_t off = ab.add(nullptr, (size_t)CL * NT * KP * 32 * 4);
   uint32_t* d = reinterpret_cast<uint32_t*>(ab.at(off));
-  for (int r = 0; r < DEC_CLUSTER; ++r)
+  for (int r = 0; r < CL; ++r)
     for (int tile = 0; tile < NT; ++tile)
       for (int kp = 0; kp < KP; ++kp)
         for (int lane = 0; lane < 32; ++lane) {
@@ -639,8 +637,12 @@ static void pack_encoder_bf16(frx_handle* h, ArenaBuilder& ab) {
 static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
   const frx_config& c = h->cfg;
   const int D = c.dec_hidden, F = c.dec_filter, V = c.num_classes, L = c.dec_layers;
-  h->dec_cluster_ok = !(D != 256 || F != DEC_FMAX || c.dec_heads != 8 || L > 4 || V > 256);
+  // the persistent cluster kernel exists for two geometries: EfficientSATRN (256 / 8 heads / 1024) and LiteSATRN
+  // (128 / 4 heads / 512); one CTA per 32-wide head, 32 columns of D and 128 of F per CTA
+  const bool geo = (D == 256 && F == 1024 && c.dec_heads == 8) || (D == 128 && F == 512 && c.dec_heads == 4);
+  h->dec_cluster_ok = geo && L <= 4 && V <= 256;
   if (!h->dec_cluster_ok) return 0;  // e.g. SwinTRN (512 / 512 / 4 layers): the greedy loop stays on the fp32 step kernels
+  const int CL = c.dec_heads, NG = 256 / CL / 8;
   auto W = [&](int l, const char* name) -> const float* {
     return find(h, "decoder.attention_layers." + std::to_string(l) + "." + name + ".weight")->f.data();
   };
@@ -657,7 +659,7 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
     Wl.wb_sqkv = pack_bf16_copy(ab, Wl.w_sqkv, (size_t)3 * D * D);
   }
   h->dpack.assign(L, DecPackW{});
-  h->dpack_first = pack_frag_stage(ab, 12, D, [&](int r, int tile, int gid) {
+  h->dpack_first = pack_frag_stage(ab, CL, 12, D, [&](int r, int tile, int gid) {
     const char* names[3] = {"self_attention_layer.q_linear", "self_attention_layer.k_linear", "self_attention_layer.v_linear"};
     return W(0, names[tile >> 2]) + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
   });
@@ -665,14 +667,14 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
     DecPackW& P = h->dpack[l];
     auto square = [&](const char* name, int K) {
       const float* w = W(l, name);
-      return pack_frag_stage(ab, 4, K, [=](int r, int tile, int gid) { return w + (size_t)(r * 32 + tile * 8 + gid) * K; });
+      return pack_frag_stage(ab, CL, 4, K, [=](int r, int tile, int gid) { return w + (size_t)(r * 32 + tile * 8 + gid) * K; });
     };
     P.w_o = square("self_attention_layer.out_linear", D);
     P.w_q2 = square("attention_layer.q_linear", D);
     P.w_o2 = square("attention_layer.out_linear", D);
     P.w_f1 = square("feedforward_layer.linear1", F);
     const float* f0 = W(l, "feedforward_layer.linear0");
-    P.w_f0 = pack_frag_stage(ab, 16, D, [=](int r, int tile, int gid) {  // CTA r: hidden units [128r, 128r+128)
+    P.w_f0 = pack_frag_stage(ab, CL, 16, D, [=](int r, int tile, int gid) {  // CTA r: hidden units [128r, 128r+128)
       return f0 + (size_t)(r * 128 + tile * 8 + gid) * D;
     });
     const float* wk = W(l, "self_attention_layer.k_linear");
@@ -681,14 +683,14 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
       const float* nq = W(l + 1, "self_attention_layer.q_linear");
       const float* nk = W(l + 1, "self_attention_layer.k_linear");
       const float* nv = W(l + 1, "self_attention_layer.v_linear");
-      P.w_next = pack_frag_stage(ab, 20, D, [=](int r, int tile, int gid) {
+      P.w_next = pack_frag_stage(ab, CL, 20, D, [=](int r, int tile, int gid) {
         const float* segs[5] = {wk, wv, nq, nk, nv};
         return segs[tile >> 2] + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
       });
     } else {
-      P.w_next = pack_frag_stage(ab, 12, D, [=](int r, int tile, int gid) -> const float* {
+      P.w_next = pack_frag_stage(ab, CL, 8 + NG, D, [=](int r, int tile, int gid) -> const float* {
         if (tile < 8) return (tile < 4 ? wk : wv) + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
-        int n = r * 32 + (tile - 8) * 8 + gid;
+        int n = r * (256 / CL) + (tile - 8) * 8 + gid;
         return n < V ? gen + (size_t)n * D : nullptr;
       });
     }
@@ -1170,7 +1172,8 @@ extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* 
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(c.device));
   if (c.network == FRX_NET_SWIN) return encode_swin(h, images, B, memory, st);
-  if (c.precision == FRX_PREC_BF16 && !h->opt_enc_fp32) return encode_bf16(h, images, B, memory, st);
+  if (c.precision == FRX_PREC_BF16 && !h->opt_enc_fp32 && c.network == FRX_NET_EFFICIENT_SATRN)
+    return encode_bf16(h, images, B, memory, st);  // LiteSATRN in bf16 mode: fp32 ShallowCNN + encoder layer, bf16 decoder
   const float* A = h->arena;
   float* t = nullptr;
   if (c.network == FRX_NET_LITE_SATRN) {
@@ -1396,7 +1399,7 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
   p.prof = h->opt_prof ? h->prof : nullptr;
   if (p.prof) CK(cudaMemsetAsync(h->prof, 0, 16 * 8, st));
   if (h->opt_timing) CK(cudaEventRecord(h->ev[3], st));
-  int rc = launch_dec_cluster_bf16(p, st);
+  int rc = D == 128 ? launch_dec_cluster_bf16_d128(p, st) : launch_dec_cluster_bf16(p, st);
   if (rc) return fail(h, "decode cluster kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
   CKL();
   if (h->opt_timing) CK(cudaEventRecord(h->ev[4], st));

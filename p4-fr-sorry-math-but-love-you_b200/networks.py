@@ -285,7 +285,8 @@ class EfficientSATRN(_FrxModule):
 class LiteSATRN(EfficientSATRN):
     """networks/LiteSATRN.py:548-590 -- the knowledge-distillation student: a 4-conv ShallowCNN trunk (1/16
     resolution, :21-70) in front of the same SATRN encoder / decoder classes; greedy decoding only (the
-    reference's LiteSATRN has no beam_search).  fp32 mode."""
+    reference's LiteSATRN has no beam_search).  precision="bf16" keeps the fp32 ShallowCNN / encoder layer and runs the
+    whole greedy loop in the persistent cluster kernel (128-wide geometry: clusters of 4 CTAs, one per head)."""
 
     _network = 1
     _down = 16
@@ -293,8 +294,6 @@ class LiteSATRN(EfficientSATRN):
     def __init__(self, FLAGS, train_dataset, checkpoint=None, decoding_manager=None, *,
                  precision="fp32", max_batch=None, max_steps=None):
         nn.Module.__init__(self)
-        if precision != "fp32":
-            raise NotImplementedError("LiteSATRN runs in the fp32 mode only")
         self._setup(FLAGS, train_dataset, precision, max_batch, max_steps)
         self.encoder = layout.build_param_tree(layout.lite_encoder_shapes(self._dims), "encoder.")
         self.decoder = layout.build_param_tree(layout.decoder_shapes(self._dims), "decoder.")

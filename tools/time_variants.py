@@ -29,10 +29,11 @@ def timed(model, x, steps):
 
 lspec = satrn.ModelSpec(**LITE_SPEC)
 lsd = synth.synth_state_dict(lspec, 0, calib_batch=4)
-for b in (64, 256):
-    m = make_lite_model(lsd, max_batch=b, max_steps=231).cuda().eval()
+for prec in ("fp32", "bf16"):
+    b = 256
+    m = make_lite_model(lsd, precision=prec, max_batch=b, max_steps=231).cuda().eval()
     ms = timed(m, synth.synth_images(lspec, b, 0).cuda(), 231)
-    print("LiteSATRN fp32  B=%3d: %.1f ms per batch -> %.0f images/s" % (b, ms, b / ms * 1e3), flush=True)
+    print("LiteSATRN %s  B=%3d: %.1f ms per batch -> %.0f images/s" % (prec, b, ms, b / ms * 1e3), flush=True)
     del m
 ck = swin.synth_state_dict(swin.swin_spec(), 0)
 for prec in ("fp32", "bf16"):
