@@ -75,6 +75,9 @@ void launch_layernorm_bf16out(const float* x, const float* res, const float* gam
 void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st);
 void launch_conv3x3_c24_bf16(const __nv_bfloat16* in, const void* wfrag, const float* scale, const float* shift,
                              __nv_bfloat16* out, int B, int H, int W, int add_res, cudaStream_t st);
+void launch_lite_conv0_pool_bf16(const float* in, const float* w, const float* scale, const float* shift, __nv_bfloat16* out,
+                                 int B, int Cin, int H, int W, int Cout, cudaStream_t st);
+void launch_maxpool2_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, float* out_f32, int B, int H, int W, int C, cudaStream_t st);
 bool launch_enc_attn_mma_bf16(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st);
 
 // bf16 persistent decode (kernels_decode_bf16.cu)

@@ -700,4 +700,105 @@ void launch_conv3x3_c24_bf16(const __nv_bfloat16* in, const void* wfrag, const f
   conv3x3_c24_mma_kernel<<<B * tiles, 256, 0, st>>>(in, reinterpret_cast<const uint2*>(wfrag), scale, shift, out, H, W, add_res);
 }
 
+// ---------------------------------------------------------------------------
+// LiteSATRN ShallowCNN in bf16 mode (networks/LiteSATRN.py:21-70).
+// Layer 0 fused: conv3x3 p1 (Cin input channels, NCHW fp32) + folded BN + ReLU + maxpool 2x2 -> NHWC bf16 at half
+// resolution.  The full-resolution activation (128 channels x 128 x 256 per image) never exists in memory.
+// One thread = one pooled pixel x 8 output channels; the 4x4 input patch per input channel is read once.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lite_conv0_pool_bf16_kernel(const float* __restrict__ in, const float* __restrict__ w,  // [O][I][3][3]
+                                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                   __nv_bfloat16* __restrict__ out, int B, int Cin, int H, int W, int Cout) {
+  extern __shared__ float ws0[];
+  for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) ws0[i] = w[i];
+  float* ssc = ws0 + Cout * Cin * 9;
+  float* ssh = ssc + Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+  __syncthreads();
+  const int OH = H / 2, OW = W / 2, C8 = Cout / 8;
+  const long long total = (long long)B * OH * OW * C8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co0 = (int)(idx % C8) * 8;
+  const long long pix = idx / C8;
+  const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+  float acc[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    float x[4][4];  // input rows 2oh-1 .. 2oh+2, columns 2ow-1 .. 2ow+2 (zero padding 1)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int ih = 2 * oh - 1 + a, iw = 2 * ow - 1 + b;
+        x[a][b] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(in + (((long long)n * Cin + ci) * H + ih) * W + iw) : 0.f;
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wp = ws0 + ((co0 + j) * Cin + ci) * 9;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float wv = wp[kh * 3 + kw];
+          acc[0][j] = fmaf(x[kh][kw], wv, acc[0][j]);
+          acc[1][j] = fmaf(x[kh][kw + 1], wv, acc[1][j]);
+          acc[2][j] = fmaf(x[kh + 1][kw], wv, acc[2][j]);
+          acc[3][j] = fmaf(x[kh + 1][kw + 1], wv, acc[3][j]);
+        }
+    }
+  }
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float s = ssc[co0 + j], t = ssh[co0 + j];
+    const float m = fmaxf(fmaxf(fmaf(acc[0][j], s, t), fmaf(acc[1][j], s, t)), fmaxf(fmaf(acc[2][j], s, t), fmaf(acc[3][j], s, t)));
+    o[j] = fmaxf(m, 0.f);  // relu(max(.)) == max(relu(.))
+  }
+  *reinterpret_cast<uint4*>(out + pix * Cout + co0) = pack8(o);
+}
+
+void launch_lite_conv0_pool_bf16(const float* in, const float* w, const float* scale, const float* shift, __nv_bfloat16* out,
+                                 int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
+  const long long total = (long long)B * (H / 2) * (W / 2) * (Cout / 8);
+  const int smem = (Cout * Cin * 9 + 2 * Cout) * sizeof(float);
+  lite_conv0_pool_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(in, w, scale, shift, out, B, Cin, H, W, Cout);
+}
+
+// Max-pool 2x2 stride 2, NHWC bf16 (8 channels per thread); out_f32 != nullptr writes fp32 instead (the last pool feeds the
+// fp32 positional-encoding / encoder-layer kernels).
+__global__ void __launch_bounds__(256) maxpool2_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                            float* __restrict__ out_f32, int B, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  const long long total = (long long)B * OH * OW * C8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C8) * 8;
+  const long long pix = idx / C8;
+  const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+  const __nv_bfloat16* base = in + (((long long)n * H + oh * 2) * W + ow * 2) * C + c;
+  float a[8], b[8], d[8], e[8], o[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base)), a);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base + C)), b);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long long)W * C)), d);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long long)W * C + C)), e);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(d[j], e[j]));
+  if (out_f32) {
+    float4* op = reinterpret_cast<float4*>(out_f32 + pix * C + c);
+    op[0] = make_float4(o[0], o[1], o[2], o[3]);
+    op[1] = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+    *reinterpret_cast<uint4*>(out + pix * C + c) = pack8(o);
+  }
+}
+
+void launch_maxpool2_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, float* out_f32, int B, int H, int W, int C, cudaStream_t st) {
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, out_f32, B, H, W, C);
+}
+
 }  // namespace frx

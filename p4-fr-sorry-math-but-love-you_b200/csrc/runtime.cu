@@ -723,6 +723,8 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
   if (want_dec && c.precision == FRX_PREC_BF16 && pack_decoder_bf16(h, ab)) return 1;
   if (c.precision == FRX_PREC_BF16) {
     if (want_enc && c.network == FRX_NET_EFFICIENT_SATRN) pack_encoder_bf16(h, ab);
+    if (want_enc && c.network == FRX_NET_LITE_SATRN)
+      for (int i = 1; i < 4; ++i) h->lite[i].wb = pack_bf16_copy(ab, h->lite[i].w, (size_t)h->lite[i].cout * 9 * h->lite[i].cin);
     if (want_enc && c.network == FRX_NET_SWIN) {
       for (SwinBlockW& b : h->sw_blocks) {
         const size_t C = b.dim;
@@ -1143,6 +1145,34 @@ static int run_trunk_lite(frx_handle* h, const float* images, int B, float** out
   int H = c.height, W = c.width;
   float* x = h->act[0];
   float* y = h->act[1];
+  if (c.precision == FRX_PREC_BF16 && !h->opt_enc_fp32 && h->lite[1].wb) {
+    // bf16 mode: layer 0 fused with its max-pool (fp32 arithmetic on the single-channel image, bf16 NHWC out), layers
+    // 1-3 as implicit GEMMs on the tcgen05 kernel (bf16 in / out, folded BN + ReLU in the epilogue), bf16 max-pools;
+    // the last pool writes fp32 for the positional encoding / encoder layer that follow.
+    typedef __nv_bfloat16 bf;
+    bf* xb = (bf*)h->act[0];
+    bf* yb = (bf*)h->act[1];
+    const LiteConvW& L0 = h->lite[0];
+    launch_lite_conv0_pool_bf16(images, A + L0.w, A + L0.sc, A + L0.sh, yb, B, L0.cin, H, W, L0.cout, st); CKL();
+    H /= 2; W /= 2;
+    for (int i = 1; i < 4; ++i) {
+      const LiteConvW& L = h->lite[i];
+      int OH, OW;
+      TcGemmP g = tc_conv(yb, B, H, W, L.cin, A, L.wb, L.cout, 3, 1, xb, &OH, &OW);
+      g.scale = A + L.sc; g.shift = A + L.sh; g.act = ACT_RELU;
+      TCL(g);
+      const bool last = i == 3;
+      // the last pooled map goes to the second half of act[1] as fp32 (the bf16 input of this layer sits in the first half)
+      float* f32_out = last ? h->act[1] + (size_t)B * (H / 2) * (W / 2) * L.cout : nullptr;
+      launch_maxpool2_bf16(xb, yb, f32_out, B, H, W, L.cout, st); CKL();
+      H /= 2; W /= 2;
+      if (last) y = f32_out;
+    }
+    if (H != h->feat_h || W != h->feat_w) return fail(h, "trunk output %dx%d != expected %dx%d", H, W, h->feat_h, h->feat_w);
+    if (tap(h, "lite_conv3", y, B, H, W, h->lite[3].cout, st)) return 1;
+    *out = y;
+    return 0;
+  }
   for (int i = 0; i < 4; ++i) {
     const LiteConvW& L = h->lite[i];
     if (i == 0) {

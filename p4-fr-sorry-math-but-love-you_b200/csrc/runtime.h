@@ -29,7 +29,7 @@ struct BlockW {
   size_t wb_a_pad = 0;         // 3x3 convs: bf16 [N][9][64] (channels zero-padded) for the TMA-im2col path
   size_t w_frag24 = 0;         // 24 -> 24 3x3 convs: mma.m16n8k16 B fragments [14][3][32] x {b0, b1} (conv3x3_c24_mma_kernel)
 };
-struct LiteConvW { int cin, cout; size_t w, sc, sh; };
+struct LiteConvW { int cin, cout; size_t w, sc, sh; size_t wb = 0; };  // wb: bf16 copy of w (layers 1-3, bf16 mode)
 struct EncLayerW {
   size_t ln_g, ln_b, w_qkv, b_qkv, w_o, b_o;
   size_t w_c0, sc_c0, sh_c0, w_dw, sc_dw, sh_dw, w_c1, sc_c1, sh_c1;

@@ -82,28 +82,30 @@ def test_lite_with_decoding_manager_matches_oracle(lite):
         assert (out - ref_probs).abs().max().item() <= 5e-5
 
 
-LITE_BF16_REL_TOL = 4e-2  # bf16 decoder (weights, KV cache) on an fp32 encoder: max |logit - ref| / max |ref|, forced decoding
+LITE_BF16_MEM_TOL = 3e-2   # bf16 mode: ShallowCNN layers 1-3 on the tcgen05 GEMM with bf16 activations (memory, max rel)
+LITE_BF16_REL_TOL = 8e-2   # + bf16 decoder (weights, KV cache): max |logit - ref| / max |ref| under forced decoding
 
 
 @pytest.mark.gpu
-def test_lite_bf16_decoder_within_tolerance(lite):
-    """bf16 mode: the greedy loop runs in the persistent cluster kernel compiled for LiteSATRN's decoder geometry
-    (hidden 128, 4 heads, filter 512 -> clusters of 4 CTAs); encoder fp32, so the memory is the fp32 one."""
+def test_lite_bf16_mode_within_tolerance(lite):
+    """bf16 mode: fused conv0 + pool, tcgen05 convs, and the greedy loop in the persistent cluster kernel compiled for
+    LiteSATRN's decoder geometry (hidden 128, 4 heads, filter 512 -> clusters of 4 CTAs)."""
     spec, sd = lite
     g = _golden()
     model = make_lite_model(sd, precision="bf16").cuda().eval()
     x = synth.synth_images(spec, 3, 0).cuda()
     with torch.no_grad():
         mem = model.encode(x)
-        assert np.abs(mem.cpu().numpy() - g["memory"]).max() <= 1e-4 * np.abs(g["memory"]).max()
         steps = g["logits"].shape[1]
         logits, _ = model.greedy(x, steps, forced=torch.from_numpy(g["tokens"]))
         _, free = model.greedy(x, steps)
+    rel_mem = np.abs(mem.cpu().numpy() - g["memory"]).max() / np.abs(g["memory"]).max()
     ref = torch.from_numpy(g["logits"])
     rel = ((logits.cpu() - ref).abs().max() / ref.abs().max()).item()
     agree_forced = (logits.cpu().argmax(-1) == ref.argmax(-1)).float().mean().item()
     agree_free = (free.cpu() == torch.from_numpy(g["tokens"])).float().mean().item()
-    print("lite bf16: forced max rel logit error %.4f, per-step argmax agreement %.4f, free-running token agreement %.4f"
-          % (rel, agree_forced, agree_free))
+    print("lite bf16: memory max rel %.4f, forced max rel logit error %.4f, per-step argmax agreement %.4f, "
+          "free-running token agreement %.4f" % (rel_mem, rel, agree_forced, agree_free))
+    assert rel_mem <= LITE_BF16_MEM_TOL
     assert rel <= LITE_BF16_REL_TOL
-    assert agree_forced >= 0.95
+    assert agree_forced >= 0.9
