@@ -84,6 +84,7 @@ bool launch_enc_attn_mma_bf16(const float* qkv, __nv_bfloat16* out, int B, int S
 size_t dec_cluster_smem_bytes();
 int launch_dec_cluster_bf16(const DecClusterP& p, cudaStream_t st);       // hidden 256, 8 heads, filter 1024 (clusters of 8)
 int launch_dec_cluster_bf16_d128(const DecClusterP& p, cudaStream_t st);  // hidden 128, 4 heads, filter 512 (clusters of 4)
+int launch_dec_cluster_bf16_p2(const DecClusterP& p, cudaStream_t st);    // hidden 256, two heads per CTA (clusters of 4 x 16 warps)
 void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc, int B, int S, int L, int Dm,
                           cudaStream_t st);
 

@@ -48,19 +48,27 @@ namespace {
 #define FRX_DEC_FF 1024
 #define FRX_DEC_NAME(x) x
 #endif
+#ifndef FRX_DEC_HPC
+#define FRX_DEC_HPC 1            // heads per CTA; 2 = kernels_decode_bf16_p2.cu: clusters of 4 CTAs x 16 warps, one CTA per SM
+#endif
 constexpr int D = FRX_DEC_D;     // decoder width
 constexpr int HD = 32;
-constexpr int H = D / HD;        // heads = CTAs per cluster
-constexpr int CL = H;
+constexpr int H = D / HD;        // heads
+constexpr int HPC = FRX_DEC_HPC;
+constexpr int CL = H / HPC;      // CTAs per cluster
 constexpr int FF = FRX_DEC_FF;
 constexpr int VP = 256;          // vocabulary columns, padded
+constexpr int SW = D / CL;       // columns of D per CTA (its heads)
+constexpr int FS = FF / CL;      // columns of the FFN hidden row per CTA
+constexpr int NTS = SW / 8, NTA = 3 * NTS, NTC = 2 * NTS, NTE = FS / 8;  // tiles: slice, q|k|v, K|V cache rows, FFN0
 constexpr int NG = VP / CL / 8;  // generator tiles per CTA
-static_assert(D / CL == 32 && FF / CL == 128 && CL <= 8 && (8 % CL) == 0, "column slices: 32 of D, 128 of FF per CTA");
+static_assert(SW == HD * HPC && CL <= 8 && (8 % CL) == 0 && FS % 8 == 0, "column slices");
 constexpr int APAD = 8;          // bf16 padding of the A-operand rows (conflict-free ldmatrix)
 constexpr int FPAD = 4;          // fp32 padding of rows that are accessed 16 bytes per lane, 8 rows at a time
 constexpr int NIMG = DEC_IMG;    // images per cluster = warps per CTA (warp w <-> image w)
-constexpr int NTHR = NIMG * 32;
-constexpr int RED_FLOATS = 2048;  // K-split reduction region: KS * NT * 32 lanes * 2 floats, NT <= 16
+constexpr int NWARP = NIMG * HPC; // warp w <-> (image w % NIMG, head-of-this-CTA w / NIMG)
+constexpr int NTHR = NWARP * 32;
+constexpr int RED_FLOATS = 2 * NTE * 64;  // K-split reduction region: KS * NT * 32 lanes * 2 floats, widest stage = FFN0
 static_assert(NIMG == 8, "the kernel maps MMA rows 0..7 to the cluster's images");
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -106,10 +114,10 @@ struct Smem {
   __nv_bfloat16 obf[NIMG][D + APAD];    // A operand: gathered attention outputs (all heads)
   __nv_bfloat16 abf2[NIMG][FF + APAD];  // A operand: gathered FFN hidden row (also the fp32 logits view)
   float red[2][RED_FLOATS];             // K-split partial fragments (two alternating regions)
-  float qh[NIMG][HD + FPAD];            // q of head r (this CTA's head)
-  __nv_bfloat16 kcur[NIMG][HD + APAD];  // k, v of the current layer input, head r (the extra "current" key)
-  __nv_bfloat16 vcur[NIMG][HD + APAD];
-  __nv_bfloat16 kvst[NIMG][2][32][HD];  // per-warp staging of one 32-key K/V block (KVStage)
+  float qh[HPC][NIMG][HD + FPAD];            // q of this CTA's head(s)
+  __nv_bfloat16 kcur[HPC][NIMG][HD + APAD];  // k, v of the current layer input (the extra "current" key)
+  __nv_bfloat16 vcur[HPC][NIMG][HD + APAD];
+  __nv_bfloat16 kvst[NWARP][2][32][HD];      // per-warp staging of one 32-key K/V block (KVStage)
   long long prof[16];
   unsigned long long bar[2];            // stage mbarriers (alternate by stage parity)
   DecClusterLayer lw[4];                // per-layer pointers (dynamic indexing of kernel params would spill them)
@@ -257,6 +265,7 @@ __device__ __forceinline__ LnParams load_ln(const float* __restrict__ g, const f
 // var = E[(x-s)^2] - (E[x-s])^2 well conditioned) so one butterfly carries both sums.
 __device__ __forceinline__ void layernorm_rows(Smem& s, const LnParams& P) {
   const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (row >= NIMG) return;  // with more than one head per CTA only the first NIMG warps own a row
   float v[D / 32];
 #pragma unroll
   for (int i = 0; i < D / 32; ++i) v[i] = s.pre[row][i * 32 + lane];
@@ -428,7 +437,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // ===========================================================================
 // The persistent decode kernel
 // ===========================================================================
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 2)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1)
 FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -445,10 +454,10 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   constexpr size_t WT = (size_t)KPD * 32;   // uint4 per tile for K = D
   constexpr int KS = 2;                     // every stage splits K over two warps
   // weight fragments (uint4 per lane) requested before the wait that precedes a stage
-  constexpr int PF_A = 6;                      // of 12 (D = 256) / 6 (D = 128)
-  constexpr int PF_S = GC<4, KPD, KS>::TOT;    // 4
-  constexpr int PF_E = GC<16, KPD, KS>::TOT < 8 ? GC<16, KPD, KS>::TOT : 8;
-  constexpr int PF_F = GC<4, KPF, KS>::TOT < 8 ? GC<4, KPF, KS>::TOT : 8;
+  constexpr int PF_A = GC<NTA, KPD, KS>::TOT < 6 ? GC<NTA, KPD, KS>::TOT : 6;
+  constexpr int PF_S = GC<NTS, KPD, KS>::TOT;
+  constexpr int PF_E = GC<NTE, KPD, KS>::TOT < 8 ? GC<NTE, KPD, KS>::TOT : 8;
+  constexpr int PF_F = GC<NTS, KPF, KS>::TOT < 8 ? GC<NTS, KPF, KS>::TOT : 8;
 
   if (tid == 0) {
 #pragma unroll
@@ -492,7 +501,9 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       tprev = now;
     }
   };
-  const int b_mine = img0 + warp;            // the image this warp attends for / normalises
+  const int wimg = warp % NIMG, whc = warp / NIMG;  // this warp attends for image wimg, head r * HPC + whc
+  const int head = r * HPC + whc;
+  const int b_mine = img0 + wimg;
   const bool mine = b_mine < B;
   KVStage& kvst = *reinterpret_cast<KVStage*>(&s.kvst[warp][0][0][0]);  // this warp's K/V staging block
 
@@ -502,7 +513,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
     const uint32_t dst = (uint32_t)(lane >> 2);
     if (dst < (uint32_t)CL) {
       const uint32_t rb = mapa_u32(sb, dst);
-      const uint32_t la = mapa_u32(smem_u32(&s.obf[warp][r * HD + 2 * (lane & 3)]), dst);
+      const uint32_t la = mapa_u32(smem_u32(&s.obf[wimg][head * HD + 2 * (lane & 3)]), dst);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) st_async_b32(la + nt * 16, pack_bf16(o[2 * nt], o[2 * nt + 1]), rb);
     }
@@ -511,7 +522,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   auto pre_epi = [&](uint32_t sb, const float* bias, bool relu) {
     return [&, sb, bias, relu](int tile, int row, float (&v)[8], int sub) {
       if (sub >= CL) return;  // 8 threads share a unit, one per destination CTA
-      const int col = r * 32 + tile * 8;
+      const int col = r * SW + tile * 8;
       const float4 b0 = ldg4(bias + col), b1 = ldg4(bias + col + 4);
       const float4 x0 = *reinterpret_cast<const float4*>(&s.xres[row][col]), x1 = *reinterpret_cast<const float4*>(&s.xres[row][col + 4]);
       float o[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
@@ -530,14 +541,14 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   auto qkv_epi = [&](const float* bias) {
     return [&, bias](int tile, int row, float (&v)[8], int sub) {
       if (sub != 0) return;
-      const int seg = tile >> 2, col = (tile & 3) * 8;
-      const float4 b0 = ldg4(bias + seg * D + r * HD + col), b1 = ldg4(bias + seg * D + r * HD + col + 4);
+      const int seg = tile / NTS, wc = (tile % NTS) * 8, hc = wc / HD, col = wc % HD;  // column wc of this CTA's slice
+      const float4 b0 = ldg4(bias + seg * D + r * SW + wc), b1 = ldg4(bias + seg * D + r * SW + wc + 4);
       const float o[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
       if (seg == 0) {
-        *reinterpret_cast<float4*>(&s.qh[row][col]) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(&s.qh[row][col + 4]) = make_float4(o[4], o[5], o[6], o[7]);
+        *reinterpret_cast<float4*>(&s.qh[hc][row][col]) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(&s.qh[hc][row][col + 4]) = make_float4(o[4], o[5], o[6], o[7]);
       } else {
-        __nv_bfloat16(*dst)[HD + APAD] = seg == 1 ? s.kcur : s.vcur;
+        __nv_bfloat16(*dst)[HD + APAD] = seg == 1 ? s.kcur[hc] : s.vcur[hc];
         *reinterpret_cast<uint4*>(&dst[row][col]) =
             make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
       }
@@ -545,51 +556,51 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   };
   // K/V cache rows (layer lc, position t) of the rows in abf: tiles 0-3 = K of head r, 4-7 = V of head r
   auto cache_rows = [&](int lc, int t, const uint4* wp, const float* bias) {
-    gemm2<8, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, WPre<0>{}, [&](int tile, int row, float (&v)[8], int sub) {
+    gemm2<NTC, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, WPre<0>{}, [&](int tile, int row, float (&v)[8], int sub) {
       const int b = img0 + row;
       if (sub != 0 || b >= B) return;
-      const int seg = tile >> 2, col = (tile & 3) * 8;
-      const float4 b0 = ldg4(bias + seg * D + r * HD + col), b1 = ldg4(bias + seg * D + r * HD + col + 4);
+      const int seg = tile / NTS, wc = (tile % NTS) * 8, hd = r * HPC + wc / HD, col = wc % HD;
+      const float4 b0 = ldg4(bias + seg * D + r * SW + wc), b1 = ldg4(bias + seg * D + r * SW + wc + 4);
       __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
-      *reinterpret_cast<uint4*>(dst + (((((size_t)lc * B + b) * H + r) * T) + t) * HD + col) =
+      *reinterpret_cast<uint4*>(dst + (((((size_t)lc * B + b) * H + hd) * T) + t) * HD + col) =
           make_uint4(pack_bf16(v[0] + b0.x, v[1] + b0.y), pack_bf16(v[2] + b0.z, v[3] + b0.w),
                      pack_bf16(v[4] + b1.x, v[5] + b1.y), pack_bf16(v[6] + b1.z, v[7] + b1.w));
     });
   };
 
-  auto pre_a = prefetch_w<12, KPD, KS, PF_A>(p.w_first + (size_t)r * 12 * WT, pol);
+  auto pre_a = prefetch_w<NTA, KPD, KS, PF_A>(p.w_first + (size_t)r * NTA * WT, pol);
   for (int t = 0; t < p.steps; ++t) {
     for (int l = 0; l < L; ++l) {
       const DecClusterLayer& W = s.lw[l];
       // ---- A: q|k|v of head r from the layer input, then self attention of (image warp, head r) -------
       {
-        const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + r) * T) * HD;
+        const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * T) * HD;
         const int n_hist = mine ? t : 0;
         if (n_hist > 0) kv_request(kvst, p.kself + base, p.vself + base, 0, n_hist);  // lands during the projection
-        const uint4* wp = l == 0 ? p.w_first + (size_t)r * 12 * WT : s.lw[l - 1].w_next + ((size_t)r * 20 + 8) * WT;
+        const uint4* wp = l == 0 ? p.w_first + (size_t)r * NTA * WT : s.lw[l - 1].w_next + ((size_t)r * (NTC + NTA) + NTC) * WT;
         const float* bias = l == 0 ? p.b_first : s.lw[l - 1].b_next + 2 * D;
-        gemm2<12, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
+        gemm2<NTA, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
         __syncthreads();
         mark(0);
         stage_begin(NIMG * D * 2u);
         const uint32_t sb = stage_bar();
         float o[8];
-        attend_mma(kvst, &s.qh[warp][0], p.kself + base, p.vself + base, n_hist, &s.kcur[warp][0], &s.vcur[warp][0], inv_temp, o);
+        attend_mma(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], inv_temp, o);
         store_attn(sb, o);
         mark(1);
       }
-      const auto pre_b = prefetch_w<4, KPD, KS, PF_S>(W.w_o + (size_t)r * 4 * WT, pol);
+      const auto pre_b = prefetch_w<NTS, KPD, KS, PF_S>(W.w_o + (size_t)r * NTS * WT, pol);
       // nobody waits for this in the current step: cache rows of the previous layer's output (= this input)
-      if (l > 0) cache_rows(l - 1, t, s.lw[l - 1].w_next + (size_t)r * 20 * WT, s.lw[l - 1].b_next);
+      if (l > 0) cache_rows(l - 1, t, s.lw[l - 1].w_next + (size_t)r * (NTC + NTA) * WT, s.lw[l - 1].b_next);
       mark(2);
       stage_end();
       mark(3);
       // ---- B: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
       stage_begin(NIMG * D * 4u);
-      gemm2<4, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o + (size_t)r * 4 * WT, pol, pre_b, pre_epi(stage_bar(), W.b_o, false));
+      gemm2<NTS, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o + (size_t)r * NTS * WT, pol, pre_b, pre_epi(stage_bar(), W.b_o, false));
       mark(4);
       const LnParams lnp1 = load_ln(W.ln1_g, W.ln1_b);
-      const auto pre_c = prefetch_w<4, KPD, KS, PF_S>(W.w_q2 + (size_t)r * 4 * WT, pol);
+      const auto pre_c = prefetch_w<NTS, KPD, KS, PF_S>(W.w_q2 + (size_t)r * NTS * WT, pol);
       stage_end();
       mark(5);
       layernorm_rows(s, lnp1);
@@ -597,16 +608,16 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       mark(6);
       // ---- C: q2 of head r, cross attention of (image warp, head r) over the S memory tokens -------
       {
-        const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + r) * p.S) * HD;
+        const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * p.S) * HD;
         const int n_keys = mine ? p.S : 0;
         if (n_keys > 0) kv_request(kvst, p.kcross + base, p.vcross + base, 0, n_keys);
-        gemm2<4, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_q2 + (size_t)r * 4 * WT, pol, pre_c,
+        gemm2<NTS, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_q2 + (size_t)r * NTS * WT, pol, pre_c,
                           [&](int tile, int row, float (&v)[8], int sub) {
                             if (sub != 0) return;
-                            const int col = tile * 8;
-                            const float4 b0 = ldg4(W.b_q2 + r * HD + col), b1 = ldg4(W.b_q2 + r * HD + col + 4);
-                            *reinterpret_cast<float4*>(&s.qh[row][col]) = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
-                            *reinterpret_cast<float4*>(&s.qh[row][col + 4]) = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
+                            const int wc = tile * 8, hc = wc / HD, col = wc % HD;
+                            const float4 b0 = ldg4(W.b_q2 + r * SW + wc), b1 = ldg4(W.b_q2 + r * SW + wc + 4);
+                            *reinterpret_cast<float4*>(&s.qh[hc][row][col]) = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
+                            *reinterpret_cast<float4*>(&s.qh[hc][row][col + 4]) = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
                           });
         __syncthreads();
         mark(4);
@@ -614,7 +625,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         const uint32_t sb = stage_bar();
         float o[8];
         if (mine) {
-          attend_mma(kvst, &s.qh[warp][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, inv_temp, o);
+          attend_mma(kvst, &s.qh[whc][wimg][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, inv_temp, o);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -622,15 +633,15 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         store_attn(sb, o);
         mark(7);
       }
-      const auto pre_d = prefetch_w<4, KPD, KS, PF_S>(W.w_o2 + (size_t)r * 4 * WT, pol);
+      const auto pre_d = prefetch_w<NTS, KPD, KS, PF_S>(W.w_o2 + (size_t)r * NTS * WT, pol);
       stage_end();
       mark(3);
       // ---- D: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
       stage_begin(NIMG * D * 4u);
-      gemm2<4, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o2 + (size_t)r * 4 * WT, pol, pre_d, pre_epi(stage_bar(), W.b_o2, false));
+      gemm2<NTS, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o2 + (size_t)r * NTS * WT, pol, pre_d, pre_epi(stage_bar(), W.b_o2, false));
       mark(4);
       const LnParams lnp2 = load_ln(W.ln2_g, W.ln2_b);
-      const auto pre_e = prefetch_w<16, KPD, KS, PF_E>(W.w_f0 + (size_t)r * 16 * WT, pol);
+      const auto pre_e = prefetch_w<NTE, KPD, KS, PF_E>(W.w_f0 + (size_t)r * NTE * WT, pol);
       stage_end();
       mark(5);
       layernorm_rows(s, lnp2);
@@ -640,27 +651,30 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       {
         stage_begin(NIMG * FF * 2u);
         const uint32_t sb = stage_bar();
-        gemm2<16, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_f0 + (size_t)r * 16 * WT, pol, pre_e,
+        gemm2<NTE, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_f0 + (size_t)r * NTE * WT, pol, pre_e,
                            [&](int tile, int row, float (&v)[8], int sub) {
-                             const int col = r * 128 + tile * 8;
+                             const int col = r * FS + tile * 8;
                              const float4 b0 = ldg4(W.b_f0 + col), b1 = ldg4(W.b_f0 + col + 4);
                              const uint4 o = make_uint4(pack_bf16(fmaxf(v[0] + b0.x, 0.f), fmaxf(v[1] + b0.y, 0.f)),
                                                         pack_bf16(fmaxf(v[2] + b0.z, 0.f), fmaxf(v[3] + b0.w, 0.f)),
                                                         pack_bf16(fmaxf(v[4] + b1.x, 0.f), fmaxf(v[5] + b1.y, 0.f)),
                                                         pack_bf16(fmaxf(v[6] + b1.z, 0.f), fmaxf(v[7] + b1.w, 0.f)));
                              const uint32_t la = smem_u32(&s.abf2[row][col]);
+                             constexpr int NSUB_E = GC<NTE, KPD, KS>::NSUB, DPT = (CL + NSUB_E - 1) / NSUB_E;  // destinations per thread
 #pragma unroll
-                             for (int d = 0; d < CL / 2; ++d)
-                               st_async_v4(mapa_u32(la, (uint32_t)(sub * (CL / 2) + d)), o, mapa_u32(sb, (uint32_t)(sub * (CL / 2) + d)));
+                             for (int d = 0; d < DPT; ++d) {
+                               const uint32_t dst = (uint32_t)(sub * DPT + d);
+                               if (dst < (uint32_t)CL) st_async_v4(mapa_u32(la, dst), o, mapa_u32(sb, dst));
+                             }
                            });
         mark(8);
       }
-      const auto pre_f = prefetch_w<4, KPF, KS, PF_F>(W.w_f1 + (size_t)r * 4 * KPF * 32, pol);
+      const auto pre_f = prefetch_w<NTS, KPF, KS, PF_F>(W.w_f1 + (size_t)r * NTS * KPF * 32, pol);
       stage_end();
       mark(5);
       // ---- F: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
       stage_begin(NIMG * D * 4u);
-      gemm2<4, KPF, KS>(next_red(), &s.abf2[0][0], LDA2, W.w_f1 + (size_t)r * 4 * KPF * 32, pol, pre_f, pre_epi(stage_bar(), W.b_f1, true));
+      gemm2<NTS, KPF, KS>(next_red(), &s.abf2[0][0], LDA2, W.w_f1 + (size_t)r * NTS * KPF * 32, pol, pre_f, pre_epi(stage_bar(), W.b_f1, true));
       mark(9);
       const LnParams lnp3 = load_ln(W.ln3_g, W.ln3_b);
       const bool last_layer = l + 1 >= L;
@@ -668,8 +682,8 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       // the 8 cache tiles in w_next
       constexpr int PF_G = GC<NG, KPD, KS>::TOT;
       WPre<PF_G> pre_g;
-      if (!last_layer) pre_a = prefetch_w<12, KPD, KS, PF_A>(W.w_next + ((size_t)r * 20 + 8) * WT, pol);
-      else pre_g = prefetch_w<NG, KPD, KS, PF_G>(W.w_next + ((size_t)r * (8 + NG) + 8) * WT, pol);
+      if (!last_layer) pre_a = prefetch_w<NTA, KPD, KS, PF_A>(W.w_next + ((size_t)r * (NTC + NTA) + NTC) * WT, pol);
+      else pre_g = prefetch_w<NG, KPD, KS, PF_G>(W.w_next + ((size_t)r * (NTC + NG) + NTC) * WT, pol);
       stage_end();
       mark(5);
       layernorm_rows(s, lnp3);
@@ -679,7 +693,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         // ---- G: vocabulary logits (V columns padded to 256; CTA r owns [32r, 32r+32)) ------------------
         stage_begin(NIMG * VP * 4u);
         const uint32_t sb = stage_bar();
-        gemm2<NG, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_next + ((size_t)r * (8 + NG) + 8) * WT, pol, pre_g,
+        gemm2<NG, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_next + ((size_t)r * (NTC + NG) + NTC) * WT, pol, pre_g,
                           [&](int tile, int row, float (&v)[8], int sub) {
                             if (sub >= CL) return;
                             const int col = r * (VP / CL) + tile * 8;
@@ -690,7 +704,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
                             st_async_v4(la, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])), rb);
                             st_async_v4(la + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])), rb);
                             const int b = img0 + row;
-                            if (sub == 1 && p.logits && b < B) {
+                            if (sub == (CL > 1 ? 1 : 0) && p.logits && b < B) {
                               float* lp = p.logits + ((size_t)b * p.steps + t) * V + col;
 #pragma unroll
                               for (int i = 0; i < 8; ++i)
@@ -698,15 +712,15 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
                             }
                           });
         mark(4);
-        pre_a = prefetch_w<12, KPD, KS, PF_A>(p.w_first + (size_t)r * 12 * WT, pol);
-        cache_rows(l, t, W.w_next + (size_t)r * (8 + NG) * WT, W.b_next);
+        pre_a = prefetch_w<NTA, KPD, KS, PF_A>(p.w_first + (size_t)r * NTA * WT, pol);
+        cache_rows(l, t, W.w_next + (size_t)r * (NTC + NG) * WT, W.b_next);
         mark(2);
         stage_end();
         mark(5);
       }
     }  // layers
     // ---- greedy pick (first max index) + next input: warp w <-> row w, every CTA does all rows ----------
-    {
+    if (warp < NIMG) {
       const int row = warp;
       float best = -INFINITY;
       int bi = 0x7fffffff;

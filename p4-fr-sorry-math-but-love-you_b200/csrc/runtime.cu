@@ -228,6 +228,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   else if (k == "graphs") h->opt_graphs = value != 0;
   else if (k == "timing") h->opt_timing = value != 0;
   else if (k == "cluster_images") {}  // accepted for compatibility: clusters always own 8 images
+  else if (k == "dec_hpc") h->opt_dec_hpc = (value == 1 || value == 2) ? (int)value : 0;  // heads per CTA of the 256-wide decode kernel, 0 = by batch size
   else if (k == "conv24") h->opt_conv24 = value != 0;  // 0: stage-0 convs through the tcgen05 im2col GEMM instead
   else if (k == "enc_fp32") h->opt_enc_fp32 = value != 0;
   else if (k == "tc_ws") h->opt_tc_ws = value != 0;
@@ -642,7 +643,6 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
   const bool geo = (D == 256 && F == 1024 && c.dec_heads == 8) || (D == 128 && F == 512 && c.dec_heads == 4);
   h->dec_cluster_ok = geo && L <= 4 && V <= 256;
   if (!h->dec_cluster_ok) return 0;  // e.g. SwinTRN (512 / 512 / 4 layers): the greedy loop stays on the fp32 step kernels
-  const int CL = c.dec_heads, NG = 256 / CL / 8;
   auto W = [&](int l, const char* name) -> const float* {
     return find(h, "decoder.attention_layers." + std::to_string(l) + "." + name + ".weight")->f.data();
   };
@@ -658,43 +658,50 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
     Wl.wb_f1 = pack_bf16_copy(ab, Wl.w_f1, (size_t)D * F);
     Wl.wb_sqkv = pack_bf16_copy(ab, Wl.w_sqkv, (size_t)3 * D * D);
   }
-  h->dpack.assign(L, DecPackW{});
-  h->dpack_first = pack_frag_stage(ab, CL, 12, D, [&](int r, int tile, int gid) {
-    const char* names[3] = {"self_attention_layer.q_linear", "self_attention_layer.k_linear", "self_attention_layer.v_linear"};
-    return W(0, names[tile >> 2]) + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
-  });
-  for (int l = 0; l < L; ++l) {
-    DecPackW& P = h->dpack[l];
-    auto square = [&](const char* name, int K) {
-      const float* w = W(l, name);
-      return pack_frag_stage(ab, CL, 4, K, [=](int r, int tile, int gid) { return w + (size_t)(r * 32 + tile * 8 + gid) * K; });
-    };
-    P.w_o = square("self_attention_layer.out_linear", D);
-    P.w_q2 = square("attention_layer.q_linear", D);
-    P.w_o2 = square("attention_layer.out_linear", D);
-    P.w_f1 = square("feedforward_layer.linear1", F);
-    const float* f0 = W(l, "feedforward_layer.linear0");
-    P.w_f0 = pack_frag_stage(ab, CL, 16, D, [=](int r, int tile, int gid) {  // CTA r: hidden units [128r, 128r+128)
-      return f0 + (size_t)(r * 128 + tile * 8 + gid) * D;
+  // fragment packing for a cluster of CL CTAs; CTA r owns SW = D / CL columns of D (its heads) and FS = F / CL of the
+  // FFN hidden row.  The 256-wide decoder is packed twice: one head per CTA (clusters of 8) and two (clusters of 4).
+  auto pack_geometry = [&](int CL, std::vector<DecPackW>& dp, size_t& first) {
+    const int SW = D / CL, FS = F / CL, NTS = SW / 8, NTE = FS / 8, NG = 256 / CL / 8;
+    dp.assign(L, DecPackW{});
+    first = pack_frag_stage(ab, CL, 3 * NTS, D, [&](int r, int tile, int gid) {
+      const char* names[3] = {"self_attention_layer.q_linear", "self_attention_layer.k_linear", "self_attention_layer.v_linear"};
+      return W(0, names[tile / NTS]) + (size_t)(r * SW + (tile % NTS) * 8 + gid) * D;
     });
-    const float* wk = W(l, "self_attention_layer.k_linear");
-    const float* wv = W(l, "self_attention_layer.v_linear");
-    if (l + 1 < L) {
-      const float* nq = W(l + 1, "self_attention_layer.q_linear");
-      const float* nk = W(l + 1, "self_attention_layer.k_linear");
-      const float* nv = W(l + 1, "self_attention_layer.v_linear");
-      P.w_next = pack_frag_stage(ab, CL, 20, D, [=](int r, int tile, int gid) {
-        const float* segs[5] = {wk, wv, nq, nk, nv};
-        return segs[tile >> 2] + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
+    for (int l = 0; l < L; ++l) {
+      DecPackW& P = dp[l];
+      auto square = [&](const char* name, int K) {
+        const float* w = W(l, name);
+        return pack_frag_stage(ab, CL, NTS, K, [=](int r, int tile, int gid) { return w + (size_t)(r * SW + tile * 8 + gid) * K; });
+      };
+      P.w_o = square("self_attention_layer.out_linear", D);
+      P.w_q2 = square("attention_layer.q_linear", D);
+      P.w_o2 = square("attention_layer.out_linear", D);
+      P.w_f1 = square("feedforward_layer.linear1", F);
+      const float* f0 = W(l, "feedforward_layer.linear0");
+      P.w_f0 = pack_frag_stage(ab, CL, NTE, D, [=](int r, int tile, int gid) {  // CTA r: hidden units [FS r, FS r + FS)
+        return f0 + (size_t)(r * FS + tile * 8 + gid) * D;
       });
-    } else {
-      P.w_next = pack_frag_stage(ab, CL, 8 + NG, D, [=](int r, int tile, int gid) -> const float* {
-        if (tile < 8) return (tile < 4 ? wk : wv) + (size_t)(r * 32 + (tile & 3) * 8 + gid) * D;
-        int n = r * (256 / CL) + (tile - 8) * 8 + gid;
-        return n < V ? gen + (size_t)n * D : nullptr;
-      });
+      const float* wk = W(l, "self_attention_layer.k_linear");
+      const float* wv = W(l, "self_attention_layer.v_linear");
+      if (l + 1 < L) {
+        const float* nq = W(l + 1, "self_attention_layer.q_linear");
+        const float* nk = W(l + 1, "self_attention_layer.k_linear");
+        const float* nv = W(l + 1, "self_attention_layer.v_linear");
+        P.w_next = pack_frag_stage(ab, CL, 5 * NTS, D, [=](int r, int tile, int gid) {
+          const float* segs[5] = {wk, wv, nq, nk, nv};
+          return segs[tile / NTS] + (size_t)(r * SW + (tile % NTS) * 8 + gid) * D;
+        });
+      } else {
+        P.w_next = pack_frag_stage(ab, CL, 2 * NTS + NG, D, [=](int r, int tile, int gid) -> const float* {
+          if (tile < 2 * NTS) return (tile < NTS ? wk : wv) + (size_t)(r * SW + (tile % NTS) * 8 + gid) * D;
+          int n = r * (256 / CL) + (tile - 2 * NTS) * 8 + gid;
+          return n < V ? gen + (size_t)n * D : nullptr;
+        });
+      }
     }
-  }
+  };
+  pack_geometry(c.dec_heads, h->dpack, h->dpack_first);
+  if (D == 256) pack_geometry(c.dec_heads / 2, h->dpack2, h->dpack2_first);
   return 0;
 }
 
@@ -1408,10 +1415,18 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
   CKL();
   DecClusterP p{};
   p.B = B; p.steps = steps; p.T = c.max_steps; p.L = L; p.V = c.num_classes; p.S = S; p.sos = c.sos_id;
-  p.w_first = reinterpret_cast<const uint4*>(A + h->dpack_first);
+  // 256-wide decoder: with one head per CTA (clusters of 8) only 15 clusters get their CTAs alone on an SM (an 8-CTA
+  // cluster must sit inside one GPC); beyond that two CTAs share an SM and step in 67 us instead of 42.  Two heads per CTA
+  // (clusters of 4 x 16 warps) keep every CTA alone on its SM up to 33 clusters; a cluster steps in ~57 us that way, so
+  // batches of up to 15 clusters keep one head per CTA.  Option "dec_hpc" = 1 / 2 forces either.
+  const int clusters = (B + DEC_IMG - 1) / DEC_IMG;
+  const int want_hpc = h->opt_dec_hpc ? h->opt_dec_hpc : (clusters > 15 ? 2 : 1);
+  const bool p2 = D == 256 && want_hpc == 2 && !h->dpack2.empty();
+  const std::vector<DecPackW>& dpk = p2 ? h->dpack2 : h->dpack;
+  p.w_first = reinterpret_cast<const uint4*>(A + (p2 ? h->dpack2_first : h->dpack_first));
   p.b_first = A + h->fused[0].b;
   for (int l = 0; l < L; ++l) {
-    const DecPackW& P = h->dpack[l];
+    const DecPackW& P = dpk[l];
     const DecLayerW& W = h->dec[l];
     DecClusterLayer& Q = p.layer[l];
     Q.w_o = reinterpret_cast<const uint4*>(A + P.w_o);   Q.w_q2 = reinterpret_cast<const uint4*>(A + P.w_q2);
@@ -1429,7 +1444,7 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
   p.prof = h->opt_prof ? h->prof : nullptr;
   if (p.prof) CK(cudaMemsetAsync(h->prof, 0, 16 * 8, st));
   if (h->opt_timing) CK(cudaEventRecord(h->ev[3], st));
-  int rc = D == 128 ? launch_dec_cluster_bf16_d128(p, st) : launch_dec_cluster_bf16(p, st);
+  int rc = D == 128 ? launch_dec_cluster_bf16_d128(p, st) : (p2 ? launch_dec_cluster_bf16_p2(p, st) : launch_dec_cluster_bf16(p, st));
   if (rc) return fail(h, "decode cluster kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
   CKL();
   if (h->opt_timing) CK(cudaEventRecord(h->ev[4], st));

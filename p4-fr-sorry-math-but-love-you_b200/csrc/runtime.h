@@ -77,6 +77,7 @@ struct frx_handle {
   bool opt_tc_im2col = true;   // 3x3 conv A tiles by TMA im2col (false: cp.async gather)
   void* hook_wpad = nullptr; size_t hook_wpad_bytes = 0;
   bool opt_tc_ws = true;       // persistent warp-specialised tcgen05 GEMM (false: one tile per CTA)
+  int opt_dec_hpc = 0;         // 256-wide bf16 decode kernel: heads per CTA (2: clusters of 4 x 16 warps, 1: clusters of 8 x 8 warps, 0: by batch)
   bool opt_conv24 = true;      // stage-0 24 -> 24 convs on the halo-tile mma.sync kernel (false: tcgen05 im2col GEMM)
   bool opt_enc_fp32 = false;   // bf16 handle, but run the encoder on the fp32 SIMT path (debug)
   long long* prof = nullptr;
@@ -107,6 +108,8 @@ struct frx_handle {
   std::vector<FusedW> fused;
   std::vector<DecPackW> dpack;
   size_t dpack_first = 0;
+  std::vector<DecPackW> dpack2;   // 256-wide decoder packed for two heads per CTA (clusters of 4)
+  size_t dpack2_first = 0;
 
   // workspaces
   float *act[2] = {nullptr, nullptr}, *mid[2] = {nullptr, nullptr}, *gate = nullptr;

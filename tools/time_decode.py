@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--batches", default="16,32,64,128,256")
 ap.add_argument("--steps", type=int, default=231)
+ap.add_argument("--dec-hpc", type=int, default=0, help="heads per CTA of the cluster decode kernel (1 or 2)")
 a = ap.parse_args()
 NAMES = ["A qkv gemm", "self-attn", "cache rows", "attn wait", "N=32 gemms (B,C,D,G)", "other waits", "layernorm", "cross-attn", "E ffn0", "F ffn1", "argmax+embed"]
 dev = torch.device("cuda", 0)
@@ -22,6 +23,7 @@ model, _ = bench.build_model(a.precision, 256)
 model = model.to(dev).eval()
 model.set_option("timing", 1)
 model.set_option("prof", 1)
+model.set_option("dec_hpc", a.dec_hpc)
 ms3 = (ctypes.c_float * 4)()
 for b in [int(x) for x in a.batches.split(",")]:
     x = bench.synthetic_images(b, 0).to(dev)
