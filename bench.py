@@ -32,6 +32,10 @@ ENCODE_FLOP_PER_IMAGE = 3.700e9 + 0.207e9
 TOTAL_FLOP_PER_IMAGE = 5.54e9
 
 
+# the decode kernel the library launches for batches of more than 15 clusters (two heads per CTA, clusters of 4)
+DECODE_KERNEL = "dec_cluster_bf16_kernel_p2"
+
+
 def ncu_traffic(kernel, batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
     (profiles/ncu_traffic.json), or None when no capture matches this kernel / batch."""
@@ -274,8 +278,8 @@ def run_frx(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(tokens_host.numel() * 8)},
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": ncu_traffic("dec_cluster_bf16_kernel", B) if single_kernel else None,
-                     "kernel": "dec_cluster_bf16_kernel (one launch = all 231 decode steps of the batch)" if single_kernel
+                     "traffic": ncu_traffic(DECODE_KERNEL, B) if single_kernel else None,
+                     "kernel": DECODE_KERNEL + " (one launch = all 231 decode steps of the batch)" if single_kernel
                      else "greedy decode loop (CUDA graph of the fp32 step kernels)",
                      "algorithmic_bytes_per_launch": dec_bytes,
                      "ms": dec_s * 1e3, "peak_source": how},
