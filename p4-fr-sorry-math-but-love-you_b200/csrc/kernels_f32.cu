@@ -441,7 +441,7 @@ __device__ __forceinline__ void store_as(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_as(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
 template <typename OutT>
-__global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(256) layernorm_f32_generic_kernel(const float* __restrict__ x,
                                                             const float* __restrict__ res,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
@@ -487,9 +487,70 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
   }
 }
 
+// PER = C / 32 values per lane (template: with a run-time bound the row lived in 64 registers per thread whatever C
+// was -- 2 CTAs per SM -- and small-C rows, e.g. SwinTRN's 128-wide stage, paid 64 predicated iterations per pass).
+// The accumulation order is the same for every PER, so results do not depend on the instantiation.
+template <typename OutT, int PER>
+__global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restrict__ x,
+                                                            const float* __restrict__ res,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            OutT* __restrict__ out, int M, int C,
+                                                            int scramble_S) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const float* xp = x + (long long)m * C;
+  const float* rp = res ? res + (long long)m * C : nullptr;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    float t = __ldg(xp + i * 32 + lane);
+    if (rp) t += __ldg(rp + i * 32 + lane);
+    v[i] = t;
+    s += t;
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    int ch = i * 32 + lane;
+    float o = (v[i] - mean) * rstd * __ldg(gamma + ch) + __ldg(beta + ch);
+    if (scramble_S > 0) {
+      int b = m / scramble_S, qd = m % scramble_S;
+      long long f = (long long)qd * C + ch;
+      int pp = (int)(f % scramble_S), cc = (int)(f / scramble_S);
+      store_as(out + ((long long)b * scramble_S + pp) * C + cc, o);
+    } else {
+      store_as(out + (long long)m * C + ch, o);
+    }
+  }
+}
+
+template <typename OutT>
+static void layernorm_launch(const float* x, const float* res, const float* gamma, const float* beta, OutT* out, int M, int C,
+                             int scramble_S, cudaStream_t st) {
+  const dim3 g((M + 7) / 8);
+  const int per = C / 32;  // C is a multiple of 32, at most 2048
+  if (per <= 4 && per * 32 == C) {
+    if (per == 4) layernorm_f32_kernel<OutT, 4><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+    else if (per == 2) layernorm_f32_kernel<OutT, 2><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+    else if (per == 1) layernorm_f32_kernel<OutT, 1><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+    else layernorm_f32_kernel<OutT, 3><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+  } else if (per == 8) layernorm_f32_kernel<OutT, 8><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+  else if (per == 16) layernorm_f32_kernel<OutT, 16><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+  else if (per == 32) layernorm_f32_kernel<OutT, 32><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+  else if (per == 64) layernorm_f32_kernel<OutT, 64><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+  else layernorm_f32_generic_kernel<OutT><<<g, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+}
+
 void launch_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta,
                           float* out, int M, int C, int scramble_S, cudaStream_t st) {
-  layernorm_f32_kernel<float><<<(M + 7) / 8, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+  layernorm_launch<float>(x, res, gamma, beta, out, M, C, scramble_S, st);
 }
 
 // Scrambled store (the reference's raw reshape) for the bf16 path: one CTA per image normalises its S
@@ -545,7 +606,7 @@ void launch_layernorm_bf16out(const float* x, const float* res, const float* gam
                                                                                                scramble_S, C);
     return;
   }
-  layernorm_f32_kernel<__nv_bfloat16><<<(M + 7) / 8, 256, 0, st>>>(x, res, gamma, beta, out, M, C, scramble_S);
+  layernorm_launch<__nv_bfloat16>(x, res, gamma, beta, out, M, C, scramble_S, st);
 }
 
 // ===========================================================================
