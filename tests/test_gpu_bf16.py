@@ -160,3 +160,18 @@ def test_bf16_edge_shapes(ckpt0, model_bf16, spec, b, steps):
     rel = ((l16 - l32.cpu()).abs().max() / l32.abs().max().cpu()).item()
     assert l16.shape == (b, steps, 245) and t16.shape == (b, steps)
     assert rel <= BF16_REL_TOL, rel
+
+
+def test_bf16_decode_geometries_agree_bitwise(ckpt0):
+    """The 256-wide decode kernel exists in two compiled geometries (one head per CTA in clusters of 8, two heads per
+    CTA in clusters of 4).  Every output element is accumulated in the same order in both, so logits and tokens must be
+    bit-identical whichever one the batch size selects."""
+    g = load_golden(0)
+    mem = torch.from_numpy(g["memory"]).cuda()
+    out = {}
+    for hpc in (1, 2):
+        model = make_model(ckpt0, precision="bf16").cuda().eval()
+        model.set_option("dec_hpc", hpc)
+        out[hpc] = _decode(model, mem, 40)
+    assert torch.equal(out[1][0], out[2][0])
+    assert torch.equal(out[1][1], out[2][1])
