@@ -422,7 +422,7 @@ constexpr int WS_ROWS_PER_PASS = WS_PROD_THREADS / 8;   // rows covered by one p
 constexpr int WS_A_PASSES = TC_BM / WS_ROWS_PER_PASS;
 
 template <int NCOLS, bool GELU>  // TMEM columns allocated = 2 accumulators of NCOLS/2 columns
-__global__ void __launch_bounds__(WS_THREADS, NCOLS >= 512 ? 1 : 2) tc_igemm_ws_kernel(const TcGemmP p, const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(WS_THREADS, NCOLS >= 256 ? 1 : 2) tc_igemm_ws_kernel(const TcGemmP p, const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW) {
   extern __shared__ unsigned char dyn_smem[];
   __shared__ __align__(8) uint64_t full_bar[WS_STAGES], empty_bar[WS_STAGES], acc_full[2], acc_empty[2];
