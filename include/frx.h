@@ -161,7 +161,18 @@ int64_t frx_device_bytes(const frx_handle* h);
  * produced by the last frx_encode into `out` (device).  Names: "stem",
  * "eff_block.<s>.<i>", "trunk", "pe2d", "enc_layer<i>".  Returns the number of
  * floats written through *count.  Only available when the handle was created
- * with taps enabled via frx_set_option(h, "taps", 1). */
+ * with taps enabled via frx_set_option(h, "taps", 1).
+ *
+ * frx_set_option keys (test / bench switches; defaults in parentheses):
+ *   "taps" (0)      keep per-block activations for frx_read_tap
+ *   "graphs" (1)    fp32 mode: replay the greedy loop as a CUDA graph
+ *   "timing" (0)    record CUDA events for frx_last_timing
+ *   "prof" (0)      in-kernel stage profiler of the bf16 decode kernel (frx_read_prof)
+ *   "parts" (3)     bit 0 encoder, bit 1 decoder (EfficientSATRN_encoder / _decoder handles); re-finalize after changing
+ *   "enc_fp32" (0)  bf16 mode: run the encoder on the fp32 kernels
+ *   "tc_ws" (1), "tc_im2col" (1), "conv24" (1)   bf16 encoder: persistent warp-specialised tcgen05 GEMM / TMA-im2col feed /
+ *                   halo-tile kernel for the 24-channel convs; 0 selects the variant each one replaced
+ *   "dec_hpc" (0)   bf16 decode, 256-wide decoder: heads per CTA (1: clusters of 8, 2: clusters of 4); 0 = by batch size */
 int frx_set_option(frx_handle* h, const char* key, int64_t value);
 int frx_read_tap(frx_handle* h, const char* name, float* out, int64_t capacity, int64_t* count,
                  int32_t* shape4, void* stream);
