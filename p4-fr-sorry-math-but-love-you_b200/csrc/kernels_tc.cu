@@ -20,6 +20,7 @@
 // Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor /
 // InstrDescriptor) of the CUTLASS tree vendored in this image.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cudaTypedefs.h>
 
 #include <cstdio>
@@ -136,6 +137,19 @@ __device__ __forceinline__ float act_fast(float v) {
   return v;
 }
 
+// SiLU of two values with ONE special-function op: x sigmoid(x) = h + h tanh(h), h = x/2, tanh as tanh.approx.f16x2
+// (ex2 + rcp per value made the 16-op/clk MUFU pipe the floor of every small-K SiLU layer: 4096 clk per 128 x 256 tile
+// against 2168 clk of MMA at K = 256). The product stays in fp32; the result is stored as bf16.
+__device__ __forceinline__ void silu_pair(float& a, float& b) {
+  const float ha = 0.5f * a, hb = 0.5f * b;
+  const __half2 h = __floats2half2_rn(ha, hb);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;\n" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&h)));
+  const float2 tf = __half22float2(*reinterpret_cast<const __half2*>(&t));
+  a = fmaf(ha, tf.x, ha);
+  b = fmaf(hb, tf.y, hb);
+}
+
 template <int ACT>
 __device__ __forceinline__ void epi_affine_act(float (&v)[16], const float* __restrict__ scale,
                                                const float* __restrict__ shift, int nb) {
@@ -144,10 +158,17 @@ __device__ __forceinline__ void epi_affine_act(float (&v)[16], const float* __re
     for (int i = 0; i < 16; i += 4) {
       const float4 s = __ldg(reinterpret_cast<const float4*>(scale + nb + i));
       const float4 h = __ldg(reinterpret_cast<const float4*>(shift + nb + i));
-      v[i] = act_fast<ACT>(fmaf(v[i], s.x, h.x));
-      v[i + 1] = act_fast<ACT>(fmaf(v[i + 1], s.y, h.y));
-      v[i + 2] = act_fast<ACT>(fmaf(v[i + 2], s.z, h.z));
-      v[i + 3] = act_fast<ACT>(fmaf(v[i + 3], s.w, h.w));
+      if (ACT == ACT_SILU) {
+        v[i] = fmaf(v[i], s.x, h.x); v[i + 1] = fmaf(v[i + 1], s.y, h.y);
+        v[i + 2] = fmaf(v[i + 2], s.z, h.z); v[i + 3] = fmaf(v[i + 3], s.w, h.w);
+        silu_pair(v[i], v[i + 1]);
+        silu_pair(v[i + 2], v[i + 3]);
+      } else {
+        v[i] = act_fast<ACT>(fmaf(v[i], s.x, h.x));
+        v[i + 1] = act_fast<ACT>(fmaf(v[i + 1], s.y, h.y));
+        v[i + 2] = act_fast<ACT>(fmaf(v[i + 2], s.z, h.z));
+        v[i + 3] = act_fast<ACT>(fmaf(v[i + 3], s.w, h.w));
+      }
     }
   } else if (shift) {
 #pragma unroll
@@ -237,8 +258,13 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
             __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
             w[i] = *reinterpret_cast<uint32_t*>(&t);
           }
-          *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          if ((p.ldc & 15) == 0) {  // one full 32-byte sector per thread (256-bit store, sm_100+)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(cp), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                         "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+          } else {
+            *reinterpret_cast<uint4*>(cp) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(cp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
         } else {
           for (int i = 0; i < 16; ++i)
             if (nb + i < p.N) cp[i] = __float2bfloat16_rn(v[i]);
@@ -414,9 +440,10 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
 constexpr int WS_STAGES = 4;
 constexpr int WS_LAG = 2;            // cp.async groups kept in flight per producer thread
 constexpr int WS_PROD_WARPS = 8;     // address generation for the gather is instruction-latency bound: spread it
-constexpr int WS_EPI_WARPS = 8;      // 2 warps per TMEM lane quarter
+constexpr int WS_EPI_WARPS = 8;      // 2 warps per TMEM lane quarter (4 when the feed is all-TMA: the gather warps join)
 constexpr int WS_MMA_WARP = WS_PROD_WARPS + WS_EPI_WARPS;
-constexpr int WS_THREADS = (WS_MMA_WARP + 1) * 32;
+constexpr int WS_TMA_WARP = WS_MMA_WARP + 1;   // issues the TMA loads when nothing is gathered
+constexpr int WS_THREADS = (WS_TMA_WARP + 1) * 32;
 constexpr int WS_PROD_THREADS = WS_PROD_WARPS * 32;
 constexpr int WS_ROWS_PER_PASS = WS_PROD_THREADS / 8;   // rows covered by one pass of the producer threads
 constexpr int WS_A_PASSES = TC_BM / WS_ROWS_PER_PASS;
@@ -446,7 +473,8 @@ __global__ void __launch_bounds__(WS_THREADS, NCOLS >= 256 ? 1 : 2) tc_igemm_ws_
 #pragma unroll
     for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&full_bar[s], (gather ? WS_PROD_THREADS : 0) + 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], WS_EPI_WARPS * 32); mbar_init(&acc_empty[1], WS_EPI_WARPS * 32);
+    const int epi_threads = (WS_EPI_WARPS + (gather ? 0 : WS_PROD_WARPS)) * 32;
+    mbar_init(&acc_empty[0], epi_threads); mbar_init(&acc_empty[1], epi_threads);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   tc_fence_before();
@@ -454,14 +482,15 @@ __global__ void __launch_bounds__(WS_THREADS, NCOLS >= 256 ? 1 : 2) tc_igemm_ws_
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < WS_PROD_WARPS) {
+  if (gather ? warp < WS_PROD_WARPS : warp == WS_TMA_WARP) {
     // ------------------------------ producers ------------------------------------------------
-    // W tiles (and A tiles of dense GEMMs) come by TMA from one elected thread; the implicit-GEMM
-    // gather of A for convolutions is done by all producer threads with 16-byte cp.async.
-    const bool tma_thread = tid == 0;
+    // W tiles (and A tiles of dense GEMMs / im2col convolutions) come by TMA from one elected thread. The fallback
+    // implicit-GEMM gather of A is done by all producer threads with 16-byte cp.async; when nothing is gathered the
+    // TMA thread lives in its own warp and the producer warps work as epilogue warps instead.
+    const bool tma_thread = gather ? tid == 0 : lane == 0;
     const uint32_t tma_bytes = (uint32_t)BN * (TC_BK * 2) + (gather ? 0u : (uint32_t)TC_A_BYTES);
     if (!gather && !tma_thread) {
-      // dense GEMM: nothing to gather
+      // lanes 1..31 of the TMA warp: nothing to do
     } else {
     const int c = tid & 7, rbase = tid >> 3;  // 16-byte chunk, rows rbase + WS_ROWS_PER_PASS*i
     int it = 0;   // flat k-block counter over all tiles of this CTA
@@ -565,10 +594,11 @@ __global__ void __launch_bounds__(WS_THREADS, NCOLS >= 256 ? 1 : 2) tc_igemm_ws_
         }
       }
     }
-  } else {
+  } else if (warp < WS_MMA_WARP) {
     // ------------------------------ epilogue warps ----------------------------------------------
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int sub = (warp - WS_PROD_WARPS) >> 2;     // which share of the column chunks
+    const int nsub = (WS_EPI_WARPS + (gather ? 0 : WS_PROD_WARPS)) / 4;    // warps sharing a quarter's column chunks
+    const int sub = (gather ? warp - WS_PROD_WARPS : warp) >> 2;
     int ti = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       const int a = ti & 1;
@@ -578,7 +608,7 @@ __global__ void __launch_bounds__(WS_THREADS, NCOLS >= 256 ? 1 : 2) tc_igemm_ws_
       const int m = m0 + q * 32 + lane;
       const bool m_ok = m < p.M;
       const uint32_t tacc = tmem + (uint32_t)(a * (NCOLS / 2)) + ((uint32_t)(q * 32) << 16);
-      for (int cc = sub; cc * 16 < BN; cc += WS_EPI_WARPS / 4) {
+      for (int cc = sub; cc * 16 < BN; cc += nsub) {
         uint32_t r[16];
         tmem_ld16(tacc + (uint32_t)(cc * 16), r);
         const int nb = n0 + cc * 16;
