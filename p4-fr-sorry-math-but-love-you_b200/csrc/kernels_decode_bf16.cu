@@ -798,22 +798,28 @@ int FRX_DEC_NAME(launch_dec_cluster_bf16)(const DecClusterP& p0, cudaStream_t st
 // ===========================================================================
 __global__ void __launch_bounds__(256) cross_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ kc,
                                                             __nv_bfloat16* __restrict__ vc, int B, int S, int L, int Dm) {
-  const int Hh = Dm / 32;
-  long long total = (long long)B * S * L * 2 * Dm;
+  // one thread = 8 consecutive features of one head (32-byte load, 16-byte store)
+  const int Hh = Dm / 32, cols8 = L * 2 * Dm / 8;
+  long long total = (long long)B * S * cols8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  int col = (int)(idx % (L * 2 * Dm));
-  long long row = idx / (L * 2 * Dm);
+  int col = (int)(idx % cols8) * 8;
+  long long row = idx / cols8;
   int sidx = (int)(row % S), b = (int)(row / S);
   int l = col / (2 * Dm), which = (col / Dm) & 1, d = col % Dm;
   int hh = d / 32, dd = d % 32;
   size_t off = (((((size_t)l * B + b) * Hh + hh) * S) + sidx) * 32 + dd;
-  (which ? vc : kc)[off] = __float2bfloat16_rn(src[idx]);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src + idx * 8)), c = __ldg(reinterpret_cast<const float4*>(src + idx * 8) + 1);
+  const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+  const __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
+  *reinterpret_cast<uint4*>((which ? vc : kc) + off) =
+      make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                 *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
 }
 
 void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc, int B, int S, int L, int Dm,
                           cudaStream_t st) {
-  long long total = (long long)B * S * L * 2 * Dm;
+  long long total = (long long)B * S * L * 2 * Dm / 8;
   cross_to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, kc, vc, B, S, L, Dm);
 }
 

@@ -242,7 +242,12 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
       }
       if (p.out_f32) {
         float* cp = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + nb;
-        if (full && (p.ldc & 3) == 0) {  // 16-byte stores need a 16-byte-aligned row stride (the logits' is 245 floats)
+        if (full && (p.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31) == 0) {  // two full 32-byte sectors per thread
+#pragma unroll
+          for (int i = 0; i < 16; i += 8)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(cp + i), "f"(v[i]), "f"(v[i + 1]),
+                         "f"(v[i + 2]), "f"(v[i + 3]), "f"(v[i + 4]), "f"(v[i + 5]), "f"(v[i + 6]), "f"(v[i + 7]) : "memory");
+        } else if (full && (p.ldc & 3) == 0) {  // 16-byte stores need a 16-byte-aligned row stride (the logits' is 245 floats)
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(cp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
@@ -258,7 +263,7 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
             __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
             w[i] = *reinterpret_cast<uint32_t*>(&t);
           }
-          if ((p.ldc & 15) == 0) {  // one full 32-byte sector per thread (256-bit store, sm_100+)
+          if ((p.ldc & 15) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31) == 0) {  // one full 32-byte sector per thread (256-bit store, sm_100+)
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(cp), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                          "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
           } else {
