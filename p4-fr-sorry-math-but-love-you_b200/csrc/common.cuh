@@ -22,6 +22,22 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   }
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: remember what each call site has opted
+// into per device, so a handle on a second GPU of the same process (model.to("cuda:1")) configures its own copy.
+struct SmemOptIn {
+  size_t bytes[64] = {};
+  template <class Kernel>
+  cudaError_t ensure(Kernel kernel, size_t smem, bool always = false) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if ((!always && smem <= 48 * 1024) || (bytes[dev] != 0 && smem <= bytes[dev])) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) bytes[dev] = smem;
+    return e;
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -543,19 +543,13 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
                               int pad_t, int pad_l, int R, cudaStream_t st) {
   dim3 g(B, (C + 63) / 64);
   const size_t smem = (size_t)H * W * 8 * 16 + 32 * 65 * sizeof(float) + 11 * 64 * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(dwconv_se_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn opt;
+  opt.ensure(dwconv_se_mean_kernel, smem);
   if (C % 8 == 0) {  // 4 channels per thread, 32-channel chunks: small CTAs, taps in registers, packed-half arithmetic
     constexpr int CH = 32;
     const size_t sm4 = (size_t)H * W * (CH / 8) * 16 + 16 * (CH + 1) * sizeof(float);
-    static size_t configured4 = 0;
-    if (sm4 > 48 * 1024 && sm4 > configured4) {
-      cudaFuncSetAttribute(dwconv4_se_mean_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
-      configured4 = sm4;
-    }
+    static SmemOptIn opt4;
+    opt4.ensure(dwconv4_se_mean_kernel<CH>, sm4);
     dwconv4_se_mean_kernel<CH><<<dim3(B, (C + CH - 1) / CH), CH * 4, sm4, st>>>(in, w, scale, shift, out, mean, H, W, C, OH, OW,
                                                                              stride, pad_t, pad_l, w1, w2, R * C);
   } else {

@@ -763,11 +763,10 @@ size_t FRX_DEC_NAME(dec_cluster_smem_bytes)() { return sizeof(Smem); }
 // One launch decodes up to DEC_MAX_CLUSTERS clusters (all co-resident: two CTAs per SM); larger batches
 // are decoded in consecutive launches over image ranges.
 int FRX_DEC_NAME(launch_dec_cluster_bf16)(const DecClusterP& p0, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(FRX_DEC_NAME(dec_cluster_bf16_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt.ensure(FRX_DEC_NAME(dec_cluster_bf16_kernel), sizeof(Smem), true);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
   }
   if (getenv("FRX_DEBUG")) {
     cudaLaunchConfig_t cfg{};

@@ -667,11 +667,8 @@ template <typename OutT>
 static void enc_attn_launch(const float* qkv, OutT* out, int B, int S, int D, int heads, cudaStream_t st) {
   int HD = D / heads;
   size_t smem = (size_t)(3 * S * (HD + 1) + 4 * S) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(enc_attn_f32_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn opt;
+  opt.ensure(enc_attn_f32_kernel<OutT>, smem);
   enc_attn_f32_kernel<OutT><<<B * heads, 128, smem, st>>>(qkv, out, S, D, heads, sqrtf((float)D));
 }
 void launch_enc_attn_f32(const float* qkv, float* out, int B, int S, int D, int heads, cudaStream_t st) {
@@ -786,12 +783,9 @@ __global__ void __launch_bounds__(256) dec_gemm_f32_kernel(const DecGemmP p) {
 
 void launch_dec_gemm_f32(const DecGemmP& p, cudaStream_t st) {
   dim3 g((p.M + DG_BM - 1) / DG_BM, (p.N + DG_BN - 1) / DG_BN);
-  static bool configured = false;
+  static SmemOptIn opt;
   const int smem = DG_BM * (DG_KC + 4) * (int)sizeof(float);
-  if (!configured) {
-    cudaFuncSetAttribute(dec_gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = true;
-  }
+  opt.ensure(dec_gemm_f32_kernel, (size_t)smem, true);
   dec_gemm_f32_kernel<<<g, 256, smem, st>>>(p);
 }
 

@@ -123,11 +123,8 @@ void launch_swin_window_attn(const float* qkv, const float* bias_table, float* o
                              int shift, cudaStream_t st) {
   const int N = ws * ws;
   const size_t smem = (size_t)(3 * N * 33 + 4 * N) * sizeof(float) + 2 * N * sizeof(int);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(swin_window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn opt;
+  opt.ensure(swin_window_attn_kernel, smem);
   const int nW = (R / ws) * (R / ws);
   swin_window_attn_kernel<<<B * nW * heads, 128, smem, st>>>(qkv, bias_table, out, R, C, heads, ws, shift);
 }

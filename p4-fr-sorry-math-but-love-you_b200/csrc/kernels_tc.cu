@@ -641,11 +641,10 @@ static int tc_pick_bn(int N) {
 template <int NCOLS>
 static int tc_launch(const TcGemmP& p, cudaStream_t st) {
   const size_t smem = (size_t)p.stages * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_igemm_kernel<NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt;
+  {
+    cudaError_t e = opt.ensure(tc_igemm_kernel<NCOLS>, smem, true);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
   }
   dim3 grid((p.M + TC_BM - 1) / TC_BM, (p.N + p.BN - 1) / p.BN);
   tc_igemm_kernel<NCOLS><<<grid, 256, smem, st>>>(p);
@@ -715,13 +714,11 @@ template <int NCOLS>
 static int tc_launch_ws(const TcGemmP& p_in, int num_sms, cudaStream_t st) {
   TcGemmP p = p_in;
   const size_t smem = (size_t)WS_STAGES * (TC_A_BYTES + (size_t)p.BN * TC_BK * 2) + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_igemm_ws_kernel<NCOLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_igemm_ws_kernel<NCOLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn opt, opt_gelu;
+  {
+    cudaError_t e = opt.ensure(tc_igemm_ws_kernel<NCOLS, false>, smem, true);
+    if (e == cudaSuccess) e = opt_gelu.ensure(tc_igemm_ws_kernel<NCOLS, true>, smem, true);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
   }
   const int tiles = ((p.M + TC_BM - 1) / TC_BM) * ((p.N + p.BN - 1) / p.BN);
   int per_sm = (int)((227 * 1024) / (smem + 2048));     // shared memory

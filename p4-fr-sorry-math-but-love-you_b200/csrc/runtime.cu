@@ -48,6 +48,28 @@ static int fail(frx_handle* h, const char* fmt, ...) {
     h->launches++;                                                                        \
   } while (0)
 
+// Every ABI call runs on the handle's device and puts the caller's current device back on return (torch keeps its own
+// notion of the current device; silently changing it would redirect the caller's later allocations and launches).
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t enter(int dev) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev != dev) {
+      e = cudaSetDevice(dev);
+      changed = e == cudaSuccess;
+    }
+    return e;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE(dev) \
+  DeviceGuard guard__;  \
+  CK(guard__.enter(dev))
+
 static int dev_alloc(frx_handle* h, void** p, size_t bytes) {
   if (bytes == 0) bytes = 256;
   cudaError_t e = cudaMalloc(p, bytes);
@@ -173,7 +195,7 @@ extern "C" int frx_create(const frx_config* cfg, frx_handle** out) {
   if (e != cudaSuccess || ndev == 0)
     return fail(h, "no CUDA device available (%s): frx has no CPU fallback", cudaGetErrorString(e));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(h, "device %d out of range", cfg->device);
-  CK(cudaSetDevice(cfg->device));
+  ON_DEVICE(cfg->device);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) return fail(h, "device is sm_%d%d; frx is built for sm_100a (B200) only", prop.major, prop.minor);
@@ -191,7 +213,8 @@ extern "C" int frx_create(const frx_config* cfg, frx_handle** out) {
 
 extern "C" void frx_destroy(frx_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard;
+  guard.enter(h->cfg.device);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& kv : h->taps) cudaFree(kv.second.data);
@@ -223,6 +246,7 @@ extern "C" int frx_load_tensor(frx_handle* h, const char* name, const void* data
 
 extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   if (!h || !key) return 1;
+  ON_DEVICE(h->cfg.device);
   std::string k(key);
   if (k == "taps") h->opt_taps = value != 0;
   else if (k == "graphs") h->opt_graphs = value != 0;
@@ -237,7 +261,13 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
     h->opt_prof = value != 0;
     if (h->opt_prof && !h->prof) { void* p; if (dev_alloc(h, &p, 16 * 8)) return 1; h->prof = (long long*)p; }
   }
-  else if (k == "parts") { h->opt_parts = (int)value & 3; h->finalized = false; }
+  else if (k == "parts") {
+    // the workspaces are sized for the parts chosen at the first finalize: a later change would leave them missing
+    if (h->ws_ready && ((int)value & 3) != h->opt_parts)
+      return fail(h, "option 'parts' cannot change after the first frx_finalize_weights (create a new handle)");
+    h->opt_parts = (int)value & 3;
+    h->finalized = false;
+  }
   else return fail(h, "unknown option '%s'", key);
   return 0;
 }
@@ -247,6 +277,7 @@ extern "C" int64_t frx_device_bytes(const frx_handle* h) { return h ? h->device_
 
 extern "C" int frx_read_prof(frx_handle* h, int64_t* out16) {
   if (!h || !out16 || !h->prof) return fail(h, "profiling not enabled (frx_set_option(h, \"prof\", 1))");
+  ON_DEVICE(h->cfg.device);
   CK(cudaMemcpy(out16, h->prof, 16 * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -708,7 +739,7 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
 extern "C" int frx_finalize_weights(frx_handle* h) {
   if (!h) return 1;
   const frx_config& c = h->cfg;
-  CK(cudaSetDevice(c.device));
+  ON_DEVICE(c.device);
   int down = c.network == FRX_NET_LITE_SATRN ? 16 : 32;
   h->feat_h = c.height / down;
   h->feat_w = c.width / down;
@@ -744,9 +775,19 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
     }
     if (want_dec) h->cross_wb = pack_bf16_copy(ab, h->w_cross, (size_t)c.dec_layers * 2 * c.dec_hidden * c.dec_src);
   }
-  // upload (re-finalize re-uses the arena when the size is unchanged)
+  // upload (re-finalize re-uses the arena when the size is unchanged).  Work enqueued earlier on ANY stream (torch side
+  // streams are non-blocking with respect to the legacy stream) may still be reading the old weights: drain the device
+  // before they are overwritten or freed.
   size_t bytes = ab.host.size() * sizeof(float);
+  if (h->arena) CK(cudaDeviceSynchronize());
   if (!h->arena || h->arena_bytes != bytes) {
+    if (h->arena) {
+      for (size_t i = 0; i < h->allocs.size(); ++i)
+        if (h->allocs[i] == (void*)h->arena) { h->allocs.erase(h->allocs.begin() + i); break; }
+      cudaFree(h->arena);
+      h->device_bytes -= (int64_t)h->arena_bytes;
+      h->arena = nullptr;
+    }
     void* p;
     if (dev_alloc(h, &p, bytes)) return 1;
     h->arena = (float*)p;
@@ -1207,7 +1248,7 @@ extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* 
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, "frx_encode: batch %d outside (0, %d]", B, h->cfg.max_batch);
   const frx_config& c = h->cfg;
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaSetDevice(c.device));
+  ON_DEVICE(c.device);
   if (c.network == FRX_NET_SWIN) return encode_swin(h, images, B, memory, st);
   if (c.precision == FRX_PREC_BF16 && !h->opt_enc_fp32 && c.network == FRX_NET_EFFICIENT_SATRN)
     return encode_bf16(h, images, B, memory, st);  // LiteSATRN in bf16 mode: fp32 ShallowCNN + encoder layer, bf16 decoder
@@ -1460,12 +1501,14 @@ static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int ste
   if (B <= 0 || B > c.max_batch) return fail(h, "decode: batch %d outside (0, %d]", B, c.max_batch);
   if (steps <= 0 || steps > c.max_steps) return fail(h, "decode: steps %d outside (0, %d]", steps, c.max_steps);
   if (steps > 500) return fail(h, "decode: steps exceed the 1-D positional table (500)");
-  CK(cudaSetDevice(c.device));
+  ON_DEVICE(c.device);
   if (run_cross_kv(h, memory, B, st)) return 1;
   if (managed && !h->have_rules) return fail(h, "managed decode: frx_set_decoding_rules has not been called");
   if (managed && forced) return fail(h, "managed decode: forced tokens are not supported");
   const int mode = managed ? 2 : (forced ? 1 : 0);
-  if (c.precision == FRX_PREC_BF16 && h->dec_cluster_ok && !managed)  // one persistent kernel; writes the caller's buffers directly
+  // bf16 mode: one persistent kernel that writes the caller's buffers directly.  Sequences longer than the kernel's
+  // history capacity (the reference decodes up to the 500 rows of its 1-D positional table) take the step-kernel loop.
+  if (c.precision == FRX_PREC_BF16 && h->dec_cluster_ok && !managed && steps <= DEC_TMAX)
     return decode_greedy_bf16(h, B, steps, logits, (long long*)(tokens ? tokens : (int64_t*)h->tokens_int),
                               (const long long*)forced, st);
   if (forced) CK(cudaMemcpyAsync(h->forced_int, forced, (size_t)B * steps * 8, cudaMemcpyDeviceToDevice, st));
@@ -1489,8 +1532,18 @@ static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int ste
       e = cudaGraphInstantiate(&ge.exec, graph, 0);
       cudaGraphDestroy(graph);
       if (e != cudaSuccess) return fail(h, "graph instantiate failed: %s", cudaGetErrorString(e));
+      // bounded cache: validation batches come in many target lengths, and a 231-step graph holds ~6 000 kernel nodes
+      if (h->graphs.size() >= FRX_MAX_GRAPHS) {
+        auto victim = h->graphs.begin();
+        for (auto g = h->graphs.begin(); g != h->graphs.end(); ++g)
+          if (g->second.last_use < victim->second.last_use) victim = g;
+        CK(cudaStreamSynchronize(st));   // the evicted exec may still be running on this stream
+        cudaGraphExecDestroy(victim->second.exec);
+        h->graphs.erase(victim);
+      }
       it = h->graphs.emplace(key, ge).first;
     }
+    it->second.last_use = ++h->graph_clock;
     CK(cudaGraphLaunch(it->second.exec, st));
     h->launches += it->second.nodes;
   } else if (run_greedy_loop(h, B, steps, mode, st)) {
@@ -1515,7 +1568,7 @@ extern "C" int frx_set_decoding_rules(frx_handle* h, const int32_t* flags, const
   if (num_classes != c.num_classes) return fail(h, "decoding rules: %d classes, the model has %d", num_classes, c.num_classes);
   for (int i = 0; i < 6; ++i)
     if (ids6[i] < 0 || ids6[i] >= num_classes) return fail(h, "decoding rules: special token id %d out of range", ids6[i]);
-  CK(cudaSetDevice(c.device));
+  ON_DEVICE(c.device);
   if (!h->sift_flags) {
     void* p;
     if (dev_alloc(h, &p, (size_t)num_classes * 4)) return 1; h->sift_flags = (int*)p;
@@ -1574,7 +1627,7 @@ extern "C" int frx_forward_greedy_host(frx_handle* h, const float* images_host, 
   const frx_config& c = h->cfg;
   if (B <= 0 || B > c.max_batch) return fail(h, "forward: batch %d outside (0, %d]", B, c.max_batch);
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaSetDevice(c.device));
+  ON_DEVICE(c.device);
   size_t img_bytes = (size_t)B * c.in_ch * c.height * c.width * 4;
   CK(cudaMemcpyAsync(h->images_int, images_host, img_bytes, cudaMemcpyHostToDevice, st));
   if (frx_forward_greedy(h, h->images_int, B, steps,
@@ -1592,7 +1645,7 @@ extern "C" int frx_decode_begin(frx_handle* h, const float* memory, int32_t B, v
   if (!h->finalized) return fail(h, "decode_begin: weights not finalized");
   if (!(h->opt_parts & 2)) return fail(h, "decode_begin: handle was created without the decoder part");
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, "decode_begin: batch %d outside (0, %d]", B, h->cfg.max_batch);
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h->cfg.device);
   if (run_cross_kv(h, memory, B, (cudaStream_t)stream)) return 1;
   h->step_idx = 0;
   h->step_batch = B;
@@ -1605,7 +1658,7 @@ extern "C" int frx_decode_step(frx_handle* h, const int64_t* target, float* logi
   if (h->step_idx >= h->cfg.max_steps) return fail(h, "decode_step: step %d exceeds max_steps %d", h->step_idx, h->cfg.max_steps);
   const frx_config& c = h->cfg;
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaSetDevice(c.device));
+  ON_DEVICE(c.device);
   launch_dec_embed_f32(nullptr, (const long long*)target, 0, h->arena + h->emb, h->arena + h->pe1d, h->step_idx, nullptr, 0,
                        sqrtf((float)c.dec_hidden), h->dx, h->step_batch, c.dec_hidden, st);
   CKL();
@@ -1631,7 +1684,7 @@ extern "C" int frx_beam_search(frx_handle* h, const float* memory, int32_t B, in
   if (max_sequence < 2 || max_sequence > c.max_steps) return fail(h, "beam_search: max_sequence %d outside [2, %d]", max_sequence, c.max_steps);
   if (c.num_classes > 256) return fail(h, "beam_search: more than 256 classes not supported");
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaSetDevice(c.device));
+  ON_DEVICE(c.device);
   const int T = c.max_steps, V = c.num_classes, D = c.dec_hidden;
   const size_t Bm = c.max_batch;
   const int cap = (T - 1) * 8 + 2;  // root + beam_width children per expansion
@@ -1686,7 +1739,7 @@ extern "C" int frx_decode_teacher_forced(frx_handle* h, const float* memory, con
   if (B <= 0 || B > c.max_batch) return fail(h, "teacher_forced: batch %d outside (0, %d]", B, c.max_batch);
   if (L <= 0 || L > c.max_steps || L > 500) return fail(h, "teacher_forced: length %d outside (0, %d]", L, c.max_steps);
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaSetDevice(c.device));
+  ON_DEVICE(c.device);
   const float* A = h->arena;
   const int D = c.dec_hidden, F = c.dec_filter, V = c.num_classes, T = c.max_steps, NL = c.dec_layers;
   const int S = h->feat_h * h->feat_w, HD = D / c.dec_heads, M = B * L;
@@ -1793,7 +1846,7 @@ extern "C" int frx_tc_gemm(frx_handle* h, const void* A, const void* W, void* C,
                            int32_t out_f32, void* stream) {
   if (!h) return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h->cfg.device);
   TcGemmP g{};
   g.A = (const __nv_bfloat16*)A; g.W = (const __nv_bfloat16*)W; g.C = C;
   g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.out_f32 = out_f32;

@@ -52,7 +52,8 @@ struct SwinMergeW { int dim, res; size_t red_w, n_g, n_b; size_t red_wb = 0; };
 struct DecPackW { size_t w_o, w_q2, w_o2, w_f0, w_f1, w_next; };
 struct Tap { float* data = nullptr; size_t capacity = 0; int shape[4] = {0, 0, 0, 0}; };
 typedef std::tuple<int, int, int> GraphKey;  // batch, steps, mode (0 greedy, 1 forced, 2 DecodingManager)
-struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; };
+struct GraphEntry { cudaGraphExec_t exec; int64_t nodes; int64_t last_use = 0; };
+constexpr size_t FRX_MAX_GRAPHS = 4;   // least-recently-used eviction beyond this many captured decode loops
 
 struct BeamWs {
   double *hscore = nullptr, *nlogp = nullptr;
@@ -123,6 +124,7 @@ struct frx_handle {
   void *kself_bf = nullptr, *vself_bf = nullptr, *kcross_bf = nullptr, *vcross_bf = nullptr;  // bf16 caches
 
   std::map<GraphKey, GraphEntry> graphs;
+  int64_t graph_clock = 0;
   std::map<std::string, Tap> taps;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float last_ms[4] = {0, 0, 0, 0};

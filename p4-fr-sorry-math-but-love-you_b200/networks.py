@@ -216,7 +216,9 @@ class EfficientSATRN(_FrxModule):
             eng.h.call("frx_decode_teacher_forced", _ptr(memory), _ptr(text), b, steps, _ptr(logits), st)
             return logits
         logits = torch.empty(b, steps, v, device=x.device)
-        if self.decoder.manager is not None:  # :536-564: every row is the manager's masked softmax, not logits
+        # :536-564: with a manager every row is its masked softmax, not logits -- inference branch only; the is_train
+        # branch that lost the teacher-forcing draw (:496-525) never consults the manager and returns raw greedy logits
+        if not is_train and self.decoder.manager is not None:
             self._attach_manager(eng)
             eng.h.call("frx_forward_greedy_managed", _ptr(x), b, steps, _ptr(logits), None, _stream(x.device))
             return logits

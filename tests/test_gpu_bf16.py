@@ -12,9 +12,12 @@ from oracle import satrn, synth
 pytestmark = pytest.mark.gpu
 
 BF16_REL_TOL = 4e-2   # decoder only: max |logit - ref| / max |ref| under forced decoding (bf16 weights + bf16 KV cache)
-BF16_E2E_REL_TOL = 0.25  # encoder + decoder in bf16 (40-block trunk with bf16 activations: measured 0.12 on the
-                          # synthetic BN-calibrated checkpoint, rel-L2 0.08; error grows ~0.2-0.5 % per block)
-MIN_AGREEMENT = 0.80  # free-running token agreement with the fp32 reference (reported, loose floor)
+BF16_E2E_REL_TOL = 0.20  # encoder + decoder in bf16, forced decoding.  Yardstick (tools/bf16_yardstick.py, same synthetic
+                          # checkpoint, 16 images): an ideal pipeline that rounds ONLY the GEMM operands to bf16 and keeps
+                          # everything else fp32 already sits at 0.105 (memory rel-L2 0.076, free-running tokens 0.81);
+                          # torch.autocast(bfloat16) over the oracle at 0.197 / 0.149 / 0.72.  frx measures 0.12 / 0.08.
+FLOOR_FACTOR = 1.35       # encoder memory: frx's rel-L2 error may exceed that operand-rounding floor by at most this factor
+MIN_AGREEMENT = 0.80  # free-running token agreement with the fp32 reference, DECODER ALONE on the golden fp32 memory
 
 
 @pytest.fixture(scope="module")
@@ -175,3 +178,39 @@ def test_bf16_decode_geometries_agree_bitwise(ckpt0):
         out[hpc] = _decode(model, mem, 40)
     assert torch.equal(out[1][0], out[2][0])
     assert torch.equal(out[1][1], out[2][1])
+
+
+def test_bf16_full_size_against_oracle_and_operand_floor(ckpt0, spec):
+    """BASELINE size (B = 256, 231 steps) in the benchmarked bf16 mode, checked on a 32-image slice against the fp32
+    oracle: forced-decoding logit error within BF16_E2E_REL_TOL, encoder-memory error within FLOOR_FACTOR of what an
+    ideal bf16-operand pipeline gives on the same images (the emulation in tools/bf16_yardstick.py), free-running token
+    agreement reported next to that floor's and required to stay within 0.10 of it."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bf16_yardstick as ys
+    B, T, NS = 256, 231, 32
+    x = synth.synth_images(spec, B, 3)
+    model = make_model(ckpt0, precision="bf16", max_batch=B, max_steps=T).cuda().eval()
+    with torch.no_grad():
+        mem_gpu = model.encode(x.cuda()).cpu()
+        _, tok_gpu = model.greedy(x.cuda(), T)
+        ref_mem = satrn.encoder_forward(ckpt0, spec, x[:NS])
+        ref_logits, ref_tok = satrn.decode_greedy(ckpt0, spec, ref_mem, T)
+        lg_forced, _ = model.greedy(x.cuda(), T, forced=torch.cat([ref_tok, ref_tok.new_zeros(B - NS, T)]))
+        floor_mem = ys.encoder_emulated(ckpt0, spec, x[:NS], ys.Policy("operands", store_wide=False, store_res=False,
+                                                                      se_twice=False))
+        _, floor_tok = satrn.decode_greedy(ckpt0, spec, floor_mem, T)
+    torch.cuda.synchronize()
+    rel_l2 = lambda a: ((a - ref_mem).norm() / ref_mem.norm()).item()
+    e_gpu, e_floor = rel_l2(mem_gpu[:NS]), rel_l2(floor_mem)
+    rel = ((lg_forced[:NS].cpu() - ref_logits).abs().max() / ref_logits.abs().max()).item()
+    step_agree = (lg_forced[:NS].cpu().argmax(-1) == ref_logits.argmax(-1)).float().mean().item()
+    a_gpu = (tok_gpu[:NS].cpu() == ref_tok).float().mean().item()
+    a_floor = (floor_tok == ref_tok).float().mean().item()
+    print("B=256 bf16 vs oracle on %d images: memory rel-L2 %.4f (bf16-operand floor %.4f), forced max-rel %.4f, "
+          "per-step argmax %.4f, free-running tokens %.4f (floor %.4f)" % (NS, e_gpu, e_floor, rel, step_agree, a_gpu, a_floor))
+    assert e_gpu <= FLOOR_FACTOR * e_floor, (e_gpu, e_floor)
+    assert rel <= BF16_E2E_REL_TOL, rel
+    assert step_agree >= 0.75, step_agree
+    assert a_gpu >= a_floor - 0.10, (a_gpu, a_floor)
