@@ -175,7 +175,54 @@ def main_manager():
     print("tokens changed by the manager: %.1f %%" % (100.0 * (plain != tokens.numpy()).mean()))
 
 
+def main_train():
+    """Three iterations of the reference's single-optimizer training step (train_modules/train_single_opt.py:72-112)
+    on the REAL reference modules in train mode: teacher forcing 1.0, CrossEntropyLoss(ignore_index=PAD),
+    clip_grad_norm_(2.0), AdamW(lr 5e-4, weight_decay 1e-6).  Every nn.Dropout is set to p = 0 (the decoder's Feedforward
+    hard-codes 0.1 whatever FLAGS.dropout_rate says, EfficientSATRN.py:327,368-370; dropout masks come from torch's global
+    RNG and cannot be reproduced by another implementation).  Stores per-step loss / gradient norm and, for step 0, the L2
+    norm of every parameter's gradient."""
+    from oracle import train
+    ref = ref_shim.load_reference()
+    spec = satrn.ModelSpec()
+    out = {}
+    for seed in (0, 1):
+        sd = synth.synth_state_dict(spec, seed)
+        model = ref.networks.EfficientSATRN(ref_shim.reference_flags(dropout=0.0), ref_shim.reference_vocab())
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = ref.utils.get_optimizer("AdamW", params, lr=5e-4, weight_decay=1e-6)
+        losses, norms = [], []
+        for it in range(3):
+            x, e = train.synth_batch(spec, 4, 24, 10 * seed + it)
+            logits = model(x, e, True, 1.0)
+            loss = model.criterion(logits.transpose(1, 2), e[:, 1:])
+            opt.zero_grad()
+            loss.backward()
+            if it == 0:
+                names = [n for n, p in model.named_parameters() if p.requires_grad]
+                out["names"] = np.array(names)
+                out["grad_l2_seed%d" % seed] = np.array([p.grad.norm().item() for p in params], np.float64)
+                out["logits0_seed%d" % seed] = logits.detach().numpy()[:, ::4].astype(np.float32)
+            norms.append(float(torch.nn.utils.clip_grad_norm_(params, max_norm=2.0)))
+            opt.step()
+            losses.append(loss.item())
+        out["loss_seed%d" % seed] = np.array(losses, np.float64)
+        out["grad_norm_seed%d" % seed] = np.array(norms, np.float64)
+        print("seed", seed, "loss", losses, "grad norm", norms)
+    path = os.path.join(GOLDEN_DIR, "efficientsatrn_train.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if "--train" in sys.argv:
+        main_train()
+        sys.exit(0)
     if "--manager" in sys.argv:
         main_manager()
         sys.exit(0)

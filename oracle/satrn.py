@@ -233,7 +233,21 @@ def _quantize_mantissa(x: torch.Tensor, bits: int = 10) -> torch.Tensor:
     return torch.ldexp(m, e)
 
 
+class TrainMode:
+    """Marker passed in the ``calib`` slot: BatchNorm in TRAIN mode (batch statistics, running statistics updated in
+    place with ``momentum`` exactly as nn.BatchNorm2d does) -- the mode the reference trains in
+    (train_modules/train_single_opt.py:54 ``model.train()``)."""
+
+    def __init__(self, momentum: float = 0.1):
+        self.momentum = momentum
+
+
 def _bn(x, sd, p, eps, calib: Optional[_Calib] = None):
+    if isinstance(calib, TrainMode):
+        if p + ".num_batches_tracked" in sd:
+            sd[p + ".num_batches_tracked"] += 1
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                            True, calib.momentum, eps)
     if calib is not None:
         # own synthetic-checkpoint procedure: running stats := batch stats of the
         # eval-mode forward so far, in fp64, rounded to 10 mantissa bits so the
