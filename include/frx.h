@@ -195,6 +195,43 @@ int frx_tc_gemm(frx_handle* h, const void* A, const void* W, void* C, int32_t M,
  * recorded by one thread of cluster 0): 16 counters, see DESIGN.md. */
 int frx_read_prof(frx_handle* h, int64_t* out16);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training step (EfficientSATRN): one iteration of train_modules/train_single_opt.py:72-112 --
+ *   model.train(); output = model(input, expected, True, 1.0)   (teacher forcing, EfficientSATRN.py:488-495, :697-706;
+ *                                                                BatchNorm batch statistics)
+ *   loss = CrossEntropyLoss(ignore_index=PAD)(output.transpose(1, 2), expected[:, 1:])   (:82-86, EfficientSATRN.py:690-692)
+ *   loss.backward(); clip_grad_norm_(params, max_grad_norm); AdamW.step()                (:92-98, utils/utils.py:91-92)
+ * fp32 like the reference (no autocast); dropout is not applied (p = 0).
+ *
+ * frx_train_create      copies the loaded parameters into the training state (one flat fp32 buffer in kernel layouts, a
+ *                       parallel gradient buffer, Adam moments, BatchNorm running statistics) and sizes the activation
+ *                       tape for max_batch images and targets of max_len tokens.  grad_buffer: caller-owned device
+ *                       buffer of frx_train_param_count floats to hold the gradients (e.g. a torch tensor the host
+ *                       all-reduces with NCCL), or NULL to let the library allocate it.
+ * frx_train_fwd_bwd     images fp32 [B, in_ch, H, W], expected int64 [B, len_plus_1] (PAD-padded, as the reference's
+ *                       d["truth"]["encoded"] with -1 replaced by PAD, :77-78) -> gradients in the flat buffer,
+ *                       *loss_out (host or device float) = the mean loss over the non-PAD targets.  While the backward
+ *                       pass runs, the bucket callback (if set) is invoked on the calling thread as soon as every kernel
+ *                       contributing to a contiguous range [offset, offset + count) of the gradient buffer has been
+ *                       enqueued on `stream`, so the host can start that range's all-reduce under the rest of the pass.
+ * frx_train_apply       gradient *= grad_scale (1 / world size after a sum all-reduce); norm = ||g||_2;
+ *                       g *= min(1, max_grad_norm / (norm + 1e-6)); AdamW(lr, betas (0.9, 0.999), eps 1e-8,
+ *                       weight_decay).  *grad_norm_out (host or device float) = norm before clipping.
+ * frx_train_export      parameter or BatchNorm running statistic by its state_dict name -> dst in the reference's
+ *                       state_dict layout (host or device pointer).  frx_train_read_grad: the same for gradients. */
+int frx_train_create(frx_handle* h, int32_t max_batch, int32_t max_len, float* grad_buffer);
+void frx_train_destroy(frx_handle* h);
+int64_t frx_train_param_count(frx_handle* h);
+int frx_train_fwd_bwd(frx_handle* h, const float* images, const int64_t* expected, int32_t batch, int32_t len_plus_1,
+                      float* loss_out, void* stream);
+int frx_train_grad_buffer(frx_handle* h, float** grads, int64_t* count);
+int frx_train_set_bucket_callback(frx_handle* h, void (*callback)(void* ctx, int64_t offset, int64_t count), void* ctx);
+int frx_train_apply(frx_handle* h, float lr, float weight_decay, float max_grad_norm, float grad_scale,
+                    float* grad_norm_out, void* stream);
+int frx_train_export(frx_handle* h, const char* name, float* dst);
+int frx_train_read_grad(frx_handle* h, const char* name, float* dst);
+int64_t frx_train_step_count(const frx_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

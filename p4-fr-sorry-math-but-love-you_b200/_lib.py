@@ -14,7 +14,11 @@ SYMBOLS = [
     "frx_decode_teacher_forced", "frx_launch_count", "frx_device_bytes", "frx_set_option",
     "frx_read_tap", "frx_last_timing", "frx_read_prof", "frx_tc_gemm",
     "frx_set_decoding_rules", "frx_decode_greedy_managed", "frx_forward_greedy_managed",
+    "frx_train_create", "frx_train_destroy", "frx_train_param_count", "frx_train_fwd_bwd", "frx_train_grad_buffer",
+    "frx_train_set_bucket_callback", "frx_train_apply", "frx_train_export", "frx_train_read_grad", "frx_train_step_count",
 ]
+
+BUCKET_CALLBACK = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64)
 
 
 class FrxConfig(ctypes.Structure):
@@ -71,6 +75,20 @@ def load_library():
     lib.frx_set_decoding_rules.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, ctypes.POINTER(i32)]
     lib.frx_decode_greedy_managed.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     lib.frx_forward_greedy_managed.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    f32 = ctypes.c_float
+    lib.frx_train_create.argtypes = [vp, i32, i32, vp]
+    lib.frx_train_destroy.argtypes = [vp]
+    lib.frx_train_destroy.restype = None
+    lib.frx_train_param_count.argtypes = [vp]
+    lib.frx_train_param_count.restype = i64
+    lib.frx_train_fwd_bwd.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.frx_train_grad_buffer.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    lib.frx_train_set_bucket_callback.argtypes = [vp, BUCKET_CALLBACK, vp]
+    lib.frx_train_apply.argtypes = [vp, f32, f32, f32, f32, vp, vp]
+    lib.frx_train_export.argtypes = [vp, ctypes.c_char_p, vp]
+    lib.frx_train_read_grad.argtypes = [vp, ctypes.c_char_p, vp]
+    lib.frx_train_step_count.argtypes = [vp]
+    lib.frx_train_step_count.restype = i64
     _LIB = lib
     return lib
 

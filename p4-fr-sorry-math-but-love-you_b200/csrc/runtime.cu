@@ -215,6 +215,7 @@ extern "C" void frx_destroy(frx_handle* h) {
   if (!h) return;
   DeviceGuard guard;
   guard.enter(h->cfg.device);
+  frx_train_destroy(h);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& kv : h->taps) cudaFree(kv.second.data);

@@ -138,5 +138,6 @@ struct frx_handle {
   bool have_rules = false;
   bool timed_kernel = false;
   bool dec_cluster_ok = false;   // bf16 mode: the persistent cluster decode kernel fits this decoder's dimensions
+  void* train = nullptr;   // TrainState (train.cu): parameters, gradients, optimiser state of the training step
   void *sw_ab = nullptr, *sw_hidb = nullptr;  // SwinTRN bf16 mode: bf16 A operands (LayerNorm / attention output, MLP hidden)
 };

@@ -225,6 +225,97 @@ class EfficientSATRN(_FrxModule):
         eng.h.call("frx_forward_greedy", _ptr(x), b, steps, _ptr(logits), None, _stream(x.device))
         return logits
 
+    # ------------------------------------------------------------------------------------------------------------
+    # training step (train_modules/train_single_opt.py:72-112)
+    # ------------------------------------------------------------------------------------------------------------
+    def _trainer(self, device, batch, length):
+        """Lazily create the library's training state (parameters, gradients, Adam moments, activation tape)."""
+        eng = self.engine(device, batch, max(length, 1))
+        tr = getattr(eng, "_train", None)
+        if tr is None or tr["max_batch"] < batch or tr["max_len"] < length:
+            if tr is not None:
+                raise RuntimeError("training state was sized for batch %d / length %d; create the model with larger "
+                                   "max_batch / max_steps" % (tr["max_batch"], tr["max_len"]))
+            mb, ml = max(batch, self._max_batch or 0), max(length, min(self._max_steps or 0, 256))
+            n = int(eng.h.lib.frx_train_param_count(eng.h.ptr))
+            if n <= 0:
+                raise RuntimeError("frx_train_param_count: " + eng.h.lib.frx_last_error(eng.h.ptr).decode())
+            grads = torch.zeros(n, dtype=torch.float32, device=eng.device)   # flat gradient buffer, all-reduced over NCCL
+            eng.h.call("frx_train_create", mb, ml, _ptr(grads))
+            tr = eng._train = {"max_batch": mb, "max_len": ml, "grads": grads, "works": [],
+                               "scalars": torch.zeros(2, dtype=torch.float32, device=eng.device)}
+        return eng, tr
+
+    def train_step(self, input, expected, lr=5e-4, weight_decay=1e-6, max_grad_norm=2.0, process_group=None,
+                   overlap=True):
+        """One iteration of the reference's single-optimizer loop (train_single_opt.py:72-112) with teacher forcing 1.0:
+        train-mode forward (BatchNorm batch statistics), CrossEntropyLoss(ignore_index=PAD), backward,
+        clip_grad_norm_(max_grad_norm), AdamW(lr, weight_decay) -- all inside the library, fp32.  Returns
+        (loss, grad_norm) as 0-dim device tensors (no host synchronisation).
+
+        Data parallel: when torch.distributed is initialised (one process per GPU, NCCL) the flat gradient buffer is
+        all-reduced (sum, then 1 / world inside the optimiser kernel) before the update; with ``overlap`` each bucket's
+        all-reduce starts as soon as the backward pass has produced it (trunk stages last), under the rest of the pass.
+        ``expected`` is [B, L + 1] int64 with -1 already replaced by PAD (:77-78)."""
+        import torch.distributed as dist
+        b, lp1 = input.size(0), expected.size(1)
+        eng, tr = self._trainer(input.device, b, lp1 - 1)
+        x = input.detach().float().contiguous()
+        e = expected.to(device=x.device, dtype=torch.int64).contiguous()
+        st = _stream(x.device)
+        world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        works = tr["works"]
+        del works[:]
+        if world > 1 and overlap:
+            grads = tr["grads"]
+
+            def on_bucket(_ctx, off, count):   # called by the library while it is still enqueueing the backward pass
+                works.append(dist.all_reduce(grads[off:off + count], group=process_group, async_op=True))
+
+            cb = _lib.BUCKET_CALLBACK(on_bucket)
+            eng.h.call("frx_train_set_bucket_callback", cb, None)
+        else:
+            cb = _lib.BUCKET_CALLBACK()   # NULL
+            eng.h.call("frx_train_set_bucket_callback", cb, None)
+        sc = tr["scalars"]
+        eng.h.call("frx_train_fwd_bwd", _ptr(x), _ptr(e), b, lp1, _ptr(sc), st)
+        if world > 1:
+            if not overlap:
+                works.append(dist.all_reduce(tr["grads"], group=process_group, async_op=True))
+            for w in works:
+                w.wait()          # the current stream waits for the NCCL stream; no host synchronisation
+        eng.h.call("frx_train_apply", float(lr), float(weight_decay), float(max_grad_norm), 1.0 / world,
+                   ctypes.c_void_p(sc.data_ptr() + 4), st)
+        self._trained = True
+        return sc[0], sc[1]
+
+    def sync_trained_weights(self):
+        """Copy the library's trained parameters and BatchNorm running statistics back into this module's
+        nn.Parameters / buffers (state_dict layout) -- before saving a checkpoint (utils/checkpoint.py:28-32) or
+        running inference with the trained weights."""
+        eng = self._engine
+        if eng is None or getattr(eng, "_train", None) is None:
+            return
+        steps = int(eng.h.lib.frx_train_step_count(eng.h.ptr))
+        with torch.no_grad():
+            for name, t in self.state_dict().items():
+                if name.endswith("num_batches_tracked"):
+                    t.fill_(int(t) + steps - getattr(self, "_synced_steps", 0))
+                    continue
+                buf = torch.empty_like(t, dtype=torch.float32).contiguous()
+                eng.h.call("frx_train_export", name.encode(), _ptr(buf))
+                t.copy_(buf)
+        self._synced_steps = steps
+        self._dirty = True
+
+    def read_grad(self, name):
+        """Gradient of one parameter (state_dict name) from the last train_step / frx_train_fwd_bwd, state_dict layout."""
+        eng = self._engine
+        t = self.state_dict()[name]
+        buf = torch.empty_like(t, dtype=torch.float32).contiguous()
+        eng.h.call("frx_train_read_grad", name.encode(), _ptr(buf))
+        return buf
+
     @property
     def memory_tokens(self):
         return (self._dims["height"] // self._down) * (self._dims["width"] // self._down)

@@ -1,0 +1,86 @@
+"""Training step (train_modules/train_single_opt.py:72-112) on the GPU against the train-step oracle (oracle/train.py,
+pinned against the real reference by tests/test_oracle_train.py) and against the reference's own numbers
+(tests/golden/efficientsatrn_train.npz).  fp32: loss, every parameter's gradient, the gradient norm and three optimiser
+steps."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from helpers import make_model
+from oracle import synth, train
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden", "efficientsatrn_train.npz")
+
+LOSS_TOL = 2e-5        # relative, step 0 (fp32 summation order only)
+GRAD_TOL = 2e-3        # per-tensor relative L2 error of the gradient, step 0
+NORM_TOL = 1e-4        # relative, global gradient norm, step 0
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_train_step_matches_oracle_and_reference(spec, seed):
+    sd = synth.synth_state_dict(spec, seed)
+    g = np.load(GOLD)
+    model = make_model(sd, max_batch=4, max_steps=24).cuda().train()
+    tr = train.Trainer(sd, spec)
+    names = [k for k in tr.sd if train.is_param(k)]
+    for it in range(3):
+        x, e = train.synth_batch(spec, 4, 24, 10 * seed + it)
+        loss, gn = model.train_step(x.cuda(), e.cuda())
+        loss, gn = loss.item(), gn.item()
+        if it == 0:
+            ref_loss, grads = tr.forward_backward(x, e)
+            worst, worst_name = 0.0, ""
+            for n in names:
+                got = model.read_grad(n).cpu()
+                want = grads[n]
+                err = (got - want).norm().item() / max(want.norm().item(), 1e-12)
+                # tensors whose gradient is pure round-off (biases in front of a train-mode BatchNorm) are compared on an
+                # absolute scale: the gradient norm of the whole model is O(10)
+                if want.norm().item() < 1e-5:
+                    err = (got - want).norm().item() / 1e-3
+                if err > worst:
+                    worst, worst_name = err, n
+            print("seed %d step 0: loss %.6f (oracle %.6f, reference %.6f), grad norm %.5f (reference %.5f), worst gradient "
+                  "rel-L2 %.2e at %s" % (seed, loss, ref_loss, g["loss_seed%d" % seed][0], gn, g["grad_norm_seed%d" % seed][0],
+                                         worst, worst_name))
+            assert abs(loss - ref_loss) <= LOSS_TOL * abs(ref_loss)
+            assert abs(loss - g["loss_seed%d" % seed][0]) <= LOSS_TOL * abs(loss)
+            assert worst <= GRAD_TOL, (worst_name, worst)
+            assert abs(gn - g["grad_norm_seed%d" % seed][0]) <= NORM_TOL * gn
+            ref_gn = float(torch.nn.utils.clip_grad_norm_(tr.params, max_norm=tr.max_grad_norm))
+            tr.opt.step()
+        else:
+            # later steps carry Adam's first-step amplification of round-off (tests/test_oracle_train.py)
+            assert abs(loss - g["loss_seed%d" % seed][it]) <= 2e-3 * abs(loss), (it, loss)
+            assert abs(gn - g["grad_norm_seed%d" % seed][it]) <= 3e-2 * gn, (it, gn)
+    # trained parameters and running statistics come back in the state_dict layout
+    model.sync_trained_weights()
+    sd_gpu = model.state_dict()
+    for it in range(1, 3):
+        tr.step(*train.synth_batch(spec, 4, 24, 10 * seed + it))
+    sd_ref = tr.state_dict()
+    for name in ("decoder.generator.bias", "encoder.shallow_cnn.conv_stem.weight", "encoder.shallow_cnn.bn1.running_mean",
+                 "encoder.shallow_cnn.eff_block.3.0.bn2.running_var", "encoder.attention_layers.1.norm.weight"):
+        a, b = sd_gpu[name].cpu().float(), sd_ref[name].float()
+        assert (a - b).abs().max().item() <= 2e-3 * max(b.abs().max().item(), 1e-3) + 2.1 * 5e-4 * 3, name
+
+
+def test_train_mode_then_inference_uses_trained_weights(spec, ckpt0):
+    """After training steps the module can be switched back to eval(): sync_trained_weights() re-packs the inference
+    weights, and the greedy decode then differs from the untrained model's."""
+    model = make_model(ckpt0, max_batch=4, max_steps=24).cuda()
+    x, e = train.synth_batch(spec, 4, 24, 3)
+    with torch.no_grad():
+        before = model.eval()(x.cuda(), e.cuda(), False, 0.0)
+    model.train()
+    for _ in range(2):
+        model.train_step(x.cuda(), e.cuda(), lr=5e-3)
+    model.sync_trained_weights()
+    with torch.no_grad():
+        after = model.eval()(x.cuda(), e.cuda(), False, 0.0)
+    assert torch.isfinite(after).all()
+    assert (after - before).abs().max().item() > 1e-3
