@@ -231,6 +231,10 @@ int frx_train_apply(frx_handle* h, float lr, float weight_decay, float max_grad_
 int frx_train_export(frx_handle* h, const char* name, float* dst);
 int frx_train_read_grad(frx_handle* h, const char* name, float* dst);
 int64_t frx_train_step_count(const frx_handle* h);
+/* Debug view into the tape of the last frx_train_fwd_bwd call (what a forward/backward hook on the reference module
+ * would see): copies the named buffer to dst (host or device, capacity floats) and returns its length; dst = NULL only
+ * returns the length; -1 = unknown name.  Names: "dec<l>.d_linear0", "dec<l>.d_linear1", "dec<l>.d_ffn_out", ... */
+int64_t frx_train_read_tap(frx_handle* h, const char* name, float* dst, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -120,6 +120,8 @@ struct TrainState {
   size_t mark_trunk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   void (*bucket_cb)(void*, int64_t, int64_t) = nullptr;
   void* bucket_ctx = nullptr;
+  // named views into the activation / gradient tape of the LAST frx_train_fwd_bwd call (frx_train_read_tap)
+  std::map<std::string, std::pair<const float*, size_t>> taps;
 };
 
 struct Ctx {   // one training call
@@ -500,6 +502,8 @@ int ln_bwd(Ctx& c, const LNS& r, const float* dy, float** dx_out) {
   return 0;
 }
 
+void tap(Ctx& c, const std::string& name, const float* p, size_t n) { c.T->taps[name] = {p, n}; }
+
 void bucket_done(Ctx& c, int idx) {
   if (c.T->bucket_cb && idx < (int)c.T->buckets.size())
     c.T->bucket_cb(c.T->bucket_ctx, (int64_t)c.T->buckets[idx].first, (int64_t)c.T->buckets[idx].second);
@@ -514,6 +518,7 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
   const frx_config& cf = h->cfg;
   const int B = c.B, L = c.L;
   T->ws_used = 0;
+  T->taps.clear();
   TCK(cudaMemsetAsync(T->G, 0, T->n * 4, c.st));
   // ================= forward =================
   const int H0 = (cf.height - 3) / 2 + 1, W0 = (cf.width - 3) / 2 + 1;
@@ -688,6 +693,11 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
     launch_act_bwd(dpre3, s.f1, df1, ACT_RELU, (long long)Md * D, c.st); TKL();       // relu'(pre) == (out > 0)
     if (lin_bwd(c, df1, D, s.f0, Md, FF, Wl.w_f1, Wl.b_f1, true, D, df0, false)) return 1;
     launch_act_bwd(df0, s.f0, df0, ACT_RELU, (long long)Md * FF, c.st); TKL();
+    {
+      const std::string tp = "dec" + std::to_string(l) + ".";
+      tap(c, tp + "d_ffn_out", dpre3, (size_t)Md * D); tap(c, tp + "d_linear1", df1, (size_t)Md * D); tap(c, tp + "d_linear0", df0, (size_t)Md * FF);
+      tap(c, tp + "f0", s.f0, (size_t)Md * FF); tap(c, tp + "f1", s.f1, (size_t)Md * D);
+    }
     launch_axpy(dw, dpre3, 1.f, (long long)Md * D, 0, c.st); TKL();
     if (lin_bwd(c, df0, FF, s.ln2.y, Md, D, Wl.w_f0, Wl.b_f0, true, FF, dw, true)) return 1;
     if (ln_bwd(c, s.ln2, dw, &dpre2)) return 1;
@@ -959,6 +969,23 @@ extern "C" int frx_train_read_grad(frx_handle* h, const char* name, float* dst) 
   if (!h || !state_of(h) || !name || !dst) return tfail(h, "train_read_grad: bad arguments");
   DevGuard g; g.enter(h->cfg.device);
   return unpack_to(h, state_of(h), state_of(h)->G, name, dst);
+}
+
+extern "C" int64_t frx_train_read_tap(frx_handle* h, const char* name, float* dst, int64_t capacity) {
+  if (!h || !state_of(h) || !name) return -1;
+  DevGuard g; g.enter(h->cfg.device);
+  TrainState* T = state_of(h);
+  auto it = T->taps.find(name);
+  if (it == T->taps.end()) { tfail(h, "train_read_tap: no tap named '%s'", name); return -1; }
+  const int64_t n = (int64_t)it->second.second;
+  if (dst) {
+    if (capacity < n) { tfail(h, "train_read_tap: '%s' holds %lld floats, capacity %lld", name, (long long)n, (long long)capacity); return -1; }
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(dst, it->second.first, (size_t)n * 4, cudaMemcpyDefault) != cudaSuccess) {
+      tfail(h, "train_read_tap: copy failed");
+      return -1;
+    }
+  }
+  return n;
 }
 
 extern "C" int64_t frx_train_step_count(const frx_handle* h) { return h && h->train ? reinterpret_cast<const TrainState*>(h->train)->step : 0; }

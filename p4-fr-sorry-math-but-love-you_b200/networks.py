@@ -316,6 +316,16 @@ class EfficientSATRN(_FrxModule):
         eng.h.call("frx_train_read_grad", name.encode(), _ptr(buf))
         return buf
 
+    def read_train_tap(self, name):
+        """Named buffer of the last training step's activation / gradient tape (frx_train_read_tap), flat fp32."""
+        eng = self._engine
+        n = int(eng.h.lib.frx_train_read_tap(eng.h.ptr, name.encode(), None, 0))
+        if n < 0:
+            raise RuntimeError("frx_train_read_tap: " + eng.h.lib.frx_last_error(eng.h.ptr).decode())
+        buf = torch.empty(n, dtype=torch.float32, device=eng.device)
+        eng.h.lib.frx_train_read_tap(eng.h.ptr, name.encode(), _ptr(buf), n)
+        return buf
+
     @property
     def memory_tokens(self):
         return (self._dims["height"] // self._down) * (self._dims["width"] // self._down)

@@ -16,8 +16,17 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(ROOT, "tests", "golden", "efficientsatrn_train.npz")
 
 LOSS_TOL = 2e-5        # relative, step 0 (fp32 summation order only)
-GRAD_TOL = 2e-3        # per-tensor relative L2 error of the gradient, step 0
 NORM_TOL = 1e-4        # relative, global gradient norm, step 0
+# Gradients: the network has ~700 k ReLU units; with fp32 round-off of ~1e-6 on pre-activations of O(1) a handful of
+# units whose pre-activation is ~0 land on the other side of the kink than in the CPU run (measured through
+# frx_train_read_tap: 1-2 units per step, e.g. one of the 98 304 hidden units of the top feed-forward layer).  One
+# flipped unit changes its row's gradient by ~6 % and every tensor BELOW it in backward order by 0.2-0.9 %.  So:
+EXACT_TOL = 5e-5       # tensors above every ReLU in backward order (generator, last feed-forward norm, last linear1)
+GRAD_TOL = 3e-2        # any tensor, relative L2
+GLOBAL_TOL = 6e-3      # relative L2 error of the whole concatenated gradient
+EXACT = ("decoder.generator.weight", "decoder.generator.bias", "decoder.attention_layers.2.feedforward_norm.weight",
+         "decoder.attention_layers.2.feedforward_norm.bias", "decoder.attention_layers.2.feedforward_layer.linear1.weight",
+         "decoder.attention_layers.2.feedforward_layer.linear1.bias")
 
 
 @pytest.mark.parametrize("seed", [0, 1])
@@ -34,6 +43,7 @@ def test_train_step_matches_oracle_and_reference(spec, seed):
         if it == 0:
             ref_loss, grads = tr.forward_backward(x, e)
             worst, worst_name = 0.0, ""
+            num = den = 0.0
             for n in names:
                 got = model.read_grad(n).cpu()
                 want = grads[n]
@@ -42,11 +52,17 @@ def test_train_step_matches_oracle_and_reference(spec, seed):
                 # absolute scale: the gradient norm of the whole model is O(10)
                 if want.norm().item() < 1e-5:
                     err = (got - want).norm().item() / 1e-3
+                num += (got - want).norm().item() ** 2
+                den += want.norm().item() ** 2
+                if n in EXACT:
+                    assert err <= EXACT_TOL, (n, err)
                 if err > worst:
                     worst, worst_name = err, n
-            print("seed %d step 0: loss %.6f (oracle %.6f, reference %.6f), grad norm %.5f (reference %.5f), worst gradient "
-                  "rel-L2 %.2e at %s" % (seed, loss, ref_loss, g["loss_seed%d" % seed][0], gn, g["grad_norm_seed%d" % seed][0],
-                                         worst, worst_name))
+            glob = (num / den) ** 0.5
+            print("seed %d step 0: loss %.6f (oracle %.6f, reference %.6f), grad norm %.5f (reference %.5f), whole-gradient "
+                  "rel-L2 %.2e, worst tensor %.2e at %s" % (seed, loss, ref_loss, g["loss_seed%d" % seed][0], gn,
+                                                             g["grad_norm_seed%d" % seed][0], glob, worst, worst_name))
+            assert glob <= GLOBAL_TOL, glob
             assert abs(loss - ref_loss) <= LOSS_TOL * abs(ref_loss)
             assert abs(loss - g["loss_seed%d" % seed][0]) <= LOSS_TOL * abs(loss)
             assert worst <= GRAD_TOL, (worst_name, worst)
