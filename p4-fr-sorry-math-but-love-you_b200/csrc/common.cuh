@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -37,6 +38,46 @@ struct SmemOptIn {
     return e;
   }
 };
+
+// ---------------------------------------------------------------------------
+// 16-bit storage / tensor-core operand type of the ENCODER side of the 16-bit mode (conv trunk, encoder layers, the
+// teacher-forced decoder's GEMMs, SwinTRN / LiteSATRN encoders): IEEE fp16 by default.  bf16 and fp16 run at the same
+// tensor-core rate (tcgen05 kind::f16, mma.sync m16n8k16) and occupy the same bytes, but fp16 keeps 11 significand bits
+// against bf16's 8: on the synthetic checkpoint the encoder memory lands within 1.1 % (rel-L2) of the fp32 reference
+// instead of 8-9 % (tools/bf16_yardstick.py: 0.080 is the floor of ANY bf16-operand pipeline).  BatchNorm-folded
+// activations are O(1..100), far inside fp16's range; conversions saturate (cvt.rn.satfinite) instead of producing inf.
+// The persistent decode kernel (KV cache, fragment-packed weights) stays bf16.  -DFRX_ENC_FP16=0 restores a bf16 encoder.
+// ---------------------------------------------------------------------------
+#ifndef FRX_ENC_FP16
+#define FRX_ENC_FP16 1
+#endif
+#if FRX_ENC_FP16
+typedef __half eh_t;
+typedef __half2 eh2_t;
+#define FRX_EH_PTX "f16"
+__device__ __forceinline__ uint32_t eh2_pack(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ eh_t eh_from_float(float f) {
+  const uint32_t r = eh2_pack(f, 0.f);
+  return __ushort_as_half((unsigned short)(r & 0xffffu));
+}
+__device__ __forceinline__ float eh_to_float(eh_t v) { return __half2float(v); }
+__device__ __forceinline__ float2 eh2_unpack(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+#else
+typedef __nv_bfloat16 eh_t;
+typedef __nv_bfloat162 eh2_t;
+#define FRX_EH_PTX "bf16"
+__device__ __forceinline__ uint32_t eh2_pack(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ eh_t eh_from_float(float f) { return __float2bfloat16_rn(f); }
+__device__ __forceinline__ float eh_to_float(eh_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ float2 eh2_unpack(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -142,14 +183,14 @@ struct BeamP {
 
 // tcgen05 implicit GEMM (kernels_tc.cu):  C[M,N] = epi( A[M,K] * W[N,K]^T ), bf16 operands
 struct TcGemmP {
-  const __nv_bfloat16* A;   // dense [M, lda] or NHWC activation (conv = 1)
-  const __nv_bfloat16* W;   // [N, ldw], K contiguous (conv K index = (kh*KW+kw)*Cin + ci)
+  const eh_t* A;            // dense [M, lda] or NHWC activation (conv = 1)
+  const eh_t* W;            // [N, ldw], K contiguous (conv K index = (kh*KW+kw)*Cin + ci)
   void* C;                  // bf16 or fp32 [M, ldc]
   int M, N, K, lda, ldw, ldc;
   int BN;                   // N tile (multiple of 16, <= 256); 0 = choose
   int stages;               // smem ring depth (set by the launcher)
   int conv, H, Wd, Cin, OH, OW, KW, stride, pad_t, pad_l;
-  const __nv_bfloat16* Wpad; // conv only, optional: weights as [N][KW*KW][64] (channels zero-padded to 64) for the
+  const eh_t* Wpad; // conv only, optional: weights as [N][KW*KW][64] (channels zero-padded to 64) for the
                              // TMA-im2col path (one filter tap = one 64-wide k-block); nullptr = cp.async gather
   int im2col;               // set by the launcher when the im2col tensor map could be built
   const float* scale;       // per-N folded BatchNorm (v*scale + shift) or nullptr

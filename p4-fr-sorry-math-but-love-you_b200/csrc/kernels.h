@@ -43,7 +43,7 @@ void launch_swin_patch_embed(const float* img, const float* w, const float* bias
                              const float* ape, float* out, int B, int IMGS, int R, int E, cudaStream_t st);
 void launch_swin_window_attn(const float* qkv, const float* bias_table, float* out, int B, int R, int C, int heads, int ws,
                              int shift, cudaStream_t st);
-bool launch_swin_window_attn_mma(const float* qkv, const float* bias_table, __nv_bfloat16* out, int B, int R, int C, int heads,
+bool launch_swin_window_attn_mma(const float* qkv, const float* bias_table, eh_t* out, int B, int R, int C, int heads,
                                  int ws, int shift, cudaStream_t st);
 void launch_swin_patch_merge(const float* x, float* out, int B, int R, int C, cudaStream_t st);
 
@@ -56,29 +56,29 @@ void launch_beam_finish(const BeamP& p, cudaStream_t st);
 // tcgen05 implicit GEMM + bf16 trunk kernels (kernels_tc.cu, kernels_bf16.cu)
 int launch_tc_igemm(TcGemmP p, cudaStream_t st);                       // one tile per CTA (first version)
 int launch_tc_igemm_ws(TcGemmP p, int num_sms, cudaStream_t st);       // persistent, warp-specialised
-void launch_pad_conv_weights(const __nv_bfloat16* in, __nv_bfloat16* out, long long rows, int Cin, cudaStream_t st);
-void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);
-void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
+void launch_pad_conv_weights(const eh_t* in, eh_t* out, long long rows, int Cin, cudaStream_t st);
+void launch_h16_to_f32(const eh_t* in, float* out, long long n, cudaStream_t st);
+void launch_f32_to_h16(const float* in, eh_t* out, long long n, cudaStream_t st);
 void launch_stem_conv_bf16(const float* in, const float* w, const float* scale, const float* shift,
-                           __nv_bfloat16* out, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st);
-void launch_dwconv_bf16(const __nv_bfloat16* in, const float* w, const float* scale, const float* shift,
-                        __nv_bfloat16* out, int B, int H, int W, int C, int OH, int OW, int stride, int pad_t,
+                           eh_t* out, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st);
+void launch_dwconv_bf16(const eh_t* in, const float* w, const float* scale, const float* shift,
+                        eh_t* out, int B, int H, int W, int C, int OH, int OW, int stride, int pad_t,
                         int pad_l, int act, cudaStream_t st);
-void launch_se_scale_bf16(__nv_bfloat16* x, const float* w1, const float* b1, const float* w2, const float* b2,
+void launch_se_scale_bf16(eh_t* x, const float* w1, const float* b1, const float* w2, const float* b2,
                           int B, int HW, int C, int R, cudaStream_t st);
-void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const float* scale, const float* shift,
-                              __nv_bfloat16* out, float* mean, float* gate, const float* w1, const float* b1,
+void launch_mbconv_dw_se_bf16(const eh_t* in, const float* w, const float* scale, const float* shift,
+                              eh_t* out, float* mean, float* gate, const float* w1, const float* b1,
                               const float* w2, const float* b2, int B, int H, int W, int C, int OH, int OW, int stride,
                               int pad_t, int pad_l, int R, cudaStream_t st);
 void launch_layernorm_bf16out(const float* x, const float* res, const float* gamma, const float* beta,
-                              __nv_bfloat16* out, int M, int C, int scramble_S, cudaStream_t st);
-void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st);
-void launch_conv3x3_c24_bf16(const __nv_bfloat16* in, const void* wfrag, const float* scale, const float* shift,
-                             __nv_bfloat16* out, int B, int H, int W, int add_res, cudaStream_t st);
-void launch_lite_conv0_pool_bf16(const float* in, const float* w, const float* scale, const float* shift, __nv_bfloat16* out,
+                              eh_t* out, int M, int C, int scramble_S, cudaStream_t st);
+void launch_enc_attn_bf16out(const float* qkv, eh_t* out, int B, int S, int D, int heads, cudaStream_t st);
+void launch_conv3x3_c24_bf16(const eh_t* in, const void* wfrag, const float* scale, const float* shift,
+                             eh_t* out, int B, int H, int W, int add_res, cudaStream_t st);
+void launch_lite_conv0_pool_bf16(const float* in, const float* w, const float* scale, const float* shift, eh_t* out,
                                  int B, int Cin, int H, int W, int Cout, cudaStream_t st);
-void launch_maxpool2_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, float* out_f32, int B, int H, int W, int C, cudaStream_t st);
-bool launch_enc_attn_mma_bf16(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st);
+void launch_maxpool2_bf16(const eh_t* in, eh_t* out, float* out_f32, int B, int H, int W, int C, cudaStream_t st);
+bool launch_enc_attn_mma_bf16(const float* qkv, eh_t* out, int B, int S, int D, int heads, cudaStream_t st);
 
 // bf16 persistent decode (kernels_decode_bf16.cu)
 size_t dec_cluster_smem_bytes();

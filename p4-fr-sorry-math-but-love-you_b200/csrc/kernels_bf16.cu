@@ -5,6 +5,10 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef FRX_DW_ACC32
+#define FRX_DW_ACC32 1
+#endif
+
 namespace frx {
 
 namespace {
@@ -12,17 +16,15 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    const float2 t = eh2_unpack(w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    w[i] = *reinterpret_cast<uint32_t*>(&t);
-  }
+  for (int i = 0; i < 4; ++i) w[i] = eh2_pack(f[2 * i], f[2 * i + 1]);
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 }  // namespace
@@ -31,7 +33,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // One thread per output pixel x 8 channels (16-byte store).
 __global__ void __launch_bounds__(256) stem_conv_bf16_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
-                                                             __nv_bfloat16* __restrict__ out, int B, int Cin, int H, int W,
+                                                             eh_t* __restrict__ out, int B, int Cin, int H, int W,
                                                              int OH, int OW, int Cout) {
   extern __shared__ float ws[];
   for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) ws[i] = w[i];
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) stem_conv_bf16_kernel(const float* __rest
 template <int COUT>
 __global__ void __launch_bounds__(128) stem_conv_px_bf16_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                __nv_bfloat16* __restrict__ out, int B, int Cin, int H, int W,
+                                                                eh_t* __restrict__ out, int B, int Cin, int H, int W,
                                                                 int OH, int OW) {
   extern __shared__ __align__(16) float ws[];   // [Cin * 9][COUT], then scale[COUT], shift[COUT]
   const int taps = Cin * 9;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(128) stem_conv_px_bf16_kernel(const float* __r
 }
 
 void launch_stem_conv_bf16(const float* in, const float* w, const float* scale, const float* shift,
-                           __nv_bfloat16* out, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st) {
+                           eh_t* out, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st) {
   if (Cout == 24) {
     const long long pixels = (long long)B * OH * OW;
     const int smem24 = ((24 * Cin * 9 + 2 * 24 + 3) & ~3) * sizeof(float) + 128 * 3 * 16;
@@ -143,9 +145,9 @@ void launch_stem_conv_bf16(const float* in, const float* w, const float* scale, 
 }
 
 // Depthwise 3x3 + folded BN (+bias) + activation; 8 channels (16 bytes) per thread.
-__global__ void __launch_bounds__(256) dwconv3x3_bf16_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) dwconv3x3_bf16_kernel(const eh_t* __restrict__ in, const float* __restrict__ w,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
-                                                             __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, int OH,
+                                                             eh_t* __restrict__ out, int B, int H, int W, int C, int OH,
                                                              int OW, int stride, int pad_t, int pad_l, int act) {
   const int C8 = C >> 3;
   long long total = (long long)B * OH * OW * C8;
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__(256) dwconv3x3_bf16_kernel(const __nv_bfloat16
   *reinterpret_cast<uint4*>(out + pix * C + c) = pack8(o);
 }
 
-void launch_dwconv_bf16(const __nv_bfloat16* in, const float* w, const float* scale, const float* shift,
-                        __nv_bfloat16* out, int B, int H, int W, int C, int OH, int OW, int stride, int pad_t,
+void launch_dwconv_bf16(const eh_t* in, const float* w, const float* scale, const float* shift,
+                        eh_t* out, int B, int H, int W, int C, int OH, int OW, int stride, int pad_t,
                         int pad_l, int act, cudaStream_t st) {
   long long total = (long long)B * OH * OW * (C / 8);
   dwconv3x3_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, w, scale, shift, out, B, H, W, C, OH, OW,
@@ -191,7 +193,7 @@ void launch_dwconv_bf16(const __nv_bfloat16* in, const float* w, const float* sc
 
 // Squeeze-excite, one CTA per image: gate = sigmoid(W2 silu(W1 mean_hw(x) + b1) + b2), then x *= gate
 // in place (so the following 1x1 projection is a plain tcgen05 GEMM).  Deterministic (no atomics).
-__global__ void __launch_bounds__(256) se_scale_bf16_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ w1,
+__global__ void __launch_bounds__(256) se_scale_bf16_kernel(eh_t* __restrict__ x, const float* __restrict__ w1,
                                                             const float* __restrict__ b1, const float* __restrict__ w2,
                                                             const float* __restrict__ b2, int HW, int C, int R) {
   extern __shared__ float sm[];
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256) se_scale_bf16_kernel(__nv_bfloat16* __res
   float* red = sm + C;    // R
   float* gate = red + R;  // C
   const int n = blockIdx.x;
-  __nv_bfloat16* xp = x + (long long)n * HW * C;
+  eh_t* xp = x + (long long)n * HW * C;
   const float inv = 1.f / (float)HW;
   for (int c8 = threadIdx.x; c8 < C / 8; c8 += blockDim.x) {
     float s[8];
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(256) se_scale_bf16_kernel(__nv_bfloat16* __res
   }
 }
 
-void launch_se_scale_bf16(__nv_bfloat16* x, const float* w1, const float* b1, const float* w2, const float* b2,
+void launch_se_scale_bf16(eh_t* x, const float* w1, const float* b1, const float* w2, const float* b2,
                           int B, int HW, int C, int R, cudaStream_t st) {
   se_scale_bf16_kernel<<<B, 256, (2 * C + R) * sizeof(float), st>>>(x, w1, b1, w2, b2, HW, C, R);
 }
@@ -258,9 +260,9 @@ void launch_se_scale_bf16(__nv_bfloat16* x, const float* w1, const float* b1, co
 // One CTA = one (image, 64-channel chunk).  The whole input tile of the chunk is staged in shared memory with
 // coalesced 16-byte loads issued up front (all in flight at once), then every output pixel reads its 9 taps
 // from shared memory; the CTA also owns the chunk's spatial mean (deterministic, no atomics).
-__global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const eh_t* __restrict__ in, const float* __restrict__ w,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
-                                                             __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
+                                                             eh_t* __restrict__ out, float* __restrict__ mean,
                                                              int H, int W, int C, int OH, int OW, int stride, int pad_t,
                                                              int pad_l, const float* __restrict__ se_w1,
                                                              const float* __restrict__ se_w2, int se_floats) {
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
   const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;  // 8 channels per thread, 32 pixel lanes
   const int c = c0 + cg * 8;
   const bool c_ok = c < C;
-  const __nv_bfloat16* ip = in + (long long)n * H * W * C;
+  const eh_t* ip = in + (long long)n * H * W * C;
   for (int i = threadIdx.x; i < H * W * 8; i += 256) {
     const int px = i >> 3, g = i & 7;
     tile[i] = (c0 + g * 8 < C) ? __ldg(reinterpret_cast<const uint4*>(ip + (long long)px * C + c0 + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
   float sc[8], sh[8];
   ld8s(9, sc);
   ld8s(10, sh);
-  __nv_bfloat16* op = out + (long long)n * OH * OW * C;
+  eh_t* op = out + (long long)n * OH * OW * C;
   if (c_ok) {
     for (int px = pl; px < OH * OW; px += 32) {
       const int oh = px / OW, ow = px - oh * OW;
@@ -359,9 +361,9 @@ __global__ void __launch_bounds__(256) dwconv_se_mean_kernel(const __nv_bfloat16
 //     bits through the 9-term sum -- more than the 8 bits the bf16 store keeps; activations and folded-BN outputs are
 //     O(1..100), far from the fp16 range limit.
 template <int CH>
-__global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+__global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const eh_t* __restrict__ in, const float* __restrict__ w,
                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                 __nv_bfloat16* __restrict__ out, float* __restrict__ mean,
+                                                                 eh_t* __restrict__ out, float* __restrict__ mean,
                                                                  int H, int W, int C, int OH, int OW, int stride, int pad_t,
                                                                  int pad_l, const float* __restrict__ se_w1,
                                                                  const float* __restrict__ se_w2, int se_floats) {
@@ -377,23 +379,64 @@ __global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const __nv_bflo
   uint4* tile = reinterpret_cast<uint4*>(dw_smem);                                               // [H*W][CH/8] x 16 B
   float (*red)[CH + 1] = reinterpret_cast<float (*)[CH + 1]>(dw_smem + (size_t)H * W * G8 * 16);  // [16][CH + 1]
   const int n = blockIdx.x, c0 = blockIdx.y * CH;
-  const __nv_bfloat16* ip = in + (long long)n * H * W * C;
+  const eh_t* ip = in + (long long)n * H * W * C;
   for (int i = threadIdx.x; i < H * W * G8; i += NT) {
     const int px = i / G8, g = i - px * G8;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (c0 + g * 8 < C) {
+#if FRX_ENC_FP16
+      v = __ldg(reinterpret_cast<const uint4*>(ip + (long long)px * C + c0 + g * 8));   // already packed halves
+#else
       float x[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(ip + (long long)px * C + c0 + g * 8)), x);
       const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
       const __half2 h2 = __floats2half2_rn(x[4], x[5]), h3 = __floats2half2_rn(x[6], x[7]);
       v = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
                      *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+#endif
     }
     tile[i] = v;
   }
   const int cg = threadIdx.x % G4, pl = threadIdx.x / G4;  // 4 channels per thread, 16 pixel lanes
   const int c = c0 + cg * 4;
   const bool c_ok = c < C;
+#if FRX_DW_ACC32
+  // fp32 taps / accumulation / folded BN / SiLU (operands stay packed halves in shared memory): the 9-term sum and the
+  // activation then add no rounding of their own to the fp16-stored trunk (FRX_DW_ACC32=0: packed-half arithmetic)
+  float4 wt[9], sc, sh;
+  {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wt[t] = c_ok ? __ldg(reinterpret_cast<const float4*>(w + t * C + c)) : z;
+    sc = c_ok ? __ldg(reinterpret_cast<const float4*>(scale + c)) : z;
+    sh = c_ok ? __ldg(reinterpret_cast<const float4*>(shift + c)) : z;
+  }
+  __syncthreads();
+  const uint2* tile2 = reinterpret_cast<const uint2*>(tile);  // [H*W][CH/4] x 8 B
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  eh_t* op = out + (long long)n * OH * OW * C;
+  if (c_ok) {
+    for (int px = pl; px < OH * OW; px += 16) {
+      const int oh = px / OW, ow = px - oh * OW;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = oh * stride - pad_t + kh;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = ow * stride - pad_l + kw;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            const uint2 u = tile2[(ih * W + iw) * G4 + cg];
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            const float4 ww = wt[kh * 3 + kw];
+            acc.x = fmaf(a.x, ww.x, acc.x); acc.y = fmaf(a.y, ww.y, acc.y); acc.z = fmaf(b.x, ww.z, acc.z); acc.w = fmaf(b.y, ww.w, acc.w);
+          }
+        }
+      }
+      float2 f0 = make_float2(fmaf(acc.x, sc.x, sh.x), fmaf(acc.y, sc.y, sh.y)), f1 = make_float2(fmaf(acc.z, sc.z, sh.z), fmaf(acc.w, sc.w, sh.w));
+      f0.x = __fdividef(f0.x, 1.f + __expf(-f0.x)); f0.y = __fdividef(f0.y, 1.f + __expf(-f0.y));
+      f1.x = __fdividef(f1.x, 1.f + __expf(-f1.x)); f1.y = __fdividef(f1.y, 1.f + __expf(-f1.y));
+#else
   __half2 wt[9][2], sc[2], sh[2];
   {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -411,7 +454,7 @@ __global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const __nv_bflo
   __syncthreads();
   const uint2* tile2 = reinterpret_cast<const uint2*>(tile);  // [H*W][CH/4] x 8 B
   float sum[4] = {0.f, 0.f, 0.f, 0.f};
-  __nv_bfloat16* op = out + (long long)n * OH * OW * C;
+  eh_t* op = out + (long long)n * OH * OW * C;
   if (c_ok) {
     for (int px = pl; px < OH * OW; px += 16) {
       const int oh = px / OW, ow = px - oh * OW;
@@ -433,14 +476,14 @@ __global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const __nv_bflo
       const __half2 o0 = __hmul2(v0, __hfma2(h2tanh_approx(__hmul2(v0, half_)), half_, half_));  // SiLU = v (0.5 tanh(v/2) + 0.5)
       const __half2 o1 = __hmul2(v1, __hfma2(h2tanh_approx(__hmul2(v1, half_)), half_, half_));
       const float2 f0 = __half22float2(o0), f1 = __half22float2(o1);
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(f0.x, f0.y), p1 = __floats2bfloat162_rn(f1.x, f1.y);
+#endif
       uint2 packed;
-      packed.x = *reinterpret_cast<const uint32_t*>(&p0);
-      packed.y = *reinterpret_cast<const uint32_t*>(&p1);
+      packed.x = eh2_pack(f0.x, f0.y);
+      packed.y = eh2_pack(f1.x, f1.y);
       *reinterpret_cast<uint2*>(op + (long long)px * C + c) = packed;
-      // the mean is taken over the stored (bf16-rounded) activations
-      sum[0] += __uint_as_float(packed.x << 16); sum[1] += __uint_as_float(packed.x & 0xffff0000u);
-      sum[2] += __uint_as_float(packed.y << 16); sum[3] += __uint_as_float(packed.y & 0xffff0000u);
+      // the mean is taken over the stored (rounded) activations
+      const float2 b0 = eh2_unpack(packed.x), b1 = eh2_unpack(packed.y);
+      sum[0] += b0.x; sum[1] += b0.y; sum[2] += b1.x; sum[3] += b1.y;
     }
   }
 #pragma unroll
@@ -520,7 +563,7 @@ __global__ void __launch_bounds__(512, 1) se_fc_kernel(const float* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) se_apply_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ gate,
+__global__ void __launch_bounds__(256) se_apply_kernel(eh_t* __restrict__ x, const float* __restrict__ gate,
                                                        long long total8, int HW, int C) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
@@ -537,8 +580,8 @@ __global__ void __launch_bounds__(256) se_apply_kernel(__nv_bfloat16* __restrict
   *ptr = pack8(v);
 }
 
-void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const float* scale, const float* shift,
-                              __nv_bfloat16* out, float* mean, float* gate, const float* w1, const float* b1,
+void launch_mbconv_dw_se_bf16(const eh_t* in, const float* w, const float* scale, const float* shift,
+                              eh_t* out, float* mean, float* gate, const float* w1, const float* b1,
                               const float* w2, const float* b2, int B, int H, int W, int C, int OH, int OW, int stride,
                               int pad_t, int pad_l, int R, cudaStream_t st) {
   dim3 g(B, (C + 63) / 64);
@@ -568,17 +611,16 @@ void launch_mbconv_dw_se_bf16(const __nv_bfloat16* in, const float* w, const flo
 // (the qkv rows are the fp32 output of the projection GEMM); 64 HMMA per warp instead of ~16k scalar instructions.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  return eh2_pack(lo, hi);
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32." FRX_EH_PTX "." FRX_EH_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 __global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restrict__ qkv,       // [B*32, 3*D]
-                                                          __nv_bfloat16* __restrict__ out,     // [B*32, D]
+                                                          eh_t* __restrict__ out,     // [B*32, D]
                                                           int D, int heads, float inv_temp) {
   constexpr int S = 32, HD = 64;
   const int b = blockIdx.x / heads, hh = blockIdx.x % heads;
@@ -644,8 +686,8 @@ __global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restric
     }
   }
   const float r0 = __fdividef(1.f, sum0), r1 = __fdividef(1.f, sum1);
-  __nv_bfloat16* o0 = out + ((long long)b * S + i0 + gid) * D + hh * HD + 2 * tig;
-  __nv_bfloat16* o1 = o0 + (long long)8 * D;
+  eh_t* o0 = out + ((long long)b * S + i0 + gid) * D + hh * HD + 2 * tig;
+  eh_t* o1 = o0 + (long long)8 * D;
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     *reinterpret_cast<uint32_t*>(o0 + 8 * n) = pack2(oacc[n][0] * r0, oacc[n][1] * r0);
@@ -654,7 +696,7 @@ __global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restric
 }
 
 // returns false when the shape is not the one the kernel is specialised for (the caller then uses the generic kernel)
-bool launch_enc_attn_mma_bf16(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st) {
+bool launch_enc_attn_mma_bf16(const float* qkv, eh_t* out, int B, int S, int D, int heads, cudaStream_t st) {
   if (S != 32 || D / heads != 64 || D % heads != 0) return false;
   enc_attn_mma_kernel<<<B * heads, 64, 0, st>>>(qkv, out, D, heads, 1.f / sqrtf((float)D));
   return true;
@@ -671,16 +713,16 @@ bool launch_enc_attn_mma_bf16(const float* qkv, __nv_bfloat16* out, int B, int S
 // ---------------------------------------------------------------------------
 constexpr int C24 = 24, C24_TH = 8, C24_TW = 32, C24_KS = 14;  // K = 216 padded to 224
 
-__global__ void __launch_bounds__(256) conv3x3_c24_mma_kernel(const __nv_bfloat16* __restrict__ in, const uint2* __restrict__ wfrag,
+__global__ void __launch_bounds__(256) conv3x3_c24_mma_kernel(const eh_t* __restrict__ in, const uint2* __restrict__ wfrag,
                                                               const float* __restrict__ scale, const float* __restrict__ shift,
-                                                              __nv_bfloat16* __restrict__ out, int H, int W, int add_res) {
+                                                              eh_t* __restrict__ out, int H, int W, int add_res) {
   constexpr int PW = C24_TW + 2, PH = C24_TH + 2;
-  __shared__ __align__(16) __nv_bfloat16 halo[PH * PW * C24];   // 16320 B
+  __shared__ __align__(16) eh_t halo[PH * PW * C24];   // 16320 B
   __shared__ uint2 wsm[C24_KS * 3 * 32];                        // 10752 B
   const int tiles_x = (W + C24_TW - 1) / C24_TW, tiles_y = (H + C24_TH - 1) / C24_TH;
   const int n = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
   const int y0 = (t / tiles_x) * C24_TH, x0 = (t % tiles_x) * C24_TW;
-  const __nv_bfloat16* ip = in + (long long)n * H * W * C24;
+  const eh_t* ip = in + (long long)n * H * W * C24;
   // halo: 3 x 16-byte chunks per pixel; a halo row is contiguous in global memory (NHWC, 48 B per pixel)
   for (int i = threadIdx.x; i < PH * PW * 3; i += 256) {
     const int pix = i / 3, ch = i - pix * 3;
@@ -730,7 +772,7 @@ __global__ void __launch_bounds__(256) conv3x3_c24_mma_kernel(const __nv_bfloat1
   // epilogue: folded BN, SiLU, residual (the centre tap of the halo), bf16 pairs
   const int y = y0 + warp;
   if (y >= H) return;
-  __nv_bfloat16* op = out + ((long long)n * H + y) * W * C24;
+  eh_t* op = out + ((long long)n * H + y) * W * C24;
 #pragma unroll
   for (int nt = 0; nt < 3; ++nt) {
     const int ch = nt * 8 + 2 * tig;
@@ -746,16 +788,17 @@ __global__ void __launch_bounds__(256) conv3x3_c24_mma_kernel(const __nv_bfloat1
         v1 = __fdividef(v1, 1.f + __expf(-v1));
         if (add_res) {
           const uint32_t r = hw[((warp + 1) * PW + px + 1) * 12 + (ch >> 1)];
-          v0 += __uint_as_float(r << 16);
-          v1 += __uint_as_float(r & 0xffff0000u);
+          const float2 rf = eh2_unpack(r);
+          v0 += rf.x;
+          v1 += rf.y;
         }
         *reinterpret_cast<uint32_t*>(op + (long long)x * C24 + ch) = pack2(v0, v1);
       }
   }
 }
 
-void launch_conv3x3_c24_bf16(const __nv_bfloat16* in, const void* wfrag, const float* scale, const float* shift,
-                             __nv_bfloat16* out, int B, int H, int W, int add_res, cudaStream_t st) {
+void launch_conv3x3_c24_bf16(const eh_t* in, const void* wfrag, const float* scale, const float* shift,
+                             eh_t* out, int B, int H, int W, int add_res, cudaStream_t st) {
   const int tiles = ((W + C24_TW - 1) / C24_TW) * ((H + C24_TH - 1) / C24_TH);
   conv3x3_c24_mma_kernel<<<B * tiles, 256, 0, st>>>(in, reinterpret_cast<const uint2*>(wfrag), scale, shift, out, H, W, add_res);
 }
@@ -768,7 +811,7 @@ void launch_conv3x3_c24_bf16(const __nv_bfloat16* in, const void* wfrag, const f
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) lite_conv0_pool_bf16_kernel(const float* __restrict__ in, const float* __restrict__ w,  // [O][I][3][3]
                                                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                   __nv_bfloat16* __restrict__ out, int B, int Cin, int H, int W, int Cout) {
+                                                                   eh_t* __restrict__ out, int B, int Cin, int H, int W, int Cout) {
   extern __shared__ float ws0[];
   for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) ws0[i] = w[i];
   float* ssc = ws0 + Cout * Cin * 9;
@@ -821,7 +864,7 @@ __global__ void __launch_bounds__(256) lite_conv0_pool_bf16_kernel(const float* 
   *reinterpret_cast<uint4*>(out + pix * Cout + co0) = pack8(o);
 }
 
-void launch_lite_conv0_pool_bf16(const float* in, const float* w, const float* scale, const float* shift, __nv_bfloat16* out,
+void launch_lite_conv0_pool_bf16(const float* in, const float* w, const float* scale, const float* shift, eh_t* out,
                                  int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
   const long long total = (long long)B * (H / 2) * (W / 2) * (Cout / 8);
   const int smem = (Cout * Cin * 9 + 2 * Cout) * sizeof(float);
@@ -830,7 +873,7 @@ void launch_lite_conv0_pool_bf16(const float* in, const float* w, const float* s
 
 // Max-pool 2x2 stride 2, NHWC bf16 (8 channels per thread); out_f32 != nullptr writes fp32 instead (the last pool feeds the
 // fp32 positional-encoding / encoder-layer kernels).
-__global__ void __launch_bounds__(256) maxpool2_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) maxpool2_bf16_kernel(const eh_t* __restrict__ in, eh_t* __restrict__ out,
                                                             float* __restrict__ out_f32, int B, int H, int W, int C) {
   const int OH = H / 2, OW = W / 2, C8 = C / 8;
   const long long total = (long long)B * OH * OW * C8;
@@ -839,7 +882,7 @@ __global__ void __launch_bounds__(256) maxpool2_bf16_kernel(const __nv_bfloat16*
   const int c = (int)(idx % C8) * 8;
   const long long pix = idx / C8;
   const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
-  const __nv_bfloat16* base = in + (((long long)n * H + oh * 2) * W + ow * 2) * C + c;
+  const eh_t* base = in + (((long long)n * H + oh * 2) * W + ow * 2) * C + c;
   float a[8], b[8], d[8], e[8], o[8];
   unpack8(__ldg(reinterpret_cast<const uint4*>(base)), a);
   unpack8(__ldg(reinterpret_cast<const uint4*>(base + C)), b);
@@ -856,7 +899,7 @@ __global__ void __launch_bounds__(256) maxpool2_bf16_kernel(const __nv_bfloat16*
   }
 }
 
-void launch_maxpool2_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, float* out_f32, int B, int H, int W, int C, cudaStream_t st) {
+void launch_maxpool2_bf16(const eh_t* in, eh_t* out, float* out_f32, int B, int H, int W, int C, cudaStream_t st) {
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
   maxpool2_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, out_f32, B, H, W, C);
 }

@@ -438,7 +438,7 @@ void launch_pe2d_f32(const float* x, const float* w0, const float* b0, const flo
 //    pixel p = f % S, channel c' = f / S.
 // ===========================================================================
 __device__ __forceinline__ void store_as(float* p, float v) { *p = v; }
-__device__ __forceinline__ void store_as(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_as(eh_t* p, float v) { *p = eh_from_float(v); }
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) layernorm_f32_generic_kernel(const float* __restrict__ x,
@@ -560,8 +560,8 @@ void launch_layernorm_f32(const float* x, const float* res, const float* gamma, 
 __global__ void __launch_bounds__(256) layernorm_scramble_bf16_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                                       const float* __restrict__ gamma,
                                                                       const float* __restrict__ beta,
-                                                                      __nv_bfloat16* __restrict__ out, int S, int C) {
-  extern __shared__ __nv_bfloat16 ln_tile[];  // [C][S + 2]
+                                                                      eh_t* __restrict__ out, int S, int C) {
+  extern __shared__ eh_t ln_tile[];  // [C][S + 2]
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = C / 32, LD = S + 2;
   for (int qd = warp; qd < S; qd += 8) {
@@ -588,11 +588,11 @@ __global__ void __launch_bounds__(256) layernorm_scramble_bf16_kernel(const floa
       if (i < per) {
         const int ch = i * 32 + lane;
         const int f = qd * C + ch;
-        ln_tile[(f / S) * LD + f % S] = __float2bfloat16_rn((v[i] - mean) * rstd * __ldg(gamma + ch) + __ldg(beta + ch));
+        ln_tile[(f / S) * LD + f % S] = eh_from_float((v[i] - mean) * rstd * __ldg(gamma + ch) + __ldg(beta + ch));
       }
   }
   __syncthreads();
-  __nv_bfloat16* op = out + (long long)b * S * C;
+  eh_t* op = out + (long long)b * S * C;
   for (int g = threadIdx.x; g < S * C; g += 256) {  // g = pp * C + cc
     const int pp = g / C, cc = g - pp * C;
     op[g] = ln_tile[cc * LD + pp];
@@ -600,13 +600,13 @@ __global__ void __launch_bounds__(256) layernorm_scramble_bf16_kernel(const floa
 }
 
 void launch_layernorm_bf16out(const float* x, const float* res, const float* gamma, const float* beta,
-                              __nv_bfloat16* out, int M, int C, int scramble_S, cudaStream_t st) {
+                              eh_t* out, int M, int C, int scramble_S, cudaStream_t st) {
   if (scramble_S > 0 && C <= 512 && C % 32 == 0 && M % scramble_S == 0 && (size_t)C * (scramble_S + 2) * 2 <= 48 * 1024) {
     layernorm_scramble_bf16_kernel<<<M / scramble_S, 256, (size_t)C * (scramble_S + 2) * 2, st>>>(x, res, gamma, beta, out,
                                                                                                scramble_S, C);
     return;
   }
-  layernorm_launch<__nv_bfloat16>(x, res, gamma, beta, out, M, C, scramble_S, st);
+  layernorm_launch<eh_t>(x, res, gamma, beta, out, M, C, scramble_S, st);
 }
 
 // ===========================================================================
@@ -674,8 +674,8 @@ static void enc_attn_launch(const float* qkv, OutT* out, int B, int S, int D, in
 void launch_enc_attn_f32(const float* qkv, float* out, int B, int S, int D, int heads, cudaStream_t st) {
   enc_attn_launch<float>(qkv, out, B, S, D, heads, st);
 }
-void launch_enc_attn_bf16out(const float* qkv, __nv_bfloat16* out, int B, int S, int D, int heads, cudaStream_t st) {
-  enc_attn_launch<__nv_bfloat16>(qkv, out, B, S, D, heads, st);
+void launch_enc_attn_bf16out(const float* qkv, eh_t* out, int B, int S, int D, int heads, cudaStream_t st) {
+  enc_attn_launch<eh_t>(qkv, out, B, S, D, heads, st);
 }
 
 // ===========================================================================

@@ -160,11 +160,10 @@ void launch_swin_patch_merge(const float* x, float* out, int B, int R, int C, cu
 // ---------------------------------------------------------------------------
 namespace {
 __device__ __forceinline__ uint32_t sw_pack2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  return eh2_pack(lo, hi);
 }
 __device__ __forceinline__ void sw_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32." FRX_EH_PTX "." FRX_EH_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -173,10 +172,10 @@ __device__ __forceinline__ void sw_mma(float (&c)[4], const uint32_t (&a)[4], ui
 constexpr int SWA_N = 144, SWA_WS = 12, SWA_LDK = 40, SWA_LDV = 152, SWA_NB = (2 * SWA_WS - 1) * (2 * SWA_WS - 1);
 
 __global__ void __launch_bounds__(128) swin_window_attn_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ bias_table,
-                                                                   __nv_bfloat16* __restrict__ out, int R, int C, int heads, int shift) {
-  __shared__ __align__(16) __nv_bfloat16 Qb[SWA_N * SWA_LDK];
-  __shared__ __align__(16) __nv_bfloat16 Kb[SWA_N * SWA_LDK];
-  __shared__ __align__(16) __nv_bfloat16 Vt[32 * SWA_LDV];
+                                                                   eh_t* __restrict__ out, int R, int C, int heads, int shift) {
+  __shared__ __align__(16) eh_t Qb[SWA_N * SWA_LDK];
+  __shared__ __align__(16) eh_t Kb[SWA_N * SWA_LDK];
+  __shared__ __align__(16) eh_t Vt[32 * SWA_LDV];
   __shared__ float bias_h[SWA_NB];
   __shared__ int tokidx[SWA_N];
   __shared__ int colinfo[SWA_N];  // y | x << 8 | region << 16 of window position j
@@ -205,9 +204,9 @@ __global__ void __launch_bounds__(128) swin_window_attn_mma_kernel(const float* 
   for (int i = threadIdx.x; i < N * 32; i += 128) {
     const int r = i >> 5, c = i & 31;
     const float* rp = base + (long long)tokidx[r] * 3 * C + c;
-    Qb[r * SWA_LDK + c] = __float2bfloat16_rn(__ldg(rp) * scale);
-    Kb[r * SWA_LDK + c] = __float2bfloat16_rn(__ldg(rp + C));
-    Vt[c * SWA_LDV + r] = __float2bfloat16_rn(__ldg(rp + 2 * C));
+    Qb[r * SWA_LDK + c] = eh_from_float(__ldg(rp) * scale);
+    Kb[r * SWA_LDK + c] = eh_from_float(__ldg(rp + C));
+    Vt[c * SWA_LDV + r] = eh_from_float(__ldg(rp + 2 * C));
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
@@ -280,8 +279,8 @@ __global__ void __launch_bounds__(128) swin_window_attn_mma_kernel(const float* 
       }
     }
     const float q0 = __fdividef(1.f, sum0), q1 = __fdividef(1.f, sum1);
-    __nv_bfloat16* o0 = out + ((long long)n * R * R + tokidx[r0]) * C + hh * 32 + 2 * tig;
-    __nv_bfloat16* o1 = out + ((long long)n * R * R + tokidx[r1]) * C + hh * 32 + 2 * tig;
+    eh_t* o0 = out + ((long long)n * R * R + tokidx[r0]) * C + hh * 32 + 2 * tig;
+    eh_t* o1 = out + ((long long)n * R * R + tokidx[r1]) * C + hh * 32 + 2 * tig;
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) {
       *reinterpret_cast<uint32_t*>(o0 + 8 * nd) = sw_pack2(oacc[nd][0] * q0, oacc[nd][1] * q0);
@@ -291,7 +290,7 @@ __global__ void __launch_bounds__(128) swin_window_attn_mma_kernel(const float* 
 }
 
 // returns false when the window is not 12 x 12 with 32-wide heads (the caller then uses the fp32 kernel)
-bool launch_swin_window_attn_mma(const float* qkv, const float* bias_table, __nv_bfloat16* out, int B, int R, int C, int heads,
+bool launch_swin_window_attn_mma(const float* qkv, const float* bias_table, eh_t* out, int B, int R, int C, int heads,
                                  int ws, int shift, cudaStream_t st) {
   if (ws != SWA_WS || C != heads * 32 || R % ws != 0) return false;
   const int nW = (R / ws) * (R / ws);

@@ -98,12 +98,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=BN.
+// kind::f16 instruction descriptor: D=F32, A=B=eh_t (format 0 = F16, 1 = BF16), both K-major, M=128, N=BN.
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  constexpr uint32_t fmt = FRX_ENC_FP16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -140,7 +141,15 @@ __device__ __forceinline__ float act_fast(float v) {
 // SiLU of two values with ONE special-function op: x sigmoid(x) = h + h tanh(h), h = x/2, tanh as tanh.approx.f16x2
 // (ex2 + rcp per value made the 16-op/clk MUFU pipe the floor of every small-K SiLU layer: 4096 clk per 128 x 256 tile
 // against 2168 clk of MMA at K = 256). The product stays in fp32; the result is stored as bf16.
+#ifndef FRX_SILU_EXACT
+#define FRX_SILU_EXACT 1
+#endif
 __device__ __forceinline__ void silu_pair(float& a, float& b) {
+#if FRX_SILU_EXACT
+  a = __fdividef(a, 1.f + __expf(-a));
+  b = __fdividef(b, 1.f + __expf(-b));
+  return;
+#endif
   const float ha = 0.5f * a, hb = 0.5f * b;
   const __half2 h = __floats2half2_rn(ha, hb);
   uint32_t t;
@@ -225,18 +234,19 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
               if (nb + i < p.N) v[i] += __ldg(rp + i);
           }
         } else {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + (size_t)m * p.ldr + nb;
+          const eh_t* rp = reinterpret_cast<const eh_t*>(p.res) + (size_t)m * p.ldr + nb;
           if (full) {
             const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp)), r1 = __ldg(reinterpret_cast<const uint4*>(rp + 8));
             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              v[2 * i] += __uint_as_float(rw[i] << 16);
-              v[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
+              const float2 rf = eh2_unpack(rw[i]);
+              v[2 * i] += rf.x;
+              v[2 * i + 1] += rf.y;
             }
           } else {
             for (int i = 0; i < 16; ++i)
-              if (nb + i < p.N) v[i] += __bfloat162float(rp[i]);
+              if (nb + i < p.N) v[i] += eh_to_float(rp[i]);
           }
         }
       }
@@ -255,14 +265,11 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
             if (nb + i < p.N) cp[i] = v[i];
         }
       } else {
-        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * p.ldc + nb;
+        eh_t* cp = reinterpret_cast<eh_t*>(p.C) + (size_t)m * p.ldc + nb;
         if (full && (p.ldc & 7) == 0) {
           uint32_t w[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            w[i] = *reinterpret_cast<uint32_t*>(&t);
-          }
+          for (int i = 0; i < 8; ++i) w[i] = eh2_pack(v[2 * i], v[2 * i + 1]);
           if ((p.ldc & 15) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31) == 0) {  // one full 32-byte sector per thread (256-bit store, sm_100+)
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(cp), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                          "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
@@ -272,7 +279,7 @@ __device__ __forceinline__ void epilogue_store16(const TcGemmP& p, const uint32_
           }
         } else {
           for (int i = 0; i < 16; ++i)
-            if (nb + i < p.N) cp[i] = __float2bfloat16_rn(v[i]);
+            if (nb + i < p.N) cp[i] = eh_from_float(v[i]);
         }
       }
 }
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
 
   // ---- loader coordinates: thread -> 16-byte chunk c of rows rbase + 32*i ----------------
   const int c = tid & 7, rbase = tid >> 3;
-  const __nv_bfloat16* a_ptr[4];
+  const eh_t* a_ptr[4];
   int a_ih0[4], a_iw0[4];
   bool a_ok[4];
 #pragma unroll
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
     for (int i = 0; i < 4; ++i) {
       const int row = rbase + 32 * i;
       const uint32_t dst = sa + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
-      const __nv_bfloat16* src = p.A;
+      const eh_t* src = p.A;
       uint32_t bytes = 0;
       if (a_ok[i] && k < p.K) {
         if (p.conv) {
@@ -396,7 +403,7 @@ __global__ void __launch_bounds__(256) tc_igemm_kernel(const TcGemmP p) {
       const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + TC_A_BYTES);
 #pragma unroll
       for (int j = 0; j < TC_BK / 16; ++j)  // +32 bytes (2 x 16-byte units) per K=16 step inside the swizzle atom
-        umma_bf16(tmem, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
+        umma_f16(tmem, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
       umma_commit(&mma_done[stage]);
       if (kb == KB - 1) umma_commit(&acc_done);
     }
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(WS_THREADS, NCOLS >= 256 ? 1 : 2) tc_igemm_ws_
     int it = 0;   // flat k-block counter over all tiles of this CTA
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
-      const __nv_bfloat16* a_ptr[WS_A_PASSES];
+      const eh_t* a_ptr[WS_A_PASSES];
       int a_ih0[WS_A_PASSES], a_iw0[WS_A_PASSES];
       bool a_ok[WS_A_PASSES];
       int bw = 0, bh = 0, bn = 0;  // im2col: base pixel of the tile's first output row
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(WS_THREADS, NCOLS >= 256 ? 1 : 2) tc_igemm_ws_
           for (int i = 0; i < WS_A_PASSES; ++i) {
             const int row = rbase + WS_ROWS_PER_PASS * i;
             const uint32_t dst = sa + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c ^ (row & 7)) << 4);
-            const __nv_bfloat16* src = p.A;
+            const eh_t* src = p.A;
             uint32_t bytes = 0;
             if (a_ok[i] && k < p.K) {
               const int ih = a_ih0[i] + kh, iw = a_iw0[i] + kw;
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(WS_THREADS, NCOLS >= 256 ? 1 : 2) tc_igemm_ws_
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + TC_A_BYTES);
 #pragma unroll
           for (int j = 0; j < TC_BK / 16; ++j)
-            umma_bf16(tacc, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
+            umma_f16(tacc, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (kb | j) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
           if (kb == KB - 1) umma_commit(&acc_full[a]);  // accumulator complete
         }
@@ -673,7 +680,7 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long 
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(tm, (FRX_ENC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
@@ -704,7 +711,7 @@ static int make_tmap_im2col(CUtensorMap* tm, const TcGemmP& p) {
   int lower[2] = {-p.pad_l, -p.pad_t};
   int upper[2] = {pad_r - (k - 1), pad_b - (k - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)p.stride, (cuuint32_t)p.stride, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(p.A), dims, strides, lower, upper,
+  CUresult r = enc(tm, (FRX_ENC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4, const_cast<eh_t*>(p.A), dims, strides, lower, upper,
                    (cuuint32_t)TC_BK, (cuuint32_t)TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
@@ -781,42 +788,41 @@ int launch_tc_igemm(TcGemmP p, cudaStream_t st) {
 }
 
 // ===========================================================================
-// small helpers of the bf16 path
+// small helpers of the 16-bit path (eh_t = the encoder operand type, common.cuh)
 // ===========================================================================
-__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+__global__ void __launch_bounds__(256) f32_to_h16_kernel(const float* __restrict__ in, eh_t* __restrict__ out, long long n) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 v = __ldg(reinterpret_cast<const float4*>(in + i));
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    *reinterpret_cast<uint2*>(out + i) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    *reinterpret_cast<uint2*>(out + i) = make_uint2(eh2_pack(v.x, v.y), eh2_pack(v.z, v.w));
   } else {
-    for (; i < n; ++i) out[i] = __float2bfloat16_rn(in[i]);
+    for (; i < n; ++i) out[i] = eh_from_float(in[i]);
   }
 }
 
-void launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
-  f32_to_bf16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(in, out, n);
+void launch_f32_to_h16(const float* in, eh_t* out, long long n, cudaStream_t st) {
+  f32_to_h16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(in, out, n);
 }
 
 
-__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+__global__ void __launch_bounds__(256) h16_to_f32_kernel(const eh_t* __restrict__ in, float* __restrict__ out, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __bfloat162float(in[i]);
+  if (i < n) out[i] = eh_to_float(in[i]);
 }
-void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st) {
-  bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+void launch_h16_to_f32(const eh_t* in, float* out, long long n, cudaStream_t st) {
+  h16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
 }
 
 
 // [N][taps][Cin] -> [N][taps][64] (zero padded) bf16, for the im2col path
-__global__ void __launch_bounds__(256) pad_conv_weights_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) pad_conv_weights_kernel(const eh_t* __restrict__ in, eh_t* __restrict__ out,
                                                                long long rows, int Cin) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * 64) return;
   const int ci = (int)(i & 63);
-  out[i] = ci < Cin ? in[(i >> 6) * Cin + ci] : __float2bfloat16_rn(0.f);
+  out[i] = ci < Cin ? in[(i >> 6) * Cin + ci] : eh_from_float(0.f);
 }
-void launch_pad_conv_weights(const __nv_bfloat16* in, __nv_bfloat16* out, long long rows, int Cin, cudaStream_t st) {
+void launch_pad_conv_weights(const eh_t* in, eh_t* out, long long rows, int Cin, cudaStream_t st) {
   pad_conv_weights_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, st>>>(in, out, rows, Cin);
 }
 

@@ -579,6 +579,30 @@ static inline uint32_t bf16_bits(float f) {  // round-to-nearest-even, like __fl
   return u >> 16;
 }
 
+// host-side fp32 -> 16-bit conversion of ENCODER-side operands (eh_t of common.cuh): IEEE fp16, round-to-nearest-even,
+// saturating like cvt.rn.satfinite; or bf16 when the library is built with -DFRX_ENC_FP16=0
+static inline uint32_t eh_bits(float f) {
+#if FRX_ENC_FP16
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t a = u & 0x7fffffffu;
+  if (a > 0x7f800000u) return sign | 0x7e00u;              // NaN
+  if (a >= 0x477ff000u) return sign | 0x7bffu;             // >= 65520 rounds past the largest finite half: saturate
+  if (a < 0x33000001u) return sign;                        // < 2^-25 (or exactly 2^-25, a tie to even 0): zero
+  const int e = (int)(a >> 23) - 127;
+  uint32_t m = (a & 0x7fffffu) | 0x800000u;                // 24-bit significand
+  int shift = e >= -14 ? 13 : 13 + (-14 - e);              // bits dropped (subnormal halves drop more)
+  uint32_t q = m >> shift;
+  const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+  if (rem > half || (rem == half && (q & 1u))) ++q;
+  if (e >= -14) return sign | (uint32_t)(((e + 15) << 10) + (q - 0x400u));   // a carry out of q bumps the exponent
+  return sign | q;                                         // subnormal (q = 0x400 becomes the smallest normal)
+#else
+  return bf16_bits(f);
+#endif
+}
+
 // B-fragment order of mma.m16n8k16 for the persistent decode kernel:
 // [cta r][tile][k-pair kp][lane] -> uint4 {b0b1(k-step 2kp), b2b3(2kp), b0b1(2kp+1), b2b3(2kp+1)}.
 // rowptr(r, tile, gid) returns the K-float weight row of output column (tile, gid) of CTA r, or nullptr.
@@ -607,7 +631,7 @@ static size_t pack_bf16_copy(ArenaBuilder& ab, size_t src_off, size_t n) {
   size_t off = ab.add(nullptr, (n + 1) / 2);
   const float* s = ab.at(src_off);
   uint16_t* d = reinterpret_cast<uint16_t*>(ab.at(off));
-  for (size_t i = 0; i < n; ++i) d[i] = (uint16_t)bf16_bits(s[i]);
+  for (size_t i = 0; i < n; ++i) d[i] = (uint16_t)eh_bits(s[i]);
   return off;
 }
 
@@ -618,7 +642,7 @@ static size_t pack_bf16_conv_padded(ArenaBuilder& ab, size_t src_off, int N, int
   const float* s = ab.at(src_off);
   uint16_t* d = reinterpret_cast<uint16_t*>(ab.at(off));
   for (size_t row = 0; row < (size_t)N * taps; ++row)
-    for (int ci = 0; ci < 64; ++ci) d[row * 64 + ci] = ci < Cin ? (uint16_t)bf16_bits(s[row * Cin + ci]) : 0;
+    for (int ci = 0; ci < 64; ++ci) d[row * 64 + ci] = ci < Cin ? (uint16_t)eh_bits(s[row * Cin + ci]) : 0;
   return off;
 }
 
@@ -635,7 +659,7 @@ static size_t pack_frag_conv24(ArenaBuilder& ab, size_t w_off) {
         const int gid = lane >> 2, tig = lane & 3, n = 8 * nt + gid;
         for (int q = 0; q < 2; ++q) {
           const int k = 16 * s + 8 * q + 2 * tig;
-          const uint32_t lo = k < K ? bf16_bits(w[(size_t)n * K + k]) : 0u, hi = k + 1 < K ? bf16_bits(w[(size_t)n * K + k + 1]) : 0u;
+          const uint32_t lo = k < K ? eh_bits(w[(size_t)n * K + k]) : 0u, hi = k + 1 < K ? eh_bits(w[(size_t)n * K + k + 1]) : 0u;
           d[((size_t)(s * 3 + nt) * 32 + lane) * 2 + q] = lo | (hi << 16);
         }
       }
@@ -915,7 +939,7 @@ static int tap_bf16(frx_handle* h, const std::string& name, const void* src, int
     t.capacity = n;
   }
   t.shape[0] = B; t.shape[1] = H; t.shape[2] = W; t.shape[3] = C;
-  launch_bf16_to_f32((const __nv_bfloat16*)src, t.data, (long long)n, st);
+  launch_h16_to_f32((const eh_t*)src, t.data, (long long)n, st);
   CKL();
   return 0;
 }
@@ -994,7 +1018,7 @@ static int run_trunk_efficientnet(frx_handle* h, const float* images, int B, flo
 
 static TcGemmP tc_dense(const void* A, int M, int K, const float* arena, size_t w_off, int N, void* C, int out_f32) {
   TcGemmP g{};
-  g.A = (const __nv_bfloat16*)A; g.W = (const __nv_bfloat16*)(arena + w_off); g.C = C;
+  g.A = (const eh_t*)A; g.W = (const eh_t*)(arena + w_off); g.C = C;
   g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.out_f32 = out_f32;
   return g;
 }
@@ -1005,7 +1029,7 @@ static TcGemmP tc_conv(const void* A, int B, int H, int W, int Cin, const float*
   int pt, pl;
   same_pad(H, k, stride, OH, &pt);
   same_pad(W, k, stride, OW, &pl);
-  g.A = (const __nv_bfloat16*)A; g.W = (const __nv_bfloat16*)(arena + w_off); g.C = C;
+  g.A = (const eh_t*)A; g.W = (const eh_t*)(arena + w_off); g.C = C;
   g.M = B * (*OH) * (*OW); g.N = Cout; g.K = k * k * Cin; g.ldw = g.K; g.ldc = Cout;
   g.conv = 1; g.H = H; g.Wd = W; g.Cin = Cin; g.OH = *OH; g.OW = *OW; g.KW = k; g.stride = stride; g.pad_t = pt; g.pad_l = pl;
   return g;
@@ -1023,7 +1047,7 @@ static TcGemmP tc_conv(const void* A, int B, int H, int W, int Cin, const float*
 static int encode_bf16(frx_handle* h, const float* images, int B, float* memory, cudaStream_t st) {
   const frx_config& c = h->cfg;
   const float* A = h->arena;
-  typedef __nv_bfloat16 bf;
+  typedef eh_t bf;
   int H = (c.height - 3) / 2 + 1, W = (c.width - 3) / 2 + 1;
   bf* x = (bf*)h->act[0];
   bf* y = (bf*)h->act[1];
@@ -1040,13 +1064,13 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
       CKL();
     } else if (b.kind == 0) {
       TcGemmP g = tc_conv(x, B, H, W, b.cin, A, b.wb_a, b.cout, b.k, b.stride, y, &OH, &OW);
-      if (b.wb_a_pad && h->opt_tc_im2col) g.Wpad = (const __nv_bfloat16*)(A + b.wb_a_pad);
+      if (b.wb_a_pad && h->opt_tc_im2col) g.Wpad = (const eh_t*)(A + b.wb_a_pad);
       g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
       if (b.residual) { g.res = x; g.ldr = b.cout; }
       TCL(g);
     } else if (b.kind == 1) {
       TcGemmP g = tc_conv(x, B, H, W, b.cin, A, b.wb_a, b.mid, b.k, b.stride, m0, &OH, &OW);
-      if (b.wb_a_pad && h->opt_tc_im2col) g.Wpad = (const __nv_bfloat16*)(A + b.wb_a_pad);
+      if (b.wb_a_pad && h->opt_tc_im2col) g.Wpad = (const eh_t*)(A + b.wb_a_pad);
       g.scale = A + b.sc_a; g.shift = A + b.sh_a; g.act = ACT_SILU;
       TCL(g);
       TcGemmP g2 = tc_dense(m0, B * OH * OW, b.mid, A, b.wb_b, b.cout, y, 0);
@@ -1134,12 +1158,12 @@ static int encode_swin(frx_handle* h, const float* images, int B, float* memory,
       if (h->cfg.precision == FRX_PREC_BF16) {
         // bf16 mode: the four linear layers of the block on the tcgen05 GEMM (bf16 operands, fp32 accumulation);
         // residual stream, LayerNorm statistics and the window attention (softmax) stay fp32
-        __nv_bfloat16* ab16 = (__nv_bfloat16*)h->sw_ab;
+        eh_t* ab16 = (eh_t*)h->sw_ab;
         launch_layernorm_bf16out(x, nullptr, A + b.n1_g, A + b.n1_b, ab16, M, C, 0, st); CKL();
         { TcGemmP g = tc_dense(ab16, M, C, A, b.qkv_wb, 3 * C, h->sw_qkv, 1); g.shift = A + b.qkv_b; TCL(g); }
         if (!launch_swin_window_attn_mma(h->sw_qkv, A + b.bias_table, ab16, B, b.res, C, b.heads, b.ws, b.shift, st)) {
           launch_swin_window_attn(h->sw_qkv, A + b.bias_table, h->sw_a, B, b.res, C, b.heads, b.ws, b.shift, st); CKL();
-          launch_f32_to_bf16(h->sw_a, ab16, (long long)M * C, st);
+          launch_f32_to_h16(h->sw_a, ab16, (long long)M * C, st);
         }
         CKL();
         { TcGemmP g = tc_dense(ab16, M, C, A, b.proj_wb, C, y, 1); g.shift = A + b.proj_b; g.res = x; g.res_f32 = 1; g.ldr = C; TCL(g); }
@@ -1171,7 +1195,7 @@ static int encode_swin(frx_handle* h, const float* images, int B, float* memory,
       const int M2 = B * (m.res / 2) * (m.res / 2);
       launch_swin_patch_merge(x, h->sw_hid, B, m.res, m.dim, st); CKL();
       if (h->cfg.precision == FRX_PREC_BF16) {
-        launch_layernorm_bf16out(h->sw_hid, nullptr, A + m.n_g, A + m.n_b, (__nv_bfloat16*)h->sw_hidb, M2, 4 * m.dim, 0, st); CKL();
+        launch_layernorm_bf16out(h->sw_hid, nullptr, A + m.n_g, A + m.n_b, (eh_t*)h->sw_hidb, M2, 4 * m.dim, 0, st); CKL();
         TcGemmP g = tc_dense(h->sw_hidb, M2, 4 * m.dim, A, m.red_wb, 2 * m.dim, x, 1);
         TCL(g);
         if (tap(h, "merge" + std::to_string(i), x, B, m.res / 2, m.res / 2, 2 * m.dim, st)) return 1;
@@ -1198,7 +1222,7 @@ static int run_trunk_lite(frx_handle* h, const float* images, int B, float** out
     // bf16 mode: layer 0 fused with its max-pool (fp32 arithmetic on the single-channel image, bf16 NHWC out), layers
     // 1-3 as implicit GEMMs on the tcgen05 kernel (bf16 in / out, folded BN + ReLU in the epilogue), bf16 max-pools;
     // the last pool writes fp32 for the positional encoding / encoder layer that follow.
-    typedef __nv_bfloat16 bf;
+    typedef eh_t bf;
     bf* xb = (bf*)h->act[0];
     bf* yb = (bf*)h->act[1];
     const LiteConvW& L0 = h->lite[0];
@@ -1309,7 +1333,7 @@ static int run_cross_kv(frx_handle* h, const float* memory, int B, cudaStream_t 
   const frx_config& c = h->cfg;
   const int S = h->feat_h * h->feat_w;
   if (c.precision == FRX_PREC_BF16) {
-    launch_f32_to_bf16(memory, (__nv_bfloat16*)h->mem_bf, (long long)B * S * c.dec_src, st); CKL();
+    launch_f32_to_h16(memory, (eh_t*)h->mem_bf, (long long)B * S * c.dec_src, st); CKL();
     TcGemmP t = tc_dense(h->mem_bf, B * S, c.dec_src, h->arena, h->cross_wb, c.dec_layers * 2 * c.dec_hidden, h->cross, 1);
     t.shift = h->arena + h->b_cross;
     TCL(t);
@@ -1771,7 +1795,7 @@ extern "C" int frx_decode_teacher_forced(frx_handle* h, const float* memory, con
       if (res) { g.res = res; g.res_f32 = 1; g.ldr = N; }
       return g;
     };
-    auto to_bf16 = [&](const float* src) { launch_f32_to_bf16(src, (__nv_bfloat16*)w.xb, (long long)M * D, st); };
+    auto to_bf16 = [&](const float* src) { launch_f32_to_h16(src, (eh_t*)w.xb, (long long)M * D, st); };
     for (int l = 0; l < NL; ++l) {
       const DecLayerW& W = h->dec[l];
       to_bf16(x); CKL();
@@ -1849,7 +1873,7 @@ extern "C" int frx_tc_gemm(frx_handle* h, const void* A, const void* W, void* C,
   cudaStream_t st = (cudaStream_t)stream;
   ON_DEVICE(h->cfg.device);
   TcGemmP g{};
-  g.A = (const __nv_bfloat16*)A; g.W = (const __nv_bfloat16*)W; g.C = C;
+  g.A = (const eh_t*)A; g.W = (const eh_t*)W; g.C = C;
   g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.out_f32 = out_f32;
   g.scale = scale; g.shift = shift; g.act = act;
   if (conv7) {  // {B, H, W, Cin, ksize, stride, same_pad(1) or zero pad(0)}
@@ -1866,8 +1890,8 @@ extern "C" int frx_tc_gemm(frx_handle* h, const void* A, const void* W, void* C,
         if (dev_alloc(h, &q, bytes)) return 1;
         h->hook_wpad = q; h->hook_wpad_bytes = bytes;
       }
-      launch_pad_conv_weights((const __nv_bfloat16*)W, (__nv_bfloat16*)h->hook_wpad, (long long)N * k * k, Cin, st); CKL();
-      g.Wpad = (const __nv_bfloat16*)h->hook_wpad;
+      launch_pad_conv_weights((const eh_t*)W, (eh_t*)h->hook_wpad, (long long)N * k * k, Cin, st); CKL();
+      g.Wpad = (const eh_t*)h->hook_wpad;
     }
   }
   TCL(g);

@@ -1,6 +1,7 @@
-"""bf16 mode (tensor-core contractions, bf16 KV cache): logits within a stated
-relative tolerance of the reference under forced decoding, free-running
-token-sequence agreement reported (BASELINE.json north_star)."""
+"""16-bit mode (precision="bf16": tensor-core contractions with fp32 accumulation; the encoder side feeds IEEE fp16
+operands -- same rate and bytes as bf16, 3 more significand bits, csrc/common.cuh eh_t -- the persistent decode kernel
+bf16 weights and a bf16 KV cache): logits within a stated relative tolerance of the reference under forced decoding,
+free-running token-sequence agreement reported (BASELINE.json north_star)."""
 import numpy as np
 import pytest
 import torch
@@ -12,11 +13,12 @@ from oracle import satrn, synth
 pytestmark = pytest.mark.gpu
 
 BF16_REL_TOL = 4e-2   # decoder only: max |logit - ref| / max |ref| under forced decoding (bf16 weights + bf16 KV cache)
-BF16_E2E_REL_TOL = 0.20  # encoder + decoder in bf16, forced decoding.  Yardstick (tools/bf16_yardstick.py, same synthetic
-                          # checkpoint, 16 images): an ideal pipeline that rounds ONLY the GEMM operands to bf16 and keeps
-                          # everything else fp32 already sits at 0.105 (memory rel-L2 0.076, free-running tokens 0.81);
-                          # torch.autocast(bfloat16) over the oracle at 0.197 / 0.149 / 0.72.  frx measures 0.12 / 0.08.
-FLOOR_FACTOR = 1.35       # encoder memory: frx's rel-L2 error may exceed that operand-rounding floor by at most this factor
+BF16_E2E_REL_TOL = 0.05  # encoder + decoder in 16-bit mode, forced decoding (measured 0.021-0.030).  Yardstick
+                          # (tools/bf16_yardstick.py, same synthetic checkpoint): with bf16 encoder operands an IDEAL pipeline
+                          # already sits at 0.105 (memory rel-L2 0.080, free-running tokens 0.81), which is why the encoder
+                          # feeds fp16: ideal fp16-operand pipeline 0.016 (memory 0.010, tokens 0.94).
+FLOOR_FACTOR = 1.35       # encoder memory: frx's rel-L2 error may exceed the fp16 operand-rounding floor by at most this factor
+STEP_AGREEMENT = 0.95     # per-step argmax agreement with the fp32 oracle under forced decoding, full size
 MIN_AGREEMENT = 0.80  # free-running token agreement with the fp32 reference, DECODER ALONE on the golden fp32 memory
 
 
@@ -73,7 +75,7 @@ def test_bf16_matches_fp32_path_on_step_zero(ckpt0, model_bf16, spec):
     print("bf16 (encoder+decoder) vs fp32 path, forced, 6 steps: max rel logit error %.4f, argmax agreement %.3f"
           % (rel, agree))
     assert rel <= BF16_E2E_REL_TOL, rel
-    assert agree >= 0.6
+    assert agree >= 0.8   # 30 positions; the synthetic checkpoint's top-2 margins are often below 1 % of the logit range
 
 
 def test_bf16_deterministic_and_batch_invariant(model_bf16, spec):
@@ -183,12 +185,13 @@ def test_bf16_decode_geometries_agree_bitwise(ckpt0):
 def test_bf16_full_size_against_oracle_and_operand_floor(ckpt0, spec):
     """BASELINE size (B = 256, 231 steps) in the benchmarked bf16 mode, checked on a 32-image slice against the fp32
     oracle: forced-decoding logit error within BF16_E2E_REL_TOL, encoder-memory error within FLOOR_FACTOR of what an
-    ideal bf16-operand pipeline gives on the same images (the emulation in tools/bf16_yardstick.py), free-running token
+    ideal fp16-operand pipeline gives on the same images (the emulation in tools/bf16_yardstick.py), free-running token
     agreement reported next to that floor's and required to stay within 0.10 of it."""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import bf16_yardstick as ys
+    ys.set_operand_dtype(torch.float16)
     B, T, NS = 256, 231, 32
     x = synth.synth_images(spec, B, 3)
     model = make_model(ckpt0, precision="bf16", max_batch=B, max_steps=T).cuda().eval()
@@ -208,9 +211,9 @@ def test_bf16_full_size_against_oracle_and_operand_floor(ckpt0, spec):
     step_agree = (lg_forced[:NS].cpu().argmax(-1) == ref_logits.argmax(-1)).float().mean().item()
     a_gpu = (tok_gpu[:NS].cpu() == ref_tok).float().mean().item()
     a_floor = (floor_tok == ref_tok).float().mean().item()
-    print("B=256 bf16 vs oracle on %d images: memory rel-L2 %.4f (bf16-operand floor %.4f), forced max-rel %.4f, "
+    print("B=256 bf16 vs oracle on %d images: memory rel-L2 %.4f (fp16-operand floor %.4f), forced max-rel %.4f, "
           "per-step argmax %.4f, free-running tokens %.4f (floor %.4f)" % (NS, e_gpu, e_floor, rel, step_agree, a_gpu, a_floor))
     assert e_gpu <= FLOOR_FACTOR * e_floor, (e_gpu, e_floor)
     assert rel <= BF16_E2E_REL_TOL, rel
-    assert step_agree >= 0.75, step_agree
+    assert step_agree >= STEP_AGREEMENT, step_agree
     assert a_gpu >= a_floor - 0.10, (a_gpu, a_floor)

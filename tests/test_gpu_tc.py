@@ -25,7 +25,7 @@ def handle(request):
 
 
 def _run(handle, a, w, m, n, k, conv=None, scale=None, shift=None, act=0, out_f32=True):
-    c = torch.empty(m, n, device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
+    c = torch.empty(m, n, device="cuda", dtype=torch.float32 if out_f32 else torch.float16)
     conv7 = (ctypes.c_int32 * 7)(*conv) if conv else None
     handle.call("frx_tc_gemm", a.data_ptr(), w.data_ptr(), c.data_ptr(), m, n, k, conv7,
                 scale.data_ptr() if scale is not None else None, shift.data_ptr() if shift is not None else None,
@@ -38,8 +38,8 @@ def _run(handle, a, w, m, n, k, conv=None, scale=None, shift=None, act=0, out_f3
                                    (128, 768, 128), (4096, 1536, 512), (130, 48, 96), (64, 512, 1536)])
 def test_dense_gemm(handle, m, n, k):
     g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
-    a = torch.randn(m, k, device="cuda", generator=g).bfloat16()
-    w = (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).bfloat16()
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    w = (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).half()
     c = _run(handle, a, w, m, n, k)
     ref = a.float() @ w.float().t()
     assert (c - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
@@ -49,8 +49,8 @@ def test_many_tiles_per_cta(handle):
     """More tiles than persistent CTAs: exercises the ring / accumulator phase wrap-around."""
     m, n, k = 128 * 700, 96, 216
     g = torch.Generator(device="cuda").manual_seed(5)
-    a = torch.randn(m, k, device="cuda", generator=g).bfloat16()
-    w = (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).bfloat16()
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    w = (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).half()
     c = _run(handle, a, w, m, n, k)
     ref = a.float() @ w.float().t()
     assert (c - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
@@ -59,8 +59,8 @@ def test_many_tiles_per_cta(handle):
 def test_epilogue_scale_shift_act_bf16_out(handle):
     m, n, k = 300, 96, 216
     g = torch.Generator(device="cuda").manual_seed(1)
-    a = torch.randn(m, k, device="cuda", generator=g).bfloat16()
-    w = (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).bfloat16()
+    a = torch.randn(m, k, device="cuda", generator=g).half()
+    w = (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).half()
     scale = torch.rand(n, device="cuda", generator=g) + 0.5
     shift = torch.randn(n, device="cuda", generator=g)
     c = _run(handle, a, w, m, n, k, scale=scale, shift=shift, act=2, out_f32=False)
@@ -75,8 +75,8 @@ def test_conv3x3_implicit_gemm(handle, b, h, w_, cin, cout, stride):
     """3x3 conv as implicit GEMM with timm's padding rule (static 1 for stride 1,
     TF-'same' (0,1) for stride 2 on even sizes / (1,1) on odd sizes)."""
     g = torch.Generator(device="cuda").manual_seed(b + cout)
-    x = torch.randn(b, h, w_, cin, device="cuda", generator=g).bfloat16()          # NHWC
-    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (9 * cin) ** 0.5).bfloat16()
+    x = torch.randn(b, h, w_, cin, device="cuda", generator=g).half()          # NHWC
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (9 * cin) ** 0.5).half()
     oh, ow = -(-h // stride), -(-w_ // stride)
     wp = wt.permute(0, 2, 3, 1).contiguous().view(cout, 9 * cin)                     # [O][kh][kw][I]
     c = _run(handle, x, wp, b * oh * ow, cout, 9 * cin, conv=(b, h, w_, cin, 3, stride, 1))

@@ -12,7 +12,12 @@ token agreement of a 231-step greedy decode (fp32 decoder fed the perturbed memo
   operands   bf16 GEMM operands only (weights + A operand rounded), everything else fp32: the floor of any pipeline
              that feeds bf16 into the tensor cores
 
-    python tools/bf16_yardstick.py [--batch 16] [--seed 0] [--steps 231]
+The library's encoder now feeds IEEE fp16 operands (common.cuh, eh_t); ``--dtype fp16`` applies the same policies with
+fp16 rounding.  Measured on 16 images, seed 0 (memory rel-L2 / forced max-rel / forced argmax / free-running tokens):
+  bf16: operands 0.0797 / 0.105 / .. / 0.81,   frx_r1 0.094 / 0.14 / 0.85 / 0.86 (measured on the GPU in round 1)
+  fp16: operands 0.0101 / 0.016 / 0.976 / 0.938, frx_r1 0.0115 / 0.021 / 0.977 / 0.920
+
+    python tools/bf16_yardstick.py [--batch 16] [--seed 0] [--steps 231] [--dtype bf16|fp16]
 """
 import argparse
 import os
@@ -26,8 +31,16 @@ import torch.nn.functional as F  # noqa: E402
 from oracle import satrn, synth  # noqa: E402
 
 
+OPERAND_DTYPE = [torch.bfloat16]
+
+
+def set_operand_dtype(dtype):
+    """Rounding applied by every policy: torch.bfloat16 (default) or torch.float16 (what the library's encoder uses)."""
+    OPERAND_DTYPE[0] = dtype
+
+
 def rb(x):
-    return x.to(torch.bfloat16).to(torch.float32)
+    return x.to(OPERAND_DTYPE[0]).to(torch.float32)
 
 
 class Policy:
@@ -111,7 +124,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--steps", type=int, default=231)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     a = ap.parse_args()
+    set_operand_dtype(torch.float16 if a.dtype == "fp16" else torch.bfloat16)
     torch.set_num_threads(os.cpu_count() or 1)
     spec = satrn.ModelSpec()
     sd = synth.synth_state_dict(spec, a.seed)
