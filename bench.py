@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+    python bench.py --workload {train,beam4,beam8,lite,swin} # the other BASELINE.json configs (3, 4, 5), same contract
 
 A "step" is one pass of the hot path (encode + 231-step greedy decode) over one
 synthetic batch of 256 images (128x256 grayscale, randn) per GPU.  `value` is
@@ -11,6 +12,7 @@ through the host-buffer C-ABI entry (frx_forward_greedy_host): H2D of the pinned
 images + compute + D2H of the tokens inside the timed region.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -165,6 +167,24 @@ def run_reference(args, rank, world):
     from helpers import flags_dict
     dims = frx.layout.dims_from_flags(frx.Flags(flags_dict()).get(), 245)
     sd = frx.synthetic.synthetic_state_dict(dims, seed=0)
+    if args.workload != "greedy":
+        wl = args.workload
+        if wl == "lite":
+            from oracle import satrn as o_satrn, synth as o_synth
+            from oracle.make_golden import LITE_SPEC
+            sd = o_synth.synth_state_dict(o_satrn.ModelSpec(**LITE_SPEC), 0, calib_batch=4)
+        elif wl == "swin":
+            from oracle import swin as o_swin
+            sd = o_swin.synth_state_dict(o_swin.swin_spec(), 0)
+        t0 = time.perf_counter()
+        cb = cpu_workload_baseline(wl, args, sd)
+        print(json.dumps({"impl": "reference", "metric": wl, "value": cb["value"], "unit": cb["unit"], "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": (time.perf_counter() - t0) * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": wl + " (bounded sample, see cpu_baseline.sample)"}, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     sample = args.cpu_sample
     for _ in range(args.warmup):
         pass  # the warm-up happens inside cpu_reference_throughput on a tiny batch
@@ -172,6 +192,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3,
+        "ms_per_step_is": "per bounded sample of %d images (the GPU arm's step is %d images)" % (sample, args.batch),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(args.batch, args.precision),
                        reference_arm="the reference's CPU algorithm (oracle port, op for op, fp32) on the host cores; "
@@ -272,6 +293,7 @@ def run_frx(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 1), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
+        "dtype_detail": "fp32" if args.precision == "fp32" else "16-bit operands, fp32 accumulation: fp16 on the encoder side (tcgen05 kind::f16), bf16 weights + KV cache in the decode kernel",
         "data": "synthetic",
         "config": workload_config(B, args.precision),
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(images_host.numel() * 4),
@@ -307,6 +329,25 @@ def run_frx(args, rank, world, local_rank):
                 _, tok = m.greedy(xs, T)
                 agree[prec] = (tok.cpu() == cpu_tok).float().mean().item()
                 del m
+        # the same port on THIS GPU in eager PyTorch (cuDNN / cuBLAS, TF32 off): what moving the reference to .cuda() gives
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            sd_gpu = {k: (v.float() if v.is_floating_point() else v).to(dev) for k, v in sd_cal.items()}
+            xg = synthetic_images(B, 0).to(dev)
+            with torch.no_grad():
+                o_satrn.forward_greedy(sd_gpu, o_satrn.ModelSpec(), xg[:8], 8, as_written=True)
+                torch.cuda.synchronize(dev)
+                g0 = time.perf_counter()
+                o_satrn.forward_greedy(sd_gpu, o_satrn.ModelSpec(), xg, T, as_written=True)
+                torch.cuda.synchronize(dev)
+                gdt = time.perf_counter() - g0
+            line["gpu_eager_baseline"] = {"value": B / gdt, "unit": "images/s", "ms_per_batch": gdt * 1e3, "kind": "port",
+                                          "sample": "1 batch of %d images x 231 steps, the oracle port of the reference's as-written "
+                                                    "algorithm in eager PyTorch %s on this GPU, fp32, TF32 disabled" % (B, torch.__version__)}
+            del sd_gpu, xg
+        except Exception as exc:  # reported, never fatal: this is a yardstick, not the product
+            line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
         line["cpu_baseline"] = {
             "value": ips, "unit": "images/s", "cores": cores, "kind": "port",
             "sample": "%d batches of %d images x 231 decode steps (%.1f s), oracle port of the reference's "
@@ -317,18 +358,271 @@ def run_frx(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+# =====================================================================================================================
+# Other workloads of BASELINE.json.configs: [2] beam search (width 4 / 8), [3] the teacher-forced training step with the
+# NCCL gradient all-reduce, [4] LiteSATRN / SwinTRN greedy inference.  Same JSON contract as the headline workload.
+# =====================================================================================================================
+# training: forward 3.907 GFLOP (trunk + encoder) + teacher-forced decoder over 231 rows (2.815 MMAC per row in the linear
+# layers, 41 MMAC self-attention, 11 MMAC cross-attention, 25 MMAC cross K/V) = 5.36 GFLOP; backward = 2x forward
+TRAIN_FLOP_PER_IMAGE = 3.0 * (3.907e9 + 2.0 * (231 * 2.815232e6 + 41.0e6 + 11.4e6 + 25.2e6))
+# LiteSATRN encoder 0.507 GFLOP / image (ShallowCNN 4 convs + 1 encoder layer at 8x16 tokens); its decode
+# (hidden 128, 2 layers, 4 heads) streams sum_t t*2*2*128*2 B of bf16 self K/V + 128 tokens of cross K/V per step
+LITE_DECODE_BYTES = sum(t * 2 * 2 * 128 * 2 for t in range(231)) + 231 * 2 * 2 * 128 * 128 * 2 + 231 * 245 * 4
+SWIN_ENC_FLOP = 2.0 * 47.1e9 / 2 * 1.0   # Swin-B/384: 47.1 GFLOP (multiply-adds counted as 2) per 384x384 image
+SWIN_DECODE_BYTES = sum(t * 4 * 2 * 512 * 4 for t in range(231)) + 231 * 4 * 2 * 144 * 512 * 4 + 231 * 245 * 4   # fp32 step kernels
+
+
+def _timed(step, steps, warmup, dev, world, flush):
+    import torch
+    import torch.distributed as dist
+    for _ in range(max(warmup, 1)):
+        step()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t_begin = time.monotonic()
+    for s, e in ev:
+        flush.zero_()
+        s.record()
+        step()
+        e.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    return sum(s.elapsed_time(e) for s, e in ev), t_begin, time.monotonic()
+
+
+def run_workload(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import frx
+    from helpers import Vocab, flags_dict, make_lite_model, make_swin_model
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl, T = args.workload, STEPS_PER_IMAGE
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    hbm, tflops, how = peaks()
+    clocks = ClockSampler(local_rank).start()
+    extra, roof, cpu = {}, None, None
+    g = torch.Generator().manual_seed(2000 + rank)
+
+    if wl == "train":
+        B = args.batch or 16                    # configs/EfficientSATRN.yaml: batch_size 16 (per GPU here)
+        model, sd = build_model("fp32", B)
+        model = model.to(dev).train()
+        x_host = torch.randn(B, 1, 128, 256, generator=g).pin_memory()
+        e_host = torch.cat([torch.zeros(B, 1, dtype=torch.long), torch.randint(3, 244, (B, MAX_SEQUENCE), generator=g),
+                            torch.ones(B, 1, dtype=torch.long)], 1).pin_memory()       # [SOS] + 230 tokens + [EOS]
+        x, e = x_host.to(dev), e_host.to(dev)
+        eng = model.engine(dev, B, T)
+        step_device = lambda: model.train_step(x, e)
+
+        def step_host():
+            loss, _ = model.train_step(x_host.to(dev, non_blocking=True), e_host.to(dev, non_blocking=True))
+            return loss.item()
+        h2d, d2h = x_host.numel() * 4 + e_host.numel() * 8, 4
+        metric = "EfficientSATRN teacher-forced training images/sec"
+        desc = ("EfficientSATRN teacher-forced training step (single_opt, teacher_forcing_ratio 1.0: train-mode BatchNorm, "
+                "CrossEntropy ignore PAD, backward, clip_grad_norm 2.0, AdamW), batch %d per GPU, 128x256x1 randn images, "
+                "231 target positions, fp32 like the reference, gradients all-reduced over NCCL (%d ranks)" % (B, world))
+        dtype = "f32"
+    elif wl in ("beam4", "beam8"):
+        B, width = args.batch or 32, int(wl[4:])   # inference.py:22 batch_size 32
+        model, sd = build_model("fp32", B)          # beam search runs on the fp32 step kernels
+        model = model.to(dev).eval()
+        x_host = synthetic_images(B, rank).pin_memory()
+        x = x_host.to(dev)
+        eng = model.engine(dev, B, T)
+        step_device = lambda: model.beam_search(x, None, 1, width, MAX_SEQUENCE)    # returns the tokens on the host
+        step_host = lambda: model.beam_search(x_host.to(dev, non_blocking=True), None, 1, width, MAX_SEQUENCE)
+        h2d, d2h = x_host.numel() * 4, B * MAX_SEQUENCE * 8
+        metric = "EfficientSATRN beam-search (width %d) images/sec" % width
+        desc = ("EfficientSATRN beam_search(topk=1, beam_width=%d, max_sequence=230) through decode(): best-first queue on the "
+                "device, batch %d per GPU, fp32 step kernels" % (width, B))
+        dtype = "f32"
+    elif wl == "lite":
+        from oracle import satrn as o_satrn, synth as o_synth
+        from oracle.make_golden import LITE_SPEC
+        B = args.batch or 256
+        lspec = o_satrn.ModelSpec(**LITE_SPEC)
+        sd = o_synth.synth_state_dict(lspec, 0, calib_batch=4)
+        model = make_lite_model(sd, precision=args.precision, max_batch=B, max_steps=T).to(dev).eval()
+        x_host = o_synth.synth_images(lspec, B, rank).pin_memory()
+        x = x_host.to(dev)
+        model.set_option("timing", 1)
+        eng = model.engine(dev, B, T)
+        tok = torch.empty(B, T, dtype=torch.int64, device=dev)
+        step_device = lambda: eng.h.call("frx_forward_greedy", x.data_ptr(), B, T, None, tok.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        step_host = lambda: model.greedy(x_host.to(dev, non_blocking=True), T, want_logits=False)[1].cpu()
+        h2d, d2h = x_host.numel() * 4, B * T * 8
+        metric = "LiteSATRN greedy-decode images/sec"
+        desc = "LiteSATRN greedy inference, batch %d per GPU, 128x256x1 images, 231 decode steps, %s mode" % (B, args.precision)
+        dtype = "bf16" if args.precision == "bf16" else "f32"
+    else:  # swin
+        from oracle import swin as o_swin
+        B = args.batch or 16
+        sd = o_swin.synth_state_dict(o_swin.swin_spec(), 0)
+        model = make_swin_model(sd, precision=args.precision, max_batch=B, max_steps=T).to(dev).eval()
+        x_host = o_swin.synth_images(B, rank).pin_memory()
+        x = x_host.to(dev)
+        model.set_option("timing", 1)
+        eng = model.engine(dev, B, T)
+        tok = torch.empty(B, T, dtype=torch.int64, device=dev)
+        step_device = lambda: eng.h.call("frx_forward_greedy", x.data_ptr(), B, T, None, tok.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        step_host = lambda: model.greedy(x_host.to(dev, non_blocking=True), T, want_logits=False)[1].cpu()
+        h2d, d2h = x_host.numel() * 4, B * T * 8
+        metric = "SwinTRN greedy-decode images/sec"
+        desc = ("SwinTRN (Swin-B/384 encoder + 4-layer decoder) greedy inference, batch %d per GPU, 384x384x3 images, 231 decode "
+                "steps, %s mode (encoder on tcgen05, decoder on the fp32 step kernels)" % (B, args.precision))
+        dtype = "bf16" if args.precision == "bf16" else "f32"
+
+    launches0 = eng.launches
+    total_ms, t0, t1 = _timed(step_device, args.steps, args.warmup, dev, world, flush)
+    clocks.t0, clocks.t1 = t0, t1
+    clocks.stop()
+    gpu_launches = eng.launches - launches0
+    ms3 = (ctypes.c_float * 4)()
+    eng.h.lib.frx_last_timing(eng.h.ptr, ms3)
+    # e2e: host buffers, H2D + D2H inside the timed region, wall clock around synchronous calls
+    for _ in range(2):
+        step_host()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e2e_ms = (time.perf_counter() - w0) * 1e3
+    allreduce = None
+    if wl == "train" and world > 1:
+        grads = eng._train["grads"]
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.all_reduce(grads)
+        torch.cuda.synchronize(dev)
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(grads)
+        a1.record()
+        torch.cuda.synchronize(dev)
+        allreduce = {"bytes": int(grads.numel() * 4), "ms_alone": a0.elapsed_time(a1) / 5,
+                     "how": "flat fp32 gradient buffer, 6 buckets started by the backward pass as it enqueues them "
+                            "(frx_train_set_bucket_callback); ms_alone = one all-reduce of the whole buffer timed by itself"}
+    total_ms = frx.sharding.max_over_ranks(total_ms, dev)
+    e2e_ms = frx.sharding.max_over_ranks(e2e_ms, dev)
+    if rank != 0:
+        return
+    n_img = B * args.steps * world
+    step_s = total_ms / args.steps / 1e3
+    if wl == "train":
+        ach = TRAIN_FLOP_PER_IMAGE * B / step_s / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tflops, "unit": "TFLOP/s", "frac": ach / tflops, "traffic": None,
+                "kernel": "whole step (fp32 FFMA implicit-GEMM forward / dgrad / wgrad kernels; the bf16 tensor-core peak is "
+                          "the yardstick the task names, the fp32 FFMA peak of a B200 is ~75 TFLOP/s)",
+                "algorithmic_flop_per_step": TRAIN_FLOP_PER_IMAGE * B, "ms": step_s * 1e3, "peak_source": how}
+    elif wl in ("beam4", "beam8"):
+        by = DECODE_BYTES_PER_IMAGE["fp32"] * B
+        dec_s = step_s    # whole step (the encoder is ~2 % of it at this batch)
+        roof = {"bound": "hbm", "achieved": by / dec_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / dec_s / 1e9 / hbm,
+                "traffic": None, "kernel": "beam rounds (fp32 step kernels + queue kernels), one node expansion per image and round",
+                "algorithmic_bytes_per_launch": by, "ms": dec_s * 1e3, "peak_source": how,
+                "note": "upper bound on the useful bytes: an explored chain of 230 nodes reads the fp32 K/V history a greedy pass reads"}
+    elif wl == "lite":
+        by = LITE_DECODE_BYTES * B
+        dec_s = max(ms3[3] if ms3[3] > 0 else ms3[1], 1e-6) / 1e3
+        roof = {"bound": "hbm", "achieved": by / dec_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / dec_s / 1e9 / hbm,
+                "traffic": None, "kernel": "dec_cluster_bf16_kernel_d128 (one launch = all 231 steps)" if args.precision == "bf16" else "fp32 step kernels",
+                "algorithmic_bytes_per_launch": by, "ms": dec_s * 1e3, "peak_source": how}
+    else:
+        enc_s = max(ms3[0], 1e-6) / 1e3
+        ach = 47.1e9 * B / enc_s / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tflops, "unit": "TFLOP/s", "frac": ach / tflops, "traffic": None,
+                "kernel": "Swin-B/384 encoder (tcgen05 GEMMs + window attention on mma.sync); 47.1 GFLOP per image",
+                "ms": enc_s * 1e3, "peak_source": how, "decode_ms": ms3[1]}
+    line = {
+        "metric": metric, "value": n_img / (total_ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": desc, "batch_per_gpu": B, "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
+        "e2e": {"value": n_img / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(gpu_launches), "roofline": roof, "clocks": clocks.summary(),
+        "timing_ms": {"encode": ms3[0], "decode": ms3[1]},
+    }
+    if allreduce:
+        line["allreduce"] = allreduce
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_workload_baseline(wl, args, sd)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_workload_baseline(wl, args, sd):
+    """The oracle's port of the reference's CPU algorithm for the workload, on a bounded sample, all host threads."""
+    import torch
+    from oracle import satrn as o_satrn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = o_satrn.ModelSpec()
+    if wl == "train":
+        from oracle import train as o_train
+        tr = o_train.Trainer(sd, spec)
+        x, e = o_train.synth_batch(spec, 4, 231, 0)
+        tr.step(x[:1], e[:1, :9])
+        t0 = time.perf_counter()
+        tr.step(x, e)
+        dt = time.perf_counter() - t0
+        return {"value": 4 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                "sample": "1 training step of 4 images x 231 positions (%.1f s), oracle port (torch %s autograd, fp32)" % (dt, torch.__version__)}
+    if wl in ("beam4", "beam8"):
+        x = synthetic_images(2, 0)
+        with torch.no_grad():
+            src = o_satrn.encoder_forward(sd, spec, x)
+            t0 = time.perf_counter()
+            o_satrn.beam_search(sd, spec, src, int(wl[4:]), MAX_SEQUENCE)
+            dt = time.perf_counter() - t0
+        return {"value": 2 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                "sample": "beam search of 2 images (%.1f s; the reference processes images one at a time), oracle port, encoder excluded" % dt}
+    if wl == "lite":
+        from oracle.make_golden import LITE_SPEC
+        from oracle import synth as o_synth
+        lspec = o_satrn.ModelSpec(**LITE_SPEC)
+        x = o_synth.synth_images(lspec, 32, 0)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            o_satrn.forward_greedy(sd, lspec, x, STEPS_PER_IMAGE, as_written=True)
+            dt = time.perf_counter() - t0
+        return {"value": 32 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                "sample": "32 images x 231 decode steps (%.1f s), oracle port of the as-written algorithm" % dt}
+    from oracle import swin as o_swin
+    x = o_swin.synth_images(2, 0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        mem = o_swin.encoder_forward(sd, x)
+        o_satrn.decode_greedy(o_swin.decoder_view(sd), o_swin.swin_spec(), mem, 24)
+        dt = time.perf_counter() - t0
+    return {"value": 2 / dt, "unit": "images/s (24 decode steps only)", "cores": cores, "kind": "port",
+            "sample": "2 images x 24 decode steps (%.1f s): encoder-dominated sample of the oracle port" % dt}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="frx", choices=["frx", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--workload", default="greedy", choices=["greedy", "train", "beam4", "beam8", "lite", "swin"])
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: 256 greedy/lite, 16 train/swin, 32 beam)")
     ap.add_argument("--precision", default=os.environ.get("FRX_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--cpu-runs", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload == "greedy" and not args.batch:
+        args.batch = 256
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -341,7 +635,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_frx(args, rank, world, local_rank)
+        if args.workload == "greedy":
+            run_frx(args, rank, world, local_rank)
+        else:
+            run_workload(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

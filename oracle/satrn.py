@@ -319,8 +319,8 @@ def pe2d_forward(sd, spec: ModelSpec, x):
     b, c, h, w = x.shape
     p = "encoder.positional_encoding."
     W = lambda n: sd[n].to(x.dtype)
-    h_enc = pe2d_table(h, c).to(x.dtype).unsqueeze(1).unsqueeze(0)  # [1,h,1,c]
-    w_enc = pe2d_table(w, c).to(x.dtype).unsqueeze(0).unsqueeze(0)  # [1,1,w,c]
+    h_enc = pe2d_table(h, c).to(x).unsqueeze(1).unsqueeze(0)  # [1,h,1,c]  (tables are host-built; .to(x): device + dtype)
+    w_enc = pe2d_table(w, c).to(x).unsqueeze(0).unsqueeze(0)  # [1,1,w,c]
     g = torch.mean(x, [2, 3])
     g = F.relu(F.linear(g, W(p + "dense0.weight"), W(p + "dense0.bias")))
     g = torch.sigmoid(F.linear(g, W(p + "dense1.weight"), W(p + "dense1.bias")))
@@ -417,8 +417,8 @@ def decode_greedy_as_written(sd, spec: ModelSpec, src, steps: int):
     K/V of the whole history and of ``src`` every step, as the reference does).
     Returns logits [B, steps, V]."""
     b = src.size(0)
-    pe = pe1d_table(spec.dec_hidden, spec.pe1d_len)
-    target = torch.full((b,), SOS_ID, dtype=torch.long)
+    pe = pe1d_table(spec.dec_hidden, spec.pe1d_len).to(src.device)
+    target = torch.full((b,), SOS_ID, dtype=torch.long, device=src.device)
     features = [None] * spec.dec_layers
     out = []
     for t in range(steps):

@@ -54,7 +54,11 @@ namespace {
 constexpr int D = FRX_DEC_D;     // decoder width
 constexpr int HD = 32;
 constexpr int H = D / HD;        // heads
+#ifndef FRX_DEC_KVDEPTH
+#define FRX_DEC_KVDEPTH 1        // K/V staging blocks per warp (blocks in flight ahead of the one being reduced)
+#endif
 constexpr int HPC = FRX_DEC_HPC;
+constexpr int KVD = FRX_DEC_KVDEPTH;
 constexpr int CL = H / HPC;      // CTAs per cluster
 constexpr int FF = FRX_DEC_FF;
 constexpr int VP = 256;          // vocabulary columns, padded
@@ -117,7 +121,7 @@ struct Smem {
   float qh[HPC][NIMG][HD + FPAD];            // q of this CTA's head(s)
   __nv_bfloat16 kcur[HPC][NIMG][HD + APAD];  // k, v of the current layer input (the extra "current" key)
   __nv_bfloat16 vcur[HPC][NIMG][HD + APAD];
-  __nv_bfloat16 kvst[NWARP][2][32][HD];      // per-warp staging of one 32-key K/V block (KVStage)
+  __nv_bfloat16 kvst[NWARP][KVD][2][32][HD]; // per-warp ring of KVD staged 32-key K/V blocks (KVStage)
   long long prof[16];
   unsigned long long bar[2];            // stage mbarriers (alternate by stage parity)
   DecClusterLayer lw[4];                // per-layer pointers (dynamic indexing of kernel params would spill them)
@@ -311,22 +315,32 @@ __device__ __forceinline__ uint32_t kv_swz(int row, int chunk) { return (uint32_
 
 __device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc,
                                            int kb, int n_hist) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
+  // one commit group per call, EMPTY when the block lies past the history: the consumer counts groups
+  if (kb < n_hist) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int id = lane + 32 * i, row = id >> 2, chunk = id & 3;
-    const int key = kb + row;
-    const uint32_t bytes = key < n_hist ? 16u : 0u;   // zero-fill past the history (also keeps V finite)
-    const size_t off = (size_t)(key < n_hist ? key : 0) * HD + chunk * 8;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ks + kv_swz(row, chunk)), "l"(Kc + off), "r"(bytes) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(vs + kv_swz(row, chunk)), "l"(Vc + off), "r"(bytes) : "memory");
+    for (int i = 0; i < 4; ++i) {
+      const int id = lane + 32 * i, row = id >> 2, chunk = id & 3;
+      const int key = kb + row;
+      const uint32_t bytes = key < n_hist ? 16u : 0u;   // zero-fill past the history (also keeps V finite)
+      const size_t off = (size_t)(key < n_hist ? key : 0) * HD + chunk * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ks + kv_swz(row, chunk)), "l"(Kc + off), "r"(bytes) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(vs + kv_swz(row, chunk)), "l"(Vc + off), "r"(bytes) : "memory");
+    }
   }
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
+// Request the first KVD blocks of a history into the warp's ring (KVD commit groups, in block order).
+__device__ __forceinline__ void kv_prime(KVStage* ring, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc, int n_hist) {
+#pragma unroll
+  for (int d = 0; d < KVD; ++d) kv_request(ring[d], Kc, Vc, 32 * d, n_hist);
+}
 
-// Block 0 must have been requested with kv_request(st, Kc, Vc, 0, n_hist) (when n_hist > 0).
-__device__ __forceinline__ void attend_mma(KVStage& st, const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
+// The history must have been primed with kv_prime(ring, Kc, Vc, n_hist): block i lives in ring[i % KVD] and is
+// complete once at most KVD - 1 younger commit groups are pending; its buffer is re-used for block i + KVD as soon as
+// its fragments are in registers, so KVD blocks are in flight while one is being reduced.
+__device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
                                            const __nv_bfloat16* __restrict__ Vc, int n_hist,
                                            const __nv_bfloat16* __restrict__ kx,
                                            const __nv_bfloat16* __restrict__ vx, float inv_temp,
@@ -345,10 +359,13 @@ __device__ __forceinline__ void attend_mma(KVStage& st, const float* __restrict_
   for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-  const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
   const int lrow = lane & 7, lmat = lane >> 3;
+  int slot = 0;
   for (int kb = 0; kb < n_hist; kb += 32) {
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    KVStage& st = ring[slot];
+    slot = slot + 1 == KVD ? 0 : slot + 1;
+    const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(KVD - 1) : "memory");
     __syncwarp();
     uint32_t kf[4][4], vf[4][4];
 #pragma unroll
@@ -364,7 +381,7 @@ __device__ __forceinline__ void attend_mma(KVStage& st, const float* __restrict_
                    : "=r"(vf[x][0]), "=r"(vf[x][1]), "=r"(vf[x][2]), "=r"(vf[x][3]) : "r"(vs + kv_swz(key, chunk)));
     }
     __syncwarp();
-    if (kb + 32 < n_hist) kv_request(st, Kc, Vc, kb + 32, n_hist);
+    kv_request(st, Kc, Vc, kb + 32 * KVD, n_hist);
     float sc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -431,6 +448,15 @@ __device__ __forceinline__ void attend_mma(KVStage& st, const float* __restrict_
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// Eight consecutive bias values of an epilogue unit, requested BEFORE the GEMM whose epilogue adds them (an L2 round
+// trip inside the epilogue sat on the critical path of every one of the 19 stages of a step).
+struct Bias8 { float4 a, b; };
+__device__ __forceinline__ Bias8 ldg_bias8(const float* p, bool active) {
+  Bias8 o;
+  o.a = o.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) { o.a = ldg4(p); o.b = ldg4(p + 4); }
+  return o;
+}
 
 }  // namespace
 
@@ -505,7 +531,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   const int head = r * HPC + whc;
   const int b_mine = img0 + wimg;
   const bool mine = b_mine < B;
-  KVStage& kvst = *reinterpret_cast<KVStage*>(&s.kvst[warp][0][0][0]);  // this warp's K/V staging block
+  KVStage* const kvst = reinterpret_cast<KVStage*>(&s.kvst[warp][0][0][0][0]);  // this warp's ring of K/V staging blocks
 
   // all-gather of this warp's attention output (head r, image `warp`) into every CTA's obf: the eight gid
   // groups of the warp hold identical copies, group g serves destination CTA g
@@ -519,11 +545,15 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
     }
   };
   // epilogue of a "pre-LayerNorm" stage: 8 columns of row `row`, + bias (+ ReLU) + residual, sent to CTA `sub`
-  auto pre_epi = [&](uint32_t sb, const float* bias, bool relu) {
+  // (bias: the unit's 8 values, loaded by pre_bias() before the stage)
+  auto pre_bias = [&](const float* bias) {   // unit of this thread in an NTS-tile stage: tile = (tid % (NTS * 8)) >> 3
+    return ldg_bias8(bias + r * SW + ((tid % (NTS * 8)) >> 3) * 8, tid < NTS * 8 * CL);
+  };
+  auto pre_epi = [&](uint32_t sb, const Bias8& bias, bool relu) {
     return [&, sb, bias, relu](int tile, int row, float (&v)[8], int sub) {
       if (sub >= CL) return;  // 8 threads share a unit, one per destination CTA
       const int col = r * SW + tile * 8;
-      const float4 b0 = ldg4(bias + col), b1 = ldg4(bias + col + 4);
+      const float4 b0 = bias.a, b1 = bias.b;
       const float4 x0 = *reinterpret_cast<const float4*>(&s.xres[row][col]), x1 = *reinterpret_cast<const float4*>(&s.xres[row][col + 4]);
       float o[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
       if (relu) {
@@ -538,11 +568,15 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
     };
   };
   // q|k|v of head r (tiles: q 0-3, k 4-7, v 8-11), biases at `bias` in natural [q|k|v] column order
-  auto qkv_epi = [&](const float* bias) {
+  auto qkv_bias = [&](const float* bias) {   // this thread's unit in the NTA-tile stage (sub 0 only: tid < NTA * 8)
+    const int tile = tid >> 3, seg = tile / NTS, wc = (tile % NTS) * 8;
+    return ldg_bias8(bias + seg * D + r * SW + wc, tid < NTA * 8);
+  };
+  auto qkv_epi = [&](const Bias8& bias) {
     return [&, bias](int tile, int row, float (&v)[8], int sub) {
       if (sub != 0) return;
       const int seg = tile / NTS, wc = (tile % NTS) * 8, hc = wc / HD, col = wc % HD;  // column wc of this CTA's slice
-      const float4 b0 = ldg4(bias + seg * D + r * SW + wc), b1 = ldg4(bias + seg * D + r * SW + wc + 4);
+      const float4 b0 = bias.a, b1 = bias.b;
       const float o[8] = {v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w, v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w};
       if (seg == 0) {
         *reinterpret_cast<float4*>(&s.qh[hc][row][col]) = make_float4(o[0], o[1], o[2], o[3]);
@@ -556,11 +590,12 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   };
   // K/V cache rows (layer lc, position t) of the rows in abf: tiles 0-3 = K of head r, 4-7 = V of head r
   auto cache_rows = [&](int lc, int t, const uint4* wp, const float* bias) {
+    const Bias8 cb = ldg_bias8(bias + ((tid >> 3) / NTS) * D + r * SW + ((tid >> 3) % NTS) * 8, tid < NTC * 8);
     gemm2<NTC, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, WPre<0>{}, [&](int tile, int row, float (&v)[8], int sub) {
       const int b = img0 + row;
       if (sub != 0 || b >= B) return;
       const int seg = tile / NTS, wc = (tile % NTS) * 8, hd = r * HPC + wc / HD, col = wc % HD;
-      const float4 b0 = ldg4(bias + seg * D + r * SW + wc), b1 = ldg4(bias + seg * D + r * SW + wc + 4);
+      const float4 b0 = cb.a, b1 = cb.b;
       __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
       *reinterpret_cast<uint4*>(dst + (((((size_t)lc * B + b) * H + hd) * T) + t) * HD + col) =
           make_uint4(pack_bf16(v[0] + b0.x, v[1] + b0.y), pack_bf16(v[2] + b0.z, v[3] + b0.w),
@@ -576,9 +611,9 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * T) * HD;
         const int n_hist = mine ? t : 0;
-        if (n_hist > 0) kv_request(kvst, p.kself + base, p.vself + base, 0, n_hist);  // lands during the projection
+        kv_prime(kvst, p.kself + base, p.vself + base, n_hist);  // lands during the projection
         const uint4* wp = l == 0 ? p.w_first + (size_t)r * NTA * WT : s.lw[l - 1].w_next + ((size_t)r * (NTC + NTA) + NTC) * WT;
-        const float* bias = l == 0 ? p.b_first : s.lw[l - 1].b_next + 2 * D;
+        const Bias8 bias = qkv_bias(l == 0 ? p.b_first : s.lw[l - 1].b_next + 2 * D);
         gemm2<NTA, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
         __syncthreads();
         mark(0);
@@ -590,6 +625,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         mark(1);
       }
       const auto pre_b = prefetch_w<NTS, KPD, KS, PF_S>(W.w_o + (size_t)r * NTS * WT, pol);
+      const Bias8 bias_b = pre_bias(W.b_o);
       // nobody waits for this in the current step: cache rows of the previous layer's output (= this input)
       if (l > 0) cache_rows(l - 1, t, s.lw[l - 1].w_next + (size_t)r * (NTC + NTA) * WT, s.lw[l - 1].b_next);
       mark(2);
@@ -597,10 +633,11 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       mark(3);
       // ---- B: out_linear(a) + x -> pre ; LN -> u -----------------------------------------
       stage_begin(NIMG * D * 4u);
-      gemm2<NTS, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o + (size_t)r * NTS * WT, pol, pre_b, pre_epi(stage_bar(), W.b_o, false));
+      gemm2<NTS, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o + (size_t)r * NTS * WT, pol, pre_b, pre_epi(stage_bar(), bias_b, false));
       mark(4);
       const LnParams lnp1 = load_ln(W.ln1_g, W.ln1_b);
       const auto pre_c = prefetch_w<NTS, KPD, KS, PF_S>(W.w_q2 + (size_t)r * NTS * WT, pol);
+      const Bias8 bias_c = ldg_bias8(W.b_q2 + r * SW + (tid >> 3) * 8, tid < NTS * 8);
       stage_end();
       mark(5);
       layernorm_rows(s, lnp1);
@@ -610,12 +647,12 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * p.S) * HD;
         const int n_keys = mine ? p.S : 0;
-        if (n_keys > 0) kv_request(kvst, p.kcross + base, p.vcross + base, 0, n_keys);
+        kv_prime(kvst, p.kcross + base, p.vcross + base, n_keys);
         gemm2<NTS, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_q2 + (size_t)r * NTS * WT, pol, pre_c,
                           [&](int tile, int row, float (&v)[8], int sub) {
                             if (sub != 0) return;
                             const int wc = tile * 8, hc = wc / HD, col = wc % HD;
-                            const float4 b0 = ldg4(W.b_q2 + r * SW + wc), b1 = ldg4(W.b_q2 + r * SW + wc + 4);
+                            const float4 b0 = bias_c.a, b1 = bias_c.b;
                             *reinterpret_cast<float4*>(&s.qh[hc][row][col]) = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
                             *reinterpret_cast<float4*>(&s.qh[hc][row][col + 4]) = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
                           });
@@ -634,14 +671,16 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         mark(7);
       }
       const auto pre_d = prefetch_w<NTS, KPD, KS, PF_S>(W.w_o2 + (size_t)r * NTS * WT, pol);
+      const Bias8 bias_d = pre_bias(W.b_o2);
       stage_end();
       mark(3);
       // ---- D: out_linear(c) + u -> pre ; LN -> w ------------------------------------------------
       stage_begin(NIMG * D * 4u);
-      gemm2<NTS, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o2 + (size_t)r * NTS * WT, pol, pre_d, pre_epi(stage_bar(), W.b_o2, false));
+      gemm2<NTS, KPD, KS>(next_red(), &s.obf[0][0], LDA, W.w_o2 + (size_t)r * NTS * WT, pol, pre_d, pre_epi(stage_bar(), bias_d, false));
       mark(4);
       const LnParams lnp2 = load_ln(W.ln2_g, W.ln2_b);
       const auto pre_e = prefetch_w<NTE, KPD, KS, PF_E>(W.w_f0 + (size_t)r * NTE * WT, pol);
+      const Bias8 bias_e = ldg_bias8(W.b_f0 + r * FS + ((tid % (NTE * 8)) >> 3) * 8, true);
       stage_end();
       mark(5);
       layernorm_rows(s, lnp2);
@@ -654,7 +693,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         gemm2<NTE, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_f0 + (size_t)r * NTE * WT, pol, pre_e,
                            [&](int tile, int row, float (&v)[8], int sub) {
                              const int col = r * FS + tile * 8;
-                             const float4 b0 = ldg4(W.b_f0 + col), b1 = ldg4(W.b_f0 + col + 4);
+                             const float4 b0 = bias_e.a, b1 = bias_e.b;
                              const uint4 o = make_uint4(pack_bf16(fmaxf(v[0] + b0.x, 0.f), fmaxf(v[1] + b0.y, 0.f)),
                                                         pack_bf16(fmaxf(v[2] + b0.z, 0.f), fmaxf(v[3] + b0.w, 0.f)),
                                                         pack_bf16(fmaxf(v[4] + b1.x, 0.f), fmaxf(v[5] + b1.y, 0.f)),
@@ -670,11 +709,12 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         mark(8);
       }
       const auto pre_f = prefetch_w<NTS, KPF, KS, PF_F>(W.w_f1 + (size_t)r * NTS * KPF * 32, pol);
+      const Bias8 bias_f = pre_bias(W.b_f1);
       stage_end();
       mark(5);
       // ---- F: relu(linear1(ff)) + w -> pre ; LN -> y -----------------------------------------------
       stage_begin(NIMG * D * 4u);
-      gemm2<NTS, KPF, KS>(next_red(), &s.abf2[0][0], LDA2, W.w_f1 + (size_t)r * NTS * KPF * 32, pol, pre_f, pre_epi(stage_bar(), W.b_f1, true));
+      gemm2<NTS, KPF, KS>(next_red(), &s.abf2[0][0], LDA2, W.w_f1 + (size_t)r * NTS * KPF * 32, pol, pre_f, pre_epi(stage_bar(), bias_f, true));
       mark(9);
       const LnParams lnp3 = load_ln(W.ln3_g, W.ln3_b);
       const bool last_layer = l + 1 >= L;
@@ -682,8 +722,19 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       // the 8 cache tiles in w_next
       constexpr int PF_G = GC<NG, KPD, KS>::TOT;
       WPre<PF_G> pre_g;
+      float gbias[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gbias[i] = 0.f;
       if (!last_layer) pre_a = prefetch_w<NTA, KPD, KS, PF_A>(W.w_next + ((size_t)r * (NTC + NTA) + NTC) * WT, pol);
-      else pre_g = prefetch_w<NG, KPD, KS, PF_G>(W.w_next + ((size_t)r * (NTC + NG) + NTC) * WT, pol);
+      else {
+        pre_g = prefetch_w<NG, KPD, KS, PF_G>(W.w_next + ((size_t)r * (NTC + NG) + NTC) * WT, pol);
+        const int col = r * (VP / CL) + ((tid % (NG * 8)) >> 3) * 8;
+        const float* gb = W.b_next + 2 * D;
+        if (tid < NG * 8 * CL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gbias[i] = col + i < V ? __ldg(gb + col + i) : 0.f;
+        }
+      }
       stage_end();
       mark(5);
       layernorm_rows(s, lnp3);
@@ -697,9 +748,8 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
                           [&](int tile, int row, float (&v)[8], int sub) {
                             if (sub >= CL) return;
                             const int col = r * (VP / CL) + tile * 8;
-                            const float* gb = W.b_next + 2 * D;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] += col + i < V ? __ldg(gb + col + i) : 0.f;
+                            for (int i = 0; i < 8; ++i) v[i] += gbias[i];
                             const uint32_t la = mapa_u32(smem_u32(logit_s + row * LGS + col), (uint32_t)sub), rb = mapa_u32(sb, (uint32_t)sub);
                             st_async_v4(la, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])), rb);
                             st_async_v4(la + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])), rb);

@@ -4,6 +4,7 @@
 #define FRX_DEC_D 256
 #define FRX_DEC_FF 1024
 #define FRX_DEC_HPC 2
+#define FRX_DEC_KVDEPTH 2     // 207 KB of shared memory per CTA (one CTA per SM): two K/V blocks in flight per warp
 #define FRX_DEC_NAME(x) x##_p2
 #define FRX_DEC_VARIANT 1
 #include "kernels_decode_bf16.cu"

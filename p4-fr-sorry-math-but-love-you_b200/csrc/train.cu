@@ -50,6 +50,7 @@ int tfail(frx_handle* h, const char* fmt, ...) {
   do {                                                                                                 \
     cudaError_t e__ = cudaGetLastError();                                                              \
     if (e__ != cudaSuccess) return tfail(h, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    h->launches++;                                                                                     \
   } while (0)
 
 struct DevGuard {
@@ -122,6 +123,14 @@ struct TrainState {
   void* bucket_ctx = nullptr;
   // named views into the activation / gradient tape of the LAST frx_train_fwd_bwd call (frx_train_read_tap)
   std::map<std::string, std::pair<const float*, size_t>> taps;
+  // CUDA graphs of the whole forward + backward pass, one per (batch, length): the pass is ~12 600 launches of mostly
+  // small kernels (launch-bound at the reference's batch size of 16).  Inputs are staged so the graph reads fixed
+  // addresses; the activation tape is a bump allocator, so every buffer address is a function of (batch, length) only.
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; long long nodes = 0; int seen = 0; unsigned long long last_use = 0; };
+  std::map<std::pair<int, int>, GraphEntry> graphs;
+  unsigned long long graph_clock = 0;
+  float* img_stage = nullptr;
+  long long* exp_stage = nullptr;
 };
 
 struct Ctx {   // one training call
@@ -857,6 +866,8 @@ extern "C" int frx_train_create(frx_handle* h, int32_t max_batch, int32_t max_le
   const double per_img = 230e6 * ((double)h->cfg.height * h->cfg.width / (128.0 * 256.0)) + (double)max_len * 80e3;
   T->ws_bytes = (size_t)(per_img * max_batch + 256e6);
   TCK(cudaMalloc(&T->ws, T->ws_bytes));
+  TCK(cudaMalloc(&T->img_stage, (size_t)max_batch * h->cfg.in_ch * h->cfg.height * h->cfg.width * 4));
+  TCK(cudaMalloc(&T->exp_stage, (size_t)max_batch * (max_len + 1) * 8));
   std::vector<float>().swap(T->hostP);
   return 0;
 }
@@ -874,7 +885,8 @@ extern "C" void frx_train_destroy(frx_handle* h) {
   DevGuard g; g.enter(h->cfg.device);
   TrainState* T = state_of(h);
   cudaFree(T->P); if (T->own_G) cudaFree(T->G); cudaFree(T->M); cudaFree(T->V); cudaFree(T->RS); cudaFree(T->acc); cudaFree(T->sumsq);
-  cudaFree(T->scal); cudaFree(T->ones); cudaFree(T->zeros); cudaFree(T->ws);
+  cudaFree(T->scal); cudaFree(T->ones); cudaFree(T->zeros); cudaFree(T->ws); cudaFree(T->img_stage); cudaFree(T->exp_stage);
+  for (auto& kv : T->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   delete T;
   h->train = nullptr;
 }
@@ -887,8 +899,50 @@ extern "C" int frx_train_fwd_bwd(frx_handle* h, const float* images, const int64
   const int L = len_plus_1 - 1;
   if (B <= 0 || B > T->max_B || L <= 0 || L > T->max_L) return tfail(h, "train_fwd_bwd: batch %d / length %d outside (%d, %d)", B, L, T->max_B, T->max_L);
   DevGuard g; g.enter(h->cfg.device);
-  Ctx c{h, T, (cudaStream_t)stream, B, L};
-  return fwd_bwd(c, images, (const long long*)expected, loss_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  // Eager when graphs are off, when a bucket callback wants to start all-reduces between the kernels of the pass, and on
+  // the first use of a shape (which also performs the one-time per-device kernel attribute set-up).
+  TrainState::GraphEntry& ge = T->graphs[{B, L}];
+  if (!h->opt_graphs || T->bucket_cb || ge.seen++ == 0) {
+    Ctx c{h, T, st, B, L};
+    return fwd_bwd(c, images, (const long long*)expected, loss_out);
+  }
+  const size_t img_floats = (size_t)B * h->cfg.in_ch * h->cfg.height * h->cfg.width;
+  TCK(cudaMemcpyAsync(T->img_stage, images, img_floats * 4, cudaMemcpyDeviceToDevice, st));
+  TCK(cudaMemcpyAsync(T->exp_stage, expected, (size_t)B * len_plus_1 * 8, cudaMemcpyDeviceToDevice, st));
+  if (!ge.exec) {
+    cudaStream_t cs;
+    TCK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const long long before = h->launches;
+    TCK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    Ctx c{h, T, cs, B, L};
+    const int rc = fwd_bwd(c, T->img_stage, T->exp_stage, nullptr);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    cudaStreamDestroy(cs);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+    if (e != cudaSuccess) return tfail(h, "training graph capture failed: %s", cudaGetErrorString(e));
+    ge.nodes = h->launches - before;
+    h->launches = before;
+    const cudaError_t e2 = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { ge.exec = nullptr; return tfail(h, "training graph instantiate failed: %s", cudaGetErrorString(e2)); }
+    // keep at most 4 shapes (variable target lengths would otherwise accumulate ~13 000-node graphs)
+    while (T->graphs.size() > 4) {
+      auto victim = T->graphs.end();
+      for (auto it = T->graphs.begin(); it != T->graphs.end(); ++it)
+        if (&it->second != &ge && (victim == T->graphs.end() || it->second.last_use < victim->second.last_use)) victim = it;
+      if (victim == T->graphs.end()) break;
+      TCK(cudaStreamSynchronize(st));
+      if (victim->second.exec) cudaGraphExecDestroy(victim->second.exec);
+      T->graphs.erase(victim);
+    }
+  }
+  ge.last_use = ++T->graph_clock;
+  TCK(cudaGraphLaunch(ge.exec, st));
+  h->launches += ge.nodes;
+  if (loss_out) TCK(cudaMemcpyAsync(loss_out, T->scal, 4, cudaMemcpyDefault, st));
+  return 0;
 }
 
 extern "C" int frx_train_grad_buffer(frx_handle* h, float** grads, int64_t* count) {

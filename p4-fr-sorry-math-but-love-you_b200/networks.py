@@ -12,7 +12,7 @@ import random
 import torch
 import torch.nn as nn
 
-from . import _lib, layout
+from . import _lib, layout, sharding
 
 START, END, PAD = "<SOS>", "<EOS>", "<PAD>"  # data/dataset.py:12-14
 
@@ -264,26 +264,21 @@ class EfficientSATRN(_FrxModule):
         e = expected.to(device=x.device, dtype=torch.int64).contiguous()
         st = _stream(x.device)
         world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        works = tr["works"]
-        del works[:]
+        reducer = tr.get("reducer")
+        if world > 1 and (reducer is None or reducer.group is not process_group):
+            reducer = tr["reducer"] = sharding.GradBucketReducer(tr["grads"], process_group)
         if world > 1 and overlap:
-            grads = tr["grads"]
-
-            def on_bucket(_ctx, off, count):   # called by the library while it is still enqueueing the backward pass
-                works.append(dist.all_reduce(grads[off:off + count], group=process_group, async_op=True))
-
-            cb = _lib.BUCKET_CALLBACK(on_bucket)
-            eng.h.call("frx_train_set_bucket_callback", cb, None)
+            reducer.begin()
+            cb = _lib.BUCKET_CALLBACK(lambda _ctx, off, count: reducer.on_bucket(off, count))
         else:
-            cb = _lib.BUCKET_CALLBACK()   # NULL
-            eng.h.call("frx_train_set_bucket_callback", cb, None)
+            cb = _lib.BUCKET_CALLBACK()   # NULL: no callback
+        eng.h.call("frx_train_set_bucket_callback", cb, None)
         sc = tr["scalars"]
         eng.h.call("frx_train_fwd_bwd", _ptr(x), _ptr(e), b, lp1, _ptr(sc), st)
         if world > 1:
             if not overlap:
-                works.append(dist.all_reduce(tr["grads"], group=process_group, async_op=True))
-            for w in works:
-                w.wait()          # the current stream waits for the NCCL stream; no host synchronisation
+                reducer.begin()
+            reducer.finish()      # the current stream waits for the NCCL stream; no host synchronisation
         eng.h.call("frx_train_apply", float(lr), float(weight_decay), float(max_grad_norm), 1.0 / world,
                    ctypes.c_void_p(sc.data_ptr() + 4), st)
         self._trained = True

@@ -50,3 +50,38 @@ def test_two_rank_gloo_sharding_and_gather():
     expect = [[i, 2 * i, 3 * i] for i in range(n_items)]
     assert ret[0][1] == expect and ret[1][1] == expect
     assert ret[0][2] == 11.0 and ret[1][2] == 11.0     # max over ranks on every rank
+
+
+def _grad_worker(rank, world, port, ret):
+    """Training data parallelism: the bucketed, callback-driven all-reduce of the flat gradient buffer (what
+    EfficientSATRN.train_step does over NCCL) equals one all-reduce of the whole buffer, whatever the buckets cover."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 1000
+        g = torch.Generator().manual_seed(rank)
+        flat = torch.randn(n, generator=g)
+        mine = flat.clone()
+        red = frx.sharding.GradBucketReducer(flat)
+        red.begin()
+        # the library reports buckets in backward completion order (decoder first, stem last); leave two gaps
+        for off, cnt in ((700, 300), (400, 250), (100, 300)):
+            red.on_bucket(off, cnt)
+        gaps = red.uncovered()
+        n_works = red.finish()
+        want = mine.clone()
+        dist.all_reduce(want)
+        ret[rank] = (gaps, n_works, bool(torch.equal(flat, want)), flat.sum().item())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bucketed_gradient_allreduce():
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_grad_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in (0, 1):
+        gaps, n_works, same, _ = ret[r]
+        assert gaps == [(0, 100), (650, 700)]
+        assert n_works == 5 and same
+    assert ret[0][3] == ret[1][3]      # both ranks hold the same summed gradient
