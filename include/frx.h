@@ -111,6 +111,14 @@ int frx_forward_greedy_host(frx_handle* h, const float* images_host, int32_t bat
 int frx_decode_begin(frx_handle* h, const float* memory, int32_t batch, void* stream);
 int frx_decode_step(frx_handle* h, const int64_t* target, float* logits, void* stream);
 
+/* Ensemble decoding, utils/ensemble_utils.py:71-118 (make_decoder_values): n_models decoder handles advance in lock
+ * step; per step every model's step_forward logits are soft-maxed and averaged (:95-105), the average optionally goes
+ * through DecodingManager.sift (:107-108; rule tables of handles[0], frx_set_decoding_rules), its arg-max is the next
+ * target of every model (:110).  memories[m]: model m's encoder output [B, S, C] (device).  probs [B, steps, V]: the
+ * stacked distributions (:112-115); tokens [B, steps] (optional): their arg-max.  All handles on one device. */
+int frx_ensemble_decode(frx_handle* const* handles, int32_t n_models, const float* const* memories, int32_t batch,
+                        int32_t steps, float* probs, int64_t* tokens, int32_t use_manager, void* stream);
+
 /* EfficientSATRN.beam_search (EfficientSATRN.py:708-867) with topk=1 via
  * decode(method="beam") (postprocessing/decoding.py:42-48): per-sample
  * best-first search, score -logp/len in fp64 (decoding.py:80), node order on
@@ -224,6 +232,18 @@ void frx_train_destroy(frx_handle* h);
 int64_t frx_train_param_count(frx_handle* h);
 int frx_train_fwd_bwd(frx_handle* h, const float* images, const int64_t* expected, int32_t batch, int32_t len_plus_1,
                       float* loss_out, void* stream);
+/* The same pass in two calls, for callers that compute the loss themselves (the reference's loop: output = model(...);
+ * loss = criterion(output.transpose(1, 2), expected[:, 1:]); loss.backward() -- train_single_opt.py:79-92):
+ * frx_train_forward  train-mode forward (BatchNorm batch statistics, running statistics updated) -> logits [B, L, V]
+ *                    (loss_out optional: the CrossEntropy(ignore PAD) of the same pass);
+ * frx_train_backward continues from the logits gradient [B, L, V] the caller's criterion produced and leaves the
+ *                    parameter gradients in the flat buffer / frx_train_read_grad.  images: the forward call's.
+ * frx_train_import   overwrite one parameter of the training state from the state_dict layout (an external optimiser
+ *                    stepped the nn.Parameters). */
+int frx_train_forward(frx_handle* h, const float* images, const int64_t* expected, int32_t batch, int32_t len_plus_1,
+                      float* logits_out, float* loss_out, void* stream);
+int frx_train_backward(frx_handle* h, const float* images, const float* dlogits, int32_t batch, int32_t len_plus_1, void* stream);
+int frx_train_import(frx_handle* h, const char* name, const float* src);
 int frx_train_grad_buffer(frx_handle* h, float** grads, int64_t* count);
 int frx_train_set_bucket_callback(frx_handle* h, void (*callback)(void* ctx, int64_t offset, int64_t count), void* ctx);
 int frx_train_apply(frx_handle* h, float lr, float weight_decay, float max_grad_norm, float grad_scale,

@@ -175,6 +175,66 @@ def main_manager():
     print("tokens changed by the manager: %.1f %%" % (100.0 * (plain != tokens.numpy()).mean()))
 
 
+def main_ensemble():
+    """utils/ensemble_utils.py:46-120 (make_decoder_values) of the REAL reference on two seeded checkpoints: the ensemble's
+    averaged distributions [B, T, V] and token sequences, without and with the DecodingManager.  The function is called
+    as written; its `torch` name is proxied only to capture the `decoded_values` tensor it hands to torch.topk."""
+    import importlib
+    import types
+    torch.set_grad_enabled(False)
+    ref = ref_shim.load_reference()
+    eu = importlib.import_module("utils.ensemble_utils")
+    pp = importlib.import_module("postprocessing.postprocessing")
+    spec = satrn.ModelSpec()
+    batch, max_sequence = 3, 23
+    flags, vocab = ref_shim.reference_flags(), ref_shim.reference_vocab()
+    sds = [synth.synth_state_dict(spec, seed) for seed in (0, 1)]
+    images = synth.synth_images(spec, batch, 5)
+    decoders, memories = [], []
+    for sd in sds:
+        enc = sys.modules[ref.networks.EfficientSATRN.__module__].EfficientSATRN_encoder(flags, vocab).eval()
+        enc.load_state_dict({k: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+        dec = sys.modules[ref.networks.EfficientSATRN.__module__].EfficientSATRN_decoder(flags, vocab).eval()
+        dec.load_state_dict({k: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+        with ref_shim.cpu_get_device():
+            memories.append(enc(images))
+        decoders.append(dec)
+    captured = []
+
+    class TorchProxy:
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        def topk(self, x, **kw):
+            captured.append(x.clone())
+            return torch.topk(x, **kw)
+
+    eu.torch = TorchProxy()
+    eu.id_to_string = lambda sequences, loader, do_eval=0: [" ".join(str(int(t)) for t in row) for row in sequences]
+    parser = types.SimpleNamespace(max_sequence=max_sequence)
+    dec_loader = [(["img%d" % i for i in range(batch)], memories)]
+    out = dict(digest0=np.array(state_dict_digest(sds[0])), digest1=np.array(state_dict_digest(sds[1])),
+               memory0=memories[0].numpy(), memory1=memories[1].numpy())
+    for tag, manager in (("plain", None), ("managed", pp.get_decoding_manager(
+            os.path.join(ref_shim.REFERENCE_ROOT, "configs", "tokens.txt"), batch_size=batch))):
+        del captured[:]
+        with ref_shim.cpu_get_device():
+            res = eu.make_decoder_values(decoders, parser, None, dec_loader, manager, torch.device("cpu"))
+        probs = captured[0]
+        if probs.dim() == 4:
+            probs = probs.squeeze(2)
+        out["probs_" + tag] = probs.numpy().astype(np.float32)            # [B, 24, 245]
+        out["tokens_" + tag] = np.array([[int(t) for t in r[1].split()] for r in res], np.int64)
+        print(tag, "tokens[0]:", out["tokens_" + tag][0][:12], "probs", out["probs_" + tag].shape)
+        if manager is not None:
+            fl, lim = compile_rules(manager.rules, manager.tokens)
+            out["flags"], out["limit"], out["vocab"] = fl, lim, np.array(manager.tokens)
+    eu.torch = torch
+    path = os.path.join(GOLDEN_DIR, "efficientsatrn_ensemble.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def main_train():
     """Three iterations of the reference's single-optimizer training step (train_modules/train_single_opt.py:72-112)
     on the REAL reference modules in train mode: teacher forcing 1.0, CrossEntropyLoss(ignore_index=PAD),
@@ -225,6 +285,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--manager" in sys.argv:
         main_manager()
+        sys.exit(0)
+    if "--ensemble" in sys.argv:
+        main_ensemble()
         sys.exit(0)
     if "--swin" in sys.argv:
         main_swin()

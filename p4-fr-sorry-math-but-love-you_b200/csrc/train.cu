@@ -93,7 +93,27 @@ struct LNS { const float* x; float* y; float* stat; int M, C; size_t g, b; };
 struct EncSave { LNS ln1, ln2; float *qkv, *att, *pre2, *scr; CB c0, c1; DWS dw; const float* x_in; };
 struct DecSave { const float* x_in; float *qkv, *att, *pre1, *q2, *kv, *catt, *pre2, *f0, *f1, *pre3; LNS ln1, ln2, ln3; };
 
+// what the backward pass needs from the forward pass of the same call (or of the preceding frx_train_forward call)
+struct Tape {
+  bool valid = false;
+  int B = 0, L = 0, H = 0, W = 0;
+  size_t ws_mark = 0;
+  float *stem_z = nullptr, *stem_stat = nullptr;
+  std::vector<BlockSave> bs;
+  CB last;
+  float *pe_mean = nullptr, *pe_hp = nullptr, *pe_h = nullptr, *pe_gp = nullptr, *pe_g = nullptr, *pe_out = nullptr;
+  std::vector<EncSave> es;
+  const float* memory = nullptr;
+  long long* text = nullptr;
+  unsigned char* mask = nullptr;
+  std::vector<DecSave> ds;
+  const float* xd = nullptr;
+  float *logits = nullptr, *dlogits = nullptr;
+};
+enum Phase { PH_BOTH = 0, PH_FWD = 1, PH_BWD = 2 };
+
 struct TrainState {
+  Tape tape;
   float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *RS = nullptr;
   size_t n = 0, n_rs = 0;
   std::vector<TParam> params;
@@ -521,46 +541,57 @@ void bucket_done(Ctx& c, int idx) {
 // ---------------------------------------------------------------------------------------------------------------------
 // forward + backward of the whole model
 // ---------------------------------------------------------------------------------------------------------------------
-int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_out) {
+// phase PH_BOTH: one training pass (forward, loss, backward).  PH_FWD: the train-mode forward alone (logits_out [B, L, V],
+// loss_out optional) leaving the tape for a later PH_BWD, which starts from dlogits_in [B, L, V] (the gradient a caller's
+// own criterion produced: EfficientSATRN.forward under model.train() + loss.backward()).
+int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_out, int phase = PH_BOTH, float* logits_out = nullptr,
+            const float* dlogits_in = nullptr) {
   frx_handle* h = c.h;
   TrainState* T = c.T;
+  Tape& tp = T->tape;
   const frx_config& cf = h->cfg;
   const int B = c.B, L = c.L;
+  const int H0 = (cf.height - 3) / 2 + 1, W0 = (cf.width - 3) / 2 + 1;
+  const int C = cf.enc_hidden, F = cf.enc_filter;
+  const int D = cf.dec_hidden, FF = cf.dec_filter, V = cf.num_classes, VP = T->VP, Md = B * L, heads = cf.dec_heads, HD = D / heads;
+  const float temp = sqrtf((float)D);
+  const float* peh = h->arena + h->pe_h;   // host-built tables (not parameters), uploaded by frx_finalize_weights
+  const float* pew = h->arena + h->pe_w;
+  if (phase != PH_BWD) {
   T->ws_used = 0;
   T->taps.clear();
-  TCK(cudaMemsetAsync(T->G, 0, T->n * 4, c.st));
+  tp.valid = false;
   // ================= forward =================
-  const int H0 = (cf.height - 3) / 2 + 1, W0 = (cf.width - 3) / 2 + 1;
-  float *stem_z, *stem_y, *stem_stat;
-  WALLOC(stem_z, (size_t)B * H0 * W0 * 24); WALLOC(stem_y, (size_t)B * H0 * W0 * 24);
-  launch_direct_conv3x3(images, T->P + T->stem_w, T->ones, T->zeros, stem_z, B, cf.in_ch, cf.height, cf.width, H0, W0, 24, 2, 0, ACT_NONE, c.st);
+  float* stem_y;
+  WALLOC(tp.stem_z, (size_t)B * H0 * W0 * 24); WALLOC(stem_y, (size_t)B * H0 * W0 * 24);
+  launch_direct_conv3x3(images, T->P + T->stem_w, T->ones, T->zeros, tp.stem_z, B, cf.in_ch, cf.height, cf.width, H0, W0, 24, 2, 0, ACT_NONE, c.st);
   TKL();
-  if (bn_fwd(c, stem_z, (long long)B * H0 * W0, T->stem_bn, ACT_SILU, nullptr, stem_y, &stem_stat)) return 1;
-  std::vector<BlockSave> bs(T->blocks.size());
+  if (bn_fwd(c, tp.stem_z, (long long)B * H0 * W0, T->stem_bn, ACT_SILU, nullptr, stem_y, &tp.stem_stat)) return 1;
+  tp.bs.assign(T->blocks.size(), BlockSave{});
   const float* x = stem_y;
-  int H = H0, W = W0;
+  tp.H = H0; tp.W = W0;
   for (size_t i = 0; i < T->blocks.size(); ++i) {
     const TBlock& b = T->blocks[i];
-    BlockSave& s = bs[i];
+    BlockSave& s = tp.bs[i];
     s.x_in = x;
     if (b.kind == 0) {
-      s.c1 = CB{}; s.c1.x = x; s.c1.B = B; s.c1.H = H; s.c1.W = W; s.c1.Cin = b.cin; s.c1.Cout = b.cout; s.c1.k = b.k; s.c1.stride = b.stride;
+      s.c1 = CB{}; s.c1.x = x; s.c1.B = B; s.c1.H = tp.H; s.c1.W = tp.W; s.c1.Cin = b.cin; s.c1.Cout = b.cout; s.c1.k = b.k; s.c1.stride = b.stride;
       s.c1.act = ACT_SILU; s.c1.w = b.w_a; s.c1.bn = b.bn1; s.c1.res = b.residual ? x : nullptr;
       if (cb_fwd(c, s.c1)) return 1;
-      x = s.c1.y; H = s.c1.OH; W = s.c1.OW;
+      x = s.c1.y; tp.H = s.c1.OH; tp.W = s.c1.OW;
     } else if (b.kind == 1) {
-      s.c1 = CB{}; s.c1.x = x; s.c1.B = B; s.c1.H = H; s.c1.W = W; s.c1.Cin = b.cin; s.c1.Cout = b.mid; s.c1.k = b.k; s.c1.stride = b.stride;
+      s.c1 = CB{}; s.c1.x = x; s.c1.B = B; s.c1.H = tp.H; s.c1.W = tp.W; s.c1.Cin = b.cin; s.c1.Cout = b.mid; s.c1.k = b.k; s.c1.stride = b.stride;
       s.c1.act = ACT_SILU; s.c1.w = b.w_a; s.c1.bn = b.bn1;
       if (cb_fwd(c, s.c1)) return 1;
       s.c2 = CB{}; s.c2.x = s.c1.y; s.c2.B = B; s.c2.H = s.c1.OH; s.c2.W = s.c1.OW; s.c2.Cin = b.mid; s.c2.Cout = b.cout; s.c2.k = 1;
       s.c2.act = ACT_NONE; s.c2.w = b.w_b; s.c2.bn = b.bn2; s.c2.res = b.residual ? x : nullptr;
       if (cb_fwd(c, s.c2)) return 1;
-      x = s.c2.y; H = s.c1.OH; W = s.c1.OW;
+      x = s.c2.y; tp.H = s.c1.OH; tp.W = s.c1.OW;
     } else {
-      s.c1 = CB{}; s.c1.x = x; s.c1.B = B; s.c1.H = H; s.c1.W = W; s.c1.Cin = b.cin; s.c1.Cout = b.mid; s.c1.k = 1;
+      s.c1 = CB{}; s.c1.x = x; s.c1.B = B; s.c1.H = tp.H; s.c1.W = tp.W; s.c1.Cin = b.cin; s.c1.Cout = b.mid; s.c1.k = 1;
       s.c1.act = ACT_SILU; s.c1.w = b.w_a; s.c1.bn = b.bn1;
       if (cb_fwd(c, s.c1)) return 1;
-      s.dw = DWS{}; s.dw.x = s.c1.y; s.dw.B = B; s.dw.H = H; s.dw.W = W; s.dw.C = b.mid; s.dw.stride = b.stride; s.dw.act = ACT_SILU;
+      s.dw = DWS{}; s.dw.x = s.c1.y; s.dw.B = B; s.dw.H = tp.H; s.dw.W = tp.W; s.dw.C = b.mid; s.dw.stride = b.stride; s.dw.act = ACT_SILU;
       s.dw.w = b.w_dw; s.dw.has_bias = false; s.dw.bn = b.bn2;
       if (dw_fwd(c, s.dw)) return 1;
       s.se = SES{}; s.se.y2 = s.dw.y; s.se.B = B; s.se.S = s.dw.OH * s.dw.OW; s.se.C = b.mid; s.se.R = b.se_r;
@@ -568,34 +599,31 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
       s.c2 = CB{}; s.c2.x = s.se.y3; s.c2.B = B; s.c2.H = s.dw.OH; s.c2.W = s.dw.OW; s.c2.Cin = b.mid; s.c2.Cout = b.cout; s.c2.k = 1;
       s.c2.act = ACT_NONE; s.c2.w = b.w_b; s.c2.bn = b.bn3; s.c2.res = b.residual ? x : nullptr;
       if (cb_fwd(c, s.c2)) return 1;
-      x = s.c2.y; H = s.dw.OH; W = s.dw.OW;
+      x = s.c2.y; tp.H = s.dw.OH; tp.W = s.dw.OW;
     }
   }
-  CB last{};
-  last.x = x; last.B = B; last.H = H; last.W = W; last.Cin = 256; last.Cout = cf.enc_hidden; last.k = 1; last.act = ACT_SILU; last.w = T->last_w;
-  last.bn = T->last_bn;
-  if (cb_fwd(c, last)) return 1;
-  if (H != h->feat_h || W != h->feat_w) return tfail(h, "training: trunk output %dx%d != %dx%d", H, W, h->feat_h, h->feat_w);
-  const int S = H * W, C = cf.enc_hidden, F = cf.enc_filter;
+  tp.last = CB{};
+  tp.last.x = x; tp.last.B = B; tp.last.H = tp.H; tp.last.W = tp.W; tp.last.Cin = 256; tp.last.Cout = cf.enc_hidden; tp.last.k = 1; tp.last.act = ACT_SILU; tp.last.w = T->last_w;
+  tp.last.bn = T->last_bn;
+  if (cb_fwd(c, tp.last)) return 1;
+  if (tp.H != h->feat_h || tp.W != h->feat_w) return tfail(h, "training: trunk output %dx%d != %dx%d", tp.H, tp.W, h->feat_h, h->feat_w);
+  const int S = tp.H * tp.W;
   // ---- adaptive 2-D positional encoding (:135-154) ----
-  float *pe_mean, *pe_hp, *pe_h, *pe_gp, *pe_g, *pe_out;
-  WALLOC(pe_mean, (size_t)B * C); WALLOC(pe_hp, (size_t)B * C / 2); WALLOC(pe_h, (size_t)B * C / 2); WALLOC(pe_gp, (size_t)B * 2 * C);
-  WALLOC(pe_g, (size_t)B * 2 * C); WALLOC(pe_out, (size_t)B * S * C);
-  const float* peh = h->arena + h->pe_h;   // host-built tables (not parameters), uploaded by frx_finalize_weights
-  const float* pew = h->arena + h->pe_w;
-  launch_spatial_dot(last.y, nullptr, pe_mean, B, S, C, 1.f / (float)S, c.st); TKL();
-  if (lin_fwd(c, pe_mean, B, C, T->pe_w0, T->pe_b0, true, C / 2, pe_hp, C / 2, ACT_NONE, nullptr)) return 1;
-  launch_act_fwd(pe_hp, pe_h, ACT_RELU, (long long)B * C / 2, c.st); TKL();
-  if (lin_fwd(c, pe_h, B, C / 2, T->pe_w1, T->pe_b1, true, 2 * C, pe_gp, 2 * C, ACT_NONE, nullptr)) return 1;
-  launch_act_fwd(pe_gp, pe_g, ACT_SIGMOID, (long long)B * 2 * C, c.st); TKL();
-  launch_pe2d_apply(last.y, pe_g, peh, pew, pe_out, B, H, W, C, c.st); TKL();
+  WALLOC(tp.pe_mean, (size_t)B * C); WALLOC(tp.pe_hp, (size_t)B * C / 2); WALLOC(tp.pe_h, (size_t)B * C / 2); WALLOC(tp.pe_gp, (size_t)B * 2 * C);
+  WALLOC(tp.pe_g, (size_t)B * 2 * C); WALLOC(tp.pe_out, (size_t)B * S * C);
+  launch_spatial_dot(tp.last.y, nullptr, tp.pe_mean, B, S, C, 1.f / (float)S, c.st); TKL();
+  if (lin_fwd(c, tp.pe_mean, B, C, T->pe_w0, T->pe_b0, true, C / 2, tp.pe_hp, C / 2, ACT_NONE, nullptr)) return 1;
+  launch_act_fwd(tp.pe_hp, tp.pe_h, ACT_RELU, (long long)B * C / 2, c.st); TKL();
+  if (lin_fwd(c, tp.pe_h, B, C / 2, T->pe_w1, T->pe_b1, true, 2 * C, tp.pe_gp, 2 * C, ACT_NONE, nullptr)) return 1;
+  launch_act_fwd(tp.pe_gp, tp.pe_g, ACT_SIGMOID, (long long)B * 2 * C, c.st); TKL();
+  launch_pe2d_apply(tp.last.y, tp.pe_g, peh, pew, tp.pe_out, B, tp.H, tp.W, C, c.st); TKL();
   // ---- encoder layers (:259-281) ----
-  std::vector<EncSave> es(T->enc.size());
-  const float* xe = pe_out;
+  tp.es.assign(T->enc.size(), EncSave{});
+  const float* xe = tp.pe_out;
   const int Me = B * S;
   for (size_t i = 0; i < T->enc.size(); ++i) {
     const TEncLayer& Lw = T->enc[i];
-    EncSave& s = es[i];
+    EncSave& s = tp.es[i];
     s.x_in = xe;
     s.ln1 = LNS{xe, nullptr, nullptr, Me, C, Lw.ln_g, Lw.ln_b};
     if (ln_fwd(c, s.ln1)) return 1;
@@ -606,51 +634,47 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
     s.ln2 = LNS{s.pre2, nullptr, nullptr, Me, C, Lw.ln_g, Lw.ln_b};
     if (ln_fwd(c, s.ln2)) return 1;
     launch_scramble(s.ln2.y, s.scr, B, S, C, 0, c.st); TKL();
-    s.c0 = CB{}; s.c0.x = s.scr; s.c0.B = B; s.c0.H = H; s.c0.W = W; s.c0.Cin = C; s.c0.Cout = F; s.c0.k = 1; s.c0.act = ACT_RELU; s.c0.w = Lw.w_c0;
+    s.c0 = CB{}; s.c0.x = s.scr; s.c0.B = B; s.c0.H = tp.H; s.c0.W = tp.W; s.c0.Cin = C; s.c0.Cout = F; s.c0.k = 1; s.c0.act = ACT_RELU; s.c0.w = Lw.w_c0;
     s.c0.bn = Lw.n0;
     if (cb_fwd(c, s.c0)) return 1;
-    s.dw = DWS{}; s.dw.x = s.c0.y; s.dw.B = B; s.dw.H = H; s.dw.W = W; s.dw.C = F; s.dw.stride = 1; s.dw.act = ACT_RELU; s.dw.w = Lw.w_dw;
+    s.dw = DWS{}; s.dw.x = s.c0.y; s.dw.B = B; s.dw.H = tp.H; s.dw.W = tp.W; s.dw.C = F; s.dw.stride = 1; s.dw.act = ACT_RELU; s.dw.w = Lw.w_dw;
     s.dw.bias = Lw.b_dw; s.dw.has_bias = true; s.dw.bn = Lw.ndw;
     if (dw_fwd(c, s.dw)) return 1;
-    s.c1 = CB{}; s.c1.x = s.dw.y; s.c1.B = B; s.c1.H = H; s.c1.W = W; s.c1.Cin = F; s.c1.Cout = C; s.c1.k = 1; s.c1.act = ACT_RELU; s.c1.w = Lw.w_c1;
+    s.c1 = CB{}; s.c1.x = s.dw.y; s.c1.B = B; s.c1.H = tp.H; s.c1.W = tp.W; s.c1.Cin = F; s.c1.Cout = C; s.c1.k = 1; s.c1.act = ACT_RELU; s.c1.w = Lw.w_c1;
     s.c1.bn = Lw.n1; s.c1.res = xe;
     if (cb_fwd(c, s.c1)) return 1;
     xe = s.c1.y;
   }
-  const float* memory = xe;   // [B, S, C]
+  tp.memory = xe;   // [B, S, C]
   // ---- teacher-forced decoder (:488-495) ----
-  const int D = cf.dec_hidden, FF = cf.dec_filter, V = cf.num_classes, VP = T->VP, Md = B * L, heads = cf.dec_heads, HD = D / heads;
-  const float temp = sqrtf((float)D);
-  long long* text;
-  { float* t; WALLOC(t, (size_t)Md * 2); text = reinterpret_cast<long long*>(t); }
-  TCK(cudaMemcpy2DAsync(text, (size_t)L * 8, expected, (size_t)(L + 1) * 8, (size_t)L * 8, B, cudaMemcpyDeviceToDevice, c.st));
-  unsigned char* mask;
-  { float* t; WALLOC(t, (size_t)(Md + 3) / 4); mask = reinterpret_cast<unsigned char*>(t); }
-  launch_pad_mask(text, mask, B, L, cf.pad_id, c.st); TKL();
+  { float* t; WALLOC(t, (size_t)Md * 2); tp.text = reinterpret_cast<long long*>(t); }
+  TCK(cudaMemcpy2DAsync(tp.text, (size_t)L * 8, expected, (size_t)(L + 1) * 8, (size_t)L * 8, B, cudaMemcpyDeviceToDevice, c.st));
+  { float* t; WALLOC(t, (size_t)(Md + 3) / 4); tp.mask = reinterpret_cast<unsigned char*>(t); }
+  launch_pad_mask(tp.text, tp.mask, B, L, cf.pad_id, c.st); TKL();
   float* x0;
   WALLOC(x0, (size_t)Md * D);
-  launch_dec_embed_f32(nullptr, text, 0, T->P + T->emb, h->arena + h->pe1d, 0, nullptr, L, temp, x0, Md, D, c.st); TKL();
-  std::vector<DecSave> ds(T->dec.size());
-  const float* xd = x0;
+  launch_dec_embed_f32(nullptr, tp.text, 0, T->P + T->emb, h->arena + h->pe1d, 0, nullptr, L, temp, x0, Md, D, c.st); TKL();
+  tp.ds.assign(T->dec.size(), DecSave{});
+  tp.xd = x0;
   for (size_t l = 0; l < T->dec.size(); ++l) {
     const TDecLayer& Wl = T->dec[l];
-    DecSave& s = ds[l];
-    s.x_in = xd;
+    DecSave& s = tp.ds[l];
+    s.x_in = tp.xd;
     WALLOC(s.qkv, (size_t)Md * 3 * D); WALLOC(s.att, (size_t)Md * D); WALLOC(s.pre1, (size_t)Md * D); WALLOC(s.q2, (size_t)Md * D);
     WALLOC(s.kv, (size_t)B * S * 2 * D); WALLOC(s.catt, (size_t)Md * D); WALLOC(s.pre2, (size_t)Md * D); WALLOC(s.f0, (size_t)Md * FF);
     WALLOC(s.f1, (size_t)Md * D); WALLOC(s.pre3, (size_t)Md * D);
-    if (lin_fwd(c, xd, Md, D, Wl.w_sqkv, Wl.b_sqkv, true, 3 * D, s.qkv, 3 * D, ACT_NONE, nullptr)) return 1;
+    if (lin_fwd(c, tp.xd, Md, D, Wl.w_sqkv, Wl.b_sqkv, true, 3 * D, s.qkv, 3 * D, ACT_NONE, nullptr)) return 1;
     {
       AttnP a{};
       a.q = s.qkv; a.ldq = 3 * D; a.kcache = s.qkv + D; a.vcache = s.qkv + 2 * D; a.rows_per_img = L; a.D = 3 * D;
-      a.causal_L = L; a.key_mask = mask; a.q_per_img = L; a.temperature = temp; a.out = s.att; a.ldo = D; a.M = Md; a.heads = heads;
+      a.causal_L = L; a.key_mask = tp.mask; a.q_per_img = L; a.temperature = temp; a.out = s.att; a.ldo = D; a.M = Md; a.heads = heads;
       launch_dec_attn_f32(a, HD, c.st); TKL();
     }
-    if (lin_fwd(c, s.att, Md, D, Wl.w_so, Wl.b_so, true, D, s.pre1, D, ACT_NONE, xd)) return 1;
+    if (lin_fwd(c, s.att, Md, D, Wl.w_so, Wl.b_so, true, D, s.pre1, D, ACT_NONE, tp.xd)) return 1;
     s.ln1 = LNS{s.pre1, nullptr, nullptr, Md, D, Wl.ln1_g, Wl.ln1_b};
     if (ln_fwd(c, s.ln1)) return 1;
     if (lin_fwd(c, s.ln1.y, Md, D, Wl.w_cq, Wl.b_cq, true, D, s.q2, D, ACT_NONE, nullptr)) return 1;
-    if (lin_fwd(c, memory, (long long)B * S, cf.dec_src, Wl.w_ckv, Wl.b_ckv, true, 2 * D, s.kv, 2 * D, ACT_NONE, nullptr)) return 1;
+    if (lin_fwd(c, tp.memory, (long long)B * S, cf.dec_src, Wl.w_ckv, Wl.b_ckv, true, 2 * D, s.kv, 2 * D, ACT_NONE, nullptr)) return 1;
     {
       AttnP a{};
       a.q = s.q2; a.ldq = D; a.kcache = s.kv; a.vcache = s.kv + D; a.rows_per_img = S; a.D = 2 * D; a.n_hist = S; a.q_per_img = L;
@@ -666,35 +690,48 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
     launch_axpy(s.pre3, s.ln2.y, 1.f, (long long)Md * D, 1, c.st); TKL();
     s.ln3 = LNS{s.pre3, nullptr, nullptr, Md, D, Wl.ln3_g, Wl.ln3_b};
     if (ln_fwd(c, s.ln3)) return 1;
-    xd = s.ln3.y;
+    tp.xd = s.ln3.y;
   }
-  float *logits, *dlogits;
-  WALLOC(logits, (size_t)Md * VP); WALLOC(dlogits, (size_t)Md * VP);
-  if (lin_fwd(c, xd, Md, D, T->gen_w, T->gen_b, true, VP, logits, VP, ACT_NONE, nullptr)) return 1;
+  WALLOC(tp.logits, (size_t)Md * VP); WALLOC(tp.dlogits, (size_t)Md * VP);
+  if (lin_fwd(c, tp.xd, Md, D, T->gen_w, T->gen_b, true, VP, tp.logits, VP, ACT_NONE, nullptr)) return 1;
+  tp.B = B; tp.L = L;
+  tp.valid = true;
+  if (logits_out) TCK(cudaMemcpy2DAsync(logits_out, (size_t)V * 4, tp.logits, (size_t)VP * 4, (size_t)V * 4, Md, cudaMemcpyDeviceToDevice, c.st));
   // ---- loss (:82-86; ignore_index = PAD) ----
-  TCK(cudaMemsetAsync(dlogits, 0, (size_t)Md * VP * 4, c.st));
-  {
-    // the CE kernel walks rows of width V; give it the padded stride through a strided view: V columns of ld VP
-    // (rows are contiguous with stride VP, so run it per row block with ld = VP by treating V = VP and masking the pad
-    // columns with -inf is NOT equivalent) -> copy the V valid columns into a dense [Md, V] buffer and back.
+  if (phase == PH_BOTH || loss_out) {
+    // the CE kernel walks dense rows of width V: copy the V valid columns of the padded logits into a dense [Md, V]
+    // buffer and its gradient back
+    TCK(cudaMemsetAsync(tp.dlogits, 0, (size_t)Md * VP * 4, c.st));
     float *ld, *dd;
     WALLOC(ld, (size_t)Md * V); WALLOC(dd, (size_t)Md * V);
-    TCK(cudaMemcpy2DAsync(ld, (size_t)V * 4, logits, (size_t)VP * 4, (size_t)V * 4, Md, cudaMemcpyDeviceToDevice, c.st));
+    TCK(cudaMemcpy2DAsync(ld, (size_t)V * 4, tp.logits, (size_t)VP * 4, (size_t)V * 4, Md, cudaMemcpyDeviceToDevice, c.st));
     launch_cross_entropy(ld, expected, dd, T->scal, B, L, V, cf.pad_id, c.st); TKL();
-    TCK(cudaMemcpy2DAsync(dlogits, (size_t)VP * 4, dd, (size_t)V * 4, (size_t)V * 4, Md, cudaMemcpyDeviceToDevice, c.st));
+    TCK(cudaMemcpy2DAsync(tp.dlogits, (size_t)VP * 4, dd, (size_t)V * 4, (size_t)V * 4, Md, cudaMemcpyDeviceToDevice, c.st));
+    if (loss_out) TCK(cudaMemcpyAsync(loss_out, T->scal, 4, cudaMemcpyDefault, c.st));
   }
-  if (loss_out) TCK(cudaMemcpyAsync(loss_out, T->scal, 4, cudaMemcpyDefault, c.st));
+  tp.ws_mark = T->ws_used;
+  }  // forward phase
+  if (phase == PH_FWD) return 0;
+  if (phase == PH_BWD) {
+    if (!tp.valid || tp.B != B || tp.L != L) return tfail(h, "train_backward: no forward pass of batch %d / length %d to continue from", B, L);
+    T->ws_used = tp.ws_mark;
+    TCK(cudaMemsetAsync(tp.dlogits, 0, (size_t)Md * VP * 4, c.st));
+    TCK(cudaMemcpy2DAsync(tp.dlogits, (size_t)VP * 4, dlogits_in, (size_t)V * 4, (size_t)V * 4, Md, cudaMemcpyDeviceToDevice, c.st));
+    tp.valid = false;   // the backward pass re-uses the tape's scratch space
+  }
+  const int S = tp.H * tp.W, Me = B * S;
+  TCK(cudaMemsetAsync(T->G, 0, T->n * 4, c.st));
 
   // ================= backward =================
   float* dy;   // gradient flowing into the current op's output
   WALLOC(dy, (size_t)Md * D);
-  if (lin_bwd(c, dlogits, VP, xd, Md, D, T->gen_w, T->gen_b, true, VP, dy, false)) return 1;
+  if (lin_bwd(c, tp.dlogits, VP, tp.xd, Md, D, T->gen_w, T->gen_b, true, VP, dy, false)) return 1;
   float* dmem;
   WALLOC(dmem, (size_t)B * S * cf.dec_src);
   TCK(cudaMemsetAsync(dmem, 0, (size_t)B * S * cf.dec_src * 4, c.st));
   for (int l = (int)T->dec.size() - 1; l >= 0; --l) {
     const TDecLayer& Wl = T->dec[l];
-    const DecSave& s = ds[l];
+    const DecSave& s = tp.ds[l];
     float *dpre3, *df1, *df0, *dw, *dpre2, *dcatt, *du, *dq2, *dkv, *dpre1, *datt, *dqkv, *dx;
     if (ln_bwd(c, s.ln3, dy, &dpre3)) return 1;
     // pre3 = f1 + w ; f1 = relu(linear1(f0)) ; f0 = relu(linear0(w))
@@ -723,7 +760,7 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
       if (rc) return tfail(h, "attention backward configuration failed (%d)", rc);
       TKL();
     }
-    if (lin_bwd(c, dkv, 2 * D, memory, (long long)B * S, cf.dec_src, Wl.w_ckv, Wl.b_ckv, true, 2 * D, dmem, true)) return 1;
+    if (lin_bwd(c, dkv, 2 * D, tp.memory, (long long)B * S, cf.dec_src, Wl.w_ckv, Wl.b_ckv, true, 2 * D, dmem, true)) return 1;
     if (lin_bwd(c, dq2, D, s.ln1.y, Md, D, Wl.w_cq, Wl.b_cq, true, D, du, true)) return 1;
     if (ln_bwd(c, s.ln1, du, &dpre1)) return 1;
     // pre1 = out_linear(att) + x
@@ -734,7 +771,7 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
       AttnBwdP a{};
       a.q = s.qkv; a.k = s.qkv + D; a.v = s.qkv + 2 * D; a.dout = datt; a.dq = dqkv; a.dk = dqkv + D; a.dv = dqkv + 2 * D;
       a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D; a.lddq = a.lddk = a.lddv = 3 * D;
-      a.Lq = L; a.Lk = L; a.heads = heads; a.HD = HD; a.causal = 1; a.key_mask = mask; a.temperature = temp;
+      a.Lq = L; a.Lk = L; a.heads = heads; a.HD = HD; a.causal = 1; a.key_mask = tp.mask; a.temperature = temp;
       int rc = launch_attn_bwd(a, B, c.st);
       if (rc) return tfail(h, "attention backward configuration failed (%d)", rc);
       TKL();
@@ -742,13 +779,13 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
     if (lin_bwd(c, dqkv, 3 * D, s.x_in, Md, D, Wl.w_sqkv, Wl.b_sqkv, true, 3 * D, dx, true)) return 1;
     dy = dx;
   }
-  launch_embed_bwd(text, dy, T->G + T->emb, Md, D, temp, c.st); TKL();
+  launch_embed_bwd(tp.text, dy, T->G + T->emb, Md, D, temp, c.st); TKL();
   bucket_done(c, 0);
   // ---- encoder layers ----
   float* de = dmem;   // gradient of the layer output [B, S, C]
   for (int i = (int)T->enc.size() - 1; i >= 0; --i) {
     const TEncLayer& Lw = T->enc[i];
-    const EncSave& s = es[i];
+    const EncSave& s = tp.es[i];
     float *d_dw, *d_c0, *d_scr, *d_ln2, *d_pre2, *d_att, *d_qkv, *d_ln1, *d_x, *dxin;
     WALLOC(dxin, (size_t)Me * C);
     launch_axpy(dxin, de, 1.f, (long long)Me * C, 0, c.st); TKL();     // residual of conv1
@@ -782,21 +819,21 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
     WALLOC(dtrunk, (size_t)Me * C); WALLOC(dg, (size_t)B * 2 * C); WALLOC(dgp, (size_t)B * 2 * C); WALLOC(dh, (size_t)B * C / 2);
     WALLOC(dhp, (size_t)B * C / 2); WALLOC(dmean, (size_t)B * C);
     launch_axpy(dtrunk, de, 1.f, (long long)Me * C, 0, c.st); TKL();
-    launch_pe2d_bwd_gate(de, peh, pew, dg, B, H, W, C, c.st); TKL();
-    launch_act_bwd(dg, pe_gp, dgp, ACT_SIGMOID, (long long)B * 2 * C, c.st); TKL();
-    if (lin_bwd(c, dgp, 2 * C, pe_h, B, C / 2, T->pe_w1, T->pe_b1, true, 2 * C, dh, false)) return 1;
-    launch_act_bwd(dh, pe_hp, dhp, ACT_RELU, (long long)B * C / 2, c.st); TKL();
-    if (lin_bwd(c, dhp, C / 2, pe_mean, B, C, T->pe_w0, T->pe_b0, true, C / 2, dmean, false)) return 1;
+    launch_pe2d_bwd_gate(de, peh, pew, dg, B, tp.H, tp.W, C, c.st); TKL();
+    launch_act_bwd(dg, tp.pe_gp, dgp, ACT_SIGMOID, (long long)B * 2 * C, c.st); TKL();
+    if (lin_bwd(c, dgp, 2 * C, tp.pe_h, B, C / 2, T->pe_w1, T->pe_b1, true, 2 * C, dh, false)) return 1;
+    launch_act_bwd(dh, tp.pe_hp, dhp, ACT_RELU, (long long)B * C / 2, c.st); TKL();
+    if (lin_bwd(c, dhp, C / 2, tp.pe_mean, B, C, T->pe_w0, T->pe_b0, true, C / 2, dmean, false)) return 1;
     launch_spatial_add(dtrunk, dmean, B, S, C, 1.f / (float)S, c.st); TKL();
   }
   float* dx;
-  if (cb_bwd(c, last, dtrunk, &dx, true)) return 1;
+  if (cb_bwd(c, tp.last, dtrunk, &dx, true)) return 1;
   bucket_done(c, 1);
   // ---- trunk blocks ----
   int stage_of_block = 5, left_in_stage = kArch[5][1];
   for (int i = (int)T->blocks.size() - 1; i >= 0; --i) {
     const TBlock& b = T->blocks[i];
-    const BlockSave& s = bs[i];
+    const BlockSave& s = tp.bs[i];
     float* dmain = nullptr;
     const long long n_in = (long long)B * s.c1.H * s.c1.W * b.cin;
     if (b.kind == 0) {
@@ -824,7 +861,7 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
   {
     float* dz;
     WALLOC(dz, (size_t)B * H0 * W0 * 24);
-    launch_bn_bwd(dx, stem_z, stem_stat, T->acc, dz, T->G + T->stem_bn.g, T->G + T->stem_bn.b, B * H0 * W0, 24, ACT_SILU, c.st); TKL();
+    launch_bn_bwd(dx, tp.stem_z, tp.stem_stat, T->acc, dz, T->G + T->stem_bn.g, T->G + T->stem_bn.b, B * H0 * W0, 24, ACT_SILU, c.st); TKL();
     launch_stem_wgrad(dz, images, T->G + T->stem_w, B, cf.in_ch, cf.height, cf.width, H0, W0, 24, c.st); TKL();
   }
   bucket_done(c, 5);
@@ -945,6 +982,28 @@ extern "C" int frx_train_fwd_bwd(frx_handle* h, const float* images, const int64
   return 0;
 }
 
+extern "C" int frx_train_forward(frx_handle* h, const float* images, const int64_t* expected, int32_t B, int32_t len_plus_1,
+                                 float* logits_out, float* loss_out, void* stream) {
+  if (!h) return 1;
+  TrainState* T = state_of(h);
+  if (!T) return tfail(h, "train_forward: call frx_train_create first");
+  const int L = len_plus_1 - 1;
+  if (B <= 0 || B > T->max_B || L <= 0 || L > T->max_L) return tfail(h, "train_forward: batch %d / length %d outside (%d, %d)", B, L, T->max_B, T->max_L);
+  DevGuard g; g.enter(h->cfg.device);
+  Ctx c{h, T, (cudaStream_t)stream, B, L};
+  return fwd_bwd(c, images, (const long long*)expected, loss_out, PH_FWD, logits_out, nullptr);
+}
+
+extern "C" int frx_train_backward(frx_handle* h, const float* images, const float* dlogits, int32_t B, int32_t len_plus_1, void* stream) {
+  if (!h) return 1;
+  TrainState* T = state_of(h);
+  if (!T) return tfail(h, "train_backward: call frx_train_create first");
+  if (!dlogits || !images) return tfail(h, "train_backward: null argument");
+  DevGuard g; g.enter(h->cfg.device);
+  Ctx c{h, T, (cudaStream_t)stream, B, len_plus_1 - 1};
+  return fwd_bwd(c, images, nullptr, nullptr, PH_BWD, nullptr, dlogits);
+}
+
 extern "C" int frx_train_grad_buffer(frx_handle* h, float** grads, int64_t* count) {
   if (!h || !state_of(h)) return tfail(h, "train_grad_buffer: call frx_train_create first");
   if (grads) *grads = state_of(h)->G;
@@ -1009,6 +1068,35 @@ static int unpack_to(frx_handle* h, TrainState* T, const float* flat_dev, const 
         return 0;
       }
     }
+  }
+  return tfail(h, "training: no parameter named '%s'", name);
+}
+
+// inverse of unpack_to for parameters: state_dict layout (host or device pointer) -> the flat parameter buffer
+extern "C" int frx_train_import(frx_handle* h, const char* name, const float* src) {
+  if (!h || !state_of(h) || !name || !src) return tfail(h, "train_import: bad arguments");
+  DevGuard g; g.enter(h->cfg.device);
+  TrainState* T = state_of(h);
+  for (const TParam& p : T->params) {
+    if (p.name != name) continue;
+    size_t n = 1;
+    for (int i = 0; i < 4; ++i) n *= (size_t)p.d[i];
+    std::vector<float> in(n), packed(p.n, 0.f);
+    TCK(cudaMemcpy(in.data(), src, n * 4, cudaMemcpyDefault));
+    if (p.kind == P_CONV) {
+      const int O = p.d[0], I = p.d[1], kk = p.d[2] * p.d[3];
+      for (int o = 0; o < O; ++o)
+        for (int i = 0; i < I; ++i)
+          for (int t = 0; t < kk; ++t) packed[((size_t)o * kk + t) * I + i] = in[((size_t)o * I + i) * kk + t];
+    } else if (p.kind == P_DW) {
+      const int C = p.d[0];
+      for (int cc = 0; cc < C; ++cc)
+        for (int t = 0; t < 9; ++t) packed[(size_t)t * C + cc] = in[(size_t)cc * 9 + t];
+    } else {
+      memcpy(packed.data(), in.data(), n * 4);
+    }
+    TCK(cudaMemcpy(T->P + p.off, packed.data(), p.n * 4, cudaMemcpyHostToDevice));
+    return 0;
   }
   return tfail(h, "training: no parameter named '%s'", name);
 }

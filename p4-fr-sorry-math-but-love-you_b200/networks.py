@@ -49,6 +49,24 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _TrainForward(torch.autograd.Function):
+    """EfficientSATRN.forward under model.train(): the library's train-mode forward as an autograd node, so that the
+    reference's own loop -- ``loss = criterion(output.transpose(1, 2), expected[:, 1:]); loss.backward()``
+    (train_modules/train_single_opt.py:79-92) -- drives the library's backward pass.  ``anchor`` is any parameter that
+    requires grad (autograd only runs nodes with a differentiable input); the parameter gradients are written to
+    ``.grad`` directly (accumulating, like autograd)."""
+
+    @staticmethod
+    def forward(ctx, module, x, expected, anchor):
+        ctx.module, ctx.x, ctx.e = module, x, expected
+        return module._train_forward(x, expected)
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        ctx.module._train_backward(ctx.x, ctx.e, grad_logits.contiguous().float())
+        return None, None, None, None
+
+
 class _Engine:
     """One frx handle bound to (device, max_batch, max_steps, precision)."""
 
@@ -201,8 +219,17 @@ class EfficientSATRN(_FrxModule):
     def forward(self, input, expected, is_train, teacher_forcing_ratio):
         """:697-706 -> logits [B, expected.size(1)-1, num_classes] fp32 on input's device."""
         if self.training:
-            raise NotImplementedError("train-mode step (BN batch statistics, dropout, backward) is not "
-                                      "built yet; call .eval() for the accelerated forward")
+            # model.train(): BatchNorm batch statistics (and running-statistics updates) like the reference's modules.  The
+            # teacher-forced branch (:488-495) is the one the training loop takes (teacher_forcing_ratio 1.0); it returns
+            # logits that carry a grad_fn, so criterion(...).backward() fills every parameter's .grad (compatibility path:
+            # parameters / gradients cross the host; EfficientSATRN.train_step is the fused fast path).  Dropout: p = 0.
+            if not (is_train and random.random() < teacher_forcing_ratio):
+                raise NotImplementedError("train mode runs the teacher-forced branch only (teacher_forcing_ratio 1.0, "
+                                          "configs/EfficientSATRN.yaml); call .eval() for greedy decoding")
+            x = input.detach().float().contiguous()
+            e = expected.to(device=x.device, dtype=torch.int64).contiguous()
+            anchor = next(p for p in self.parameters() if p.requires_grad)
+            return _TrainForward.apply(self, x, e, anchor)
         b, steps = input.size(0), expected.size(1) - 1
         eng = self.engine(input.device, b, steps)
         x = input.detach().float().contiguous()
@@ -281,27 +308,76 @@ class EfficientSATRN(_FrxModule):
             reducer.finish()      # the current stream waits for the NCCL stream; no host synchronisation
         eng.h.call("frx_train_apply", float(lr), float(weight_decay), float(max_grad_norm), 1.0 / world,
                    ctypes.c_void_p(sc.data_ptr() + 4), st)
-        self._trained = True
+        self._trained, self._train_path = True, "fused"
         return sc[0], sc[1]
 
-    def sync_trained_weights(self):
+    # -- compatibility path: forward / backward as separate calls around the caller's own criterion and optimiser --------
+    def _param_signature(self):
+        return tuple(p._version for p in self.parameters())
+
+    def _train_forward(self, x, e):
+        b, lp1 = x.size(0), e.size(1)
+        eng, tr = self._trainer(x.device, b, lp1 - 1)
+        sig = self._param_signature()
+        if tr.get("sig") is not None and tr["sig"] != sig:
+            # an external optimiser stepped the nn.Parameters: push them into the library's training state
+            with torch.no_grad():
+                for name, p in self.named_parameters():
+                    eng.h.call("frx_train_import", name.encode(), _ptr(p.detach().float().contiguous()))
+        tr["sig"] = sig
+        logits = torch.empty(b, lp1 - 1, self._dims["num_classes"], device=x.device)
+        eng.h.call("frx_train_forward", _ptr(x), _ptr(e), b, lp1, _ptr(logits), None, _stream(x.device))
+        self._trained, self._train_path = True, "compat"
+        self._compat_steps = getattr(self, "_compat_steps", 0) + 1
+        return logits
+
+    def _train_backward(self, x, e, grad_logits):
+        eng = self._engine
+        b, lp1 = x.size(0), e.size(1)
+        eng.h.call("frx_train_backward", _ptr(x), _ptr(grad_logits), b, lp1, _stream(x.device))
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if not p.requires_grad:
+                    continue
+                g = torch.empty_like(p, dtype=torch.float32).contiguous()
+                eng.h.call("frx_train_read_grad", name.encode(), _ptr(g))
+                p.grad = g if p.grad is None else p.grad + g
+
+    def sync_trained_weights(self, buffers_only=None):
         """Copy the library's trained parameters and BatchNorm running statistics back into this module's
         nn.Parameters / buffers (state_dict layout) -- before saving a checkpoint (utils/checkpoint.py:28-32) or
-        running inference with the trained weights."""
+        running inference with the trained weights.  After the compatibility path (forward + loss.backward() + a torch
+        optimiser) the nn.Parameters are the master copy, so only the buffers are pulled (``buffers_only`` defaults to
+        that case); ``state_dict()`` calls this automatically."""
         eng = self._engine
         if eng is None or getattr(eng, "_train", None) is None:
             return
-        steps = int(eng.h.lib.frx_train_step_count(eng.h.ptr))
-        with torch.no_grad():
-            for name, t in self.state_dict().items():
-                if name.endswith("num_batches_tracked"):
-                    t.fill_(int(t) + steps - getattr(self, "_synced_steps", 0))
-                    continue
-                buf = torch.empty_like(t, dtype=torch.float32).contiguous()
-                eng.h.call("frx_train_export", name.encode(), _ptr(buf))
-                t.copy_(buf)
+        if buffers_only is None:
+            buffers_only = getattr(self, "_train_path", "fused") == "compat"
+        steps = int(eng.h.lib.frx_train_step_count(eng.h.ptr)) if not buffers_only else getattr(self, "_compat_steps", 0)
+        params = {n for n, _ in self.named_parameters()}
+        self._syncing = True
+        try:
+            with torch.no_grad():
+                for name, t in super().state_dict().items():
+                    if name.endswith("num_batches_tracked"):
+                        t.fill_(int(t) + steps - getattr(self, "_synced_steps", 0))
+                        continue
+                    if buffers_only and name in params:
+                        continue
+                    buf = torch.empty_like(t, dtype=torch.float32).contiguous()
+                    eng.h.call("frx_train_export", name.encode(), _ptr(buf))
+                    t.copy_(buf)
+        finally:
+            self._syncing = False
         self._synced_steps = steps
+        self._trained = False
         self._dirty = True
+
+    def state_dict(self, *args, **kwargs):
+        if getattr(self, "_trained", False) and not getattr(self, "_syncing", False):
+            self.sync_trained_weights()
+        return super().state_dict(*args, **kwargs)
 
     def read_grad(self, name):
         """Gradient of one parameter (state_dict name) from the last train_step / frx_train_fwd_bwd, state_dict layout."""

@@ -100,3 +100,31 @@ def test_train_mode_then_inference_uses_trained_weights(spec, ckpt0):
         after = model.eval()(x.cuda(), e.cuda(), False, 0.0)
     assert torch.isfinite(after).all()
     assert (after - before).abs().max().item() > 1e-3
+
+
+def test_reference_style_loop_forward_criterion_backward(spec, ckpt0):
+    """The reference's loop as written (train_single_opt.py:79-98): output = model(input, expected, True, 1.0);
+    loss = criterion(output.transpose(1, 2), expected[:, 1:]); loss.backward(); clip; optimizer.step() -- with a torch
+    AdamW over the module's nn.Parameters.  Loss, .grad and the updated parameters against the train-step oracle."""
+    model = make_model(ckpt0, max_batch=4, max_steps=24).cuda().train()
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=1e-6)
+    crit = torch.nn.CrossEntropyLoss(ignore_index=2)
+    tr = train.Trainer(ckpt0, spec)
+    for it in range(2):
+        x, e = train.synth_batch(spec, 4, 24, 40 + it)
+        opt.zero_grad()
+        out = model(x.cuda(), e.cuda(), True, 1.0)
+        assert out.shape == (4, 24, 245) and out.requires_grad
+        loss = crit(out.transpose(1, 2), e[:, 1:].cuda())
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 2.0)
+        opt.step()
+        ref_loss, ref_gn = tr.step(x, e)
+        print("reference-style loop step %d: loss %.6f (oracle %.6f), grad norm %.5f (oracle %.5f)" % (it, loss.item(), ref_loss, gn.item(), ref_gn))
+        tol = 2e-5 if it == 0 else 2e-3      # step 1 sees Adam's first update (sign-like: amplifies round-off)
+        assert abs(loss.item() - ref_loss) <= tol * abs(ref_loss)
+        assert abs(gn.item() - ref_gn) <= (1e-4 if it == 0 else 3e-2) * ref_gn
+    sd_ref = tr.state_dict()
+    for name in ("decoder.generator.weight", "encoder.shallow_cnn.conv_stem.weight", "encoder.attention_layers.1.norm.weight"):
+        a, b = dict(model.named_parameters())[name].detach().cpu(), sd_ref[name]
+        assert (a - b).abs().max().item() <= 2e-3 * max(b.abs().max().item(), 1e-3) + 2.1 * 5e-4 * 2, name
