@@ -111,6 +111,16 @@ int frx_forward_greedy_host(frx_handle* h, const float* images_host, int32_t bat
 int frx_decode_begin(frx_handle* h, const float* memory, int32_t batch, void* stream);
 int frx_decode_step(frx_handle* h, const int64_t* target, float* logits, void* stream);
 
+/* Image input pipeline on the device (data/dataset.py:62-83, data/augmentations.py:27-46): for `batch` decoded uint8
+ * images (HWC, tightly packed one after another in the device buffer `packed`; offsets / heights / widths are HOST
+ * arrays) -> optional 90-degree rotation of tall images (h / w > 2), cv2.resize(INTER_LINEAR) to out_h x out_w (OpenCV's
+ * 8-bit fixed-point arithmetic, bit for bit), (x - mean * 255) * (1 / (std * 255)), HWC -> CHW: out fp32
+ * [batch, channels, out_h, out_w] on the device -- the tensor EfficientSATRN.forward takes.  No handle: stateless.
+ * Returns 0, 1 (bad argument), 2 (allocation / copy failed), 3 (launch failed). */
+int frx_preprocess_u8(const uint8_t* packed, const int64_t* offsets, const int32_t* heights, const int32_t* widths,
+                      int32_t batch, int32_t channels, int32_t out_h, int32_t out_w, const float* mean, const float* stddev,
+                      int32_t rotate_tall, float* out, void* stream);
+
 /* Ensemble decoding, utils/ensemble_utils.py:71-118 (make_decoder_values): n_models decoder handles advance in lock
  * step; per step every model's step_forward logits are soft-maxed and averaged (:95-105), the average optionally goes
  * through DecodingManager.sift (:107-108; rule tables of handles[0], frx_set_decoding_rules), its arg-max is the next

@@ -14,7 +14,7 @@ The compute lives in ``lib/libfrx.so`` (C ABI in include/frx.h).  There is no
 CPU or PyTorch fallback: importing works anywhere, but creating a model handle
 without the compiled library or without a B200 raises RuntimeError.
 """
-from . import _lib, decoding, ensemble, flags, layout, networks, sharding, synthetic  # noqa: F401
+from . import _lib, data, decoding, ensemble, flags, layout, networks, sharding, synthetic  # noqa: F401
 from ._lib import library_path, load_library  # noqa: F401
 from .decoding import decode  # noqa: F401
 from .flags import Flags  # noqa: F401
