@@ -258,6 +258,10 @@ int frx_train_grad_buffer(frx_handle* h, float** grads, int64_t* count);
 int frx_train_set_bucket_callback(frx_handle* h, void (*callback)(void* ctx, int64_t offset, int64_t count), void* ctx);
 int frx_train_apply(frx_handle* h, float lr, float weight_decay, float max_grad_norm, float grad_scale,
                     float* grad_norm_out, void* stream);
+/* The dual-optimizer loop (train_modules/train_dual_opt.py:95-112): clip_grad_norm_ and AdamW separately over
+ * model.encoder.parameters() (enc_lr) and model.decoder.parameters() (dec_lr). */
+int frx_train_apply_dual(frx_handle* h, float enc_lr, float dec_lr, float weight_decay, float max_grad_norm, float grad_scale,
+                         float* enc_grad_norm_out, float* dec_grad_norm_out, void* stream);
 int frx_train_export(frx_handle* h, const char* name, float* dst);
 int frx_train_read_grad(frx_handle* h, const char* name, float* dst);
 int64_t frx_train_step_count(const frx_handle* h);

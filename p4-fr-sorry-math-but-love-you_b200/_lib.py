@@ -16,7 +16,7 @@ SYMBOLS = [
     "frx_set_decoding_rules", "frx_decode_greedy_managed", "frx_forward_greedy_managed",
     "frx_train_create", "frx_train_destroy", "frx_train_param_count", "frx_train_fwd_bwd", "frx_train_grad_buffer",
     "frx_train_set_bucket_callback", "frx_train_apply", "frx_train_export", "frx_train_read_grad", "frx_train_step_count", "frx_train_read_tap",
-    "frx_train_forward", "frx_train_backward", "frx_train_import", "frx_ensemble_decode", "frx_preprocess_u8",
+    "frx_train_forward", "frx_train_backward", "frx_train_import", "frx_ensemble_decode", "frx_preprocess_u8", "frx_train_apply_dual",
 ]
 
 BUCKET_CALLBACK = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64)
@@ -86,6 +86,7 @@ def load_library():
     lib.frx_train_grad_buffer.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
     lib.frx_train_set_bucket_callback.argtypes = [vp, BUCKET_CALLBACK, vp]
     lib.frx_train_apply.argtypes = [vp, f32, f32, f32, f32, vp, vp]
+    lib.frx_train_apply_dual.argtypes = [vp, f32, f32, f32, f32, f32, vp, vp, vp]
     lib.frx_train_export.argtypes = [vp, ctypes.c_char_p, vp]
     lib.frx_train_read_grad.argtypes = [vp, ctypes.c_char_p, vp]
     lib.frx_preprocess_u8.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i32), ctypes.POINTER(i32), i32, i32, i32, i32,

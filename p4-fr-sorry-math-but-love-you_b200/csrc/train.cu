@@ -893,7 +893,7 @@ extern "C" int frx_train_create(frx_handle* h, int32_t max_batch, int32_t max_le
   TCK(cudaMemcpy(T->P, T->hostP.data(), T->n * 4, cudaMemcpyHostToDevice));
   TCK(cudaMemcpy(T->RS, T->hostRS.data(), T->n_rs * 4, cudaMemcpyHostToDevice));
   TCK(cudaMemset(T->M, 0, T->n * 4)); TCK(cudaMemset(T->V, 0, T->n * 4)); TCK(cudaMemset(T->G, 0, T->n * 4));
-  TCK(cudaMalloc(&T->acc, 2 * 4096 * sizeof(double))); TCK(cudaMalloc(&T->sumsq, sizeof(double)));
+  TCK(cudaMalloc(&T->acc, 2 * 4096 * sizeof(double))); TCK(cudaMalloc(&T->sumsq, 2 * sizeof(double)));
   TCK(cudaMalloc(&T->scal, 64)); TCK(cudaMalloc(&T->ones, 4096 * 4)); TCK(cudaMalloc(&T->zeros, 4096 * 4));
   TCK(cudaMemset(T->zeros, 0, 4096 * 4));
   launch_fill(T->ones, 1.f, 4096, 0);
@@ -1018,18 +1018,38 @@ extern "C" int frx_train_set_bucket_callback(frx_handle* h, void (*cb)(void*, in
   return 0;
 }
 
+// clip + AdamW over one contiguous range of the flat buffers (the whole model, or the encoder / decoder parameter group
+// of the dual-optimizer loop, train_modules/train_dual_opt.py:95-112: separate clip_grad_norm_ and optimizers)
+static int apply_range(frx_handle* h, TrainState* T, size_t off, size_t count, float lr, float weight_decay, float max_grad_norm,
+                       float grad_scale, float* grad_norm_out, int slot, cudaStream_t st) {
+  launch_sumsq(T->G + off, (long long)count, T->sumsq + slot, st); TKL();
+  launch_adamw(T->P + off, T->G + off, T->M + off, T->V + off, T->sumsq + slot, T->scal + 4 + slot, (long long)count, lr, weight_decay, T->step,
+               max_grad_norm, grad_scale, st);
+  TKL();
+  if (grad_norm_out) TCK(cudaMemcpyAsync(grad_norm_out, T->scal + 4 + slot, 4, cudaMemcpyDefault, st));
+  return 0;
+}
+
 extern "C" int frx_train_apply(frx_handle* h, float lr, float weight_decay, float max_grad_norm, float grad_scale, float* grad_norm_out,
                                void* stream) {
   if (!h) return 1;
   TrainState* T = state_of(h);
   if (!T) return tfail(h, "train_apply: call frx_train_create first");
   DevGuard g; g.enter(h->cfg.device);
-  cudaStream_t st = (cudaStream_t)stream;
   T->step += 1;
-  launch_sumsq(T->G, (long long)T->n, T->sumsq, st); TKL();
-  launch_adamw(T->P, T->G, T->M, T->V, T->sumsq, T->scal + 4, (long long)T->n, lr, weight_decay, T->step, max_grad_norm, grad_scale, st); TKL();
-  if (grad_norm_out) TCK(cudaMemcpyAsync(grad_norm_out, T->scal + 4, 4, cudaMemcpyDefault, st));
-  return 0;
+  return apply_range(h, T, 0, T->n, lr, weight_decay, max_grad_norm, grad_scale, grad_norm_out, 0, (cudaStream_t)stream);
+}
+
+extern "C" int frx_train_apply_dual(frx_handle* h, float enc_lr, float dec_lr, float weight_decay, float max_grad_norm, float grad_scale,
+                                    float* enc_grad_norm_out, float* dec_grad_norm_out, void* stream) {
+  if (!h) return 1;
+  TrainState* T = state_of(h);
+  if (!T) return tfail(h, "train_apply_dual: call frx_train_create first");
+  DevGuard g; g.enter(h->cfg.device);
+  T->step += 1;
+  const size_t enc_end = T->mark_trunk[6];   // parameters are laid out encoder first (model.encoder.parameters()), decoder after
+  if (apply_range(h, T, 0, enc_end, enc_lr, weight_decay, max_grad_norm, grad_scale, enc_grad_norm_out, 0, (cudaStream_t)stream)) return 1;
+  return apply_range(h, T, enc_end, T->n - enc_end, dec_lr, weight_decay, max_grad_norm, grad_scale, dec_grad_norm_out, 1, (cudaStream_t)stream);
 }
 
 static int unpack_to(frx_handle* h, TrainState* T, const float* flat_dev, const char* name, float* dst) {

@@ -270,11 +270,11 @@ class EfficientSATRN(_FrxModule):
             grads = torch.zeros(n, dtype=torch.float32, device=eng.device)   # flat gradient buffer, all-reduced over NCCL
             eng.h.call("frx_train_create", mb, ml, _ptr(grads))
             tr = eng._train = {"max_batch": mb, "max_len": ml, "grads": grads, "works": [],
-                               "scalars": torch.zeros(2, dtype=torch.float32, device=eng.device)}
+                               "scalars": torch.zeros(4, dtype=torch.float32, device=eng.device)}
         return eng, tr
 
     def train_step(self, input, expected, lr=5e-4, weight_decay=1e-6, max_grad_norm=2.0, process_group=None,
-                   overlap=True):
+                   overlap=True, enc_lr=None, dec_lr=None):
         """One iteration of the reference's single-optimizer loop (train_single_opt.py:72-112) with teacher forcing 1.0:
         train-mode forward (BatchNorm batch statistics), CrossEntropyLoss(ignore_index=PAD), backward,
         clip_grad_norm_(max_grad_norm), AdamW(lr, weight_decay) -- all inside the library, fp32.  Returns
@@ -283,7 +283,11 @@ class EfficientSATRN(_FrxModule):
         Data parallel: when torch.distributed is initialised (one process per GPU, NCCL) the flat gradient buffer is
         all-reduced (sum, then 1 / world inside the optimiser kernel) before the update; with ``overlap`` each bucket's
         all-reduce starts as soon as the backward pass has produced it (trunk stages last), under the rest of the pass.
-        ``expected`` is [B, L + 1] int64 with -1 already replaced by PAD (:77-78)."""
+        ``expected`` is [B, L + 1] int64 with -1 already replaced by PAD (:77-78).
+
+        ``enc_lr`` / ``dec_lr`` (both given): the dual-optimizer loop (train_modules/train_dual_opt.py:95-112) -- gradient
+        clipping and AdamW run separately over the encoder and the decoder parameters; returns
+        (loss, enc_grad_norm, dec_grad_norm)."""
         import torch.distributed as dist
         b, lp1 = input.size(0), expected.size(1)
         eng, tr = self._trainer(input.device, b, lp1 - 1)
@@ -306,9 +310,13 @@ class EfficientSATRN(_FrxModule):
             if not overlap:
                 reducer.begin()
             reducer.finish()      # the current stream waits for the NCCL stream; no host synchronisation
+        self._trained, self._train_path = True, "fused"
+        if enc_lr is not None and dec_lr is not None:
+            eng.h.call("frx_train_apply_dual", float(enc_lr), float(dec_lr), float(weight_decay), float(max_grad_norm), 1.0 / world,
+                       ctypes.c_void_p(sc.data_ptr() + 4), ctypes.c_void_p(sc.data_ptr() + 8), st)
+            return sc[0], sc[1], sc[2]
         eng.h.call("frx_train_apply", float(lr), float(weight_decay), float(max_grad_norm), 1.0 / world,
                    ctypes.c_void_p(sc.data_ptr() + 4), st)
-        self._trained, self._train_path = True, "fused"
         return sc[0], sc[1]
 
     # -- compatibility path: forward / backward as separate calls around the caller's own criterion and optimiser --------

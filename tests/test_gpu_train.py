@@ -128,3 +128,67 @@ def test_reference_style_loop_forward_criterion_backward(spec, ckpt0):
     for name in ("decoder.generator.weight", "encoder.shallow_cnn.conv_stem.weight", "encoder.attention_layers.1.norm.weight"):
         a, b = dict(model.named_parameters())[name].detach().cpu(), sd_ref[name]
         assert (a - b).abs().max().item() <= 2e-3 * max(b.abs().max().item(), 1e-3) + 2.1 * 5e-4 * 2, name
+
+
+def test_dual_optimizer_step_matches_oracle(spec, ckpt0):
+    """train_modules/train_dual_opt.py:95-112: separate clip_grad_norm_ + AdamW for model.encoder / model.decoder
+    parameters (enc_lr != dec_lr), fused in the library, against two torch optimizers over the oracle's parameters."""
+    model = make_model(ckpt0, max_batch=4, max_steps=24).cuda().train()
+    tr = train.Trainer(ckpt0, spec)
+    enc = [v for k, v in tr.sd.items() if train.is_param(k) and k.startswith("encoder.")]
+    dec = [v for k, v in tr.sd.items() if train.is_param(k) and k.startswith("decoder.")]
+    assert len(enc) + len(dec) == len(tr.params)
+    oe, od = torch.optim.AdamW(enc, lr=1e-3, weight_decay=1e-6), torch.optim.AdamW(dec, lr=2e-4, weight_decay=1e-6)
+    x, e = train.synth_batch(spec, 4, 24, 77)
+    loss, gne, gnd = model.train_step(x.cuda(), e.cuda(), enc_lr=1e-3, dec_lr=2e-4)
+    ref_loss, _ = tr.forward_backward(x, e)
+    ref_e = float(torch.nn.utils.clip_grad_norm_(enc, max_norm=2.0))
+    ref_d = float(torch.nn.utils.clip_grad_norm_(dec, max_norm=2.0))
+    oe.step(); od.step()
+    print("dual-opt: loss %.6f (oracle %.6f), encoder grad norm %.5f (%.5f), decoder grad norm %.5f (%.5f)"
+          % (loss.item(), ref_loss, gne.item(), ref_e, gnd.item(), ref_d))
+    assert abs(loss.item() - ref_loss) <= LOSS_TOL * abs(ref_loss)
+    # a ReLU unit on the other side of its kink (see GRAD_TOL above) moves a group's norm by a few 1e-4
+    assert abs(gne.item() - ref_e) <= 1e-3 * ref_e and abs(gnd.item() - ref_d) <= 1e-3 * ref_d
+    model.sync_trained_weights()
+    sd_gpu, sd_ref = model.state_dict(), tr.state_dict()
+    for name, lr in (("decoder.generator.weight", 2e-4), ("encoder.shallow_cnn.conv_stem.weight", 1e-3)):
+        d = (sd_gpu[name].cpu().float() - sd_ref[name].float()).abs()
+        step = (sd_ref[name].float() - ckpt0[name].float()).abs().max().item()
+        assert abs(step - lr) <= 0.05 * lr, (name, step)              # each group moved by ITS learning rate
+        assert d.max().item() <= 2.1 * lr and d.mean().item() <= 0.02 * lr, name
+
+
+def test_distillation_loss_through_the_autograd_bridge(spec, ckpt0):
+    """train_modules/train_distillation.py:49-55, :103-117: the student's train-mode forward, a teacher's greedy logits
+    and loss_fn_kd (KL at temperature 10 + CE, no ignore_index) computed by the CALLER; loss.backward() must hand the
+    library's backward pass the criterion's own logit gradient.  Student gradients against torch autograd on the oracle."""
+    import torch.nn.functional as F
+
+    def loss_fn_kd(outputs, labels, teacher_outputs, T=10, alpha=0.1):
+        return torch.nn.KLDivLoss(reduction="batchmean")(F.log_softmax(outputs / T, dim=1), F.softmax(teacher_outputs / T, dim=1)) \
+            * (alpha * T * T) + F.cross_entropy(outputs, labels) * (1.0 - alpha)
+
+    student = make_model(ckpt0, max_batch=4, max_steps=24).cuda().train()
+    teacher = make_model(synth.synth_state_dict(spec, 1), max_batch=4, max_steps=24).cuda().eval()
+    x, e = train.synth_batch(spec, 4, 24, 91)
+    e[e == 2] = 5                                           # the KD criterion has no ignore_index: use real labels everywhere
+    with torch.no_grad():
+        t_out = teacher(x.cuda(), e.cuda(), False, 0.0)
+    s_out = student(x.cuda(), e.cuda(), True, 1.0)
+    loss = loss_fn_kd(s_out.transpose(1, 2), e[:, 1:].cuda(), t_out.transpose(1, 2))
+    loss.backward()
+    tr = train.Trainer(ckpt0, spec)
+    with torch.enable_grad():
+        ref_out = train.train_forward(tr.sd, spec, x, e)
+        ref_loss = loss_fn_kd(ref_out.transpose(1, 2), e[:, 1:], t_out.cpu().transpose(1, 2))
+        ref_loss.backward()
+    got = dict(student.named_parameters())
+    num = den = 0.0
+    for k, v in tr.sd.items():
+        if train.is_param(k):
+            num += (got[k].grad.cpu() - v.grad).norm().item() ** 2
+            den += v.grad.norm().item() ** 2
+    print("KD: loss %.6f (oracle %.6f), whole-gradient rel-L2 %.2e" % (loss.item(), ref_loss.item(), (num / den) ** 0.5))
+    assert abs(loss.item() - ref_loss.item()) <= 2e-5 * abs(ref_loss.item())
+    assert (num / den) ** 0.5 <= GLOBAL_TOL
