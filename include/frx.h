@@ -103,6 +103,14 @@ int frx_forward_greedy(frx_handle* h, const float* images, int32_t batch, int32_
 int frx_forward_greedy_host(frx_handle* h, const float* images_host, int32_t batch, int32_t steps,
                             float* logits_host, int64_t* tokens_host, void* stream);
 
+/* The same entry, pipelined over consecutive batches (an inference loop over a DataLoader, inference_single.py:50-61):
+ * _submit enqueues H2D (own stream) -> encode + decode (`stream`) -> D2H of the tokens (own stream) for one of two slots
+ * and returns at once; _wait blocks until that slot's tokens are in tokens_host.  With two batches in flight the copies
+ * of batch i +- 1 run under the compute of batch i.  The host buffers must stay valid (and should be pinned) until _wait. */
+int frx_forward_greedy_host_submit(frx_handle* h, const float* images_host, int32_t batch, int32_t steps,
+                                   int64_t* tokens_host, int32_t slot, void* stream);
+int frx_forward_greedy_host_wait(frx_handle* h, int32_t slot);
+
 /* EfficientSATRN_decoder.reset_status / step_forward (EfficientSATRN.py:932-952),
  * the stateful API the ensemble driver uses (utils/ensemble_utils.py:83-118).
  * frx_decode_begin projects the cross-attention K/V of `memory` once and

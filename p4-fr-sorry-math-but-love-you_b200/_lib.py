@@ -10,7 +10,7 @@ _LIB = None
 SYMBOLS = [
     "frx_version", "frx_create", "frx_destroy", "frx_last_error", "frx_load_tensor",
     "frx_finalize_weights", "frx_encode", "frx_decode_greedy", "frx_forward_greedy",
-    "frx_forward_greedy_host", "frx_decode_begin", "frx_decode_step", "frx_beam_search",
+    "frx_forward_greedy_host", "frx_forward_greedy_host_submit", "frx_forward_greedy_host_wait", "frx_decode_begin", "frx_decode_step", "frx_beam_search",
     "frx_decode_teacher_forced", "frx_launch_count", "frx_device_bytes", "frx_set_option",
     "frx_read_tap", "frx_last_timing", "frx_read_prof", "frx_tc_gemm",
     "frx_set_decoding_rules", "frx_decode_greedy_managed", "frx_forward_greedy_managed",
@@ -56,6 +56,8 @@ def load_library():
     lib.frx_destroy.restype = None
     lib.frx_load_tensor.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32, i32]
     lib.frx_finalize_weights.argtypes = [vp]
+    lib.frx_forward_greedy_host_submit.argtypes = [vp, vp, i32, i32, vp, i32, vp]
+    lib.frx_forward_greedy_host_wait.argtypes = [vp, i32]
     lib.frx_encode.argtypes = [vp, vp, i32, vp, vp]
     lib.frx_decode_greedy.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     lib.frx_forward_greedy.argtypes = [vp, vp, i32, i32, vp, vp, vp]

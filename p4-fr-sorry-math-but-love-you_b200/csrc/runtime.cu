@@ -220,6 +220,10 @@ extern "C" void frx_destroy(frx_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (auto& kv : h->taps) cudaFree(kv.second.data);
   if (h->ev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(h->ev[i]);
+  for (auto& sl : h->pipe) {
+    if (sl.h2d) { cudaEventDestroy(sl.h2d); cudaEventDestroy(sl.done); cudaEventDestroy(sl.d2h); }
+  }
+  if (h->pipe_h2d) { cudaStreamDestroy(h->pipe_h2d); cudaStreamDestroy(h->pipe_d2h); }
   delete h;
 }
 
@@ -1662,6 +1666,57 @@ extern "C" int frx_forward_greedy_host(frx_handle* h, const float* images_host, 
   if (tokens_host) CK(cudaMemcpyAsync(tokens_host, h->tokens_int, (size_t)B * steps * 8, cudaMemcpyDeviceToHost, st));
   if (logits_host) CK(cudaMemcpyAsync(logits_host, h->logits_int, (size_t)B * steps * c.num_classes * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// Pipelined host entry: batch i + 1's images travel host -> device and batch i - 1's tokens device -> host on their own
+// streams while batch i computes on `stream`.  Two slots; a slot may be re-submitted after frx_forward_greedy_host_wait.
+extern "C" int frx_forward_greedy_host_submit(frx_handle* h, const float* images_host, int32_t B, int32_t steps,
+                                              int64_t* tokens_host, int32_t slot, void* stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "forward: weights not finalized");
+  const frx_config& c = h->cfg;
+  if (B <= 0 || B > c.max_batch) return fail(h, "forward: batch %d outside (0, %d]", B, c.max_batch);
+  if (steps <= 0 || steps > c.max_steps) return fail(h, "forward: steps %d outside (0, %d]", steps, c.max_steps);
+  if (slot < 0 || slot > 1 || !images_host || !tokens_host) return fail(h, "host_submit: slot must be 0 or 1 and both host buffers given");
+  if (h->opt_timing) return fail(h, "host_submit: option 'timing' synchronises every call; switch it off for the pipelined entry");
+  cudaStream_t st = (cudaStream_t)stream;
+  ON_DEVICE(c.device);
+  frx_handle::PipeSlot& sl = h->pipe[slot];
+  if (sl.busy) return fail(h, "host_submit: slot %d is still in flight (call frx_forward_greedy_host_wait first)", slot);
+  if (!h->pipe_h2d) {
+    CK(cudaStreamCreateWithFlags(&h->pipe_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->pipe_d2h, cudaStreamNonBlocking));
+  }
+  if (!sl.img) {
+    void* p;
+    if (dev_alloc(h, &p, (size_t)c.max_batch * c.in_ch * c.height * c.width * 4)) return 1; sl.img = (float*)p;
+    if (dev_alloc(h, &p, (size_t)c.max_batch * c.max_steps * 8)) return 1; sl.tok = (long long*)p;
+    CK(cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.d2h, cudaEventDisableTiming));
+  }
+  const size_t img_bytes = (size_t)B * c.in_ch * c.height * c.width * 4;
+  CK(cudaMemcpyAsync(sl.img, images_host, img_bytes, cudaMemcpyHostToDevice, h->pipe_h2d));
+  CK(cudaEventRecord(sl.h2d, h->pipe_h2d));
+  CK(cudaStreamWaitEvent(st, sl.h2d, 0));
+  if (frx_forward_greedy(h, sl.img, B, steps, nullptr, (int64_t*)sl.tok, stream)) return 1;
+  CK(cudaEventRecord(sl.done, st));
+  CK(cudaStreamWaitEvent(h->pipe_d2h, sl.done, 0));
+  CK(cudaMemcpyAsync(tokens_host, sl.tok, (size_t)B * steps * 8, cudaMemcpyDeviceToHost, h->pipe_d2h));
+  CK(cudaEventRecord(sl.d2h, h->pipe_d2h));
+  sl.busy = true;
+  return 0;
+}
+
+extern "C" int frx_forward_greedy_host_wait(frx_handle* h, int32_t slot) {
+  if (!h) return 1;
+  if (slot < 0 || slot > 1) return fail(h, "host_wait: slot must be 0 or 1");
+  frx_handle::PipeSlot& sl = h->pipe[slot];
+  if (!sl.busy) return 0;
+  ON_DEVICE(h->cfg.device);
+  CK(cudaEventSynchronize(sl.d2h));
+  sl.busy = false;
   return 0;
 }
 

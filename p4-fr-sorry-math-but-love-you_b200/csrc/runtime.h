@@ -127,6 +127,10 @@ struct frx_handle {
   int64_t graph_clock = 0;
   std::map<std::string, Tap> taps;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // pipelined host entry (frx_forward_greedy_host_submit / _wait): two staging slots, one stream per copy direction
+  struct PipeSlot { float* img = nullptr; long long* tok = nullptr; cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr; bool busy = false; };
+  PipeSlot pipe[2];
+  cudaStream_t pipe_h2d = nullptr, pipe_d2h = nullptr;
   float last_ms[4] = {0, 0, 0, 0};
   BeamWs beam;
   TfWs tf;

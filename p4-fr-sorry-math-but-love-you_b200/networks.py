@@ -418,6 +418,19 @@ class EfficientSATRN(_FrxModule):
         eng.h.call("frx_encode", _ptr(x), b, _ptr(memory), _stream(x.device))
         return memory
 
+    def submit_host(self, images_host, tokens_host, steps, slot):
+        """Pipelined host entry (frx_forward_greedy_host_submit): enqueue H2D of ``images_host`` (CPU fp32, ideally
+        pinned) -> encode + greedy decode -> D2H of the tokens into ``tokens_host`` (CPU int64 [B, steps]) for ``slot``
+        0 / 1 and return at once; ``wait_host(slot)`` blocks until the tokens have arrived.  With both slots in flight
+        the copies of the neighbouring batches run under the current batch's compute."""
+        b = images_host.size(0)
+        dev = torch.device("cuda", torch.cuda.current_device()) if self._engine is None else self._engine.device
+        eng = self.engine(dev, b, steps)
+        eng.h.call("frx_forward_greedy_host_submit", _ptr(images_host), b, steps, _ptr(tokens_host), int(slot), _stream(dev))
+
+    def wait_host(self, slot):
+        self._engine.h.call("frx_forward_greedy_host_wait", int(slot))
+
     def greedy(self, input, steps, forced=None, want_logits=True):
         """Encode + greedy loop returning (logits | None, tokens [B, steps] int64)
         on the input's device; ``forced`` feeds given tokens (forced decoding)."""

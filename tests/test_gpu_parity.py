@@ -162,3 +162,30 @@ def test_host_buffer_entry_point(spec, ckpt0, model0):
     with torch.no_grad():
         _, ref = model0.greedy(x.cuda(), 231)
     assert torch.equal(tok, ref.cpu())
+
+
+def test_pipelined_host_entry_matches_synchronous_entry(ckpt0, spec):
+    """frx_forward_greedy_host_submit / _wait (copies on their own streams, two batches in flight) returns, batch by
+    batch, exactly the tokens of the synchronous host entry."""
+    model = make_model(ckpt0, max_batch=6, max_steps=16).cuda().eval()
+    batches = [synth.synth_images(spec, 6, 50 + i).pin_memory() for i in range(5)]
+    want = []
+    eng = model.engine(torch.device("cuda", 0), 6, 16)
+    st = torch.cuda.current_stream().cuda_stream
+    for x in batches:
+        t = torch.empty(6, 16, dtype=torch.int64).pin_memory()
+        eng.h.call("frx_forward_greedy_host", x.data_ptr(), 6, 16, None, t.data_ptr(), st)
+        want.append(t.clone())
+    got = [torch.empty(6, 16, dtype=torch.int64).pin_memory() for _ in batches]
+    for i, x in enumerate(batches):
+        if i >= 2:
+            model.wait_host(i % 2)
+        model.submit_host(x, got[i], 16, i % 2)
+    model.wait_host(0)
+    model.wait_host(1)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):          # a slot in flight cannot be re-submitted
+        model.submit_host(batches[0], got[0], 16, 0)
+        model.submit_host(batches[1], got[1], 16, 0)
+    model.wait_host(0)
