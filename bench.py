@@ -40,12 +40,22 @@ DECODE_KERNEL = "dec_cluster_bf16_kernel_p2"
 
 def ncu_traffic(kernel, batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-    (profiles/ncu_traffic.json), or None when no capture matches this kernel / batch."""
+    (profiles/ncu_traffic.json), or None when no capture matches this kernel / batch -- or when the kernel's source files
+    have changed since the capture (the entry carries a hash of them), so the figure can never go stale silently."""
+    import hashlib
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
         return None
     for e in json.load(open(path)):
         if e["kernel"] == kernel and e["batch"] == batch:
+            h = hashlib.sha256()
+            try:
+                for f in e.get("kernel_source_files", []):
+                    h.update(open(os.path.join(ROOT, "p4-fr-sorry-math-but-love-you_b200", f), "rb").read())
+            except OSError:
+                return None
+            if e.get("kernel_source_sha256_16") != h.hexdigest()[:16]:
+                return None
             return e["dram_bytes_per_launch"]
     return None
 

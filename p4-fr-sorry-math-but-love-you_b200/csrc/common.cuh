@@ -209,7 +209,7 @@ struct SiftIds { int sos, eos, empty, lbrace, rbrace, underbar; };
 constexpr int DEC_CLUSTER = 8;   // CTAs per cluster
 constexpr int DEC_IMG = 8;       // images per cluster (rows 0..7 of the mma.m16n8k16 tile)
 constexpr int DEC_FMAX = 1024;   // decoder filter_dim the kernel is specialised for
-constexpr int DEC_TMAX = 232;    // max decode steps
+constexpr int DEC_TMAX = 500;    // max decode steps of the cluster kernel = length of the 1-D positional table (PositionEncoder1D max_len, EfficientSATRN.py:408); nothing in the kernel is sized by it
 constexpr int DEC_MAX_CLUSTERS = 32;  // clusters per launch; 33 8-CTA clusters are co-resident at 2 CTAs/SM on B200
 
 struct DecClusterLayer {

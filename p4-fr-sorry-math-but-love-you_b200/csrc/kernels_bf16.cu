@@ -6,7 +6,7 @@
 #include "kernels.h"
 
 #ifndef FRX_DW_ACC32
-#define FRX_DW_ACC32 1
+#define FRX_DW_ACC32 2
 #endif
 
 namespace frx {
@@ -404,10 +404,17 @@ __global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const eh_t* __r
   // fp32 taps / accumulation / folded BN / SiLU (operands stay packed halves in shared memory): the 9-term sum and the
   // activation then add no rounding of their own to the fp16-stored trunk (FRX_DW_ACC32=0: packed-half arithmetic)
   float4 wt[9], sc, sh;
+#if FRX_DW_ACC32 == 2
+  __half2 wh[9][2];
+#endif
   {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < 9; ++t) wt[t] = c_ok ? __ldg(reinterpret_cast<const float4*>(w + t * C + c)) : z;
+#if FRX_DW_ACC32 == 2
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { wh[t][0] = __floats2half2_rn(wt[t].x, wt[t].y); wh[t][1] = __floats2half2_rn(wt[t].z, wt[t].w); }
+#endif
     sc = c_ok ? __ldg(reinterpret_cast<const float4*>(scale + c)) : z;
     sh = c_ok ? __ldg(reinterpret_cast<const float4*>(shift + c)) : z;
   }
@@ -422,6 +429,21 @@ __global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const eh_t* __r
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int ih = oh * stride - pad_t + kh;
+#if FRX_DW_ACC32 == 2
+        // one filter row (3 taps) in packed halves, rows combined in fp32: a third of the conversions of the all-fp32 form
+        __half2 r0 = __floats2half2_rn(0.f, 0.f), r1 = r0;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = ow * stride - pad_l + kw;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            const uint2 u = tile2[(ih * W + iw) * G4 + cg];
+            r0 = __hfma2(*reinterpret_cast<const __half2*>(&u.x), wh[kh * 3 + kw][0], r0);
+            r1 = __hfma2(*reinterpret_cast<const __half2*>(&u.y), wh[kh * 3 + kw][1], r1);
+          }
+        }
+        const float2 a = __half22float2(r0), b = __half22float2(r1);
+        acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+#else
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const int iw = ow * stride - pad_l + kw;
@@ -432,6 +454,7 @@ __global__ void __launch_bounds__(CH * 4) dwconv4_se_mean_kernel(const eh_t* __r
             acc.x = fmaf(a.x, ww.x, acc.x); acc.y = fmaf(a.y, ww.y, acc.y); acc.z = fmaf(b.x, ww.z, acc.z); acc.w = fmaf(b.y, ww.w, acc.w);
           }
         }
+#endif
       }
       float2 f0 = make_float2(fmaf(acc.x, sc.x, sh.x), fmaf(acc.y, sc.y, sh.y)), f1 = make_float2(fmaf(acc.z, sc.z, sh.z), fmaf(acc.w, sc.w, sh.w));
       f0.x = __fdividef(f0.x, 1.f + __expf(-f0.x)); f0.y = __fdividef(f0.y, 1.f + __expf(-f0.y));

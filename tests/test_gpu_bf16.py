@@ -217,3 +217,21 @@ def test_bf16_full_size_against_oracle_and_operand_floor(ckpt0, spec):
     assert rel <= BF16_E2E_REL_TOL, rel
     assert step_agree >= STEP_AGREEMENT, step_agree
     assert a_gpu >= a_floor - 0.10, (a_gpu, a_floor)
+
+
+def test_bf16_long_sequence_runs_in_the_cluster_kernel(ckpt0, spec):
+    """Sequences longer than the benchmark's 231 steps (the 1-D positional table allows 500) stay on the persistent
+    cluster kernel: 300 forced steps against the fp32 mode of the same library."""
+    x = synth.synth_images(spec, 3, 21).cuda()
+    m32 = make_model(ckpt0, max_batch=3, max_steps=300).cuda().eval()
+    m16 = make_model(ckpt0, precision="bf16", max_batch=3, max_steps=300).cuda().eval()
+    with torch.no_grad():
+        mem = m32.encode(x)
+        l32, t32 = _decode(m32, mem, 300)
+        before = m16.engine(x.device, 3, 300).launches
+        l16, _ = _decode(m16, mem, 300, forced=t32)
+        launches = m16._engine.launches - before
+    rel = ((l16 - l32).abs().max() / l32.abs().max()).item()
+    print("300 forced steps: max rel logit error %.4f, launches %d" % (rel, launches))
+    assert launches < 20            # cross K/V projection + conversions + ONE decode launch, not 300 x 26 step kernels
+    assert rel <= BF16_REL_TOL
