@@ -465,8 +465,8 @@ def run_workload(args, rank, world, local_rank):
                 "231 target positions, fp32 like the reference, gradients all-reduced over NCCL (%d ranks)" % (B, world))
         dtype = "f32"
     elif wl in ("beam4", "beam8"):
-        B, width = args.batch or 32, int(wl[4:])   # inference.py:22 batch_size 32
-        model, sd = build_model("fp32", B)          # beam search runs on the fp32 step kernels
+        B, width = args.batch or 256, int(wl[4:])  # the headline batch (the reference's inference.py default is 32)
+        model, sd = build_model(args.precision, B)  # 16-bit: every node expansion is one cluster-kernel launch (step mode)
         model = model.to(dev).eval()
         x_host = synthetic_images(B, rank).pin_memory()
         x = x_host.to(dev)
@@ -476,8 +476,9 @@ def run_workload(args, rank, world, local_rank):
         h2d, d2h = x_host.numel() * 4, B * MAX_SEQUENCE * 8
         metric = "EfficientSATRN beam-search (width %d) images/sec" % width
         desc = ("EfficientSATRN beam_search(topk=1, beam_width=%d, max_sequence=230) through decode(): best-first queue on the "
-                "device, batch %d per GPU, fp32 step kernels" % (width, B))
-        dtype = "f32"
+                "device, batch %d per GPU, %s" % (width, B, "16-bit mode: one cluster-kernel launch per round (step mode)"
+                                                  if args.precision == "bf16" else "fp32 step kernels"))
+        dtype = "bf16" if args.precision == "bf16" else "f32"
     elif wl == "lite":
         from oracle import satrn as o_satrn, synth as o_synth
         from oracle.make_golden import LITE_SPEC
@@ -561,10 +562,10 @@ def run_workload(args, rank, world, local_rank):
                           "the yardstick the task names, the fp32 FFMA peak of a B200 is ~75 TFLOP/s)",
                 "algorithmic_flop_per_step": TRAIN_FLOP_PER_IMAGE * B, "ms": step_s * 1e3, "peak_source": how}
     elif wl in ("beam4", "beam8"):
-        by = DECODE_BYTES_PER_IMAGE["fp32"] * B
+        by = DECODE_BYTES_PER_IMAGE["fp32" if args.precision == "fp32" else "bf16"] * B
         dec_s = step_s    # whole step (the encoder is ~2 % of it at this batch)
         roof = {"bound": "hbm", "achieved": by / dec_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / dec_s / 1e9 / hbm,
-                "traffic": None, "kernel": "beam rounds (fp32 step kernels + queue kernels), one node expansion per image and round",
+                "traffic": None, "kernel": "beam rounds (select + decoder step + push), one node expansion per image and round",
                 "algorithmic_bytes_per_launch": by, "ms": dec_s * 1e3, "peak_source": how,
                 "note": "upper bound on the useful bytes: an explored chain of 230 nodes reads the fp32 K/V history a greedy pass reads"}
     elif wl == "lite":

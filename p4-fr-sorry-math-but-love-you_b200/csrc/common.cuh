@@ -233,6 +233,13 @@ struct DecClusterP {
   float* logits;                 // [B][steps][V] or nullptr
   long long* tokens;             // [B][steps] or nullptr
   const long long* forced;       // [B][steps] or nullptr
+  // "step mode" (step_forward / ensemble / best-first search): one launch = `steps` steps (normally 1) that CONTINUE a
+  // history instead of starting at <SOS>.  All nullptr = a greedy decode from position 0.
+  const int* hist_len;           // [B] keys already cached for the image = position of this launch's first step
+  const int* chain;              // [B][T] cache rows of those keys in attention order (ancestor chain); nullptr = rows 0..n-1
+  const int* slot;               // [B] cache row that receives the first step's K/V; nullptr = hist_len[b] (+ step)
+  const int* first_tok32;        // [B] token fed at the first step (int32), or
+  const long long* first_tok64;  // [B] the same as int64; both nullptr = <SOS>
   long long* prof;               // optional [16] per-stage cycle totals (cluster 0, CTA 0, thread 0)
 };
 

@@ -203,4 +203,10 @@ void launch_beam_select(const BeamP& p, cudaStream_t st) { beam_select_kernel<<<
 void launch_beam_push(const BeamP& p, cudaStream_t st) { beam_push_kernel<<<(p.B + 7) / 8, 256, 0, st>>>(p); }
 void launch_beam_finish(const BeamP& p, cudaStream_t st) { beam_finish_kernel<<<(p.B + 127) / 128, 128, 0, st>>>(p); }
 
+__global__ void fill_i32_kernel(int* p, int v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+void launch_fill_i32(int* p, int v, int n, cudaStream_t st) { fill_i32_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, v, n); }
+
 }  // namespace frx

@@ -314,8 +314,9 @@ struct KVStage { __nv_bfloat16 k[32][HD], v[32][HD]; };  // one 32-key block of 
 __device__ __forceinline__ uint32_t kv_swz(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc,
-                                           int kb, int n_hist) {
-  // one commit group per call, EMPTY when the block lies past the history: the consumer counts groups
+                                           int kb, int n_hist, const int* __restrict__ chain) {
+  // one commit group per call, EMPTY when the block lies past the history: the consumer counts groups.  chain != nullptr:
+  // key j of the history lives in cache row chain[j] (the ancestors of a search-tree node), otherwise in row j.
   if (kb < n_hist) {
     const int lane = threadIdx.x & 31;
     const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
@@ -324,7 +325,9 @@ __device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __r
       const int id = lane + 32 * i, row = id >> 2, chunk = id & 3;
       const int key = kb + row;
       const uint32_t bytes = key < n_hist ? 16u : 0u;   // zero-fill past the history (also keeps V finite)
-      const size_t off = (size_t)(key < n_hist ? key : 0) * HD + chunk * 8;
+      int src = key < n_hist ? key : 0;
+      if (chain) src = __ldg(chain + src);
+      const size_t off = (size_t)src * HD + chunk * 8;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ks + kv_swz(row, chunk)), "l"(Kc + off), "r"(bytes) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(vs + kv_swz(row, chunk)), "l"(Vc + off), "r"(bytes) : "memory");
     }
@@ -332,16 +335,17 @@ __device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __r
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
 // Request the first KVD blocks of a history into the warp's ring (KVD commit groups, in block order).
-__device__ __forceinline__ void kv_prime(KVStage* ring, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc, int n_hist) {
+__device__ __forceinline__ void kv_prime(KVStage* ring, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc, int n_hist,
+                                         const int* __restrict__ chain) {
 #pragma unroll
-  for (int d = 0; d < KVD; ++d) kv_request(ring[d], Kc, Vc, 32 * d, n_hist);
+  for (int d = 0; d < KVD; ++d) kv_request(ring[d], Kc, Vc, 32 * d, n_hist, chain);
 }
 
 // The history must have been primed with kv_prime(ring, Kc, Vc, n_hist): block i lives in ring[i % KVD] and is
 // complete once at most KVD - 1 younger commit groups are pending; its buffer is re-used for block i + KVD as soon as
 // its fragments are in registers, so KVD blocks are in flight while one is being reduced.
 __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
-                                           const __nv_bfloat16* __restrict__ Vc, int n_hist,
+                                           const __nv_bfloat16* __restrict__ Vc, int n_hist, const int* __restrict__ chain,
                                            const __nv_bfloat16* __restrict__ kx,
                                            const __nv_bfloat16* __restrict__ vx, float inv_temp,
                                            float (&o)[8]) {
@@ -381,7 +385,7 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
                    : "=r"(vf[x][0]), "=r"(vf[x][1]), "=r"(vf[x][2]), "=r"(vf[x][3]) : "r"(vs + kv_swz(key, chunk)));
     }
     __syncwarp();
-    kv_request(st, Kc, Vc, kb + 32 * KVD, n_hist);
+    kv_request(st, Kc, Vc, kb + 32 * KVD, n_hist, chain);
     float sc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -489,10 +493,15 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) s.lw[l] = p.layer[l];
   }
-  // ---- step 0 input: <SOS> embedding + position 0 --------------------------------
+  // ---- first input: <SOS> at position 0, or (step mode) the given token at the image's current position -----------
   for (int i = tid; i < NIMG * D; i += NTHR) {
     const int row = i / D, c = i % D;
-    float v = __ldg(p.emb + (size_t)p.sos * D + c) * emb_scale + __ldg(p.pe + c);
+    const int b = min(img0 + row, p.B - 1);
+    long long tok = p.sos;
+    if (p.first_tok32) tok = __ldg(p.first_tok32 + b);
+    else if (p.first_tok64) tok = __ldg(p.first_tok64 + b);
+    const int pos0 = p.hist_len ? __ldg(p.hist_len + b) : 0;
+    float v = __ldg(p.emb + (size_t)tok * D + c) * emb_scale + __ldg(p.pe + (size_t)pos0 * D + c);
     s.xres[row][c] = v;
     s.abf[row][c] = __float2bfloat16_rn(v);
   }
@@ -531,6 +540,8 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   const int head = r * HPC + whc;
   const int b_mine = img0 + wimg;
   const bool mine = b_mine < B;
+  const int hist0 = (mine && p.hist_len) ? __ldg(p.hist_len + b_mine) : 0;      // keys cached before this launch
+  const int* const chain = (mine && p.chain) ? p.chain + (size_t)b_mine * T : nullptr;
   KVStage* const kvst = reinterpret_cast<KVStage*>(&s.kvst[warp][0][0][0][0]);  // this warp's ring of K/V staging blocks
 
   // all-gather of this warp's attention output (head r, image `warp`) into every CTA's obf: the eight gid
@@ -597,7 +608,8 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       const int seg = tile / NTS, wc = (tile % NTS) * 8, hd = r * HPC + wc / HD, col = wc % HD;
       const float4 b0 = cb.a, b1 = cb.b;
       __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
-      *reinterpret_cast<uint4*>(dst + (((((size_t)lc * B + b) * H + hd) * T) + t) * HD + col) =
+      const int wrow = (p.slot ? __ldg(p.slot + b) : (p.hist_len ? __ldg(p.hist_len + b) : 0)) + t;   // cache row of this step
+      *reinterpret_cast<uint4*>(dst + (((((size_t)lc * B + b) * H + hd) * T) + wrow) * HD + col) =
           make_uint4(pack_bf16(v[0] + b0.x, v[1] + b0.y), pack_bf16(v[2] + b0.z, v[3] + b0.w),
                      pack_bf16(v[4] + b1.x, v[5] + b1.y), pack_bf16(v[6] + b1.z, v[7] + b1.w));
     });
@@ -610,8 +622,8 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       // ---- A: q|k|v of head r from the layer input, then self attention of (image warp, head r) -------
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * T) * HD;
-        const int n_hist = mine ? t : 0;
-        kv_prime(kvst, p.kself + base, p.vself + base, n_hist);  // lands during the projection
+        const int n_hist = mine ? hist0 + t : 0;
+        kv_prime(kvst, p.kself + base, p.vself + base, n_hist, chain);  // lands during the projection
         const uint4* wp = l == 0 ? p.w_first + (size_t)r * NTA * WT : s.lw[l - 1].w_next + ((size_t)r * (NTC + NTA) + NTC) * WT;
         const Bias8 bias = qkv_bias(l == 0 ? p.b_first : s.lw[l - 1].b_next + 2 * D);
         gemm2<NTA, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
@@ -620,7 +632,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         stage_begin(NIMG * D * 2u);
         const uint32_t sb = stage_bar();
         float o[8];
-        attend_mma(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], inv_temp, o);
+        attend_mma(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, chain, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], inv_temp, o);
         store_attn(sb, o);
         mark(1);
       }
@@ -647,7 +659,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * p.S) * HD;
         const int n_keys = mine ? p.S : 0;
-        kv_prime(kvst, p.kcross + base, p.vcross + base, n_keys);
+        kv_prime(kvst, p.kcross + base, p.vcross + base, n_keys, nullptr);
         gemm2<NTS, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_q2 + (size_t)r * NTS * WT, pol, pre_c,
                           [&](int tile, int row, float (&v)[8], int sub) {
                             if (sub != 0) return;
@@ -662,7 +674,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         const uint32_t sb = stage_bar();
         float o[8];
         if (mine) {
-          attend_mma(kvst, &s.qh[whc][wimg][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, inv_temp, o);
+          attend_mma(kvst, &s.qh[whc][wimg][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, nullptr, inv_temp, o);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -791,7 +803,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         if (r == 0 && lane == 0 && p.tokens) p.tokens[(size_t)b_mine * p.steps + t] = bi;
       }
       if (t + 1 < p.steps) {
-        const float* pe = p.pe + (size_t)(t + 1) * D;
+        const float* pe = p.pe + (size_t)(hist0 + t + 1) * D;
 #pragma unroll
         for (int i = 0; i < D / 32; ++i) {
           const int c = i * 32 + lane;

@@ -255,6 +255,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   std::string k(key);
   if (k == "taps") h->opt_taps = value != 0;
   else if (k == "graphs") h->opt_graphs = value != 0;
+  else if (k == "step16") h->opt_step16 = value != 0;
   else if (k == "timing") h->opt_timing = value != 0;
   else if (k == "cluster_images") {}  // accepted for compatibility: clusters always own 8 images
   else if (k == "dec_hpc") h->opt_dec_hpc = (value == 1 || value == 2) ? (int)value : 0;  // heads per CTA of the 256-wide decode kernel, 0 = by batch size
@@ -1475,15 +1476,32 @@ static int run_greedy_loop(frx_handle* h, int B, int steps, int mode, cudaStream
   return 0;
 }
 
+// "step mode" of the cluster kernel: continue per-image histories instead of decoding from <SOS> (DecClusterP)
+struct ClusterStep {
+  const int* hist_len = nullptr;
+  const int* chain = nullptr;
+  const int* slot = nullptr;
+  const int* tok32 = nullptr;
+  const long long* tok64 = nullptr;
+};
+
+static int cross_kv_to_bf16(frx_handle* h, int B, cudaStream_t st) {
+  const frx_config& c = h->cfg;
+  launch_cross_to_bf16(h->cross, (__nv_bfloat16*)h->kcross_bf, (__nv_bfloat16*)h->vcross_bf, B, h->feat_h * h->feat_w, c.dec_layers,
+                       c.dec_hidden, st);
+  CKL();
+  return 0;
+}
+
 static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, long long* tokens,
-                              const long long* forced, cudaStream_t st) {
+                              const long long* forced, cudaStream_t st, const ClusterStep* sm = nullptr) {
   const frx_config& c = h->cfg;
   const float* A = h->arena;
   const int S = h->feat_h * h->feat_w, L = c.dec_layers, D = c.dec_hidden;
   if (steps > DEC_TMAX) return fail(h, "bf16 decode kernel supports at most %d steps", DEC_TMAX);
-  launch_cross_to_bf16(h->cross, (__nv_bfloat16*)h->kcross_bf, (__nv_bfloat16*)h->vcross_bf, B, S, L, D, st);
-  CKL();
+  if (!sm && cross_kv_to_bf16(h, B, st)) return 1;      // step mode: converted once by the caller
   DecClusterP p{};
+  if (sm) { p.hist_len = sm->hist_len; p.chain = sm->chain; p.slot = sm->slot; p.first_tok32 = sm->tok32; p.first_tok64 = sm->tok64; }
   p.B = B; p.steps = steps; p.T = c.max_steps; p.L = L; p.V = c.num_classes; p.S = S; p.sos = c.sos_id;
   // 256-wide decoder: with one head per CTA (clusters of 8) only 15 clusters get their CTAs alone on an SM (an 8-CTA
   // cluster must sit inside one GPC); beyond that two CTAs share an SM and step in 67 us instead of 42.  Two heads per CTA
@@ -1669,6 +1687,12 @@ extern "C" int frx_forward_greedy_host(frx_handle* h, const float* images_host, 
   return 0;
 }
 
+// 16-bit handles run single decoder steps (step_forward, ensembles, best-first search) on the cluster kernel too;
+// option "step16" = 0 keeps them on the fp32 step kernels (the bit-faithful path the fp32 goldens pin).
+static bool step16(const frx_handle* h) {
+  return h->cfg.precision == FRX_PREC_BF16 && h->dec_cluster_ok && h->opt_step16 && h->cfg.max_steps <= DEC_TMAX;
+}
+
 // Pipelined host entry: batch i + 1's images travel host -> device and batch i - 1's tokens device -> host on their own
 // streams while batch i computes on `stream`.  Two slots; a slot may be re-submitted after frx_forward_greedy_host_wait.
 extern "C" int frx_forward_greedy_host_submit(frx_handle* h, const float* images_host, int32_t B, int32_t steps,
@@ -1727,6 +1751,7 @@ extern "C" int frx_decode_begin(frx_handle* h, const float* memory, int32_t B, v
   if (B <= 0 || B > h->cfg.max_batch) return fail(h, "decode_begin: batch %d outside (0, %d]", B, h->cfg.max_batch);
   ON_DEVICE(h->cfg.device);
   if (run_cross_kv(h, memory, B, (cudaStream_t)stream)) return 1;
+  if (step16(h) && cross_kv_to_bf16(h, B, (cudaStream_t)stream)) return 1;
   h->step_idx = 0;
   h->step_batch = B;
   return 0;
@@ -1739,6 +1764,17 @@ extern "C" int frx_decode_step(frx_handle* h, const int64_t* target, float* logi
   const frx_config& c = h->cfg;
   cudaStream_t st = (cudaStream_t)stream;
   ON_DEVICE(c.device);
+  if (step16(h)) {
+    // 16-bit handle: ONE launch of the cluster kernel in step mode (history length = step_idx for every image) instead
+    // of the ~26 fp32 step kernels
+    if (!h->step_hist) { void* q; if (dev_alloc(h, &q, (size_t)c.max_batch * 4)) return 1; h->step_hist = (int*)q; }
+    launch_fill_i32(h->step_hist, h->step_idx, h->step_batch, st); CKL();
+    ClusterStep sm;
+    sm.hist_len = h->step_hist; sm.tok64 = (const long long*)target;
+    if (decode_greedy_bf16(h, h->step_batch, 1, logits, nullptr, nullptr, st, &sm)) return 1;
+    h->step_idx++;
+    return 0;
+  }
   launch_dec_embed_f32(nullptr, (const long long*)target, 0, h->arena + h->emb, h->arena + h->pe1d, h->step_idx, nullptr, 0,
                        sqrtf((float)c.dec_hidden), h->dx, h->step_batch, c.dec_hidden, st);
   CKL();
@@ -1787,6 +1823,8 @@ extern "C" int frx_beam_search(frx_handle* h, const float* memory, int32_t B, in
   p.active = s + 10 * Bm; p.n_active = s + 11 * Bm;
   p.logits = w.logits; p.out = (long long*)tokens;
   if (run_cross_kv(h, memory, B, st)) return 1;
+  const bool s16 = step16(h);
+  if (s16 && cross_kv_to_bf16(h, B, st)) return 1;
   launch_beam_init(p, st); CKL();
   StepRows rows;
   rows.hist_len = p.pos; rows.slot = p.slot; rows.chain = p.chain;
@@ -1795,9 +1833,15 @@ extern "C" int frx_beam_search(frx_handle* h, const float* memory, int32_t B, in
   for (int round = 0; round < max_rounds; ++round) {
     CK(cudaMemsetAsync(p.n_active, 0, sizeof(int), st));
     launch_beam_select(p, st); CKL();
-    launch_dec_embed_f32(p.cur_tok, nullptr, 0, h->arena + h->emb, h->arena + h->pe1d, 0, p.pos, 0, scale, h->dx, B, D, st);
-    CKL();
-    if (run_decode_step(h, B, 0, w.logits, V, st, rows)) return 1;
+    if (s16) {   // one cluster-kernel launch per round: history = the node's ancestor chain, K/V row = the node's slot
+      ClusterStep sm;
+      sm.hist_len = p.pos; sm.chain = p.chain; sm.slot = p.slot; sm.tok32 = p.cur_tok;
+      if (decode_greedy_bf16(h, B, 1, w.logits, nullptr, nullptr, st, &sm)) return 1;
+    } else {
+      launch_dec_embed_f32(p.cur_tok, nullptr, 0, h->arena + h->emb, h->arena + h->pe1d, 0, p.pos, 0, scale, h->dx, B, D, st);
+      CKL();
+      if (run_decode_step(h, B, 0, w.logits, V, st, rows)) return 1;
+    }
     launch_beam_push(p, st); CKL();
     if ((round & 7) == 7 || round == max_rounds - 1) {  // every 8 rounds: has every sample finished?
       CK(cudaMemcpyAsync(w.host_flag, p.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));

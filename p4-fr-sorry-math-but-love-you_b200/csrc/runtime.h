@@ -73,7 +73,8 @@ struct frx_handle {
   int num_sms = 0;
   std::map<std::string, HostTensor> raw;
   bool finalized = false, ws_ready = false;
-  bool opt_taps = false, opt_graphs = true, opt_timing = false;
+  bool opt_taps = false, opt_graphs = true, opt_timing = false, opt_step16 = true;
+  int* step_hist = nullptr;   // [max_batch] history length of the step_forward state (cluster kernel in step mode)
   bool opt_prof = false;
   bool opt_tc_im2col = true;   // 3x3 conv A tiles by TMA im2col (false: cp.async gather)
   void* hook_wpad = nullptr; size_t hook_wpad_bytes = 0;
