@@ -240,6 +240,12 @@ struct DecClusterP {
   const int* slot;               // [B] cache row that receives the first step's K/V; nullptr = hist_len[b] (+ step)
   const int* first_tok32;        // [B] token fed at the first step (int32), or
   const long long* first_tok64;  // [B] the same as int64; both nullptr = <SOS>
+  // rule-constrained decoding (DecodingManager.sift, postprocessing/postprocessing.py:193-391): per-class rule tables;
+  // sift_flags != nullptr -> the pick stage soft-maxes, black-lists and takes the constrained arg-max, `logits` receives
+  // the masked probabilities (EfficientSATRN.py:553-555) and the MemoryNode state lives in the pick warps' registers
+  const int* sift_flags;
+  const int* sift_limit;
+  SiftIds sift_ids;
   long long* prof;               // optional [16] per-stage cycle totals (cluster 0, CTA 0, thread 0)
 };
 

@@ -123,6 +123,7 @@ struct Smem {
   __nv_bfloat16 vcur[HPC][NIMG][HD + APAD];
   __nv_bfloat16 kvst[NWARP][KVD][2][32][HD]; // per-warp ring of KVD staged 32-key K/V blocks (KVStage)
   long long prof[16];
+  int4 sift[NIMG];                      // DecodingManager: MemoryNode of each row {current token, run length, #'{', #'}'}
   unsigned long long bar[2];            // stage mbarriers (alternate by stage parity)
   DecClusterLayer lw[4];                // per-layer pointers (dynamic indexing of kernel params would spill them)
 };
@@ -452,6 +453,65 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// DecodingManager.sift on one row, by one converged warp (postprocessing/postprocessing.py): softmax (:216),
+// MemoryNode._look_back black list (:327-391), constrained arg-max (first maximum, like torch.argmax), MemoryNode.record
+// (:303-325).  The masked probabilities are what the reference appends to its output (EfficientSATRN.py:553-555).
+// Kept out of line: only rule-constrained decodes pay for its registers.
+__device__ __noinline__ int sift_pick(const float* lrow, int V, int4* state, const int* __restrict__ flags, const int* __restrict__ limit,
+                                      SiftIds ids, float* prow) {
+  const int lane = threadIdx.x & 31;
+  const int4 stt = *state;
+  float mx = -INFINITY;
+  for (int i = lane; i < V; i += 32) mx = fmaxf(mx, lrow[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int i = lane; i < V; i += 32) sum += expf(lrow[i] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const int cur = stt.x;
+  const int cf = (cur >= 0 && cur < V) ? __ldg(flags + cur) : 0;
+  const int clim = (cur >= 0 && cur < V) ? __ldg(limit + cur) : 0;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < V; i += 32) {
+    bool black = (i == ids.sos) || (i == ids.empty) || (i == ids.rbrace && stt.z == stt.w);
+    if (cur == ids.eos) {
+    } else if (cur == ids.sos) {
+      black = black || (__ldg(flags + i) & 1);
+    } else if (cf & 2) {
+      black = black || (i != ids.underbar);
+    } else if (cf & 4) {
+      black = black || (i != ids.lbrace);
+    } else {
+      if ((cf & 8) && i == ids.underbar) black = true;
+      if ((cf & 16) && i == ids.lbrace) black = true;
+      if (clim > 0 && stt.y >= clim && i == cur) black = true;
+    }
+    const float pv = black ? 0.f : expf(lrow[i] - mx) / sum;
+    if (prow) prow[i] = pv;
+    if (pv > best) { best = pv; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (bi < 0 || bi >= V) bi = 0;
+  __syncwarp();
+  if (lane == 0) {
+    int4 n = stt;
+    n.y = (bi == stt.x) ? stt.y + 1 : 1;
+    if (bi == ids.lbrace) n.z += 1;
+    else if (bi == ids.rbrace) n.w += 1;
+    n.x = bi;
+    *state = n;
+  }
+  __syncwarp();
+  return bi;
+}
 // Eight consecutive bias values of an epilogue unit, requested BEFORE the GEMM whose epilogue adds them (an L2 round
 // trip inside the epilogue sat on the critical path of every one of the 19 stages of a step).
 struct Bias8 { float4 a, b; };
@@ -505,6 +565,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
     s.xres[row][c] = v;
     s.abf[row][c] = __float2bfloat16_rn(v);
   }
+  if (tid < NIMG) s.sift[tid] = make_int4(p.sift_ids.sos, 1, 0, 0);   // MemoryNode.__init__: <SOS>, run length 1, no braces
   const uint32_t bar0 = smem_u32(&s.bar[0]), bar1 = smem_u32(&s.bar[1]);
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -766,7 +827,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
                             st_async_v4(la, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])), rb);
                             st_async_v4(la + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])), rb);
                             const int b = img0 + row;
-                            if (sub == (CL > 1 ? 1 : 0) && p.logits && b < B) {
+                            if (sub == (CL > 1 ? 1 : 0) && p.logits && b < B && !p.sift_flags) {
                               float* lp = p.logits + ((size_t)b * p.steps + t) * V + col;
 #pragma unroll
                               for (int i = 0; i < 8; ++i)
@@ -784,19 +845,25 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
     // ---- greedy pick (first max index) + next input: warp w <-> row w, every CTA does all rows ----------
     if (warp < NIMG) {
       const int row = warp;
-      float best = -INFINITY;
-      int bi = 0x7fffffff;
-      for (int i = lane; i < V; i += 32) {
-        float v = logit_s[row * LGS + i];
-        if (v > best) { best = v; bi = i; }
-      }
+      int bi;
+      if (p.sift_flags) {
+        float* prow = (mine && r == 0 && p.logits) ? p.logits + ((size_t)b_mine * p.steps + t) * V : nullptr;
+        bi = sift_pick(logit_s + row * LGS, V, &s.sift[row], p.sift_flags, p.sift_limit, p.sift_ids, prow);
+      } else {
+        float best = -INFINITY;
+        bi = 0x7fffffff;
+        for (int i = lane; i < V; i += 32) {
+          float v = logit_s[row * LGS + i];
+          if (v > best) { best = v; bi = i; }
+        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        for (int o = 16; o > 0; o >>= 1) {
+          float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (bi < 0 || bi >= V) bi = 0;
       }
-      if (bi < 0 || bi >= V) bi = 0;
       int nxt = bi;
       if (mine) {
         if (p.forced) nxt = (int)p.forced[(size_t)b_mine * p.steps + t];

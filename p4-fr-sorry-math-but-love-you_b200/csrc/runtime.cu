@@ -1494,7 +1494,7 @@ static int cross_kv_to_bf16(frx_handle* h, int B, cudaStream_t st) {
 }
 
 static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, long long* tokens,
-                              const long long* forced, cudaStream_t st, const ClusterStep* sm = nullptr) {
+                              const long long* forced, cudaStream_t st, const ClusterStep* sm = nullptr, bool managed = false) {
   const frx_config& c = h->cfg;
   const float* A = h->arena;
   const int S = h->feat_h * h->feat_w, L = c.dec_layers, D = c.dec_hidden;
@@ -1502,6 +1502,10 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
   if (!sm && cross_kv_to_bf16(h, B, st)) return 1;      // step mode: converted once by the caller
   DecClusterP p{};
   if (sm) { p.hist_len = sm->hist_len; p.chain = sm->chain; p.slot = sm->slot; p.first_tok32 = sm->tok32; p.first_tok64 = sm->tok64; }
+  if (managed) {   // DecodingManager: the rule tables go to the kernel's pick stage
+    p.sift_flags = h->sift_flags; p.sift_limit = h->sift_limit;
+    p.sift_ids = SiftIds{h->sift_ids[0], h->sift_ids[1], h->sift_ids[2], h->sift_ids[3], h->sift_ids[4], h->sift_ids[5]};
+  }
   p.B = B; p.steps = steps; p.T = c.max_steps; p.L = L; p.V = c.num_classes; p.S = S; p.sos = c.sos_id;
   // 256-wide decoder: with one head per CTA (clusters of 8) only 15 clusters get their CTAs alone on an SM (an 8-CTA
   // cluster must sit inside one GPC); beyond that two CTAs share an SM and step in 67 us instead of 42.  Two heads per CTA
@@ -1555,9 +1559,9 @@ static int decode_greedy_impl(frx_handle* h, const float* memory, int B, int ste
   const int mode = managed ? 2 : (forced ? 1 : 0);
   // bf16 mode: one persistent kernel that writes the caller's buffers directly.  Sequences longer than the kernel's
   // history capacity (the reference decodes up to the 500 rows of its 1-D positional table) take the step-kernel loop.
-  if (c.precision == FRX_PREC_BF16 && h->dec_cluster_ok && !managed && steps <= DEC_TMAX)
+  if (c.precision == FRX_PREC_BF16 && h->dec_cluster_ok && steps <= DEC_TMAX && (!managed || h->opt_step16))
     return decode_greedy_bf16(h, B, steps, logits, (long long*)(tokens ? tokens : (int64_t*)h->tokens_int),
-                              (const long long*)forced, st);
+                              (const long long*)forced, st, nullptr, managed);
   if (forced) CK(cudaMemcpyAsync(h->forced_int, forced, (size_t)B * steps * 8, cudaMemcpyDeviceToDevice, st));
   if (h->opt_graphs) {
     GraphKey key{B, steps, mode};
