@@ -86,7 +86,8 @@ size_t dec_cluster_smem_bytes();
 int launch_dec_cluster_bf16(const DecClusterP& p, cudaStream_t st);       // hidden 256, 8 heads, filter 1024 (clusters of 8)
 int launch_dec_cluster_bf16_d128(const DecClusterP& p, cudaStream_t st);  // hidden 128, 4 heads, filter 512 (clusters of 4)
 int launch_dec_cluster_bf16_p2(const DecClusterP& p, cudaStream_t st);    // hidden 256, two heads per CTA (clusters of 4 x 16 warps)
-void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc, int B, int S, int L, int Dm,
+int launch_dec_cluster_bf16_d512(const DecClusterP& p, cudaStream_t st);  // hidden 512, 8 heads x 64, filter 512 (SwinTRN decoder)
+void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc, int B, int S, int L, int Dm, int head_dim,
                           cudaStream_t st);
 
 }  // namespace frx

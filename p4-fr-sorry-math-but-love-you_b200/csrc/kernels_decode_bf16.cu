@@ -51,8 +51,11 @@ namespace {
 #ifndef FRX_DEC_HPC
 #define FRX_DEC_HPC 1            // heads per CTA; 2 = kernels_decode_bf16_p2.cu: clusters of 4 CTAs x 16 warps, one CTA per SM
 #endif
+#ifndef FRX_DEC_HD
+#define FRX_DEC_HD 32            // head width (64: kernels_decode_bf16_d512.cu, the SwinTRN decoder)
+#endif
 constexpr int D = FRX_DEC_D;     // decoder width
-constexpr int HD = 32;
+constexpr int HD = FRX_DEC_HD;
 constexpr int H = D / HD;        // heads
 #ifndef FRX_DEC_KVDEPTH
 #define FRX_DEC_KVDEPTH 1        // K/V staging blocks per warp (blocks in flight ahead of the one being reduced)
@@ -72,7 +75,7 @@ constexpr int FPAD = 4;          // fp32 padding of rows that are accessed 16 by
 constexpr int NIMG = DEC_IMG;    // images per cluster = warps per CTA (warp w <-> image w)
 constexpr int NWARP = NIMG * HPC; // warp w <-> (image w % NIMG, head-of-this-CTA w / NIMG)
 constexpr int NTHR = NWARP * 32;
-constexpr int RED_FLOATS = 2 * NTE * 64;  // K-split reduction region: KS * NT * 32 lanes * 2 floats, widest stage = FFN0
+constexpr int RED_FLOATS = 2 * (NTE > NTA ? NTE : NTA) * 64;  // K-split reduction region: KS * NT * 32 lanes * 2 floats, widest stage
 static_assert(NIMG == 8, "the kernel maps MMA rows 0..7 to the cluster's images");
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -167,13 +170,6 @@ __device__ __forceinline__ void gemm2(float* __restrict__ red, const __nv_bfloat
   using C = GC<NT, KP, KS>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = warp % KS, tg = warp / KS;
-  uint4 w[C::TOT];
-#pragma unroll
-  for (int idx = 0; idx < C::TOT; ++idx) {
-    const int kk = idx / C::TPW, j = idx % C::TPW;
-    if (idx < PF) w[idx] = pre.w[idx];
-    else w[idx] = ldg_weights(Wp + ((size_t)(tg + j * C::TG) * KP + ks * C::KPW + kk) * 32 + lane, pol);
-  }
   // A fragments of two k16 steps with two ldmatrix.x4: lane -> row address of matrix (lane >> 3):
   // {rows 0-7, k lo}, {rows 8-15, k lo}, {rows 0-7, k hi}, {rows 8-15, k hi}; rows 8-15 alias rows 0-7.
   const uint32_t a_lane = smem_u32(A + (lane & 7) * lda + ((lane >> 4) & 1) * 8);
@@ -184,8 +180,10 @@ __device__ __forceinline__ void gemm2(float* __restrict__ red, const __nv_bfloat
     for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[j][h][e] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < C::KPW; ++kk) {
+  auto wload = [&](int kk, int j) {
+    return ldg_weights(Wp + ((size_t)(tg + j * C::TG) * KP + ks * C::KPW + kk) * 32 + lane, pol);
+  };
+  auto kstep = [&](int kk, const uint4* wk) {
     const uint32_t addr = a_lane + (uint32_t)(ks * C::KPW + kk) * 64u;  // 32 bf16 per k-pair
     uint32_t a0[4], a1[4];
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
@@ -194,9 +192,39 @@ __device__ __forceinline__ void gemm2(float* __restrict__ red, const __nv_bfloat
                  : "=r"(a1[0]), "=r"(a1[1]), "=r"(a1[2]), "=r"(a1[3]) : "r"(addr + 32u));
 #pragma unroll
     for (int j = 0; j < C::TPW; ++j) {
-      const uint4 ww = w[kk * C::TPW + j];
-      mma_bf16(acc[j][0], a0, ww.x, ww.y);
-      mma_bf16(acc[j][1], a1, ww.z, ww.w);
+      mma_bf16(acc[j][0], a0, wk[j].x, wk[j].y);
+      mma_bf16(acc[j][1], a1, wk[j].z, wk[j].w);
+    }
+  };
+  if constexpr (C::TOT <= 16) {
+    // the warp's whole share of the stage's weights in registers (requested up front: one L2 round trip)
+    uint4 w[C::TOT];
+#pragma unroll
+    for (int idx = 0; idx < C::TOT; ++idx) {
+      const int kk = idx / C::TPW, j = idx % C::TPW;
+      if (idx < PF) w[idx] = pre.w[idx];
+      else w[idx] = wload(kk, j);
+    }
+#pragma unroll
+    for (int kk = 0; kk < C::KPW; ++kk) kstep(kk, &w[kk * C::TPW]);
+  } else {
+    // wide stages (512-wide decoder): stream the fragments two k-pairs ahead through a register ring
+    static_assert(PF == 0 || PF == C::TPW, "streaming stages prefetch exactly their first k-pair");
+    constexpr int RING = 3;
+    uint4 w[RING][C::TPW];
+#pragma unroll
+    for (int r = 0; r < RING - 1; ++r)
+#pragma unroll
+      for (int j = 0; j < C::TPW; ++j) {
+        if (r < C::KPW) w[r][j] = (PF > 0 && r == 0) ? pre.w[j] : wload(r, j);
+      }
+#pragma unroll
+    for (int kk = 0; kk < C::KPW; ++kk) {
+      if (kk + RING - 1 < C::KPW) {
+#pragma unroll
+        for (int j = 0; j < C::TPW; ++j) w[(kk + RING - 1) % RING][j] = wload(kk + RING - 1, j);
+      }
+      kstep(kk, w[kk % RING]);
     }
   }
   // partial fragments -> red[ks][tile][lane] (float2: row lane>>2, columns (lane&3)*2 + {0,1})
@@ -312,7 +340,11 @@ __device__ __forceinline__ void layernorm_rows(Smem& s, const LnParams& P) {
 // ---------------------------------------------------------------------------
 struct KVStage { __nv_bfloat16 k[32][HD], v[32][HD]; };  // one 32-key block of one warp (4 KB)
 
-__device__ __forceinline__ uint32_t kv_swz(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+// row = key (HD * 2 bytes), chunk = 16-byte piece of it; XOR swizzle so that cp.async writes and ldmatrix reads are conflict-free
+__device__ __forceinline__ uint32_t kv_swz(int row, int chunk) {
+  if constexpr (HD == 32) return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+  else return (uint32_t)(row * (HD * 2) + ((chunk ^ (row & (HD / 8 - 1))) << 4));
+}
 
 __device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc,
                                            int kb, int n_hist, const int* __restrict__ chain) {
@@ -322,8 +354,8 @@ __device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __r
     const int lane = threadIdx.x & 31;
     const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int id = lane + 32 * i, row = id >> 2, chunk = id & 3;
+    for (int i = 0; i < HD / 8; ++i) {
+      const int id = lane + 32 * i, row = id / (HD / 8), chunk = id % (HD / 8);
       const int key = kb + row;
       const uint32_t bytes = key < n_hist ? 16u : 0u;   // zero-fill past the history (also keeps V finite)
       int src = key < n_hist ? key : 0;
@@ -349,19 +381,20 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
                                            const __nv_bfloat16* __restrict__ Vc, int n_hist, const int* __restrict__ chain,
                                            const __nv_bfloat16* __restrict__ kx,
                                            const __nv_bfloat16* __restrict__ vx, float inv_temp,
-                                           float (&o)[8]) {
+                                           float (&o)[HD / 4]) {
+  constexpr int NK = HD / 16;   // k16 steps of q . k
+  constexpr int ND = HD / 8;    // 8-wide n-tiles of the output row
   const int lane = threadIdx.x & 31, tig = lane & 3;
-  uint32_t aq0[4], aq1[4];
-  {
-    const float2 qa = *reinterpret_cast<const float2*>(q + 2 * tig), qb = *reinterpret_cast<const float2*>(q + 8 + 2 * tig);
-    const float2 qc = *reinterpret_cast<const float2*>(q + 16 + 2 * tig), qd = *reinterpret_cast<const float2*>(q + 24 + 2 * tig);
-    aq0[0] = pack_bf16(qa.x, qa.y); aq0[1] = 0u; aq0[2] = pack_bf16(qb.x, qb.y); aq0[3] = 0u;
-    aq1[0] = pack_bf16(qc.x, qc.y); aq1[1] = 0u; aq1[2] = pack_bf16(qd.x, qd.y); aq1[3] = 0u;
+  uint32_t aq[NK][4];
+#pragma unroll
+  for (int ks = 0; ks < NK; ++ks) {
+    const float2 qa = *reinterpret_cast<const float2*>(q + 16 * ks + 2 * tig), qb = *reinterpret_cast<const float2*>(q + 16 * ks + 8 + 2 * tig);
+    aq[ks][0] = pack_bf16(qa.x, qa.y); aq[ks][1] = 0u; aq[ks][2] = pack_bf16(qb.x, qb.y); aq[ks][3] = 0u;
   }
   float m = -INFINITY, l = 0.f;
-  float acc[4][4];
+  float acc[ND][4];
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt)
+  for (int nt = 0; nt < ND; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
   const int lrow = lane & 7, lmat = lane >> 3;
@@ -372,19 +405,24 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
     const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
     asm volatile("cp.async.wait_group %0;\n" ::"n"(KVD - 1) : "memory");
     __syncwarp();
-    uint32_t kf[4][4], vf[4][4];
+    uint32_t kf[4][ND], vf[2][ND / 2][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {  // score tile j: keys 8j..8j+7; matrices = dim chunks 0..3
-      const int key = 8 * j + lrow;
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                   : "=r"(kf[j][0]), "=r"(kf[j][1]), "=r"(kf[j][2]), "=r"(kf[j][3]) : "r"(ks + kv_swz(key, lmat)));
-    }
+    for (int j = 0; j < 4; ++j)     // score tile j: keys 8j..8j+7; one ldmatrix.x4 = four 8-dim chunks of those keys
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {  // x = 2 * (16-key k-step) + (pair of 8-dim n-tiles)
-      const int key = 16 * (x >> 1) + (lmat & 1) * 8 + lrow, chunk = 2 * (x & 1) + (lmat >> 1);
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                   : "=r"(vf[x][0]), "=r"(vf[x][1]), "=r"(vf[x][2]), "=r"(vf[x][3]) : "r"(vs + kv_swz(key, chunk)));
-    }
+      for (int c4 = 0; c4 < ND / 4; ++c4) {
+        const int key = 8 * j + lrow;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(kf[j][4 * c4 + 0]), "=r"(kf[j][4 * c4 + 1]), "=r"(kf[j][4 * c4 + 2]), "=r"(kf[j][4 * c4 + 3])
+                     : "r"(ks + kv_swz(key, 4 * c4 + lmat)));
+      }
+#pragma unroll
+    for (int ks2 = 0; ks2 < 2; ++ks2)        // 16-key k-step of P . V
+#pragma unroll
+      for (int np = 0; np < ND / 2; ++np) {  // pair of 8-dim n-tiles
+        const int key = 16 * ks2 + (lmat & 1) * 8 + lrow, chunk = 2 * np + (lmat >> 1);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(vf[ks2][np][0]), "=r"(vf[ks2][np][1]), "=r"(vf[ks2][np][2]), "=r"(vf[ks2][np][3]) : "r"(vs + kv_swz(key, chunk)));
+      }
     __syncwarp();
     kv_request(st, Kc, Vc, kb + 32 * KVD, n_hist, chain);
     float sc[4][4];
@@ -392,8 +430,8 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
-      mma_bf16(sc[j], aq0, kf[j][0], kf[j][1]);
-      mma_bf16(sc[j], aq1, kf[j][2], kf[j][3]);
+#pragma unroll
+      for (int k2 = 0; k2 < NK; ++k2) mma_bf16(sc[j], aq[k2], kf[j][2 * k2], kf[j][2 * k2 + 1]);
     }
     float cm = m;
 #pragma unroll
@@ -409,7 +447,7 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
     const float scale = (m == -INFINITY) ? 0.f : __expf(m - cm);
     l *= scale;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] *= scale; acc[nt][1] *= scale; }
+    for (int nt = 0; nt < ND; ++nt) { acc[nt][0] *= scale; acc[nt][1] *= scale; }
     float pr[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -419,9 +457,9 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
     for (int ks2 = 0; ks2 < 2; ++ks2) {  // 16 keys per k-step: score tiles 2 ks2 (k lo) and 2 ks2 + 1 (k hi)
       const uint32_t ap[4] = {pack_bf16(pr[2 * ks2][0], pr[2 * ks2][1]), 0u, pack_bf16(pr[2 * ks2 + 1][0], pr[2 * ks2 + 1][1]), 0u};
 #pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        mma_bf16(acc[2 * np], ap, vf[2 * ks2 + np][0], vf[2 * ks2 + np][1]);
-        mma_bf16(acc[2 * np + 1], ap, vf[2 * ks2 + np][2], vf[2 * ks2 + np][3]);
+      for (int np = 0; np < ND / 2; ++np) {
+        mma_bf16(acc[2 * np], ap, vf[ks2][np][0], vf[ks2][np][1]);
+        mma_bf16(acc[2 * np + 1], ap, vf[ks2][np][2], vf[ks2][np][3]);
       }
     }
     m = cm;
@@ -429,10 +467,15 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
   if (kx) {
-    const float4 q0 = *reinterpret_cast<const float4*>(q + 8 * tig), q1 = *reinterpret_cast<const float4*>(q + 8 * tig + 4);
-    float kf[8];
-    unpack8(*reinterpret_cast<const uint4*>(kx + tig * 8), kf);
-    float part = q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] + q1.z * kf[6] + q1.w * kf[7];
+    constexpr int DPT = HD / 4;   // dims of the "current input" key per lane of a quad
+    float part = 0.f;
+#pragma unroll
+    for (int c8 = 0; c8 < DPT / 8; ++c8) {
+      const float4 q0 = *reinterpret_cast<const float4*>(q + DPT * tig + 8 * c8), q1 = *reinterpret_cast<const float4*>(q + DPT * tig + 8 * c8 + 4);
+      float kf[8];
+      unpack8(*reinterpret_cast<const uint4*>(kx + DPT * tig + 8 * c8), kf);
+      part += q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] + q1.z * kf[6] + q1.w * kf[7];
+    }
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     const float s_cur = part * inv_temp;
@@ -441,7 +484,7 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
     const float pc = __expf(s_cur - M);
     l = l * gs + pc;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < ND; ++nt) {
       const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vx + 8 * nt + 2 * tig);
       acc[nt][0] = fmaf(pc, __low2float(v2), acc[nt][0] * gs);
       acc[nt][1] = fmaf(pc, __high2float(v2), acc[nt][1] * gs);
@@ -449,7 +492,7 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
   }
   const float inv = __fdividef(1.f, l);
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) { o[2 * nt] = acc[nt][0] * inv; o[2 * nt + 1] = acc[nt][1] * inv; }
+  for (int nt = 0; nt < ND; ++nt) { o[2 * nt] = acc[nt][0] * inv; o[2 * nt + 1] = acc[nt][1] * inv; }
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -527,7 +570,10 @@ __device__ __forceinline__ Bias8 ldg_bias8(const float* p, bool active) {
 // ===========================================================================
 // The persistent decode kernel
 // ===========================================================================
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, NTHR <= 256 ? 2 : 1)
+#ifndef FRX_DEC_MINBLOCKS
+#define FRX_DEC_MINBLOCKS (NTHR <= 256 ? 2 : 1)
+#endif
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, FRX_DEC_MINBLOCKS)
 FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -544,7 +590,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   constexpr size_t WT = (size_t)KPD * 32;   // uint4 per tile for K = D
   constexpr int KS = 2;                     // every stage splits K over two warps
   // weight fragments (uint4 per lane) requested before the wait that precedes a stage
-  constexpr int PF_A = GC<NTA, KPD, KS>::TOT < 6 ? GC<NTA, KPD, KS>::TOT : 6;
+  constexpr int PF_A = GC<NTA, KPD, KS>::TOT > 16 ? GC<NTA, KPD, KS>::TPW : (GC<NTA, KPD, KS>::TOT < 6 ? GC<NTA, KPD, KS>::TOT : 6);
   constexpr int PF_S = GC<NTS, KPD, KS>::TOT;
   constexpr int PF_E = GC<NTE, KPD, KS>::TOT < 8 ? GC<NTE, KPD, KS>::TOT : 8;
   constexpr int PF_F = GC<NTS, KPF, KS>::TOT < 8 ? GC<NTS, KPF, KS>::TOT : 8;
@@ -607,23 +653,25 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
 
   // all-gather of this warp's attention output (head r, image `warp`) into every CTA's obf: the eight gid
   // groups of the warp hold identical copies, group g serves destination CTA g
-  auto store_attn = [&](uint32_t sb, const float (&o)[8]) {
+  auto store_attn = [&](uint32_t sb, const float (&o)[HD / 4]) {
     const uint32_t dst = (uint32_t)(lane >> 2);
     if (dst < (uint32_t)CL) {
       const uint32_t rb = mapa_u32(sb, dst);
       const uint32_t la = mapa_u32(smem_u32(&s.obf[wimg][head * HD + 2 * (lane & 3)]), dst);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) st_async_b32(la + nt * 16, pack_bf16(o[2 * nt], o[2 * nt + 1]), rb);
+      for (int nt = 0; nt < HD / 8; ++nt) st_async_b32(la + nt * 16, pack_bf16(o[2 * nt], o[2 * nt + 1]), rb);
     }
   };
   // epilogue of a "pre-LayerNorm" stage: 8 columns of row `row`, + bias (+ ReLU) + residual, sent to CTA `sub`
   // (bias: the unit's 8 values, loaded by pre_bias() before the stage)
   auto pre_bias = [&](const float* bias) {   // unit of this thread in an NTS-tile stage: tile = (tid % (NTS * 8)) >> 3
-    return ldg_bias8(bias + r * SW + ((tid % (NTS * 8)) >> 3) * 8, tid < NTS * 8 * CL);
+    return ldg_bias8(bias + r * SW + ((tid % (NTS * 8)) >> 3) * 8, true);
   };
   auto pre_epi = [&](uint32_t sb, const Bias8& bias, bool relu) {
     return [&, sb, bias, relu](int tile, int row, float (&v)[8], int sub) {
-      if (sub >= CL) return;  // 8 threads share a unit, one per destination CTA
+      // NSUB threads share a unit and split the CL destination CTAs between them (one each when NSUB >= CL)
+      constexpr int NSUB_S = GC<NTS, KPD, KS>::NSUB, DPT = (CL + NSUB_S - 1) / NSUB_S;
+      if (sub * DPT >= CL) return;
       const int col = r * SW + tile * 8;
       const float4 b0 = bias.a, b1 = bias.b;
       const float4 x0 = *reinterpret_cast<const float4*>(&s.xres[row][col]), x1 = *reinterpret_cast<const float4*>(&s.xres[row][col + 4]);
@@ -632,11 +680,16 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
       }
-      const uint32_t la = mapa_u32(smem_u32(&s.pre[row][col]), (uint32_t)sub), rb = mapa_u32(sb, (uint32_t)sub);
-      st_async_v4(la, make_uint4(__float_as_uint(o[0] + x0.x), __float_as_uint(o[1] + x0.y), __float_as_uint(o[2] + x0.z),
-                                 __float_as_uint(o[3] + x0.w)), rb);
-      st_async_v4(la + 16, make_uint4(__float_as_uint(o[4] + x1.x), __float_as_uint(o[5] + x1.y), __float_as_uint(o[6] + x1.z),
-                                      __float_as_uint(o[7] + x1.w)), rb);
+      const uint4 lo = make_uint4(__float_as_uint(o[0] + x0.x), __float_as_uint(o[1] + x0.y), __float_as_uint(o[2] + x0.z), __float_as_uint(o[3] + x0.w));
+      const uint4 hi = make_uint4(__float_as_uint(o[4] + x1.x), __float_as_uint(o[5] + x1.y), __float_as_uint(o[6] + x1.z), __float_as_uint(o[7] + x1.w));
+#pragma unroll
+      for (int d = 0; d < DPT; ++d) {
+        const uint32_t dst = (uint32_t)(sub * DPT + d);
+        if (dst >= (uint32_t)CL) break;
+        const uint32_t la = mapa_u32(smem_u32(&s.pre[row][col]), dst), rb = mapa_u32(sb, dst);
+        st_async_v4(la, lo, rb);
+        st_async_v4(la + 16, hi, rb);
+      }
     };
   };
   // q|k|v of head r (tiles: q 0-3, k 4-7, v 8-11), biases at `bias` in natural [q|k|v] column order
@@ -692,7 +745,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         mark(0);
         stage_begin(NIMG * D * 2u);
         const uint32_t sb = stage_bar();
-        float o[8];
+        float o[HD / 4];
         attend_mma(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, chain, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], inv_temp, o);
         store_attn(sb, o);
         mark(1);
@@ -733,12 +786,12 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         mark(4);
         stage_begin(NIMG * D * 2u);
         const uint32_t sb = stage_bar();
-        float o[8];
+        float o[HD / 4];
         if (mine) {
           attend_mma(kvst, &s.qh[whc][wimg][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, nullptr, inv_temp, o);
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = 0.f;
+          for (int i = 0; i < HD / 4; ++i) o[i] = 0.f;
         }
         store_attn(sb, o);
         mark(7);
@@ -819,13 +872,19 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         const uint32_t sb = stage_bar();
         gemm2<NG, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_next + ((size_t)r * (NTC + NG) + NTC) * WT, pol, pre_g,
                           [&](int tile, int row, float (&v)[8], int sub) {
-                            if (sub >= CL) return;
+                            constexpr int NSUB_G = GC<NG, KPD, KS>::NSUB, DPT = (CL + NSUB_G - 1) / NSUB_G;
+                            if (sub * DPT >= CL) return;
                             const int col = r * (VP / CL) + tile * 8;
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] += gbias[i];
-                            const uint32_t la = mapa_u32(smem_u32(logit_s + row * LGS + col), (uint32_t)sub), rb = mapa_u32(sb, (uint32_t)sub);
-                            st_async_v4(la, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])), rb);
-                            st_async_v4(la + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])), rb);
+#pragma unroll
+                            for (int d = 0; d < DPT; ++d) {
+                              const uint32_t dst = (uint32_t)(sub * DPT + d);
+                              if (dst >= (uint32_t)CL) break;
+                              const uint32_t la = mapa_u32(smem_u32(logit_s + row * LGS + col), dst), rb = mapa_u32(sb, dst);
+                              st_async_v4(la, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])), rb);
+                              st_async_v4(la + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])), rb);
+                            }
                             const int b = img0 + row;
                             if (sub == (CL > 1 ? 1 : 0) && p.logits && b < B && !p.sift_flags) {
                               float* lp = p.logits + ((size_t)b * p.steps + t) * V + col;
@@ -925,9 +984,9 @@ int FRX_DEC_NAME(launch_dec_cluster_bf16)(const DecClusterP& p0, cudaStream_t st
 // [L][B][H][S][32] caches
 // ===========================================================================
 __global__ void __launch_bounds__(256) cross_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ kc,
-                                                            __nv_bfloat16* __restrict__ vc, int B, int S, int L, int Dm) {
+                                                            __nv_bfloat16* __restrict__ vc, int B, int S, int L, int Dm, int hd) {
   // one thread = 8 consecutive features of one head (32-byte load, 16-byte store)
-  const int Hh = Dm / 32, cols8 = L * 2 * Dm / 8;
+  const int Hh = Dm / hd, cols8 = L * 2 * Dm / 8;
   long long total = (long long)B * S * cols8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -935,8 +994,8 @@ __global__ void __launch_bounds__(256) cross_to_bf16_kernel(const float* __restr
   long long row = idx / cols8;
   int sidx = (int)(row % S), b = (int)(row / S);
   int l = col / (2 * Dm), which = (col / Dm) & 1, d = col % Dm;
-  int hh = d / 32, dd = d % 32;
-  size_t off = (((((size_t)l * B + b) * Hh + hh) * S) + sidx) * 32 + dd;
+  int hh = d / hd, dd = d % hd;
+  size_t off = (((((size_t)l * B + b) * Hh + hh) * S) + sidx) * hd + dd;
   const float4 a = __ldg(reinterpret_cast<const float4*>(src + idx * 8)), c = __ldg(reinterpret_cast<const float4*>(src + idx * 8) + 1);
   const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
   const __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
@@ -945,10 +1004,10 @@ __global__ void __launch_bounds__(256) cross_to_bf16_kernel(const float* __restr
                  *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
 }
 
-void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc, int B, int S, int L, int Dm,
+void launch_cross_to_bf16(const float* src, __nv_bfloat16* kc, __nv_bfloat16* vc, int B, int S, int L, int Dm, int head_dim,
                           cudaStream_t st) {
   long long total = (long long)B * S * L * 2 * Dm / 8;
-  cross_to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, kc, vc, B, S, L, Dm);
+  cross_to_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, kc, vc, B, S, L, Dm, head_dim);
 }
 
 #endif  // FRX_DEC_VARIANT

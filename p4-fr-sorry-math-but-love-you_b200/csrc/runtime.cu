@@ -701,7 +701,8 @@ static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
   const int D = c.dec_hidden, F = c.dec_filter, V = c.num_classes, L = c.dec_layers;
   // the persistent cluster kernel exists for two geometries: EfficientSATRN (256 / 8 heads / 1024) and LiteSATRN
   // (128 / 4 heads / 512); one CTA per 32-wide head, 32 columns of D and 128 of F per CTA
-  const bool geo = (D == 256 && F == 1024 && c.dec_heads == 8) || (D == 128 && F == 512 && c.dec_heads == 4);
+  const bool geo = (D == 256 && F == 1024 && c.dec_heads == 8) || (D == 128 && F == 512 && c.dec_heads == 4) ||
+                   (D == 512 && F == 512 && c.dec_heads == 8);   // SwinTRN decoder: 64-wide heads, one per CTA
   h->dec_cluster_ok = geo && L <= 4 && V <= 256;
   if (!h->dec_cluster_ok) return 0;  // e.g. SwinTRN (512 / 512 / 4 layers): the greedy loop stays on the fp32 step kernels
   auto W = [&](int l, const char* name) -> const float* {
@@ -1488,7 +1489,7 @@ struct ClusterStep {
 static int cross_kv_to_bf16(frx_handle* h, int B, cudaStream_t st) {
   const frx_config& c = h->cfg;
   launch_cross_to_bf16(h->cross, (__nv_bfloat16*)h->kcross_bf, (__nv_bfloat16*)h->vcross_bf, B, h->feat_h * h->feat_w, c.dec_layers,
-                       c.dec_hidden, st);
+                       c.dec_hidden, c.dec_hidden / c.dec_heads, st);
   CKL();
   return 0;
 }
@@ -1536,7 +1537,8 @@ static int decode_greedy_bf16(frx_handle* h, int B, int steps, float* logits, lo
   p.prof = h->opt_prof ? h->prof : nullptr;
   if (p.prof) CK(cudaMemsetAsync(h->prof, 0, 16 * 8, st));
   if (h->opt_timing) CK(cudaEventRecord(h->ev[3], st));
-  int rc = D == 128 ? launch_dec_cluster_bf16_d128(p, st) : (p2 ? launch_dec_cluster_bf16_p2(p, st) : launch_dec_cluster_bf16(p, st));
+  int rc = D == 128 ? launch_dec_cluster_bf16_d128(p, st)
+                    : D == 512 ? launch_dec_cluster_bf16_d512(p, st) : (p2 ? launch_dec_cluster_bf16_p2(p, st) : launch_dec_cluster_bf16(p, st));
   if (rc) return fail(h, "decode cluster kernel configuration failed: %s", cudaGetErrorString((cudaError_t)rc));
   CKL();
   if (h->opt_timing) CK(cudaEventRecord(h->ev[4], st));
