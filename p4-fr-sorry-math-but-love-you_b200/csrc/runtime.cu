@@ -221,9 +221,9 @@ extern "C" void frx_destroy(frx_handle* h) {
   for (auto& kv : h->taps) cudaFree(kv.second.data);
   if (h->ev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(h->ev[i]);
   for (auto& sl : h->pipe) {
-    if (sl.h2d) { cudaEventDestroy(sl.h2d); cudaEventDestroy(sl.done); cudaEventDestroy(sl.d2h); }
+    if (sl.h2d) { cudaEventDestroy(sl.h2d); cudaEventDestroy(sl.enc); cudaEventDestroy(sl.done); cudaEventDestroy(sl.d2h); }
   }
-  if (h->pipe_h2d) { cudaStreamDestroy(h->pipe_h2d); cudaStreamDestroy(h->pipe_d2h); }
+  if (h->pipe_h2d) { cudaStreamDestroy(h->pipe_h2d); cudaStreamDestroy(h->pipe_d2h); cudaStreamDestroy(h->pipe_enc); }
   delete h;
 }
 
@@ -256,6 +256,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   if (k == "taps") h->opt_taps = value != 0;
   else if (k == "graphs") h->opt_graphs = value != 0;
   else if (k == "step16") h->opt_step16 = value != 0;
+  else if (k == "pipe_enc") h->opt_pipe_enc = value != 0;   // pipelined host entry: next batch's encoder on its own stream
   else if (k == "timing") h->opt_timing = value != 0;
   else if (k == "cluster_images") {}  // accepted for compatibility: clusters always own 8 images
   else if (k == "dec_hpc") h->opt_dec_hpc = (value == 1 || value == 2) ? (int)value : 0;  // heads per CTA of the 256-wide decode kernel, 0 = by batch size
@@ -1701,6 +1702,10 @@ static bool step16(const frx_handle* h) {
 
 // Pipelined host entry: batch i + 1's images travel host -> device and batch i - 1's tokens device -> host on their own
 // streams while batch i computes on `stream`.  Two slots; a slot may be re-submitted after frx_forward_greedy_host_wait.
+// The ENCODER of batch i + 1 also runs on its own stream: the persistent decode kernel of batch i occupies 128 of the 148
+// SMs (one 512-thread CTA each) for ~15 ms with a quarter of its issue slots busy, so the next batch's encoder kernels
+// start on the 20 idle SMs under it and finish at full width once it retires (encoder and decoder share no workspace:
+// each slot has its own encoder-output buffer).
 extern "C" int frx_forward_greedy_host_submit(frx_handle* h, const float* images_host, int32_t B, int32_t steps,
                                               int64_t* tokens_host, int32_t slot, void* stream) {
   if (!h) return 1;
@@ -1717,23 +1722,36 @@ extern "C" int frx_forward_greedy_host_submit(frx_handle* h, const float* images
   if (!h->pipe_h2d) {
     CK(cudaStreamCreateWithFlags(&h->pipe_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->pipe_d2h, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->pipe_enc, cudaStreamNonBlocking));
   }
   if (!sl.img) {
     void* p;
     if (dev_alloc(h, &p, (size_t)c.max_batch * c.in_ch * c.height * c.width * 4)) return 1; sl.img = (float*)p;
     if (dev_alloc(h, &p, (size_t)c.max_batch * c.max_steps * 8)) return 1; sl.tok = (long long*)p;
+    if (dev_alloc(h, &p, (size_t)c.max_batch * h->feat_h * h->feat_w * c.enc_hidden * 4)) return 1; sl.mem = (float*)p;
     CK(cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.enc, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&sl.d2h, cudaEventDisableTiming));
   }
   const size_t img_bytes = (size_t)B * c.in_ch * c.height * c.width * 4;
-  CK(cudaMemcpyAsync(sl.img, images_host, img_bytes, cudaMemcpyHostToDevice, h->pipe_h2d));
+  CK(cudaMemcpyAsync(sl.img, images_host, img_bytes, cudaMemcpyDefault, h->pipe_h2d));   // host (pinned) or device source
   CK(cudaEventRecord(sl.h2d, h->pipe_h2d));
-  CK(cudaStreamWaitEvent(st, sl.h2d, 0));
-  if (frx_forward_greedy(h, sl.img, B, steps, nullptr, (int64_t*)sl.tok, stream)) return 1;
+  const bool split = h->opt_pipe_enc && (h->opt_parts & 3) == 3;
+  if (split) {
+    // encoder on its own stream (its activations are private to it and calls are serialised on that stream)
+    CK(cudaStreamWaitEvent(h->pipe_enc, sl.h2d, 0));
+    if (frx_encode(h, sl.img, B, sl.mem, (void*)h->pipe_enc)) return 1;
+    CK(cudaEventRecord(sl.enc, h->pipe_enc));
+    CK(cudaStreamWaitEvent(st, sl.enc, 0));
+    if (decode_greedy_impl(h, sl.mem, B, steps, nullptr, (int64_t*)sl.tok, nullptr, st)) return 1;
+  } else {
+    CK(cudaStreamWaitEvent(st, sl.h2d, 0));
+    if (frx_forward_greedy(h, sl.img, B, steps, nullptr, (int64_t*)sl.tok, stream)) return 1;
+  }
   CK(cudaEventRecord(sl.done, st));
   CK(cudaStreamWaitEvent(h->pipe_d2h, sl.done, 0));
-  CK(cudaMemcpyAsync(tokens_host, sl.tok, (size_t)B * steps * 8, cudaMemcpyDeviceToHost, h->pipe_d2h));
+  CK(cudaMemcpyAsync(tokens_host, sl.tok, (size_t)B * steps * 8, cudaMemcpyDefault, h->pipe_d2h));
   CK(cudaEventRecord(sl.d2h, h->pipe_d2h));
   sl.busy = true;
   return 0;

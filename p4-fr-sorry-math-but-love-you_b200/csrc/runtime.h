@@ -73,7 +73,7 @@ struct frx_handle {
   int num_sms = 0;
   std::map<std::string, HostTensor> raw;
   bool finalized = false, ws_ready = false;
-  bool opt_taps = false, opt_graphs = true, opt_timing = false, opt_step16 = true;
+  bool opt_taps = false, opt_graphs = true, opt_timing = false, opt_step16 = true, opt_pipe_enc = true;
   int* step_hist = nullptr;   // [max_batch] history length of the step_forward state (cluster kernel in step mode)
   bool opt_prof = false;
   bool opt_tc_im2col = true;   // 3x3 conv A tiles by TMA im2col (false: cp.async gather)
@@ -129,9 +129,14 @@ struct frx_handle {
   std::map<std::string, Tap> taps;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // pipelined host entry (frx_forward_greedy_host_submit / _wait): two staging slots, one stream per copy direction
-  struct PipeSlot { float* img = nullptr; long long* tok = nullptr; cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr; bool busy = false; };
+  struct PipeSlot {
+    float *img = nullptr, *mem = nullptr;   // staged images, this batch's encoder output
+    long long* tok = nullptr;
+    cudaEvent_t h2d = nullptr, enc = nullptr, done = nullptr, d2h = nullptr;
+    bool busy = false;
+  };
   PipeSlot pipe[2];
-  cudaStream_t pipe_h2d = nullptr, pipe_d2h = nullptr;
+  cudaStream_t pipe_h2d = nullptr, pipe_d2h = nullptr, pipe_enc = nullptr;
   float last_ms[4] = {0, 0, 0, 0};
   BeamWs beam;
   TfWs tf;

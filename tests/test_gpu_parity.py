@@ -164,10 +164,12 @@ def test_host_buffer_entry_point(spec, ckpt0, model0):
     assert torch.equal(tok, ref.cpu())
 
 
-def test_pipelined_host_entry_matches_synchronous_entry(ckpt0, spec):
-    """frx_forward_greedy_host_submit / _wait (copies on their own streams, two batches in flight) returns, batch by
-    batch, exactly the tokens of the synchronous host entry."""
-    model = make_model(ckpt0, max_batch=6, max_steps=16).cuda().eval()
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pipelined_host_entry_matches_synchronous_entry(ckpt0, spec, precision):
+    """frx_forward_greedy_host_submit / _wait (copies on their own streams, the next batch's encoder on a third stream
+    under the current batch's decode, two batches in flight) returns, batch by batch, exactly the tokens of the
+    synchronous host entry."""
+    model = make_model(ckpt0, precision=precision, max_batch=6, max_steps=16).cuda().eval()
     batches = [synth.synth_images(spec, 6, 50 + i).pin_memory() for i in range(5)]
     want = []
     eng = model.engine(torch.device("cuda", 0), 6, 16)
