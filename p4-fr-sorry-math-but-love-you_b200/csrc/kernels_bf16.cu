@@ -642,18 +642,19 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restrict__ qkv,       // [B*32, 3*D]
-                                                          eh_t* __restrict__ out,     // [B*32, D]
-                                                          int D, int heads, float inv_temp) {
-  constexpr int S = 32, HD = 64;
+template <int S>   // tokens per image: 32 (EfficientSATRN, 4 x 8 map) or 128 (LiteSATRN, 8 x 16 map); one warp per 16 query rows
+__global__ void __launch_bounds__(S * 2) enc_attn_mma_kernel(const float* __restrict__ qkv,       // [B*S, 3*D]
+                                                             eh_t* __restrict__ out,              // [B*S, D]
+                                                             int D, int heads, float inv_temp) {
+  constexpr int HD = 64, NT = S / 8;
   const int b = blockIdx.x / heads, hh = blockIdx.x % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   const int ld = 3 * D;
   const float* qb = qkv + (long long)b * S * ld + hh * HD;  // q of token 0; k at +D, v at +2D
   const int i0 = warp * 16;
-  float sacc[4][4];
+  float sacc[NT][4];
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt)
+  for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
 #pragma unroll
@@ -664,16 +665,16 @@ __global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restric
     const float2 a01 = __ldg(reinterpret_cast<const float2*>(q0 + 8)), a11 = __ldg(reinterpret_cast<const float2*>(q1 + 8));
     const uint32_t a[4] = {pack2(a00.x, a00.y), pack2(a10.x, a10.y), pack2(a01.x, a01.y), pack2(a11.x, a11.y)};
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       const float* kp = qb + D + (long long)(8 * nt + gid) * ld + 16 * ks + 2 * tig;
       const float2 k0 = __ldg(reinterpret_cast<const float2*>(kp)), k1 = __ldg(reinterpret_cast<const float2*>(kp + 8));
       mma16816(sacc[nt], a, pack2(k0.x, k0.y), pack2(k1.x, k1.y));
     }
   }
-  // softmax over the 32 keys of rows gid (c0, c1) and gid + 8 (c2, c3)
+  // softmax over the S keys of rows gid (c0, c1) and gid + 8 (c2, c3)
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
+  for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) sacc[nt][e] *= inv_temp;
     mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restric
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
+  for (int nt = 0; nt < NT; ++nt) {
     sacc[nt][0] = __expf(sacc[nt][0] - mx0); sacc[nt][1] = __expf(sacc[nt][1] - mx0);
     sacc[nt][2] = __expf(sacc[nt][2] - mx1); sacc[nt][3] = __expf(sacc[nt][3] - mx1);
     sum0 += sacc[nt][0] + sacc[nt][1];
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restric
 #pragma unroll
     for (int e = 0; e < 4; ++e) oacc[n][e] = 0.f;
 #pragma unroll
-  for (int kk = 0; kk < 2; ++kk) {  // 16 keys per k-step = score tiles 2kk (k lo) and 2kk + 1 (k hi)
+  for (int kk = 0; kk < S / 16; ++kk) {  // 16 keys per k-step = score tiles 2kk (k lo) and 2kk + 1 (k hi)
     const uint32_t a[4] = {pack2(sacc[2 * kk][0], sacc[2 * kk][1]), pack2(sacc[2 * kk][2], sacc[2 * kk][3]),
                            pack2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]), pack2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3])};
     const float* vp = qb + 2 * D + (long long)(16 * kk + 2 * tig) * ld + gid;
@@ -718,10 +719,13 @@ __global__ void __launch_bounds__(64) enc_attn_mma_kernel(const float* __restric
   }
 }
 
-// returns false when the shape is not the one the kernel is specialised for (the caller then uses the generic kernel)
+// returns false when the shape is not one the kernel is compiled for (the caller then uses the generic kernel)
 bool launch_enc_attn_mma_bf16(const float* qkv, eh_t* out, int B, int S, int D, int heads, cudaStream_t st) {
-  if (S != 32 || D / heads != 64 || D % heads != 0) return false;
-  enc_attn_mma_kernel<<<B * heads, 64, 0, st>>>(qkv, out, D, heads, 1.f / sqrtf((float)D));
+  if (D / heads != 64 || D % heads != 0) return false;
+  const float inv_temp = 1.f / sqrtf((float)D);
+  if (S == 32) enc_attn_mma_kernel<32><<<B * heads, 64, 0, st>>>(qkv, out, D, heads, inv_temp);
+  else if (S == 128) enc_attn_mma_kernel<128><<<B * heads, 256, 0, st>>>(qkv, out, D, heads, inv_temp);
+  else return false;
   return true;
 }
 

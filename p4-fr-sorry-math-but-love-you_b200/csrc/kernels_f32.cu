@@ -601,8 +601,11 @@ __global__ void __launch_bounds__(256) layernorm_scramble_bf16_kernel(const floa
 
 void launch_layernorm_bf16out(const float* x, const float* res, const float* gamma, const float* beta,
                               eh_t* out, int M, int C, int scramble_S, cudaStream_t st) {
-  if (scramble_S > 0 && C <= 512 && C % 32 == 0 && M % scramble_S == 0 && (size_t)C * (scramble_S + 2) * 2 <= 48 * 1024) {
-    layernorm_scramble_bf16_kernel<<<M / scramble_S, 256, (size_t)C * (scramble_S + 2) * 2, st>>>(x, res, gamma, beta, out,
+  const size_t scr_smem = (size_t)C * (scramble_S + 2) * 2;
+  static SmemOptIn scr_opt;
+  if (scramble_S > 0 && C <= 512 && C % 32 == 0 && M % scramble_S == 0 && scr_smem <= 160 * 1024 &&
+      scr_opt.ensure(layernorm_scramble_bf16_kernel, scr_smem) == cudaSuccess) {
+    layernorm_scramble_bf16_kernel<<<M / scramble_S, 256, scr_smem, st>>>(x, res, gamma, beta, out,
                                                                                                scramble_S, C);
     return;
   }

@@ -672,6 +672,16 @@ static size_t pack_frag_conv24(ArenaBuilder& ab, size_t w_off) {
   return off;
 }
 
+static void pack_encoder_layers_bf16(frx_handle* h, ArenaBuilder& ab) {
+  const size_t C = h->cfg.enc_hidden, F = h->cfg.enc_filter;
+  for (EncLayerW& L : h->enc) {
+    L.wb_qkv = pack_bf16_copy(ab, L.w_qkv, 3 * C * C);
+    L.wb_o = pack_bf16_copy(ab, L.w_o, C * C);
+    L.wb_c0 = pack_bf16_copy(ab, L.w_c0, F * C);
+    L.wb_c1 = pack_bf16_copy(ab, L.w_c1, C * F);
+  }
+}
+
 static void pack_encoder_bf16(frx_handle* h, ArenaBuilder& ab) {
   const frx_config& c = h->cfg;
   for (BlockW& b : h->blocks) {
@@ -687,14 +697,8 @@ static void pack_encoder_bf16(frx_handle* h, ArenaBuilder& ab) {
       b.wb_b = pack_bf16_copy(ab, b.w_b, (size_t)b.cout * b.mid);
     }
   }
-  const size_t C = c.enc_hidden, F = c.enc_filter;
-  h->last_wb = pack_bf16_copy(ab, h->last_w, C * 256);
-  for (EncLayerW& L : h->enc) {
-    L.wb_qkv = pack_bf16_copy(ab, L.w_qkv, 3 * C * C);
-    L.wb_o = pack_bf16_copy(ab, L.w_o, C * C);
-    L.wb_c0 = pack_bf16_copy(ab, L.w_c0, F * C);
-    L.wb_c1 = pack_bf16_copy(ab, L.w_c1, C * F);
-  }
+  h->last_wb = pack_bf16_copy(ab, h->last_w, (size_t)c.enc_hidden * 256);
+  pack_encoder_layers_bf16(h, ab);
 }
 
 static int pack_decoder_bf16(frx_handle* h, ArenaBuilder& ab) {
@@ -793,8 +797,10 @@ extern "C" int frx_finalize_weights(frx_handle* h) {
   if (want_dec && c.precision == FRX_PREC_BF16 && pack_decoder_bf16(h, ab)) return 1;
   if (c.precision == FRX_PREC_BF16) {
     if (want_enc && c.network == FRX_NET_EFFICIENT_SATRN) pack_encoder_bf16(h, ab);
-    if (want_enc && c.network == FRX_NET_LITE_SATRN)
+    if (want_enc && c.network == FRX_NET_LITE_SATRN) {
       for (int i = 1; i < 4; ++i) h->lite[i].wb = pack_bf16_copy(ab, h->lite[i].w, (size_t)h->lite[i].cout * 9 * h->lite[i].cin);
+      pack_encoder_layers_bf16(h, ab);
+    }
     if (want_enc && c.network == FRX_NET_SWIN) {
       for (SwinBlockW& b : h->sw_blocks) {
         const size_t C = b.dim;
@@ -1051,6 +1057,46 @@ static TcGemmP tc_conv(const void* A, int B, int H, int W, int Cin, const float*
 
 // bf16 encoder: tcgen05 implicit GEMMs for every dense contraction, bf16 NHWC activations in the trunk,
 // fp32 residual stream in the SATRN encoder layers.
+// The SATRN encoder layers (EfficientSATRN.py:259-281) in 16-bit mode, shared by EfficientSATRN and LiteSATRN: LayerNorm
+// (fp32 in, 16-bit out), q|k|v / out / conv0 / conv1 on the tcgen05 GEMM, attention on mma.sync, depthwise 3x3 on 16-bit
+// NHWC.  xf: the positionally encoded tokens fp32 [M, C]; tf: a second fp32 [M, C] buffer (ping-pong for > 1 layer);
+// m0 / m1: scratch (16-bit [M, max(C, F)] and fp32 [M, 3C]).
+static int encoder_layers_16(frx_handle* h, float* tf, float* xf, eh_t* m0, eh_t* m1, int B, float* memory, cudaStream_t st) {
+  typedef eh_t bf;
+  const frx_config& c = h->cfg;
+  const float* A = h->arena;
+  const int fh = h->feat_h, fw = h->feat_w, S = fh * fw, C = c.enc_hidden, F = c.enc_filter, M = B * S;
+  float* other = tf;
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const EncLayerW& L = h->enc[i];
+    launch_layernorm_bf16out(xf, nullptr, A + L.ln_g, A + L.ln_b, m0, M, C, 0, st); CKL();
+    float* qkv = (float*)m1;
+    TcGemmP g = tc_dense(m0, M, C, A, L.wb_qkv, 3 * C, qkv, 1);
+    g.shift = A + L.b_qkv;
+    TCL(g);
+    if (!launch_enc_attn_mma_bf16(qkv, m0, B, S, C, c.enc_heads, st)) launch_enc_attn_bf16out(qkv, m0, B, S, C, c.enc_heads, st);
+    CKL();
+    float* proj = (float*)m1;
+    TcGemmP go = tc_dense(m0, M, C, A, L.wb_o, C, proj, 1);
+    go.shift = A + L.b_o;
+    TCL(go);
+    launch_layernorm_bf16out(proj, xf, A + L.ln_g, A + L.ln_b, m0, M, C, S, st); CKL();  // reinterpreted (:269) layout
+    TcGemmP g0 = tc_dense(m0, M, C, A, L.wb_c0, F, m1, 0);
+    g0.scale = A + L.sc_c0; g0.shift = A + L.sh_c0; g0.act = ACT_RELU;
+    TCL(g0);
+    launch_dwconv_bf16(m1, A + L.w_dw, A + L.sc_dw, A + L.sh_dw, m0, B, fh, fw, F, fh, fw, 1, 1, 1, ACT_RELU, st); CKL();
+    float* dst = (i == c.enc_layers - 1) ? memory : other;
+    TcGemmP g1 = tc_dense(m0, M, F, A, L.wb_c1, C, dst, 1);
+    g1.scale = A + L.sc_c1; g1.shift = A + L.sh_c1; g1.act = ACT_RELU; g1.res = xf; g1.res_f32 = 1; g1.ldr = C;
+    TCL(g1);
+    if (tap(h, "enc_layer" + std::to_string(i), dst, B, fh, fw, C, st)) return 1;
+    other = xf;
+    xf = dst;
+  }
+  return 0;
+}
+
+
 static int encode_bf16(frx_handle* h, const float* images, int B, float* memory, cudaStream_t st) {
   const frx_config& c = h->cfg;
   const float* A = h->arena;
@@ -1117,34 +1163,7 @@ static int encode_bf16(frx_handle* h, const float* images, int B, float* memory,
   launch_pe2d_f32(tf, A + h->pe_w0, A + h->pe_b0, A + h->pe_w1, A + h->pe_b1, A + h->pe_h, A + h->pe_w, xf, B, fh, fw, C, st);
   CKL();
   if (tap(h, "pe2d", xf, B, fh, fw, C, st)) return 1;
-  float* other = tf;
-  for (int i = 0; i < c.enc_layers; ++i) {
-    const EncLayerW& L = h->enc[i];
-    launch_layernorm_bf16out(xf, nullptr, A + L.ln_g, A + L.ln_b, m0, M, C, 0, st); CKL();
-    float* qkv = (float*)m1;
-    TcGemmP g = tc_dense(m0, M, C, A, L.wb_qkv, 3 * C, qkv, 1);
-    g.shift = A + L.b_qkv;
-    TCL(g);
-    if (!launch_enc_attn_mma_bf16(qkv, m0, B, S, C, c.enc_heads, st)) launch_enc_attn_bf16out(qkv, m0, B, S, C, c.enc_heads, st);
-    CKL();
-    float* proj = (float*)m1;
-    TcGemmP go = tc_dense(m0, M, C, A, L.wb_o, C, proj, 1);
-    go.shift = A + L.b_o;
-    TCL(go);
-    launch_layernorm_bf16out(proj, xf, A + L.ln_g, A + L.ln_b, m0, M, C, S, st); CKL();  // reinterpreted (:269) layout
-    TcGemmP g0 = tc_dense(m0, M, C, A, L.wb_c0, F, m1, 0);
-    g0.scale = A + L.sc_c0; g0.shift = A + L.sh_c0; g0.act = ACT_RELU;
-    TCL(g0);
-    launch_dwconv_bf16(m1, A + L.w_dw, A + L.sc_dw, A + L.sh_dw, m0, B, fh, fw, F, fh, fw, 1, 1, 1, ACT_RELU, st); CKL();
-    float* dst = (i == c.enc_layers - 1) ? memory : other;
-    TcGemmP g1 = tc_dense(m0, M, F, A, L.wb_c1, C, dst, 1);
-    g1.scale = A + L.sc_c1; g1.shift = A + L.sh_c1; g1.act = ACT_RELU; g1.res = xf; g1.res_f32 = 1; g1.ldr = C;
-    TCL(g1);
-    if (tap(h, "enc_layer" + std::to_string(i), dst, B, fh, fw, C, st)) return 1;
-    other = xf;
-    xf = dst;
-  }
-  return 0;
+  return encoder_layers_16(h, tf, xf, m0, m1, B, memory, st);
 }
 
 // SwinTransformer.forward_features (SWIN.py:725-736) -> memory [B, 144, 1024]
@@ -1297,6 +1316,8 @@ extern "C" int frx_encode(frx_handle* h, const float* images, int32_t B, float* 
   launch_pe2d_f32(t, A + h->pe_w0, A + h->pe_b0, A + h->pe_w1, A + h->pe_b1, A + h->pe_h, A + h->pe_w, x, B, fh, fw, C, st);
   CKL();
   if (tap(h, "pe2d", x, B, fh, fw, C, st)) return 1;
+  if (c.network == FRX_NET_LITE_SATRN && c.precision == FRX_PREC_BF16 && !h->opt_enc_fp32 && h->enc[0].wb_qkv)
+    return encoder_layers_16(h, t, x, (eh_t*)h->mid[0], (eh_t*)h->mid[1], B, memory, st);   // LiteSATRN, 16-bit mode
   float* other = t;
   const int M = B * S;
   for (int i = 0; i < c.enc_layers; ++i) {
