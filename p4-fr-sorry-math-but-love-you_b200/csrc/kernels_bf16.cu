@@ -891,8 +891,84 @@ __global__ void __launch_bounds__(256) lite_conv0_pool_bf16_kernel(const float* 
   *reinterpret_cast<uint4*>(out + pix * Cout + co0) = pack8(o);
 }
 
+// The same layer on mma.sync (Cout = 64 or 128): one warp = 4 pooled pixels = 16 conv pixels x Cout channels, K = 9 Cin padded to 16 KS.
+// MMA row r <-> (position r / 4 of the 2 x 2 pool window, pooled pixel r % 4), so a thread's two rows (gid, gid + 8) are two
+// window positions of ONE pooled pixel and lane ^ 16 holds the other two: max-pool = one fmax + one shuffle.  The patches come
+// straight from the fp32 image (L1-resident: 3 loads per thread and k-step), weights as B fragments in registers.
+template <int KS, int Cout>
+__global__ void __launch_bounds__(256) lite_conv0_pool_mma_kernel(const float* __restrict__ in, const float* __restrict__ w,  // [Cout][Cin][3][3]
+                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                  eh_t* __restrict__ out, int B, int Cin, int H, int W) {
+  constexpr int NT = Cout / 8;
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int OH = H / 2, OW = W / 2, K = 9 * Cin;
+  const long long tiles = (long long)B * OH * (OW / 4);
+  const long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tile >= tiles) return;
+  uint32_t bf[KS][NT][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int k = 16 * ks + 8 * h2 + 2 * tig, n = 8 * nt + gid;
+        const float lo = k < K ? __ldg(w + (long long)n * K + k) : 0.f, hi = k + 1 < K ? __ldg(w + (long long)n * K + k + 1) : 0.f;
+        bf[ks][nt][h2] = pack2(lo, hi);
+      }
+  const int owq = (int)(tile % (OW / 4));
+  const long long t2 = tile / (OW / 4);
+  const int oh = (int)(t2 % OH), n = (int)(t2 / OH);
+  // this thread's rows: gid (position gid / 4, pooled pixel gid % 4) and gid + 8 (position gid / 4 + 2, same pooled pixel)
+  const int pp = gid & 3, pos0 = gid >> 2;
+  const int ow = owq * 4 + pp;
+  const float* img = in + (long long)n * Cin * H * W;
+  auto patch = [&](int pos, int k) -> float {   // input value of conv pixel `pos` of the pool window, im2col column k
+    if (k >= K) return 0.f;
+    const int ci = k / 9, tap = k - ci * 9, kh = tap / 3, kw = tap - kh * 3;
+    const int ih = 2 * oh + (pos >> 1) + kh - 1, iw = 2 * ow + (pos & 1) + kw - 1;
+    return (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(img + ((long long)ci * H + ih) * W + iw) : 0.f;
+  };
+  float acc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int k0 = 16 * ks + 2 * tig;
+    const uint32_t a[4] = {pack2(patch(pos0, k0), patch(pos0, k0 + 1)), pack2(patch(pos0 + 2, k0), patch(pos0 + 2, k0 + 1)),
+                           pack2(patch(pos0, k0 + 8), patch(pos0, k0 + 9)), pack2(patch(pos0 + 2, k0 + 8), patch(pos0 + 2, k0 + 9))};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) mma16816(acc[nt], a, bf[ks][nt][0], bf[ks][nt][1]);
+  }
+  eh_t* op = out + (((long long)n * OH + oh) * OW + ow) * Cout;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int ch = 8 * nt + 2 * tig;
+    const float s0 = __ldg(scale + ch), s1 = __ldg(scale + ch + 1), t0 = __ldg(shift + ch), t1 = __ldg(shift + ch + 1);
+    float m0 = fmaxf(fmaf(acc[nt][0], s0, t0), fmaf(acc[nt][2], s0, t0));   // rows gid and gid + 8: window positions pos0, pos0 + 2
+    float m1 = fmaxf(fmaf(acc[nt][1], s1, t1), fmaf(acc[nt][3], s1, t1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 16));                   // lane ^ 16 = gid ^ 4: the other two positions
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 16));
+    if (gid < 4) *reinterpret_cast<uint32_t*>(op + ch) = pack2(fmaxf(m0, 0.f), fmaxf(m1, 0.f));   // relu(max(.)) == max(relu(.))
+  }
+}
+
 void launch_lite_conv0_pool_bf16(const float* in, const float* w, const float* scale, const float* shift, eh_t* out,
                                  int B, int Cin, int H, int W, int Cout, cudaStream_t st) {
+  if ((Cout == 64 || Cout == 128) && Cin <= 3 && (W / 2) % 4 == 0 && H % 2 == 0) {
+    const long long tiles = (long long)B * (H / 2) * (W / 2 / 4);
+    const unsigned grid = (unsigned)((tiles + 7) / 8);
+    if (Cout == 64) {
+      if (Cin == 1) lite_conv0_pool_mma_kernel<1, 64><<<grid, 256, 0, st>>>(in, w, scale, shift, out, B, Cin, H, W);
+      else lite_conv0_pool_mma_kernel<2, 64><<<grid, 256, 0, st>>>(in, w, scale, shift, out, B, Cin, H, W);
+    } else {
+      if (Cin == 1) lite_conv0_pool_mma_kernel<1, 128><<<grid, 256, 0, st>>>(in, w, scale, shift, out, B, Cin, H, W);
+      else lite_conv0_pool_mma_kernel<2, 128><<<grid, 256, 0, st>>>(in, w, scale, shift, out, B, Cin, H, W);
+    }
+    return;
+  }
   const long long total = (long long)B * (H / 2) * (W / 2) * (Cout / 8);
   const int smem = (Cout * Cin * 9 + 2 * Cout) * sizeof(float);
   lite_conv0_pool_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(in, w, scale, shift, out, B, Cin, H, W, Cout);
