@@ -62,6 +62,10 @@ constexpr int H = D / HD;        // heads
 #endif
 constexpr int HPC = FRX_DEC_HPC;
 constexpr int KVD = FRX_DEC_KVDEPTH;
+#ifndef FRX_DEC_KVBULK
+#define FRX_DEC_KVBULK (FRX_DEC_KVDEPTH >= 2)   // contiguous K/V histories by bulk copies: pays with two blocks in flight (see kv_request_bulk)
+#endif
+constexpr bool KV_BULK = FRX_DEC_KVBULK;
 constexpr int CL = H / HPC;      // CTAs per cluster
 constexpr int FF = FRX_DEC_FF;
 constexpr int VP = 256;          // vocabulary columns, padded
@@ -128,6 +132,7 @@ struct Smem {
   long long prof[16];
   int4 sift[NIMG];                      // DecodingManager: MemoryNode of each row {current token, run length, #'{', #'}'}
   unsigned long long bar[2];            // stage mbarriers (alternate by stage parity)
+  unsigned long long kvbar[NWARP][KVD]; // per-warp mbarriers of the K/V ring slots (bulk copies of contiguous histories)
   DecClusterLayer lw[4];                // per-layer pointers (dynamic indexing of kernel params would spill them)
 };
 
@@ -340,11 +345,15 @@ __device__ __forceinline__ void layernorm_rows(Smem& s, const LnParams& P) {
 // ---------------------------------------------------------------------------
 struct KVStage { __nv_bfloat16 k[32][HD], v[32][HD]; };  // one 32-key block of one warp (4 KB)
 
-// row = key (HD * 2 bytes), chunk = 16-byte piece of it; XOR swizzle so that cp.async writes and ldmatrix reads are conflict-free
-__device__ __forceinline__ uint32_t kv_swz(int row, int chunk) {
-  if constexpr (HD == 32) return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
-  else return (uint32_t)(row * (HD * 2) + ((chunk ^ (row & (HD / 8 - 1))) << 4));
+// row = key (HD * 2 bytes), chunk = 16-byte piece of it; XOR swizzle of the chunk position inside the row so that the
+// staging writes and the ldmatrix reads are conflict-free.  The K/V caches in HBM keep every row in the SAME permuted
+// chunk order (kv_perm of the cache row; the permutation has period 8 in the row index and blocks start at multiples of
+// 32), so a 32-key block of a contiguous history is one contiguous, already-swizzled piece of memory: one bulk copy.
+__device__ __forceinline__ int kv_perm(int row) {
+  if constexpr (HD == 32) return (row >> 1) & 3;
+  else return row & (HD / 8 - 1);
 }
+__device__ __forceinline__ uint32_t kv_swz(int row, int chunk) { return (uint32_t)(row * (HD * 2) + ((chunk ^ kv_perm(row)) << 4)); }
 
 __device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc,
                                            int kb, int n_hist, const int* __restrict__ chain) {
@@ -360,18 +369,41 @@ __device__ __forceinline__ void kv_request(KVStage& st, const __nv_bfloat16* __r
       const uint32_t bytes = key < n_hist ? 16u : 0u;   // zero-fill past the history (also keeps V finite)
       int src = key < n_hist ? key : 0;
       if (chain) src = __ldg(chain + src);
-      const size_t off = (size_t)src * HD + chunk * 8;
+      const size_t off = (size_t)src * HD + ((chunk ^ kv_perm(src)) << 3);   // the cache row keeps its chunks permuted
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ks + kv_swz(row, chunk)), "l"(Kc + off), "r"(bytes) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(vs + kv_swz(row, chunk)), "l"(Vc + off), "r"(bytes) : "memory");
     }
   }
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
-// Request the first KVD blocks of a history into the warp's ring (KVD commit groups, in block order).
+// Contiguous history (no ancestor chain): the block is ONE bulk copy per operand (cp.async.bulk, issued by lane 0,
+// completing on the warp's mbarrier of that ring slot) instead of 2 * HD / 8 cp.async per lane -- the per-lane copies and
+// their address arithmetic were where the attention phase stalled (mio_throttle / long_scoreboard on the LDGSTS).  Only
+// the valid rows travel; the rows behind them keep older (finite) K/V data or the zeros of the kernel prologue, and their
+// probabilities are exactly 0.  Blocks past the history are neither requested nor waited for.
+__device__ __forceinline__ void kv_request_bulk(KVStage& st, uint32_t bar, const __nv_bfloat16* __restrict__ Kc,
+                                                const __nv_bfloat16* __restrict__ Vc, int kb, int n_hist) {
+  if (kb < n_hist && (threadIdx.x & 31) == 0) {
+    const int rows = n_hist - kb < 32 ? n_hist - kb : 32;
+    const uint32_t bytes = (uint32_t)rows * (HD * 2);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(&st.k[0][0])), "l"(Kc + (size_t)kb * HD), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(&st.v[0][0])), "l"(Vc + (size_t)kb * HD), "r"(bytes), "r"(bar) : "memory");
+  }
+}
+// Request the first KVD blocks of a history into the warp's ring (in block order; with an ancestor chain: KVD commit
+// groups of per-lane cp.async, otherwise bulk copies on the ring slots' mbarriers kvbar, kvbar + 8, ...).
 __device__ __forceinline__ void kv_prime(KVStage* ring, const __nv_bfloat16* __restrict__ Kc, const __nv_bfloat16* __restrict__ Vc, int n_hist,
-                                         const int* __restrict__ chain) {
+                                         const int* __restrict__ chain, uint32_t kvbar) {
+  if (!KV_BULK || chain) {
 #pragma unroll
-  for (int d = 0; d < KVD; ++d) kv_request(ring[d], Kc, Vc, 32 * d, n_hist, chain);
+    for (int d = 0; d < KVD; ++d) kv_request(ring[d], Kc, Vc, 32 * d, n_hist, chain);
+  } else {
+#pragma unroll
+    for (int d = 0; d < KVD; ++d) kv_request_bulk(ring[d], kvbar + 8u * d, Kc, Vc, 32 * d, n_hist);
+  }
 }
 
 // The history must have been primed with kv_prime(ring, Kc, Vc, n_hist): block i lives in ring[i % KVD] and is
@@ -379,9 +411,9 @@ __device__ __forceinline__ void kv_prime(KVStage* ring, const __nv_bfloat16* __r
 // its fragments are in registers, so KVD blocks are in flight while one is being reduced.
 __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
                                            const __nv_bfloat16* __restrict__ Vc, int n_hist, const int* __restrict__ chain,
-                                           const __nv_bfloat16* __restrict__ kx,
+                                           uint32_t kvbar, uint32_t& kvphase, const __nv_bfloat16* __restrict__ kx,
                                            const __nv_bfloat16* __restrict__ vx, float inv_temp,
-                                           float (&o)[HD / 4]) {
+                                           float (&o)[HD / 4], long long* pw = nullptr) {
   constexpr int NK = HD / 16;   // k16 steps of q . k
   constexpr int ND = HD / 8;    // 8-wide n-tiles of the output row
   const int lane = threadIdx.x & 31, tig = lane & 3;
@@ -403,7 +435,16 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
     KVStage& st = ring[slot];
     slot = slot + 1 == KVD ? 0 : slot + 1;
     const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(KVD - 1) : "memory");
+    const int cur = slot == 0 ? KVD - 1 : slot - 1;   // ring slot of this block
+    long long tw = 0;
+    if (pw) tw = clock64();
+    if (!KV_BULK || chain) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(KVD - 1) : "memory");
+    } else {
+      mbar_wait(kvbar + 8u * cur, (kvphase >> cur) & 1u);
+      kvphase ^= 1u << cur;
+    }
+    if (pw) { pw[0] += clock64() - tw; pw[1] += 1; }   // profiler: cycles spent waiting for K/V blocks, blocks reduced
     __syncwarp();
     uint32_t kf[4][ND], vf[2][ND / 2][4];
 #pragma unroll
@@ -424,7 +465,8 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
                      : "=r"(vf[ks2][np][0]), "=r"(vf[ks2][np][1]), "=r"(vf[ks2][np][2]), "=r"(vf[ks2][np][3]) : "r"(vs + kv_swz(key, chunk)));
       }
     __syncwarp();
-    kv_request(st, Kc, Vc, kb + 32 * KVD, n_hist, chain);
+    if (!KV_BULK || chain) kv_request(st, Kc, Vc, kb + 32 * KVD, n_hist, chain);
+    else kv_request_bulk(st, kvbar + 8u * cur, Kc, Vc, kb + 32 * KVD, n_hist);
     float sc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -618,6 +660,14 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
     mbar_init(bar1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  // K/V ring: one mbarrier per (warp, slot), armed by the warp's lane 0 with every bulk request; the staging blocks start
+  // as zeros so that rows a partial block never fills hold finite values (their probabilities are 0)
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < KVD; ++d) mbar_init(smem_u32(&s.kvbar[warp][d]), 1);
+  }
+  for (int i = tid; i < (int)(sizeof(s.kvst) / 16); i += NTHR) reinterpret_cast<uint4*>(&s.kvst[0][0][0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the zeros (generic proxy) precede the first bulk copy (async proxy)
   __syncthreads();
   cl.sync();  // every CTA of the cluster is resident and its barriers initialised before the first remote store
   // Stage protocol: thread 0 arms the stage's barrier with the bytes THIS CTA will receive, everybody
@@ -650,6 +700,8 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   const int hist0 = (mine && p.hist_len) ? __ldg(p.hist_len + b_mine) : 0;      // keys cached before this launch
   const int* const chain = (mine && p.chain) ? p.chain + (size_t)b_mine * T : nullptr;
   KVStage* const kvst = reinterpret_cast<KVStage*>(&s.kvst[warp][0][0][0][0]);  // this warp's ring of K/V staging blocks
+  const uint32_t kvbar = smem_u32(&s.kvbar[warp][0]);
+  uint32_t kvphase = 0;   // bit d: parity of the next completion of ring slot d
 
   // all-gather of this warp's attention output (head r, image `warp`) into every CTA's obf: the eight gid
   // groups of the warp hold identical copies, group g serves destination CTA g
@@ -723,9 +775,11 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       const float4 b0 = cb.a, b1 = cb.b;
       __nv_bfloat16* dst = seg == 0 ? p.kself : p.vself;
       const int wrow = (p.slot ? __ldg(p.slot + b) : (p.hist_len ? __ldg(p.hist_len + b) : 0)) + t;   // cache row of this step
-      *reinterpret_cast<uint4*>(dst + (((((size_t)lc * B + b) * H + hd) * T) + wrow) * HD + col) =
+      *reinterpret_cast<uint4*>(dst + (((((size_t)lc * B + b) * H + hd) * T) + wrow) * HD + (((col >> 3) ^ kv_perm(wrow)) << 3)) =
           make_uint4(pack_bf16(v[0] + b0.x, v[1] + b0.y), pack_bf16(v[2] + b0.z, v[3] + b0.w),
                      pack_bf16(v[4] + b1.x, v[5] + b1.y), pack_bf16(v[6] + b1.z, v[7] + b1.w));
+      // the row is read back by bulk copies (async proxy) from the next step on: order this generic-proxy write before them
+      asm volatile("fence.proxy.async.global;\n" ::: "memory");
     });
   };
 
@@ -737,7 +791,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * T) * HD;
         const int n_hist = mine ? hist0 + t : 0;
-        kv_prime(kvst, p.kself + base, p.vself + base, n_hist, chain);  // lands during the projection
+        kv_prime(kvst, p.kself + base, p.vself + base, n_hist, chain, kvbar);  // lands during the projection
         const uint4* wp = l == 0 ? p.w_first + (size_t)r * NTA * WT : s.lw[l - 1].w_next + ((size_t)r * (NTC + NTA) + NTC) * WT;
         const Bias8 bias = qkv_bias(l == 0 ? p.b_first : s.lw[l - 1].b_next + 2 * D);
         gemm2<NTA, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
@@ -746,7 +800,8 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         stage_begin(NIMG * D * 2u);
         const uint32_t sb = stage_bar();
         float o[HD / 4];
-        attend_mma(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, chain, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], inv_temp, o);
+        attend_mma(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, chain, kvbar, kvphase, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], inv_temp, o,
+                   profiling ? &s.prof[11] : nullptr);
         store_attn(sb, o);
         mark(1);
       }
@@ -773,7 +828,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * p.S) * HD;
         const int n_keys = mine ? p.S : 0;
-        kv_prime(kvst, p.kcross + base, p.vcross + base, n_keys, nullptr);
+        kv_prime(kvst, p.kcross + base, p.vcross + base, n_keys, nullptr, kvbar);
         gemm2<NTS, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_q2 + (size_t)r * NTS * WT, pol, pre_c,
                           [&](int tile, int row, float (&v)[8], int sub) {
                             if (sub != 0) return;
@@ -788,7 +843,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         const uint32_t sb = stage_bar();
         float o[HD / 4];
         if (mine) {
-          attend_mma(kvst, &s.qh[whc][wimg][0], p.kcross + base, p.vcross + base, n_keys, nullptr, nullptr, nullptr, inv_temp, o);
+          attend_mma(kvst, &s.qh[whc][wimg][0], p.kcross + base, p.vcross + base, n_keys, nullptr, kvbar, kvphase, nullptr, nullptr, inv_temp, o);
         } else {
 #pragma unroll
           for (int i = 0; i < HD / 4; ++i) o[i] = 0.f;
@@ -995,6 +1050,9 @@ __global__ void __launch_bounds__(256) cross_to_bf16_kernel(const float* __restr
   int sidx = (int)(row % S), b = (int)(row / S);
   int l = col / (2 * Dm), which = (col / Dm) & 1, d = col % Dm;
   int hh = d / hd, dd = d % hd;
+  // rows keep their 16-byte chunks in the permuted order the decode kernel's staging blocks use (kv_perm there)
+  const int perm = hd == 32 ? ((sidx >> 1) & 3) : (sidx & (hd / 8 - 1));
+  dd = ((dd >> 3) ^ perm) << 3;
   size_t off = (((((size_t)l * B + b) * Hh + hh) * S) + sidx) * hd + dd;
   const float4 a = __ldg(reinterpret_cast<const float4*>(src + idx * 8)), c = __ldg(reinterpret_cast<const float4*>(src + idx * 8) + 1);
   const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);

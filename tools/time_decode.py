@@ -39,5 +39,7 @@ for b in [int(x) for x in a.batches.split(",")]:
     if a.precision == "bf16":
         prof = (ctypes.c_int64 * 16)()
         eng.h.call("frx_read_prof", prof)
-        tot = sum(prof)
+        tot = sum(prof[:len(NAMES)])
         print("   stage cycles (cluster 0, per step): " + ", ".join("%s %.0f" % (n, prof[i] / a.steps) for i, n in enumerate(NAMES)) + "  | total %.0f cyc/step" % (tot / a.steps), flush=True)
+        if prof[12]:
+            print("   self-attention of warp 0: %.0f cycles per step waiting for K/V blocks, %.2f blocks per call" % (prof[11] / a.steps, prof[12] / (3.0 * a.steps)), flush=True)
