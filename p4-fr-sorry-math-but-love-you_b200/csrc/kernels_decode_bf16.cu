@@ -276,6 +276,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // Bounded spin: a byte-accounting bug traps (error reaches the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+#pragma unroll 1
   for (int spins = 0; spins < (1 << 26); ++spins) {
     asm volatile(
         "{\n"
@@ -406,13 +407,27 @@ __device__ __forceinline__ void kv_prime(KVStage* ring, const __nv_bfloat16* __r
   }
 }
 
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // The history must have been primed with kv_prime(ring, Kc, Vc, n_hist): block i lives in ring[i % KVD] and is
-// complete once at most KVD - 1 younger commit groups are pending; its buffer is re-used for block i + KVD as soon as
-// its fragments are in registers, so KVD blocks are in flight while one is being reduced.
+// complete once at most KVD - 1 younger commit groups are pending (cp.async path) / its slot's mbarrier phase has
+// completed (bulk path); its buffer is re-used for block i + KVD as soon as its fragments are in registers, so KVD
+// blocks are in flight while one is being reduced.
+// The phase is ISSUE-bound with 16 warps per SM (~300 executed instructions per warp and 32-key block against 16 HMMA),
+// so the loop body is kept lean: q is pre-multiplied by qscale = log2(e) / sqrt(d_model) when it is packed (scores come
+// out of the MMA in exp2 units: no per-score scaling, ex2 instead of exp), the key mask runs in the one partial block
+// only, the running-maximum rescale only when the maximum moved (warp-uniform: the eight MMA rows are replicas), and the
+// ldmatrix offsets are lane constants.  BULK selects the staging path at compile time (false: cp.async, also the only
+// path for ancestor chains).
+template <bool BULK>
 __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
                                            const __nv_bfloat16* __restrict__ Vc, int n_hist, const int* __restrict__ chain,
                                            uint32_t kvbar, uint32_t& kvphase, const __nv_bfloat16* __restrict__ kx,
-                                           const __nv_bfloat16* __restrict__ vx, float inv_temp,
+                                           const __nv_bfloat16* __restrict__ vx, float qscale,
                                            float (&o)[HD / 4], long long* pw = nullptr) {
   constexpr int NK = HD / 16;   // k16 steps of q . k
   constexpr int ND = HD / 8;    // 8-wide n-tiles of the output row
@@ -421,7 +436,8 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
 #pragma unroll
   for (int ks = 0; ks < NK; ++ks) {
     const float2 qa = *reinterpret_cast<const float2*>(q + 16 * ks + 2 * tig), qb = *reinterpret_cast<const float2*>(q + 16 * ks + 8 + 2 * tig);
-    aq[ks][0] = pack_bf16(qa.x, qa.y); aq[ks][1] = 0u; aq[ks][2] = pack_bf16(qb.x, qb.y); aq[ks][3] = 0u;
+    aq[ks][0] = pack_bf16(qa.x * qscale, qa.y * qscale); aq[ks][1] = 0u;
+    aq[ks][2] = pack_bf16(qb.x * qscale, qb.y * qscale); aq[ks][3] = 0u;
   }
   float m = -INFINITY, l = 0.f;
   float acc[ND][4];
@@ -430,43 +446,48 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
   const int lrow = lane & 7, lmat = lane >> 3;
+  // ldmatrix lane offsets inside a staged block (the swizzle term has period 8 in the key index, so tile j / k-step ks2
+  // add a constant): K tile j = keys 8j..8j+7, four 8-dim chunks per x4; V k-step ks2, n-tile pair np
+  uint32_t koff[ND / 4], voff[ND / 2];
+#pragma unroll
+  for (int c4 = 0; c4 < ND / 4; ++c4) koff[c4] = kv_swz(lrow, 4 * c4 + lmat);
+#pragma unroll
+  for (int np = 0; np < ND / 2; ++np) voff[np] = kv_swz((lmat & 1) * 8 + lrow, 2 * np + (lmat >> 1));
   int slot = 0;
   for (int kb = 0; kb < n_hist; kb += 32) {
     KVStage& st = ring[slot];
+    const int cur = slot;   // ring slot of this block
     slot = slot + 1 == KVD ? 0 : slot + 1;
     const uint32_t ks = smem_u32(&st.k[0][0]), vs = smem_u32(&st.v[0][0]);
-    const int cur = slot == 0 ? KVD - 1 : slot - 1;   // ring slot of this block
     long long tw = 0;
     if (pw) tw = clock64();
-    if (!KV_BULK || chain) {
+    if (!BULK) {
       asm volatile("cp.async.wait_group %0;\n" ::"n"(KVD - 1) : "memory");
     } else {
       mbar_wait(kvbar + 8u * cur, (kvphase >> cur) & 1u);
       kvphase ^= 1u << cur;
     }
-    if (pw) { pw[0] += clock64() - tw; pw[1] += 1; }   // profiler: cycles spent waiting for K/V blocks, blocks reduced
+    if (pw) { const long long tn = clock64(); pw[0] += tn - tw; pw[1] += 1; tw = tn; }   // profiler: cycles spent waiting for K/V blocks, blocks reduced
     __syncwarp();
     uint32_t kf[4][ND], vf[2][ND / 2][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)     // score tile j: keys 8j..8j+7; one ldmatrix.x4 = four 8-dim chunks of those keys
 #pragma unroll
-      for (int c4 = 0; c4 < ND / 4; ++c4) {
-        const int key = 8 * j + lrow;
+      for (int c4 = 0; c4 < ND / 4; ++c4)
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                      : "=r"(kf[j][4 * c4 + 0]), "=r"(kf[j][4 * c4 + 1]), "=r"(kf[j][4 * c4 + 2]), "=r"(kf[j][4 * c4 + 3])
-                     : "r"(ks + kv_swz(key, 4 * c4 + lmat)));
-      }
+                     : "r"(ks + koff[c4] + (uint32_t)(j * 8 * HD * 2)));
 #pragma unroll
     for (int ks2 = 0; ks2 < 2; ++ks2)        // 16-key k-step of P . V
 #pragma unroll
-      for (int np = 0; np < ND / 2; ++np) {  // pair of 8-dim n-tiles
-        const int key = 16 * ks2 + (lmat & 1) * 8 + lrow, chunk = 2 * np + (lmat >> 1);
+      for (int np = 0; np < ND / 2; ++np)    // pair of 8-dim n-tiles
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                     : "=r"(vf[ks2][np][0]), "=r"(vf[ks2][np][1]), "=r"(vf[ks2][np][2]), "=r"(vf[ks2][np][3]) : "r"(vs + kv_swz(key, chunk)));
-      }
+                     : "=r"(vf[ks2][np][0]), "=r"(vf[ks2][np][1]), "=r"(vf[ks2][np][2]), "=r"(vf[ks2][np][3])
+                     : "r"(vs + voff[np] + (uint32_t)(ks2 * 16 * HD * 2)));
     __syncwarp();
-    if (!KV_BULK || chain) kv_request(st, Kc, Vc, kb + 32 * KVD, n_hist, chain);
+    if (!BULK) kv_request(st, Kc, Vc, kb + 32 * KVD, n_hist, chain);
     else kv_request_bulk(st, kvbar + 8u * cur, Kc, Vc, kb + 32 * KVD, n_hist);
+    if (pw) { const long long tn = clock64(); pw[2] += tn - tw; tw = tn; }   // fragments loaded, next block requested
     float sc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -475,26 +496,30 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
 #pragma unroll
       for (int k2 = 0; k2 < NK; ++k2) mma_bf16(sc[j], aq[k2], kf[j][2 * k2], kf[j][2 * k2 + 1]);
     }
-    float cm = m;
+    if (kb + 32 > n_hist) {   // the one partial block of a history: keys past it score -inf
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int key = kb + 8 * j + 2 * tig + e;
-        sc[j][e] = key < n_hist ? sc[j][e] * inv_temp : -INFINITY;
-        cm = fmaxf(cm, sc[j][e]);
-      }
+        for (int e = 0; e < 2; ++e)
+          if (kb + 8 * j + 2 * tig + e >= n_hist) sc[j][e] = -INFINITY;
+    }
+    float cm = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1])), fmaxf(fmaxf(sc[2][0], sc[2][1]), fmaxf(sc[3][0], sc[3][1])));
     cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
     cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-    const float scale = (m == -INFINITY) ? 0.f : __expf(m - cm);
-    l *= scale;
+    if (cm > m) {             // the running maximum moved: rescale what has been accumulated (ex2(-inf) = 0 the first time)
+      const float scale = ex2f(m - cm);
+      m = cm;
+      l *= scale;
 #pragma unroll
-    for (int nt = 0; nt < ND; ++nt) { acc[nt][0] *= scale; acc[nt][1] *= scale; }
+      for (int nt = 0; nt < ND; ++nt) { acc[nt][0] *= scale; acc[nt][1] *= scale; }
+    }
+    if (pw) { const long long tn = clock64(); pw[3] += tn - tw; tw = tn; }   // scores, running maximum
     float pr[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) { pr[j][e] = __expf(sc[j][e] - cm); l += pr[j][e]; }
+      for (int e = 0; e < 2; ++e) pr[j][e] = ex2f(sc[j][e] - m);
+    l += ((pr[0][0] + pr[0][1]) + (pr[1][0] + pr[1][1])) + ((pr[2][0] + pr[2][1]) + (pr[3][0] + pr[3][1]));
 #pragma unroll
     for (int ks2 = 0; ks2 < 2; ++ks2) {  // 16 keys per k-step: score tiles 2 ks2 (k lo) and 2 ks2 + 1 (k hi)
       const uint32_t ap[4] = {pack_bf16(pr[2 * ks2][0], pr[2 * ks2][1]), 0u, pack_bf16(pr[2 * ks2 + 1][0], pr[2 * ks2 + 1][1]), 0u};
@@ -504,7 +529,7 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
         mma_bf16(acc[2 * np + 1], ap, vf[ks2][np][2], vf[ks2][np][3]);
       }
     }
-    m = cm;
+    if (pw) pw[4] += clock64() - tw;   // probabilities, P . V issued
   }
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
@@ -520,10 +545,10 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
     }
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
-    const float s_cur = part * inv_temp;
+    const float s_cur = part * qscale;
     const float M = fmaxf(m, s_cur);
-    const float gs = (m == -INFINITY) ? 0.f : __expf(m - M);
-    const float pc = __expf(s_cur - M);
+    const float gs = ex2f(m - M);   // 0 when there is no history (m = -inf)
+    const float pc = ex2f(s_cur - M);
     l = l * gs + pc;
 #pragma unroll
     for (int nt = 0; nt < ND; ++nt) {
@@ -624,7 +649,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   const int img0 = p.img_base + (blockIdx.x / CL) * NIMG;    // first image of this cluster
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint64_t pol = make_evict_last_policy();
-  const float inv_temp = 1.f / sqrtf((float)D);  // D = 256: exact reciprocal of 16
+  const float qscale = 1.4426950408889634f / sqrtf((float)D);  // scores / sqrt(d_model), in exp2 units (see attend_mma)
   const float emb_scale = sqrtf((float)D);
   const int L = p.L, T = p.T, V = p.V, B = p.B;
   constexpr int LDA = D + APAD, LDA2 = FF + APAD;
@@ -800,8 +825,12 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         stage_begin(NIMG * D * 2u);
         const uint32_t sb = stage_bar();
         float o[HD / 4];
-        attend_mma(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, chain, kvbar, kvphase, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], inv_temp, o,
-                   profiling ? &s.prof[11] : nullptr);
+        if (!KV_BULK || chain)
+          attend_mma<false>(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, chain, kvbar, kvphase, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], qscale, o,
+                            profiling ? &s.prof[11] : nullptr);
+        else
+          attend_mma<true>(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, nullptr, kvbar, kvphase, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], qscale, o,
+                           profiling ? &s.prof[11] : nullptr);
         store_attn(sb, o);
         mark(1);
       }
@@ -843,7 +872,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
         const uint32_t sb = stage_bar();
         float o[HD / 4];
         if (mine) {
-          attend_mma(kvst, &s.qh[whc][wimg][0], p.kcross + base, p.vcross + base, n_keys, nullptr, kvbar, kvphase, nullptr, nullptr, inv_temp, o);
+          attend_mma<KV_BULK>(kvst, &s.qh[whc][wimg][0], p.kcross + base, p.vcross + base, n_keys, nullptr, kvbar, kvphase, nullptr, nullptr, qscale, o);
         } else {
 #pragma unroll
           for (int i = 0; i < HD / 4; ++i) o[i] = 0.f;

@@ -42,4 +42,5 @@ for b in [int(x) for x in a.batches.split(",")]:
         tot = sum(prof[:len(NAMES)])
         print("   stage cycles (cluster 0, per step): " + ", ".join("%s %.0f" % (n, prof[i] / a.steps) for i, n in enumerate(NAMES)) + "  | total %.0f cyc/step" % (tot / a.steps), flush=True)
         if prof[12]:
-            print("   self-attention of warp 0: %.0f cycles per step waiting for K/V blocks, %.2f blocks per call" % (prof[11] / a.steps, prof[12] / (3.0 * a.steps)), flush=True)
+            print("   self-attention of warp 0, cycles per step: K/V wait %.0f, ldmatrix + next request %.0f, scores + maximum %.0f, exp + P.V %.0f; %.2f blocks per call"
+                  % (prof[11] / a.steps, prof[13] / a.steps, prof[14] / a.steps, prof[15] / a.steps, prof[12] / (3.0 * a.steps)), flush=True)
