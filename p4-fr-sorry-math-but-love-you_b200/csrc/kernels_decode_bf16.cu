@@ -66,6 +66,10 @@ constexpr int KVD = FRX_DEC_KVDEPTH;
 #define FRX_DEC_KVBULK (FRX_DEC_KVDEPTH >= 2)   // contiguous K/V histories by bulk copies: pays with two blocks in flight (see kv_request_bulk)
 #endif
 constexpr bool KV_BULK = FRX_DEC_KVBULK;
+#ifndef FRX_DEC_EARLYPRIME
+#define FRX_DEC_EARLYPRIME FRX_DEC_KVBULK   // request the next attention phase's first K/V blocks as soon as the ring is idle (measured: pays with the bulk-copy ring only)
+#endif
+constexpr bool EARLY_PRIME = FRX_DEC_EARLYPRIME;
 constexpr int CL = H / HPC;      // CTAs per cluster
 constexpr int FF = FRX_DEC_FF;
 constexpr int VP = 256;          // vocabulary columns, padded
@@ -496,7 +500,9 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
 #pragma unroll
       for (int k2 = 0; k2 < NK; ++k2) mma_bf16(sc[j], aq[k2], kf[j][2 * k2], kf[j][2 * k2 + 1]);
     }
-    if (kb + 32 > n_hist) {   // the one partial block of a history: keys past it score -inf
+    // (the branches pay in the issue-bound two-heads-per-CTA geometry; with 8 warps per SM the phase is latency-bound and
+    // the same arithmetic runs straight-line: masking every block, scaling by ex2(0) = 1 when the maximum did not move)
+    if (!BULK || kb + 32 > n_hist) {   // the one partial block of a history: keys past it score -inf
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -506,7 +512,8 @@ __device__ __forceinline__ void attend_mma(KVStage* ring, const float* __restric
     float cm = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1])), fmaxf(fmaxf(sc[2][0], sc[2][1]), fmaxf(sc[3][0], sc[3][1])));
     cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
     cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-    if (cm > m) {             // the running maximum moved: rescale what has been accumulated (ex2(-inf) = 0 the first time)
+    cm = fmaxf(cm, m);
+    if (!BULK || cm > m) {    // the running maximum moved: rescale what has been accumulated (ex2(-inf) = 0 the first time)
       const float scale = ex2f(m - cm);
       m = cm;
       l *= scale;
@@ -687,12 +694,14 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
   }
   // K/V ring: one mbarrier per (warp, slot), armed by the warp's lane 0 with every bulk request; the staging blocks start
   // as zeros so that rows a partial block never fills hold finite values (their probabilities are 0)
-  if (lane == 0) {
+  if (KV_BULK) {
+    if (lane == 0) {
 #pragma unroll
-    for (int d = 0; d < KVD; ++d) mbar_init(smem_u32(&s.kvbar[warp][d]), 1);
+      for (int d = 0; d < KVD; ++d) mbar_init(smem_u32(&s.kvbar[warp][d]), 1);
+    }
+    for (int i = tid; i < (int)(sizeof(s.kvst) / 16); i += NTHR) reinterpret_cast<uint4*>(&s.kvst[0][0][0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the zeros (generic proxy) precede the first bulk copy (async proxy)
   }
-  for (int i = tid; i < (int)(sizeof(s.kvst) / 16); i += NTHR) reinterpret_cast<uint4*>(&s.kvst[0][0][0][0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the zeros (generic proxy) precede the first bulk copy (async proxy)
   __syncthreads();
   cl.sync();  // every CTA of the cluster is resident and its barriers initialised before the first remote store
   // Stage protocol: thread 0 arms the stage's barrier with the bytes THIS CTA will receive, everybody
@@ -804,11 +813,25 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
           make_uint4(pack_bf16(v[0] + b0.x, v[1] + b0.y), pack_bf16(v[2] + b0.z, v[3] + b0.w),
                      pack_bf16(v[4] + b1.x, v[5] + b1.y), pack_bf16(v[6] + b1.z, v[7] + b1.w));
       // the row is read back by bulk copies (async proxy) from the next step on: order this generic-proxy write before them
-      asm volatile("fence.proxy.async.global;\n" ::: "memory");
+      if (KV_BULK) asm volatile("fence.proxy.async.global;\n" ::: "memory");
     });
   };
 
   auto pre_a = prefetch_w<NTA, KPD, KS, PF_A>(p.w_first + (size_t)r * NTA * WT, pol);
+  // The K/V ring is idle between two attention phases, so the first blocks of the NEXT phase are requested as soon as
+  // the current one has handed its result over: the cross K/V of a layer right after its self-attention, the self K/V of
+  // the next layer (next step: layer 0, whose newest cache row was written during this step's layer 1) right after the
+  // cross-attention -- they land under the stages in between instead of under one short projection.
+  auto prime_self = [&](int l, int t) {
+    const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * T) * HD;
+    kv_prime(kvst, p.kself + base, p.vself + base, mine ? hist0 + t : 0, chain, kvbar);
+  };
+  auto prime_cross = [&](int l) {
+    const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * p.S) * HD;
+    kv_prime(kvst, p.kcross + base, p.vcross + base, mine ? p.S : 0, nullptr, kvbar);
+  };
+  prime_self(0, 0);
+  bool self_primed = true;
   for (int t = 0; t < p.steps; ++t) {
     for (int l = 0; l < L; ++l) {
       const DecClusterLayer& W = s.lw[l];
@@ -816,7 +839,8 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * T) * HD;
         const int n_hist = mine ? hist0 + t : 0;
-        kv_prime(kvst, p.kself + base, p.vself + base, n_hist, chain, kvbar);  // lands during the projection
+        if (!self_primed) prime_self(l, t);   // single-layer decoders only: the newest cache row is written late in the step
+        self_primed = false;
         const uint4* wp = l == 0 ? p.w_first + (size_t)r * NTA * WT : s.lw[l - 1].w_next + ((size_t)r * (NTC + NTA) + NTC) * WT;
         const Bias8 bias = qkv_bias(l == 0 ? p.b_first : s.lw[l - 1].b_next + 2 * D);
         gemm2<NTA, KPD, KS>(next_red(), &s.abf[0][0], LDA, wp, pol, pre_a, qkv_epi(bias));
@@ -832,6 +856,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
           attend_mma<true>(kvst, &s.qh[whc][wimg][0], p.kself + base, p.vself + base, n_hist, nullptr, kvbar, kvphase, &s.kcur[whc][wimg][0], &s.vcur[whc][wimg][0], qscale, o,
                            profiling ? &s.prof[11] : nullptr);
         store_attn(sb, o);
+        if (EARLY_PRIME) prime_cross(l);
         mark(1);
       }
       const auto pre_b = prefetch_w<NTS, KPD, KS, PF_S>(W.w_o + (size_t)r * NTS * WT, pol);
@@ -857,7 +882,7 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
       {
         const size_t base = ((((size_t)l * B + (mine ? b_mine : 0)) * H + head) * p.S) * HD;
         const int n_keys = mine ? p.S : 0;
-        kv_prime(kvst, p.kcross + base, p.vcross + base, n_keys, nullptr, kvbar);
+        if (!EARLY_PRIME) prime_cross(l);
         gemm2<NTS, KPD, KS>(next_red(), &s.abf[0][0], LDA, W.w_q2 + (size_t)r * NTS * WT, pol, pre_c,
                           [&](int tile, int row, float (&v)[8], int sub) {
                             if (sub != 0) return;
@@ -878,6 +903,10 @@ FRX_DEC_NAME(dec_cluster_bf16_kernel)(const DecClusterP p) {
           for (int i = 0; i < HD / 4; ++i) o[i] = 0.f;
         }
         store_attn(sb, o);
+        if (EARLY_PRIME) {
+          if (l + 1 < L) { prime_self(l + 1, t); self_primed = true; }
+          else if (L >= 2 && t + 1 < p.steps) { prime_self(0, t + 1); self_primed = true; }
+        }
         mark(7);
       }
       const auto pre_d = prefetch_w<NTS, KPD, KS, PF_S>(W.w_o2 + (size_t)r * NTS * WT, pol);

@@ -16,13 +16,14 @@ ap.add_argument("--precision", default="bf16")
 ap.add_argument("--batches", default="16,32,64,128,256")
 ap.add_argument("--steps", type=int, default=231)
 ap.add_argument("--dec-hpc", type=int, default=0, help="heads per CTA of the cluster decode kernel (1 or 2)")
+ap.add_argument("--prof", type=int, default=1, help="0: no in-kernel stage profile (its clock reads serialise the profiled warp: use 0 for A/B timings)")
 a = ap.parse_args()
 NAMES = ["A qkv gemm", "self-attn", "cache rows", "attn wait", "N=32 gemms (B,C,D,G)", "other waits", "layernorm", "cross-attn", "E ffn0", "F ffn1", "argmax+embed"]
 dev = torch.device("cuda", 0)
 model, _ = bench.build_model(a.precision, 256)
 model = model.to(dev).eval()
 model.set_option("timing", 1)
-model.set_option("prof", 1)
+model.set_option("prof", a.prof)
 model.set_option("dec_hpc", a.dec_hpc)
 ms3 = (ctypes.c_float * 4)()
 for b in [int(x) for x in a.batches.split(",")]:
@@ -36,7 +37,7 @@ for b in [int(x) for x in a.batches.split(",")]:
     eng.h.lib.frx_last_timing(eng.h.ptr, ms3)
     print("B=%4d steps=%d  encode %.3f ms  decode %.3f ms (%.1f us/step)  total %.3f ms  -> %.0f img/s"
           % (b, a.steps, ms3[0], ms3[1], ms3[1] * 1e3 / a.steps, ms3[2], b / ms3[2] * 1e3), flush=True)
-    if a.precision == "bf16":
+    if a.precision == "bf16" and a.prof:
         prof = (ctypes.c_int64 * 16)()
         eng.h.call("frx_read_prof", prof)
         tot = sum(prof[:len(NAMES)])
