@@ -280,8 +280,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // Bounded spin: a byte-accounting bug traps (error reaches the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+#ifndef FRX_DEC_SPINLIMIT
+#define FRX_DEC_SPINLIMIT (1ll << 26)
+#endif
 #pragma unroll 1
-  for (int spins = 0; spins < (1 << 26); ++spins) {
+  for (long long spins = 0; spins < FRX_DEC_SPINLIMIT; ++spins) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
