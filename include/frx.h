@@ -222,7 +222,8 @@ int frx_tc_gemm(frx_handle* h, const void* A, const void* W, void* C, int32_t M,
 int frx_read_prof(frx_handle* h, int64_t* out16);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Training step (EfficientSATRN): one iteration of train_modules/train_single_opt.py:72-112 --
+ * Training step (EfficientSATRN, and LiteSATRN -- the student of train_modules/train_distillation.py:95-117, networks/
+ * LiteSATRN.py:21-70, :581-590): one iteration of train_modules/train_single_opt.py:72-112 --
  *   model.train(); output = model(input, expected, True, 1.0)   (teacher forcing, EfficientSATRN.py:488-495, :697-706;
  *                                                                BatchNorm batch statistics)
  *   loss = CrossEntropyLoss(ignore_index=PAD)(output.transpose(1, 2), expected[:, 1:])   (:82-86, EfficientSATRN.py:690-692)

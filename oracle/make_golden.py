@@ -244,11 +244,16 @@ def main_train():
     norm of every parameter's gradient."""
     from oracle import train
     ref = ref_shim.load_reference()
-    spec = satrn.ModelSpec()
+    lite = "--lite" in sys.argv     # LiteSATRN student of the distillation loop (train_distillation.py:95-96): same step
+    spec = satrn.ModelSpec(**LITE_SPEC) if lite else satrn.ModelSpec()
     out = {}
     for seed in (0, 1):
-        sd = synth.synth_state_dict(spec, seed)
-        model = ref.networks.EfficientSATRN(ref_shim.reference_flags(dropout=0.0), ref_shim.reference_vocab())
+        if lite:
+            sd = synth.synth_state_dict(spec, seed, calib_batch=4)
+            model = ref.networks.LiteSATRN(ref_shim.reference_flags("LiteSATRN", dropout=0.0), ref_shim.reference_vocab())
+        else:
+            sd = synth.synth_state_dict(spec, seed)
+            model = ref.networks.EfficientSATRN(ref_shim.reference_flags(dropout=0.0), ref_shim.reference_vocab())
         model.load_state_dict(sd, strict=True)
         model.train()
         for m in model.modules():
@@ -274,7 +279,7 @@ def main_train():
         out["loss_seed%d" % seed] = np.array(losses, np.float64)
         out["grad_norm_seed%d" % seed] = np.array(norms, np.float64)
         print("seed", seed, "loss", losses, "grad norm", norms)
-    path = os.path.join(GOLDEN_DIR, "efficientsatrn_train.npz")
+    path = os.path.join(GOLDEN_DIR, "litesatrn_train.npz" if lite else "efficientsatrn_train.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 

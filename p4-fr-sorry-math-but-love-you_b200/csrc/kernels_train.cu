@@ -795,6 +795,103 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   __syncthreads();
   for (int i = threadIdx.x; i < nW; i += 256) atomicAdd(dw + i, sm[i]);
 }
+// Weight gradient of a 3 x 3 convolution that reads the NCHW input image (any stride / padding, Cout a divisor of 256):
+// LiteSATRN's conv0 (networks/LiteSATRN.py:24-26: 1 -> 128 channels, stride 1, padding 1).  dw [Cout][Cin][3][3].
+__global__ void __launch_bounds__(256) image_conv_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ img, float* __restrict__ dw,
+                                                               int B, int Cin, int H, int W, int OH, int OW, int Cout, int stride, int pad,
+                                                               int pix_per_cta) {
+  extern __shared__ float sm[];   // [Cout * Cin * 9]
+  const int nW = Cout * Cin * 9;
+  for (int i = threadIdx.x; i < nW; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const long long P = (long long)B * OH * OW;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  const long long p1 = p0 + pix_per_cta < P ? p0 + pix_per_cta : P;
+  const int lanes = 256 / Cout, co = threadIdx.x % Cout, pl = threadIdx.x / Cout;
+  for (int ci = 0; ci < Cin; ++ci) {
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    for (long long pp = p0 + pl; pp < p1; pp += lanes) {
+      const int ow = (int)(pp % OW), oh = (int)((pp / OW) % OH);
+      const long long n = pp / ((long long)OW * OH);
+      const float g = __ldg(dz + pp * Cout + co);
+      const float* ip = img + (n * Cin + ci) * (long long)H * W;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = oh * stride - pad + kh;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = ow * stride - pad + kw;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) acc[kh * 3 + kw] = fmaf(g, __ldg(ip + (long long)ih * W + iw), acc[kh * 3 + kw]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(&sm[(co * Cin + ci) * 9 + t], acc[t]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nW; i += 256) atomicAdd(dw + i, sm[i]);
+}
+int launch_image_conv_wgrad(const float* dz, const float* img, float* dw, int B, int Cin, int H, int W, int OH, int OW, int Cout, int stride,
+                            int pad, cudaStream_t st) {
+  if (Cout <= 0 || Cout > 256 || 256 % Cout != 0 || (size_t)Cout * Cin * 9 * sizeof(float) > 48 * 1024) return 1;
+  const long long P = (long long)B * OH * OW;
+  const int per = 2048;
+  image_conv_wgrad_kernel<<<(unsigned)((P + per - 1) / per), 256, (size_t)Cout * Cin * 9 * sizeof(float), st>>>(dz, img, dw, B, Cin, H, W, OH, OW,
+                                                                                                              Cout, stride, pad, per);
+  return 0;
+}
+
+// 2 x 2 / stride 2 max pooling over NHWC (nn.MaxPool2d(2, 2), LiteSATRN.py:29) and its backward pass.  The gradient goes
+// to the FIRST maximum of the window in (row, column) scan order, like ATen's max_pool2d_with_indices (after a ReLU whole
+// windows of zeros are common); every input element belongs to exactly one window (H, W even), so dx is written, not
+// accumulated.
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, C4 = C / 4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * OH * OW * C4) return;
+  const int c = (int)(i % C4) * 4;
+  long long pix = i / C4;
+  const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+  const float* xp = x + (((long long)n * H + 2 * oh) * W + 2 * ow) * C + c;
+  const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(xp + C);
+  const float4 d = *reinterpret_cast<const float4*>(xp + (long long)W * C), e = *reinterpret_cast<const float4*>(xp + (long long)W * C + C);
+  float4 o;
+  o.x = fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)); o.y = fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y));
+  o.z = fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)); o.w = fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w));
+  *reinterpret_cast<float4*>(y + i * 4) = o;
+}
+void launch_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st) {
+  const long long n = (long long)B * (H / 2) * (W / 2) * (C / 4);
+  maxpool2_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, B, H, W, C);
+}
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B,
+                                                           int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * OH * OW * C) return;
+  const int c = (int)(i % C);
+  long long pix = i / C;
+  const int ow = (int)(pix % OW), oh = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+  const long long base = (((long long)n * H + 2 * oh) * W + 2 * ow) * C + c;
+  const long long off[4] = {0, C, (long long)W * C, (long long)W * C + C};
+  int best = 0;
+  float bv = x[base];
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    const float v = x[base + off[k]];
+    if (v > bv) { bv = v; best = k; }
+  }
+  const float g = dy[i];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dx[base + off[k]] = k == best ? g : 0.f;
+}
+void launch_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, cudaStream_t st) {
+  const long long n = (long long)B * (H / 2) * (W / 2) * C;
+  maxpool2_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, dy, dx, B, H, W, C);
+}
+
 void launch_stem_wgrad(const float* dz, const float* img, float* dw, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st) {
   const long long P = (long long)B * OH * OW;
   const int per = 2048;

@@ -101,6 +101,11 @@ struct Tape {
   float *stem_z = nullptr, *stem_stat = nullptr;
   std::vector<BlockSave> bs;
   CB last;
+  // LiteSATRN's ShallowCNN (networks/LiteSATRN.py:21-70): conv0 reads the image directly, conv1-3 are implicit GEMMs
+  float *lite_z0 = nullptr, *lite_y0 = nullptr, *lite_stat0 = nullptr;
+  CB lite_cb[3];
+  float* lite_pool[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* trunk_out = nullptr;   // [B, H, W, enc_hidden]: what the 2-D positional encoding reads
   float *pe_mean = nullptr, *pe_hp = nullptr, *pe_h = nullptr, *pe_gp = nullptr, *pe_g = nullptr, *pe_out = nullptr;
   std::vector<EncSave> es;
   const float* memory = nullptr;
@@ -129,6 +134,8 @@ struct TrainState {
   long long launches = 0;
   // network description
   size_t stem_w = 0; TBN stem_bn;
+  bool lite = false;                 // LiteSATRN: ShallowCNN trunk instead of the EfficientNetV2-S blocks
+  size_t lite_w[4] = {0, 0, 0, 0}; TBN lite_bn[4];
   std::vector<TBlock> blocks;
   size_t last_w = 0; TBN last_bn;
   size_t pe_w0 = 0, pe_b0 = 0, pe_w1 = 0, pe_b1 = 0;
@@ -245,6 +252,15 @@ int build_network(frx_handle* h, TrainState* T) {
   const frx_config& c = h->cfg;
   Builder bd{h, T};
   const std::string e = "encoder.shallow_cnn.";
+  T->lite = c.network == FRX_NET_LITE_SATRN;
+  if (T->lite) {
+    // LiteSATRN.py:24-44: conv0 [C/2][Cin][3][3] (read by the direct kernel as is), conv1-3 as implicit GEMMs
+    for (int i = 0; i < 4; ++i) {
+      T->lite_w[i] = bd.add(e + "conv" + std::to_string(i) + ".weight", i == 0 ? P_PLAIN : P_CONV);
+      T->lite_bn[i] = bd.bn(e + "batch_norm" + std::to_string(i), i == 0 ? c.enc_hidden / 2 : c.enc_hidden, 1e-5f);
+    }
+    for (int s = 0; s < 6; ++s) T->mark_trunk[s] = T->hostP.size();   // one trunk bucket (the last one in backward order)
+  } else {
   T->stem_w = bd.add(e + "conv_stem.weight", P_PLAIN);   // [24][Cin][3][3], read by the direct stem kernel as is
   T->stem_bn = bd.bn(e + "bn1", 24, 1e-3f);
   int cin = 24;
@@ -282,6 +298,7 @@ int build_network(frx_handle* h, TrainState* T) {
   }
   T->last_w = bd.add(e + "conv_last.weight", P_CONV);
   T->last_bn = bd.bn(e + "bn2", c.enc_hidden, 1e-5f);
+  }
   const std::string pe = "encoder.positional_encoding.";
   T->pe_w0 = bd.add(pe + "dense0.weight", P_PLAIN); T->pe_b0 = bd.add(pe + "dense0.bias", P_PLAIN);
   T->pe_w1 = bd.add(pe + "dense1.weight", P_PLAIN); T->pe_b1 = bd.add(pe + "dense1.bias", P_PLAIN);
@@ -534,7 +551,7 @@ int ln_bwd(Ctx& c, const LNS& r, const float* dy, float** dx_out) {
 void tap(Ctx& c, const std::string& name, const float* p, size_t n) { c.T->taps[name] = {p, n}; }
 
 void bucket_done(Ctx& c, int idx) {
-  if (c.T->bucket_cb && idx < (int)c.T->buckets.size())
+  if (c.T->bucket_cb && idx < (int)c.T->buckets.size() && c.T->buckets[idx].second > 0)
     c.T->bucket_cb(c.T->bucket_ctx, (int64_t)c.T->buckets[idx].first, (int64_t)c.T->buckets[idx].second);
 }
 
@@ -562,6 +579,30 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
   T->taps.clear();
   tp.valid = false;
   // ================= forward =================
+  if (T->lite) {
+    // ShallowCNN: 4 x (conv3x3 p1 -> train-mode BN -> ReLU -> maxpool 2x2), LiteSATRN.py:50-70
+    const int C0 = C / 2;
+    int Hc = cf.height, Wc = cf.width;
+    WALLOC(tp.lite_z0, (size_t)B * Hc * Wc * C0); WALLOC(tp.lite_y0, (size_t)B * Hc * Wc * C0);
+    launch_direct_conv3x3(images, T->P + T->lite_w[0], T->ones, T->zeros, tp.lite_z0, B, cf.in_ch, Hc, Wc, Hc, Wc, C0, 1, 1, ACT_NONE, c.st);
+    TKL();
+    if (bn_fwd(c, tp.lite_z0, (long long)B * Hc * Wc, T->lite_bn[0], ACT_RELU, nullptr, tp.lite_y0, &tp.lite_stat0)) return 1;
+    WALLOC(tp.lite_pool[0], (size_t)B * (Hc / 2) * (Wc / 2) * C0);
+    launch_maxpool2_fwd(tp.lite_y0, tp.lite_pool[0], B, Hc, Wc, C0, c.st); TKL();
+    Hc /= 2; Wc /= 2;
+    for (int i = 1; i < 4; ++i) {
+      CB& r = tp.lite_cb[i - 1];
+      r = CB{};
+      r.x = tp.lite_pool[i - 1]; r.B = B; r.H = Hc; r.W = Wc; r.Cin = i == 1 ? C0 : C; r.Cout = C; r.k = 3; r.stride = 1; r.act = ACT_RELU;
+      r.w = T->lite_w[i]; r.bn = T->lite_bn[i];
+      if (cb_fwd(c, r)) return 1;
+      WALLOC(tp.lite_pool[i], (size_t)B * (Hc / 2) * (Wc / 2) * C);
+      launch_maxpool2_fwd(r.y, tp.lite_pool[i], B, Hc, Wc, C, c.st); TKL();
+      Hc /= 2; Wc /= 2;
+    }
+    tp.H = Hc; tp.W = Wc;
+    tp.trunk_out = tp.lite_pool[3];
+  } else {
   float* stem_y;
   WALLOC(tp.stem_z, (size_t)B * H0 * W0 * 24); WALLOC(stem_y, (size_t)B * H0 * W0 * 24);
   launch_direct_conv3x3(images, T->P + T->stem_w, T->ones, T->zeros, tp.stem_z, B, cf.in_ch, cf.height, cf.width, H0, W0, 24, 2, 0, ACT_NONE, c.st);
@@ -606,17 +647,19 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
   tp.last.x = x; tp.last.B = B; tp.last.H = tp.H; tp.last.W = tp.W; tp.last.Cin = 256; tp.last.Cout = cf.enc_hidden; tp.last.k = 1; tp.last.act = ACT_SILU; tp.last.w = T->last_w;
   tp.last.bn = T->last_bn;
   if (cb_fwd(c, tp.last)) return 1;
+  tp.trunk_out = tp.last.y;
+  }
   if (tp.H != h->feat_h || tp.W != h->feat_w) return tfail(h, "training: trunk output %dx%d != %dx%d", tp.H, tp.W, h->feat_h, h->feat_w);
   const int S = tp.H * tp.W;
   // ---- adaptive 2-D positional encoding (:135-154) ----
   WALLOC(tp.pe_mean, (size_t)B * C); WALLOC(tp.pe_hp, (size_t)B * C / 2); WALLOC(tp.pe_h, (size_t)B * C / 2); WALLOC(tp.pe_gp, (size_t)B * 2 * C);
   WALLOC(tp.pe_g, (size_t)B * 2 * C); WALLOC(tp.pe_out, (size_t)B * S * C);
-  launch_spatial_dot(tp.last.y, nullptr, tp.pe_mean, B, S, C, 1.f / (float)S, c.st); TKL();
+  launch_spatial_dot(tp.trunk_out, nullptr, tp.pe_mean, B, S, C, 1.f / (float)S, c.st); TKL();
   if (lin_fwd(c, tp.pe_mean, B, C, T->pe_w0, T->pe_b0, true, C / 2, tp.pe_hp, C / 2, ACT_NONE, nullptr)) return 1;
   launch_act_fwd(tp.pe_hp, tp.pe_h, ACT_RELU, (long long)B * C / 2, c.st); TKL();
   if (lin_fwd(c, tp.pe_h, B, C / 2, T->pe_w1, T->pe_b1, true, 2 * C, tp.pe_gp, 2 * C, ACT_NONE, nullptr)) return 1;
   launch_act_fwd(tp.pe_gp, tp.pe_g, ACT_SIGMOID, (long long)B * 2 * C, c.st); TKL();
-  launch_pe2d_apply(tp.last.y, tp.pe_g, peh, pew, tp.pe_out, B, tp.H, tp.W, C, c.st); TKL();
+  launch_pe2d_apply(tp.trunk_out, tp.pe_g, peh, pew, tp.pe_out, B, tp.H, tp.W, C, c.st); TKL();
   // ---- encoder layers (:259-281) ----
   tp.es.assign(T->enc.size(), EncSave{});
   const float* xe = tp.pe_out;
@@ -826,6 +869,28 @@ int fwd_bwd(Ctx& c, const float* images, const long long* expected, float* loss_
     if (lin_bwd(c, dhp, C / 2, tp.pe_mean, B, C, T->pe_w0, T->pe_b0, true, C / 2, dmean, false)) return 1;
     launch_spatial_add(dtrunk, dmean, B, S, C, 1.f / (float)S, c.st); TKL();
   }
+  if (T->lite) {
+    bucket_done(c, 1);
+    const int C0 = C / 2;
+    float* d = dtrunk;   // gradient of pool[3]
+    for (int i = 3; i >= 1; --i) {
+      const CB& r = tp.lite_cb[i - 1];
+      float* dyc;
+      WALLOC(dyc, (size_t)B * r.OH * r.OW * C);
+      launch_maxpool2_bwd(r.y, d, dyc, B, r.OH, r.OW, C, c.st); TKL();
+      if (cb_bwd(c, r, dyc, &d, true)) return 1;
+    }
+    const long long M0 = (long long)B * cf.height * cf.width;
+    float *dy0, *dz0;
+    WALLOC(dy0, (size_t)M0 * C0); WALLOC(dz0, (size_t)M0 * C0);
+    launch_maxpool2_bwd(tp.lite_y0, d, dy0, B, cf.height, cf.width, C0, c.st); TKL();
+    launch_bn_bwd(dy0, tp.lite_z0, tp.lite_stat0, T->acc, dz0, T->G + T->lite_bn[0].g, T->G + T->lite_bn[0].b, (int)M0, C0, ACT_RELU, c.st); TKL();
+    if (launch_image_conv_wgrad(dz0, images, T->G + T->lite_w[0], B, cf.in_ch, cf.height, cf.width, cf.height, cf.width, C0, 1, 1, c.st))
+      return tfail(h, "training: conv0 weight gradient does not support %d output channels", C0);
+    TKL();
+    bucket_done(c, 5);
+    return 0;
+  }
   float* dx;
   if (cb_bwd(c, tp.last, dtrunk, &dx, true)) return 1;
   bucket_done(c, 1);
@@ -878,7 +943,8 @@ TrainState* state_of(frx_handle* h) { return reinterpret_cast<TrainState*>(h->tr
 extern "C" int frx_train_create(frx_handle* h, int32_t max_batch, int32_t max_len, float* grad_buffer) {
   if (!h) return 1;
   if (!h->finalized) return tfail(h, "train_create: weights not finalized");
-  if (h->cfg.network != FRX_NET_EFFICIENT_SATRN) return tfail(h, "train_create: only EfficientSATRN has a training step");
+  if (h->cfg.network != FRX_NET_EFFICIENT_SATRN && h->cfg.network != FRX_NET_LITE_SATRN)
+    return tfail(h, "train_create: EfficientSATRN and LiteSATRN have a training step (SwinTRN has not)");
   if (max_batch <= 0 || max_len <= 0 || max_len > 256) return tfail(h, "train_create: max_batch / max_len out of range (max_len <= 256)");
   DevGuard g; g.enter(h->cfg.device);
   if (h->train) frx_train_destroy(h);

@@ -54,6 +54,10 @@ int launch_attn_bwd(const AttnBwdP& p, int B, cudaStream_t st);
 void launch_embed_bwd(const long long* tok, const float* dx, float* dE, int M, int D, float scale, cudaStream_t st);
 void launch_cross_entropy(const float* logits, const long long* expected, float* dlogits, float* out2, int B, int L, int V, int pad, cudaStream_t st);
 void launch_stem_wgrad(const float* dz, const float* img, float* dw, int B, int Cin, int H, int W, int OH, int OW, int Cout, cudaStream_t st);
+int launch_image_conv_wgrad(const float* dz, const float* img, float* dw, int B, int Cin, int H, int W, int OH, int OW, int Cout, int stride,
+                            int pad, cudaStream_t st);
+void launch_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st);
+void launch_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, cudaStream_t st);
 void launch_sumsq(const float* g, long long n, double* out, cudaStream_t st);
 void launch_adamw(float* p, const float* g, float* m, float* v, const double* sumsq, float* norm_out, long long n, float lr, float wd, int step,
                   float max_norm, float grad_scale, cudaStream_t st);

@@ -192,3 +192,109 @@ def test_distillation_loss_through_the_autograd_bridge(spec, ckpt0):
     print("KD: loss %.6f (oracle %.6f), whole-gradient rel-L2 %.2e" % (loss.item(), ref_loss.item(), (num / den) ** 0.5))
     assert abs(loss.item() - ref_loss.item()) <= 2e-5 * abs(ref_loss.item())
     assert (num / den) ** 0.5 <= GLOBAL_TOL
+
+
+LITE_GOLD = os.path.join(ROOT, "tests", "golden", "litesatrn_train.npz")
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_lite_train_step_matches_oracle_and_reference(seed):
+    """LiteSATRN (networks/LiteSATRN.py: ShallowCNN trunk, max pooling) through the same training step -- the student of
+    the reference's distillation loop (train_modules/train_distillation.py:95-96): loss, every gradient, the gradient norm
+    and three optimiser steps against the oracle and the real reference's numbers."""
+    from helpers import make_lite_model
+    from oracle import satrn
+    from oracle.make_golden import LITE_SPEC
+    lspec = satrn.ModelSpec(**LITE_SPEC)
+    sd = synth.synth_state_dict(lspec, seed, calib_batch=4)
+    g = np.load(LITE_GOLD)
+    model = make_lite_model(sd, max_batch=4, max_steps=24).cuda().train()
+    tr = train.Trainer(sd, lspec)
+    names = [k for k in tr.sd if train.is_param(k)]
+    for it in range(3):
+        x, e = train.synth_batch(lspec, 4, 24, 10 * seed + it)
+        loss, gn = model.train_step(x.cuda(), e.cuda())
+        loss, gn = loss.item(), gn.item()
+        if it == 0:
+            ref_loss, grads = tr.forward_backward(x, e)
+            worst, worst_name, num, den = 0.0, "", 0.0, 0.0
+            for n in names:
+                got, want = model.read_grad(n).cpu(), grads[n]
+                err = (got - want).norm().item() / max(want.norm().item(), 1e-12)
+                if want.norm().item() < 1e-5:
+                    err = (got - want).norm().item() / 1e-3
+                num += (got - want).norm().item() ** 2
+                den += want.norm().item() ** 2
+                if err > worst:
+                    worst, worst_name = err, n
+            glob = (num / den) ** 0.5
+            print("LiteSATRN seed %d step 0: loss %.6f (oracle %.6f, reference %.6f), grad norm %.5f (reference %.5f), "
+                  "whole-gradient rel-L2 %.2e, worst tensor %.2e at %s"
+                  % (seed, loss, ref_loss, g["loss_seed%d" % seed][0], gn, g["grad_norm_seed%d" % seed][0], glob, worst, worst_name))
+            assert abs(loss - ref_loss) <= LOSS_TOL * abs(ref_loss)
+            assert abs(loss - g["loss_seed%d" % seed][0]) <= LOSS_TOL * abs(loss)
+            assert glob <= GLOBAL_TOL, glob
+            assert worst <= GRAD_TOL, (worst_name, worst)
+            assert abs(gn - g["grad_norm_seed%d" % seed][0]) <= NORM_TOL * gn
+            torch.nn.utils.clip_grad_norm_(tr.params, max_norm=tr.max_grad_norm)
+            tr.opt.step()
+        else:
+            assert abs(loss - g["loss_seed%d" % seed][it]) <= 2e-3 * abs(loss), (it, loss)
+            assert abs(gn - g["grad_norm_seed%d" % seed][it]) <= 3e-2 * gn, (it, gn)
+    # trained weights come back in the state_dict layout and keep working for inference
+    model.sync_trained_weights()
+    sd_gpu = model.state_dict()
+    for it in range(1, 3):
+        tr.step(*train.synth_batch(lspec, 4, 24, 10 * seed + it))
+    sd_ref = tr.state_dict()
+    for k in ("encoder.shallow_cnn.conv0.weight", "encoder.shallow_cnn.batch_norm2.running_var", "decoder.generator.weight"):
+        a, b = sd_gpu[k].detach().float().cpu(), sd_ref[k].float()
+        assert (a - b).norm().item() <= 2e-3 * max(b.norm().item(), 1e-6), k
+
+
+def test_distillation_with_a_litesatrn_student(spec, ckpt0):
+    """The reference's pairing (train_distillation.py:95-117): an EfficientSATRN teacher in eval mode, a LiteSATRN student
+    in train mode, loss_fn_kd on the caller's side, loss.backward() through the autograd bridge, a torch AdamW over the
+    student's nn.Parameters.  Loss and student gradients against torch autograd on the oracle."""
+    import torch.nn.functional as F
+    from helpers import make_lite_model
+    from oracle import satrn
+    from oracle.make_golden import LITE_SPEC
+
+    def loss_fn_kd(outputs, labels, teacher_outputs, T=10, alpha=0.1):
+        return torch.nn.KLDivLoss(reduction="batchmean")(F.log_softmax(outputs / T, dim=1), F.softmax(teacher_outputs / T, dim=1)) \
+            * (alpha * T * T) + F.cross_entropy(outputs, labels) * (1.0 - alpha)
+
+    lspec = satrn.ModelSpec(**LITE_SPEC)
+    lsd = synth.synth_state_dict(lspec, 0, calib_batch=4)
+    student = make_lite_model(lsd, max_batch=4, max_steps=24).cuda().train()
+    teacher = make_model(ckpt0, max_batch=4, max_steps=24).cuda().eval()
+    opt = torch.optim.AdamW(student.parameters(), lr=5e-4, weight_decay=1e-6)
+    x, e = train.synth_batch(spec, 4, 24, 93)
+    e[e == 2] = 5
+    with torch.no_grad():
+        t_out = teacher(x.cuda(), e.cuda(), False, 0.0)
+    opt.zero_grad()
+    s_out = student(x.cuda(), e.cuda(), True, 1.0)
+    assert s_out.shape == (4, 24, 245) and s_out.requires_grad
+    loss = loss_fn_kd(s_out.transpose(1, 2), e[:, 1:].cuda(), t_out.transpose(1, 2))
+    loss.backward()
+    tr = train.Trainer(lsd, lspec)
+    with torch.enable_grad():
+        ref_out = train.train_forward(tr.sd, lspec, x, e)
+        ref_loss = loss_fn_kd(ref_out.transpose(1, 2), e[:, 1:], t_out.cpu().transpose(1, 2))
+        ref_loss.backward()
+    got = dict(student.named_parameters())
+    num = den = 0.0
+    for k, v in tr.sd.items():
+        if train.is_param(k):
+            num += (got[k].grad.cpu() - v.grad).norm().item() ** 2
+            den += v.grad.norm().item() ** 2
+    print("KD, LiteSATRN student: loss %.6f (oracle %.6f), whole-gradient rel-L2 %.2e" % (loss.item(), ref_loss.item(), (num / den) ** 0.5))
+    assert abs(loss.item() - ref_loss.item()) <= 2e-5 * abs(ref_loss.item())
+    assert (num / den) ** 0.5 <= GLOBAL_TOL
+    torch.nn.utils.clip_grad_norm_(student.parameters(), 2.0)
+    opt.step()
+    with torch.no_grad():
+        after = student.eval()(x.cuda(), e.cuda(), False, 0.0)   # the stepped parameters drive the inference path
+    assert torch.isfinite(after).all()

@@ -47,3 +47,33 @@ def test_train_forward_is_teacher_forced_with_batch_statistics(spec, ckpt0):
     assert lt.shape == le.shape == (2, 12, spec.num_classes)
     assert (lt - le).abs().max() > 1e-3
     assert int(sd["encoder.shallow_cnn.bn1.num_batches_tracked"]) == int(ckpt0["encoder.shallow_cnn.bn1.num_batches_tracked"]) + 1
+
+
+LITE_GOLD = os.path.join(ROOT, "tests", "golden", "litesatrn_train.npz")
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_lite_train_step_oracle_matches_reference(seed):
+    """The same training step for LiteSATRN -- the student of the reference's distillation loop
+    (train_modules/train_distillation.py:95-96) -- against oracle/make_golden.py --train --lite (the real
+    networks.LiteSATRN in train mode)."""
+    from oracle.make_golden import LITE_SPEC
+    lspec = satrn.ModelSpec(**LITE_SPEC)
+    g = np.load(LITE_GOLD)
+    tr = train.Trainer(synth.synth_state_dict(lspec, seed, calib_batch=4), lspec)
+    names = [k for k in tr.sd if train.is_param(k)]
+    assert names == list(g["names"])
+    for it in range(3):
+        x, e = train.synth_batch(lspec, 4, 24, 10 * seed + it)
+        if it == 0:
+            loss, grads = tr.forward_backward(x, e)
+            l2 = np.array([grads[n].norm().item() for n in names])
+            ref = g["grad_l2_seed%d" % seed]
+            assert np.all(np.abs(l2 - ref) <= 2e-4 * ref + 1e-7), np.abs(l2 - ref).max()
+            gn = float(torch.nn.utils.clip_grad_norm_(tr.params, max_norm=tr.max_grad_norm))
+            tr.opt.step()
+        else:
+            loss, gn = tr.step(x, e)
+        tol_l, tol_g = (1e-6, 1e-5) if it == 0 else (1e-3, 2e-2)
+        assert abs(loss - g["loss_seed%d" % seed][it]) <= tol_l * abs(loss), (it, loss)
+        assert abs(gn - g["grad_norm_seed%d" % seed][it]) <= tol_g * gn, (it, gn)
