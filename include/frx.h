@@ -196,6 +196,9 @@ int64_t frx_device_bytes(const frx_handle* h);
  *   "prof" (0)      in-kernel stage profiler of the bf16 decode kernel (frx_read_prof)
  *   "parts" (3)     bit 0 encoder, bit 1 decoder (EfficientSATRN_encoder / _decoder handles); re-finalize after changing
  *   "enc_fp32" (0)  bf16 mode: run the encoder on the fp32 kernels
+ *   "train_splitk" (1)  training step: GEMM launches of few output tiles (squeeze-excite FCs, late-stage 1x1 convolutions
+ *                       of a 16-image batch) split K over CTAs; partials are summed in split order by a second kernel (no
+ *                       atomics).  0 = one pass over K per tile
  *   "tc_ws" (1), "tc_im2col" (1), "conv24" (1)   bf16 encoder: persistent warp-specialised tcgen05 GEMM / TMA-im2col feed /
  *                   halo-tile kernel for the 24-channel convs; 0 selects the variant each one replaced
  *   "dec_hpc" (0)   bf16 decode, 256-wide decoder: heads per CTA (1: clusters of 8, 2: clusters of 4); 0 = by batch size */

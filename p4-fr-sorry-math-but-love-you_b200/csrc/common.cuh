@@ -109,6 +109,12 @@ struct GemmP {
   int act;
   const float* res;    // residual added after the activation, [M, ldr]
   int ldr;
+  // deterministic split-K (training step: skinny GEMMs whose few tiles would walk a long K serially): the launcher picks
+  // the split when a workspace is given; partial tiles go to ws [split][M][N], a second kernel sums them in split order
+  // and applies the epilogue
+  float* ws;           // nullptr: never split (the inference paths)
+  long long ws_floats;
+  int splitk, k_chunk; // set by the launcher
 };
 
 struct DwP {

@@ -132,13 +132,16 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const GemmP p) {
     b_base[i] = p.W + (long long)(b_ok[i] ? n : 0) * p.K;
   }
 
+  // split-K: this CTA reduces k in [kbeg, kend) (the whole K without a split)
+  const int kbeg = p.splitk > 1 ? blockIdx.z * p.k_chunk : 0;
+  const int kend = p.splitk > 1 ? min(p.K, kbeg + p.k_chunk) : p.K;
   float4 a_reg[AL], b_reg[BL];
   auto load_slab = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < AL; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       int k = k0 + a_kq[i];
-      if (a_ok[i] && k < p.K) {
+      if (a_ok[i] && k < kend) {
         if (p.conv) {
           int tap = k / p.Cin;
           int ci = k - tap * p.Cin;
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const GemmP p) {
     for (int i = 0; i < BL; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       int k = k0 + b_kq[i];
-      if (b_ok[i] && k < p.K) v = __ldg(reinterpret_cast<const float4*>(b_base[i] + k));
+      if (b_ok[i] && k < kend) v = __ldg(reinterpret_cast<const float4*>(b_base[i] + k));
       b_reg[i] = v;
     }
   };
@@ -190,11 +193,11 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const GemmP p) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  load_slab(0);
+  load_slab(kbeg);
   store_slab();
   __syncthreads();
-  for (int k0 = 0; k0 < p.K; k0 += BK) {
-    const bool more = k0 + BK < p.K;
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = k0 + BK < kend;
     if (more) load_slab(k0 + BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const GemmP p) {
       int n = n0 + tx * TN + j;
       if (n >= p.N) continue;
       float v = acc[i][j];
+      if (p.splitk > 1) { p.ws[((long long)blockIdx.z * p.M + m) * p.N + n] = v; continue; }   // partial tile: epilogue in splitk_reduce
       if (p.scale) v = v * __ldg(p.scale + n) + __ldg(p.shift + n);
       else if (p.shift) v += __ldg(p.shift + n);
       v = act_apply(v, p.act);
@@ -240,16 +244,56 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const GemmP p) {
   }
 }
 
-void launch_igemm_f32(const GemmP& p, cudaStream_t st) {
+// sums the split-K partials in split order and applies the GEMM epilogue
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmP p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.M * p.N) return;
+  const int n = (int)(i % p.N);
+  const long long m = i / p.N;
+  float v = 0.f;
+  for (int z = 0; z < p.splitk; ++z) v += p.ws[(long long)z * p.M * p.N + i];
+  if (p.scale) v = v * __ldg(p.scale + n) + __ldg(p.shift + n);
+  else if (p.shift) v += __ldg(p.shift + n);
+  v = act_apply(v, p.act);
+  if (p.res) v += __ldg(p.res + m * p.ldr + n);
+  p.C[m * p.ldc + n] = v;
+}
+
+void launch_igemm_f32(const GemmP& p0, cudaStream_t st) {
+  GemmP p = p0;
+  p.splitk = 1; p.k_chunk = p.K;
+  if (p.ws && p.K >= 256) {
+    // tiles of the launch below; a launch of few tiles walks K serially in every CTA (the squeeze-excite FCs of a
+    // 16-image batch are ONE tile over K = 1536): split K until ~240 CTAs exist
+    const long long tiles = p.N <= 32 ? (long long)((p.M + 127) / 128) * ((p.N + 31) / 32)
+                            : p.M >= 16384 ? (long long)((p.M + 127) / 128) * ((p.N + 63) / 64)
+                                           : (long long)((p.M + 63) / 64) * ((p.N + 63) / 64);
+    if (tiles < 120) {
+      long long S = (240 + tiles - 1) / tiles;
+      if (S > p.K / 64) S = p.K / 64;
+      if (S > 32) S = 32;
+      while (S > 1 && (long long)p.M * p.N * S > p.ws_floats) --S;
+      if (S > 1) {
+        p.k_chunk = (int)(((p.K + S - 1) / S + 15) / 16 * 16);
+        p.splitk = (p.K + p.k_chunk - 1) / p.k_chunk;
+        if (p.splitk <= 1) { p.splitk = 1; p.k_chunk = p.K; }
+      }
+    }
+  }
+  const unsigned gz = (unsigned)p.splitk;
   if (p.N <= 32) {
-    dim3 g((p.M + 127) / 128, (p.N + 31) / 32);
+    dim3 g((p.M + 127) / 128, (p.N + 31) / 32, gz);
     igemm_f32_kernel<128, 32, 4, 4><<<g, 256, 0, st>>>(p);
   } else if (p.M >= 16384) {
-    dim3 g((p.M + 127) / 128, (p.N + 63) / 64);
+    dim3 g((p.M + 127) / 128, (p.N + 63) / 64, gz);
     igemm_f32_kernel<128, 64, 8, 4><<<g, 256, 0, st>>>(p);
   } else {
-    dim3 g((p.M + 63) / 64, (p.N + 63) / 64);
+    dim3 g((p.M + 63) / 64, (p.N + 63) / 64, gz);
     igemm_f32_kernel<64, 64, 4, 4><<<g, 256, 0, st>>>(p);
+  }
+  if (p.splitk > 1) {
+    const long long n = (long long)p.M * p.N;
+    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
   }
 }
 

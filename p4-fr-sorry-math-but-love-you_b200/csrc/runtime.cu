@@ -263,6 +263,7 @@ extern "C" int frx_set_option(frx_handle* h, const char* key, int64_t value) {
   else if (k == "conv24") h->opt_conv24 = value != 0;  // 0: stage-0 convs through the tcgen05 im2col GEMM instead
   else if (k == "enc_fp32") h->opt_enc_fp32 = value != 0;
   else if (k == "tc_ws") h->opt_tc_ws = value != 0;
+  else if (k == "train_splitk") h->opt_train_splitk = value != 0;  // 0: every training GEMM reduces K in one CTA pass (the summation order of the r2 parity runs)
   else if (k == "tc_im2col") h->opt_tc_im2col = value != 0;
   else if (k == "prof") {
     h->opt_prof = value != 0;

@@ -147,6 +147,7 @@ struct frx_handle {
   int sift_ids[6] = {0, 0, 0, 0, 0, 0};  // <SOS>, <EOS>, "", "{", "}", "_"
   bool have_rules = false;
   bool timed_kernel = false;
+  bool opt_train_splitk = true;   // training step: deterministic split-K for the GEMM launches of few tiles (train.cu)
   bool dec_cluster_ok = false;   // bf16 mode: the persistent cluster decode kernel fits this decoder's dimensions
   void* train = nullptr;   // TrainState (train.cu): parameters, gradients, optimiser state of the training step
   void *sw_ab = nullptr, *sw_hidb = nullptr;  // SwinTRN bf16 mode: bf16 A operands (LayerNorm / attention output, MLP hidden)

@@ -117,6 +117,8 @@ struct Tape {
 };
 enum Phase { PH_BOTH = 0, PH_FWD = 1, PH_BWD = 2 };
 
+constexpr long long kSplitKFloats = 8ll << 20;   // 32 MB: e.g. 32 splits of a 512 x 512 output
+
 struct TrainState {
   Tape tape;
   float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *RS = nullptr;
@@ -129,6 +131,7 @@ struct TrainState {
   size_t ws_bytes = 0, ws_used = 0;
   double *acc = nullptr, *sumsq = nullptr;
   float *scal = nullptr, *ones = nullptr, *zeros = nullptr;
+  float* splitk_ws = nullptr;   // partial tiles of the split-K GEMM launches (kSplitKFloats floats, re-used stream-ordered)
   int step = 0, max_B = 0, max_L = 0;
   bool own_G = true;
   long long launches = 0;
@@ -378,7 +381,7 @@ int lin_fwd(Ctx& c, const float* x, long long M, int K, size_t w, size_t b, bool
   if (has_b) g.shift = c.T->P + b;
   g.act = act;
   if (res) { g.res = res; g.ldr = ldy; }
-  launch_igemm_f32(g, c.st); TKL();
+  g.ws = h->opt_train_splitk ? c.T->splitk_ws : nullptr; g.ws_floats = kSplitKFloats; launch_igemm_f32(g, c.st); TKL();
   return 0;
 }
 // dW += dy^T x; db += colsum(dy); dx (=|+=) dy * W          (dy [M, ldy >= N], x [M, K])
@@ -402,7 +405,7 @@ int lin_bwd(Ctx& c, const float* dy, int ldy, const float* x, long long M, int K
     }
     GemmP g = dense(dy, M, ldy, wt, K, dx, K);
     if (accumulate) { g.res = dx; g.ldr = K; }
-    launch_igemm_f32(g, c.st); TKL();
+    g.ws = h->opt_train_splitk ? c.T->splitk_ws : nullptr; g.ws_floats = kSplitKFloats; launch_igemm_f32(g, c.st); TKL();
   }
   return 0;
 }
@@ -434,7 +437,7 @@ int cb_fwd(Ctx& c, CB& r) {
     g.conv = 1; g.H = r.H; g.Wd = r.W; g.Cin = r.Cin; g.OH = r.OH; g.OW = r.OW; g.KH = r.k; g.KW = r.k; g.stride = r.stride; g.pad_t = pt; g.pad_l = pl;
     g.lda = 0;
   }
-  launch_igemm_f32(g, c.st); TKL();
+  g.ws = h->opt_train_splitk ? c.T->splitk_ws : nullptr; g.ws_floats = kSplitKFloats; launch_igemm_f32(g, c.st); TKL();
   return bn_fwd(c, r.z, M, r.bn, r.act, r.res, r.y, &r.stat);
 }
 
@@ -474,7 +477,7 @@ int cb_bwd(Ctx& c, const CB& r, const float* dy, float** dx_out, bool want_dx) {
     g.A = zsrc; g.conv = 1; g.H = ZH; g.Wd = ZW; g.Cin = r.Cout; g.OH = r.H; g.OW = r.W; g.KH = r.k; g.KW = r.k; g.stride = 1;
     g.pad_t = r.k - 1 - r.pt; g.pad_l = r.k - 1 - r.pl;
   }
-  launch_igemm_f32(g, c.st); TKL();
+  g.ws = h->opt_train_splitk ? c.T->splitk_ws : nullptr; g.ws_floats = kSplitKFloats; launch_igemm_f32(g, c.st); TKL();
   *dx_out = dx;
   return 0;
 }
@@ -962,6 +965,7 @@ extern "C" int frx_train_create(frx_handle* h, int32_t max_batch, int32_t max_le
   TCK(cudaMalloc(&T->acc, 2 * 4096 * sizeof(double))); TCK(cudaMalloc(&T->sumsq, 2 * sizeof(double)));
   TCK(cudaMalloc(&T->scal, 64)); TCK(cudaMalloc(&T->ones, 4096 * 4)); TCK(cudaMalloc(&T->zeros, 4096 * 4));
   TCK(cudaMemset(T->zeros, 0, 4096 * 4));
+  TCK(cudaMalloc(&T->splitk_ws, kSplitKFloats * 4));
   launch_fill(T->ones, 1.f, 4096, 0);
   TCK(cudaDeviceSynchronize());
   // activation tape: ~75 MB (forward) + ~150 MB (backward) of fp32 per image at 128 x 256, plus the decoder's
@@ -988,7 +992,7 @@ extern "C" void frx_train_destroy(frx_handle* h) {
   DevGuard g; g.enter(h->cfg.device);
   TrainState* T = state_of(h);
   cudaFree(T->P); if (T->own_G) cudaFree(T->G); cudaFree(T->M); cudaFree(T->V); cudaFree(T->RS); cudaFree(T->acc); cudaFree(T->sumsq);
-  cudaFree(T->scal); cudaFree(T->ones); cudaFree(T->zeros); cudaFree(T->ws); cudaFree(T->img_stage); cudaFree(T->exp_stage);
+  cudaFree(T->scal); cudaFree(T->ones); cudaFree(T->zeros); cudaFree(T->splitk_ws); cudaFree(T->ws); cudaFree(T->img_stage); cudaFree(T->exp_stage);
   for (auto& kv : T->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   delete T;
   h->train = nullptr;
@@ -1005,7 +1009,7 @@ extern "C" int frx_train_fwd_bwd(frx_handle* h, const float* images, const int64
   cudaStream_t st = (cudaStream_t)stream;
   // Eager when graphs are off, when a bucket callback wants to start all-reduces between the kernels of the pass, and on
   // the first use of a shape (which also performs the one-time per-device kernel attribute set-up).
-  TrainState::GraphEntry& ge = T->graphs[{B, L}];
+  TrainState::GraphEntry& ge = T->graphs[{B, 2 * L + (h->opt_train_splitk ? 1 : 0)}];   // the launch plan is part of the key
   if (!h->opt_graphs || T->bucket_cb || ge.seen++ == 0) {
     Ctx c{h, T, st, B, L};
     return fwd_bwd(c, images, (const long long*)expected, loss_out);
