@@ -695,12 +695,123 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdP p) {
     else { *dk = sdk[j * (HD + 1) + d]; *dv = sdv[j * (HD + 1) + d]; }
   }
 }
+// The same backward pass with the queries split over CTAs: grid (batch x head, chunks of ATT_QB queries).  A CTA keeps the
+// head's K and V, recomputes the probabilities P and the score gradients dS of its query rows into shared memory (one
+// warp per row, writing dq on the way), then reduces dV = P^T dO and dK = dS^T Q over ITS rows with one thread per
+// (key, dim) -- no shared-memory atomics -- and adds the result to global dk / dv (zeroed by the launcher unless they
+// accumulate).  One CTA per (batch, head) walked 231 x 231 x 32 x 2 shared atomics serially: 625 us per launch.
+constexpr int ATT_QB = 32;
+__global__ void __launch_bounds__(256) attn_bwd_split_kernel(const AttnBwdP p) {
+  extern __shared__ float sm[];
+  const int HD = p.HD, Lk = p.Lk, Lq = p.Lq;
+  float* sk = sm;                       // [Lk][HD+1]
+  float* sv = sk + Lk * (HD + 1);       // [Lk][HD+1]
+  float* sP = sv + Lk * (HD + 1);       // [ATT_QB][Lk]  probabilities
+  float* sS = sP + ATT_QB * Lk;         // [ATT_QB][Lk]  dS
+  float* sq = sS + ATT_QB * Lk;         // [ATT_QB][HD]
+  float* sdo = sq + ATT_QB * HD;        // [ATT_QB][HD]
+  const int b = blockIdx.x / p.heads, hh = blockIdx.x % p.heads;
+  const int i0 = blockIdx.y * ATT_QB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < Lk * HD; i += 256) {
+    const int j = i / HD, d = i % HD;
+    sk[j * (HD + 1) + d] = p.k[((long long)b * Lk + j) * p.ldk + hh * HD + d];
+    sv[j * (HD + 1) + d] = p.v[((long long)b * Lk + j) * p.ldv + hh * HD + d];
+  }
+  for (int i = threadIdx.x; i < ATT_QB * HD; i += 256) {
+    const int r = i / HD, d = i % HD;
+    const bool ok = i0 + r < Lq;
+    sq[i] = ok ? p.q[((long long)b * Lq + i0 + r) * p.ldq + hh * HD + d] : 0.f;
+    sdo[i] = ok ? p.dout[((long long)b * Lq + i0 + r) * p.ldo + hh * HD + d] : 0.f;
+  }
+  __syncthreads();
+  const float inv_t = 1.f / p.temperature;
+  for (int r = warp; r < ATT_QB; r += 8) {
+    const int i = i0 + r;
+    float* pw = sP + r * Lk;
+    float* dsw = sS + r * Lk;
+    if (i >= Lq) {
+      for (int j = lane; j < Lk; j += 32) { pw[j] = 0.f; dsw[j] = 0.f; }
+      continue;
+    }
+    const float* qp = sq + r * HD;
+    const float* dop = sdo + r * HD;
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) {
+      const bool masked = (p.causal && j > i) || (p.key_mask && p.key_mask[(long long)b * Lk + j]);
+      float sc = -INFINITY;
+      if (!masked) {
+        sc = 0.f;
+        for (int d = 0; d < HD; ++d) sc = fmaf(qp[d], sk[j * (HD + 1) + d], sc);
+        sc *= inv_t;
+      }
+      pw[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+      const float e = pw[j] == -INFINITY ? 0.f : expf(pw[j] - mx);
+      pw[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float delta = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+      const float pj = pw[j] * inv;
+      float dp = 0.f;
+      for (int d = 0; d < HD; ++d) dp = fmaf(dop[d], sv[j * (HD + 1) + d], dp);
+      pw[j] = pj;
+      dsw[j] = dp;
+      delta = fmaf(pj, dp, delta);
+    }
+    delta = warp_sum(delta);
+    for (int j = lane; j < Lk; j += 32) dsw[j] = pw[j] * (dsw[j] - delta) * inv_t;
+    __syncwarp();
+    for (int d = lane; d < HD; d += 32) {   // dq_i = sum_j ds_j k_j
+      float acc = 0.f;
+      for (int j = 0; j < Lk; ++j) acc = fmaf(dsw[j], sk[j * (HD + 1) + d], acc);
+      p.dq[((long long)b * Lq + i) * p.lddq + hh * HD + d] = acc;
+    }
+  }
+  __syncthreads();
+  // dV[j][d] = sum_r P[r][j] dO[r][d],  dK[j][d] = sum_r dS[r][j] Q[r][d] over this CTA's rows
+  for (int j = warp; j < Lk; j += 8) {
+    for (int d = lane; d < HD; d += 32) {
+      float av = 0.f, ak = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < ATT_QB; ++r) {
+        av = fmaf(sP[r * Lk + j], sdo[r * HD + d], av);
+        ak = fmaf(sS[r * Lk + j], sq[r * HD + d], ak);
+      }
+      atomicAdd(p.dv + ((long long)b * Lk + j) * p.lddv + hh * HD + d, av);
+      atomicAdd(p.dk + ((long long)b * Lk + j) * p.lddk + hh * HD + d, ak);
+    }
+  }
+}
+
 int launch_attn_bwd(const AttnBwdP& p, int B, cudaStream_t st) {
+  if (p.Lk > 256) return (int)cudaErrorInvalidValue;
+  const size_t smem2 = ((size_t)2 * p.Lk * (p.HD + 1) + 2 * ATT_QB * p.Lk + 2 * ATT_QB * p.HD) * sizeof(float);
+  if (smem2 <= 200 * 1024) {
+    static SmemOptIn opt2;
+    cudaError_t e = opt2.ensure(attn_bwd_split_kernel, smem2);
+    if (e != cudaSuccess) return (int)e;
+    if (!p.accumulate_kv) {   // the CTAs of a (batch, head) add their partial dk / dv
+      const size_t w = (size_t)p.heads * p.HD * sizeof(float);
+      e = cudaMemset2DAsync(p.dk, (size_t)p.lddk * sizeof(float), 0, w, (size_t)B * p.Lk, st);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaMemset2DAsync(p.dv, (size_t)p.lddv * sizeof(float), 0, w, (size_t)B * p.Lk, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    attn_bwd_split_kernel<<<dim3(B * p.heads, (p.Lq + ATT_QB - 1) / ATT_QB), 256, smem2, st>>>(p);
+    return 0;
+  }
   const size_t smem = ((size_t)4 * p.Lk * (p.HD + 1) + 8 * p.Lk) * sizeof(float);
   static SmemOptIn opt;
   cudaError_t e = opt.ensure(attn_bwd_kernel, smem);
   if (e != cudaSuccess) return (int)e;
-  if (p.Lk > 256) return (int)cudaErrorInvalidValue;
   attn_bwd_kernel<<<B * p.heads, 256, smem, st>>>(p);
   return 0;
 }
