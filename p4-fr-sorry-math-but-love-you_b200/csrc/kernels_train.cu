@@ -253,10 +253,17 @@ __global__ void __launch_bounds__(256) bn_bwd_params_kernel(const double* __rest
 void launch_bn_bwd(const float* dy, const float* z, const float* stat, double* acc, float* dz, float* dgamma, float* dbeta, int M, int C,
                    int act, cudaStream_t st) {
   cudaMemsetAsync(acc, 0, (size_t)C * 2 * sizeof(double), st);
+  // rows per CTA: 512 for the large early-stage maps; for the small late-stage ones (M = 512 rows at 16 images) one CTA
+  // per 32 channels would walk all rows serially (41 us for 6 MB): split the rows until ~600 CTAs exist (the per-CTA
+  // partial sums meet in fp64 atomics either way)
   int chunks = (M + 511) / 512;
+  const int cgroups = (C + 31) / 32;
+  if (cgroups * chunks < 600) chunks = (600 + cgroups - 1) / cgroups;
+  if (chunks > (M + 31) / 32) chunks = (M + 31) / 32;
   if (chunks > 1024) chunks = 1024;
+  if (chunks < 1) chunks = 1;
   const int rows = (M + chunks - 1) / chunks;
-  bn_bwd_reduce_kernel<<<dim3((C + 31) / 32, (M + rows - 1) / rows), 256, 0, st>>>(dy, z, stat, acc, M, C, act, rows);
+  bn_bwd_reduce_kernel<<<dim3(cgroups, (M + rows - 1) / rows), 256, 0, st>>>(dy, z, stat, acc, M, C, act, rows);
   const long long n = (long long)M * C;
   bn_bwd_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, z, stat, acc, dz, n, M, C, act);
   bn_bwd_params_kernel<<<(C + 255) / 256, 256, 0, st>>>(acc, dgamma, dbeta, C);
@@ -459,7 +466,11 @@ void launch_dw_bwd(const float* dz, const float* x, const float* w, float* dx, f
   dw_bwd_data_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dz, w, dx, B, H, W, C, OH, OW, stride, pad_t, pad_l);
   const long long P = (long long)B * OH * OW;
   long long chunks = (P + 255) / 256;
+  const long long cgroups = (C + 31) / 32;
+  if (cgroups * chunks < 600) chunks = (600 + cgroups - 1) / cgroups;   // small late-stage maps: more pixel chunks, not two long serial walks
+  if (chunks > (P + 7) / 8) chunks = (P + 7) / 8;
   if (chunks > 256) chunks = 256;
+  if (chunks < 1) chunks = 1;
   const int per = (int)((P + chunks - 1) / chunks);
   dw_bwd_filter_kernel<<<dim3((C + 31) / 32, (unsigned)((P + per - 1) / per)), 256, 0, st>>>(dz, x, dw, db, B, H, W, C, OH, OW, stride, pad_t,
                                                                                              pad_l, per);
