@@ -17,8 +17,11 @@
 //     trip at most; every stage is K-split over two warps, the partial fragments meet in shared memory and
 //     the epilogue works on 8-column row pieces so that all DSMEM / global stores are 16 bytes wide;
 //   * attention of (image w, head r) is one warp on the tensor cores (q replicated over the MMA rows), K/V
-//     rows staged global -> shared by cp.async one 32-key block ahead (block 0 is requested before the
-//     projection GEMM that produces q) and turned into B fragments with ldmatrix / ldmatrix.trans;
+//     rows staged global -> shared one or two 32-key blocks ahead and turned into B fragments with ldmatrix /
+//     ldmatrix.trans.  The caches keep every row's 16-byte chunks pre-swizzled in HBM, so a block of a contiguous
+//     history is one contiguous piece: the two-block-ring geometry fetches it with ONE bulk copy per operand
+//     (cp.async.bulk on a per-slot mbarrier) and requests the next phase's first blocks as soon as the ring is idle;
+//     the other geometries (and ancestor-chain histories) use per-lane cp.async;
 //   * work that nobody waits for in this step -- the K/V cache rows of the layer OUTPUT (the
 //     reference caches layer outputs) -- runs between a stage's stores and its wait.
 // LayerNorm / residual are recomputed redundantly per CTA on the gathered rows (cheaper than another
