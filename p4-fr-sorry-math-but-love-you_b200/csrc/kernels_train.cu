@@ -349,9 +349,10 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradP p) {
 }
 void launch_wgrad(WgradP p, int num_sms, cudaStream_t st) {
   const int tn = (p.N + 63) / 64, tk = (p.K + 63) / 64;
-  // enough m-splits for ~4 waves of CTAs, at least 256 rows each
+  // enough m-splits for ~4 waves of CTAs, at least 64 rows each (256 left the late-stage layers of a 16-image batch,
+  // M = 512 rows, at two splits: 192 CTAs walking 16 slabs each)
   long long splits = (4LL * num_sms + tn * tk - 1) / (tn * tk);
-  const long long max_splits = (p.M + 255) / 256;
+  const long long max_splits = (p.M + 63) / 64;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.m_chunk = ((p.M + splits - 1) / splits + 15) / 16 * 16;
