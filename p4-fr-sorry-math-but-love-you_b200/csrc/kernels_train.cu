@@ -492,7 +492,28 @@ __global__ void __launch_bounds__(256) spatial_dot_kernel(const float* __restric
   for (int q = 0; q < S; ++q) s = bp ? fmaf(__ldg(ap + (long long)q * C), __ldg(bp + (long long)q * C), s) : s + __ldg(ap + (long long)q * C);
   out[(long long)b * C + c] = s * scale;
 }
+// the same product-sum (b2 != nullptr: the backward pass of the squeeze-excite gate) with the S rows split over four row
+// lanes per channel: 4x the CTAs and a quarter of the serial walk (the forward means keep the kernel above and its order)
+__global__ void __launch_bounds__(256) spatial_dot4_kernel(const float* __restrict__ a, const float* __restrict__ b2, float* __restrict__ out, int S, int C,
+                                                           float scale) {
+  __shared__ float part[4][64];
+  const int b = blockIdx.y, cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  float s = 0.f;
+  if (c < C) {
+    const float* ap = a + (long long)b * S * C + c;
+    const float* bp = b2 + (long long)b * S * C + c;
+    for (int q = rl; q < S; q += 4) s = fmaf(__ldg(ap + (long long)q * C), __ldg(bp + (long long)q * C), s);
+  }
+  part[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) out[(long long)b * C + c] = ((part[0][cl] + part[1][cl]) + (part[2][cl] + part[3][cl])) * scale;
+}
 void launch_spatial_dot(const float* a, const float* b2, float* out, int B, int S, int C, float scale, cudaStream_t st) {
+  if (b2 && S >= 16) {
+    spatial_dot4_kernel<<<dim3((C + 63) / 64, B), 256, 0, st>>>(a, b2, out, S, C, scale);
+    return;
+  }
   spatial_dot_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(a, b2, out, S, C, scale);
 }
 // out[b][q][c] = x[b][q][c] * g[b][c] (+ add[b][c])   (SE excite; and its backward dy = dout*g + ds/S)
