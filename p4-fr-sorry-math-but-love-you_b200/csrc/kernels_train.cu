@@ -633,8 +633,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 }
 void launch_ln_bwd(const float* dy, const float* x, const float* stat, const float* gamma, float* dx, float* dgamma, float* dbeta, int M, int C,
                    cudaStream_t st) {
-  int ctas = (M + 63) / 64;
-  if (ctas > 296) ctas = 296;
+  int ctas = (M + 15) / 16;   // two rows per warp: the 512-row LayerNorms of a 16-image batch used 8 CTAs
+  if (ctas > 592) ctas = 592;
   const int rows = (M + ctas - 1) / ctas;
   ln_bwd_kernel<<<(M + rows - 1) / rows, 256, 2 * C * sizeof(float), st>>>(dy, x, stat, gamma, dx, dgamma, dbeta, M, C, rows);
 }
