@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnBwdP p) {
 // warp per row, writing dq on the way), then reduces dV = P^T dO and dK = dS^T Q over ITS rows with one thread per
 // (key, dim) -- no shared-memory atomics -- and adds the result to global dk / dv (zeroed by the launcher unless they
 // accumulate).  One CTA per (batch, head) walked 231 x 231 x 32 x 2 shared atomics serially: 625 us per launch.
-constexpr int ATT_QB = 32;
+constexpr int ATT_QB = 16;
 __global__ void __launch_bounds__(256) attn_bwd_split_kernel(const AttnBwdP p) {
   extern __shared__ float sm[];
   const int HD = p.HD, Lk = p.Lk, Lq = p.Lq;
